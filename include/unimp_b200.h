@@ -1,0 +1,189 @@
+/*
+ * unimp_b200.h — C ABI of the B200-native UniMP / OpenFlamingo hot path.
+ *
+ * The reference (weitianxin/UniMP) has NO native code and NO FFI: every GPU kernel it
+ * runs is reached through PyTorch modules of the un-vendored `open_flamingo==2.0.1`
+ * package (reference requirements.txt:35, imported at UniMP/mmrec.py:20-22) and through
+ * the in-tree loss arithmetic (UniMP/mmrec.py:190-213).  Each entry point below names
+ * the Python interface it replaces.  SURVEY.md §8(b) is the contract this header meets.
+ *
+ * Conventions (all functions):
+ *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises or allocates;
+ *   - returns 0 on success, <0 for an invalid argument (UNIMP_E_*), >0 = cudaError_t;
+ *     unimp_last_error_string() describes the last failure on the calling thread;
+ *   - `dtype` is the storage type of activation tensors: accumulation, softmax and
+ *     LayerNorm statistics are always fp32;
+ *   - re-entrant and thread-safe; safe to capture in a CUDA graph.
+ *   - compiled for sm_100a only.  There is no CPU path.
+ */
+#ifndef UNIMP_B200_H_
+#define UNIMP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIMP_ABI_VERSION 1
+
+typedef enum { UNIMP_F32 = 0, UNIMP_BF16 = 1 } unimp_dtype_t;
+
+enum {
+  UNIMP_E_NULL = -1,      /* required pointer is NULL */
+  UNIMP_E_SHAPE = -2,     /* unsupported / inconsistent shape */
+  UNIMP_E_DTYPE = -3,     /* unsupported dtype */
+  UNIMP_E_ALIGN = -4,     /* pointer or stride not 16-byte aligned */
+  UNIMP_E_DEVICE = -5     /* not running on an sm_100 device */
+};
+
+/* Strided (batch, row, head, d) view; d is contiguous, head stride = dh elements.
+ * Element (b, r, h, d) lives at base + b*batch_stride + r*row_stride + h*dh + d
+ * (strides in ELEMENTS).  This is what `to_q(x)` / `to_kv(media).chunk(2)` /
+ * `in_proj(x).chunk(3)` produce without any copy. */
+typedef struct {
+  const void* ptr;
+  int64_t batch_stride;
+  int64_t row_stride;
+} unimp_view_t;
+
+typedef struct {
+  void* ptr;
+  int64_t batch_stride;
+  int64_t row_stride;
+} unimp_mview_t;
+
+int unimp_version(void);
+const char* unimp_last_error_string(void);
+/* 1 if the current device is sm_100 (B200), else 0. Host-side query, no stream. */
+int unimp_device_ok(void);
+
+/* ---- a4: media_locations -> text_time ------------------------------------------------
+ * Replaces `FlamingoLMMixin.forward`'s `media_locations = input_ids == media_token_id`
+ * plus MaskedCrossAttention's `text_time = media_locations.cumsum(-1)` (or, with
+ * use_cached != 0, `count_nonzero(media_locations)` of the CACHED prompt broadcast over
+ * the T_out new tokens) — SURVEY §9; call site UniMP/mmrec.py:177-181.
+ * lang_x (B,T) int64 -> text_time (B,T_out) int32.  T_out = T unless use_cached. */
+int unimp_text_time(const int64_t* lang_x, int64_t media_token_id, int B, int T,
+                    int use_cached, int T_out, int32_t* text_time, void* stream);
+
+/* ---- a7 / K1: masked, media-located cross-attention core ------------------------------
+ * Replaces the einsum/masked_fill/amax/softmax/masked_fill/einsum core of
+ * `MaskedCrossAttention.forward`, only_attend_immediate_media=True.
+ * q (B,T,H,dh) pre-projection-scaled NOT required: `scale` is applied in-kernel.
+ * k,v (B,Ti*n,H,dh).  Row i of sample b attends the n keys of image text_time[b,i]-1;
+ * text_time==0 -> output row 0, lse = -inf;  text_time > Ti -> uniform attention over
+ * all Ti*n keys (upstream's all-masked softmax; kept for parity).
+ * o (B,T,H,dh) ; lse (B,H,T) fp32 = log-sum-exp of scale*q.k over the attended keys.
+ * dh must be 64; n (latents per image) must be 64 for the tensor-core path. */
+int unimp_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* text_time,
+                    unimp_mview_t o, float* lse, int B, int T, int Ti, int n, int H, int dh,
+                    float scale, int dtype, void* stream);
+/* Backward.  workspace: caller scratch of unimp_attn_bwd_workspace(B,T,Ti*n,H,dh) bytes,
+ * 16-byte aligned.  dq/dk/dv are fully written (zero where nothing attends). */
+int64_t unimp_attn_bwd_workspace(int Bt, int Lq, int Lk, int H, int dh);
+int unimp_xattn_bwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* text_time,
+                    unimp_view_t o, unimp_view_t d_o, const float* lse, void* workspace,
+                    unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, int B, int T, int Ti,
+                    int n, int H, int dh, float scale, int dtype, void* stream);
+
+/* Test hooks (CUDA-core implementation forced; tt may be NULL = unmasked). */
+int unimp__attn_fwd_simt(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
+                         unimp_mview_t o, float* lse, int B, int Lq, int Lk, int H, int n, int Ti,
+                         int dh, float scale, int dtype, void* stream);
+int unimp__attn_bwd_simt(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
+                         unimp_view_t o, unimp_view_t d_o, const float* lse, void* workspace,
+                         unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, int B, int Lq,
+                         int Lk, int H, int n, int Ti, int dh, float scale, int dtype,
+                         void* stream);
+
+/* ---- K2 / K3: unmasked attention core (Perceiver 64x320, ViT-L/14 257x257) ------------
+ * Replaces `PerceiverAttention.forward`'s einsum/softmax/einsum and the
+ * ViT `nn.MultiheadAttention` core (the dead UniMP/xformers_model/clip.py:130-136 is
+ * the same shape).  q (Bt,Lq,H,dh), k/v (Bt,Lk,H,dh) -> o (Bt,Lq,H,dh), lse (Bt,H,Lq). */
+int unimp_attn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o, float* lse,
+                   int Bt, int Lq, int Lk, int H, int dh, float scale, int dtype, void* stream);
+int unimp_attn_bwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t o,
+                   unimp_view_t d_o, const float* lse, void* workspace, unimp_mview_t dq,
+                   unimp_mview_t dk, unimp_mview_t dv, int Bt, int Lq, int Lk, int H, int dh,
+                   float scale, int dtype, void* stream);
+
+/* ---- a12: decode step against cached cross-attention K/V ------------------------------
+ * One new token per sequence attends the LAST image's n cached keys.  Upstream
+ * recomputes to_kv(media) every step; the cache is new here.
+ * q (B,1,H,dh); k,v (B,Ti*n,H,dh) cached; n_media[b] = count of <image> in the prompt. */
+int unimp_xattn_decode(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* n_media,
+                       unimp_mview_t o, int B, int Ti, int n, int H, int dh, float scale,
+                       int dtype, void* stream);
+
+/* ---- a6 / K5: tanh-gate + residual + LayerNorm epilogue -------------------------------
+ * Replaces `x = f(x) * tanh(gate) + x` of `GatedCrossAttentionBlock.forward` fused with
+ * the LayerNorm that consumes it (the FF's LN, or MaskedCrossAttention.norm) — SURVEY §9.
+ *   x_out = branch * tanh(*gate) + x        (branch == NULL: x_out = x, not written;
+ *                                            gate is one element of `dtype`;
+ *                                            gate == NULL: plain residual, factor 1)
+ *   ln_out = LN(x_out) * gamma + beta       (gamma == NULL: LN skipped)
+ * rows x D, D % 8 == 0, D <= 8192.  mean/rstd (rows) fp32 saved for backward. */
+int unimp_gate_residual_ln_fwd(const void* branch, const void* x, const void* gate,
+                               const void* gamma, const void* beta, void* x_out, void* ln_out,
+                               float* mean, float* rstd, int64_t rows, int D, float eps,
+                               int dtype, void* stream);
+/* Backward.  g_xout / g_ln are the incoming grads of the two outputs (either may be NULL).
+ * d_x = g_xout + LNbwd(g_ln);  d_branch = d_x * tanh(gate);
+ * d_gate = sum(d_x * branch) * (1 - tanh^2)  ; d_gamma/d_beta = column sums (`dtype`,
+ * written not accumulated; any of the three may be NULL).
+ * partial is caller scratch of unimp_gate_residual_ln_bwd_workspace() bytes. */
+int64_t unimp_gate_residual_ln_bwd_workspace(int64_t rows, int D);
+int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void* branch,
+                               const void* x_out, const void* gate, const void* gamma,
+                               const float* mean, const float* rstd, void* d_x, void* d_branch,
+                               void* d_gate, void* d_gamma, void* d_beta, void* partial,
+                               int64_t rows, int D, int dtype, void* stream);
+
+/* ---- a10 / K6: task-weighted focal cross-entropy head ---------------------------------
+ * Replaces reference UniMP/mmrec.py:190-213 (shift-by-one CE * weights * (1-pt)^gamma,
+ * divided by the number of valid labels) in ONE read pass over the valid rows.
+ * logits (B,T,V) with row stride `ld` elements (ld >= V); labels (B,T) int64 with -100;
+ * row (b,t), t < T-1, is scored against labels[b,t+1].  weights (B) fp32.
+ * use_focal == 0 reproduces plain weighted CE (reference --use_reweight off).
+ * Outputs: row_lse, row_pt (B*T) fp32 (undefined on ignored rows);
+ *          acc[0] = sum_i w*CE*(1-pt)^gamma, acc[1] = n_valid (fp32);
+ *          *loss = acc[0]/acc[1]  (NaN when n_valid == 0, as the reference does).
+ * The sum runs in a fixed order: the loss is bit-reproducible run to run.
+ * workspace: unimp_focal_ce_workspace(B,T,V,dtype) bytes of caller scratch. */
+int64_t unimp_focal_ce_workspace(int B, int T, int V, int dtype);
+int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t* labels,
+                       const float* weights, float gamma, int use_focal, float* row_lse,
+                       float* row_pt, float* acc, float* loss, void* workspace, int B, int T,
+                       int V, int dtype, void* stream);
+/* d_logits (B,T,V) row stride ld_out, fully written: zero on ignored rows and at t = T-1.
+ * g_loss: device scalar (fp32) upstream gradient of the loss. */
+int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t* labels,
+                       const float* weights, float gamma, int use_focal, const float* row_lse,
+                       const float* row_pt, const float* acc, const float* g_loss,
+                       void* d_logits, int64_t ld_out, int B, int T, int V, int dtype,
+                       void* stream);
+
+/* ---- a9 (f2): answer-span label masking on the GPU -----------------------------------
+ * Replaces the Python double loop of reference UniMP/mmrec.py:143-168. */
+int unimp_mask_labels(const int64_t* input_ids, int64_t answer_id, int64_t endofchunk_id,
+                      int64_t media_id, int64_t pad_id, int64_t* labels, int B, int T,
+                      void* stream);
+
+/* ---- f1: fused AdamW over a flat parameter group --------------------------------------
+ * Replaces torch.optim.AdamW.step for one param group (reference UniMP/mmrec.py:671) with
+ * grad-clip scaling folded in (clip coefficient = min(1, max_norm/(norm+1e-6)),
+ * UniMP/mmrec.py:247-248).  master/m/v fp32, grad `dtype`; writes the `dtype` working
+ * copy `param`.  gnorm_sq: device scalar, sum of squared grads (NULL = no clipping). */
+int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
+                     float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, const float* gnorm_sq,
+                     float max_norm, float grad_scale, int dtype, void* stream);
+/* acc[0] += sum(grad^2) (fp32). */
+int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIMP_B200_H_ */

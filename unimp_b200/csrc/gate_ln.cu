@@ -1,0 +1,327 @@
+// K5 — fused tanh-gate + residual + LayerNorm epilogue of GatedCrossAttentionBlock
+// (`x = f(x) * tanh(gate) + x`, then the LayerNorm that consumes x).
+//
+// HBM-bound.  One CTA per row keeps the whole row in registers (<= 4 x 16 B per thread), so
+// forward touches every tensor once: read branch, read x, write x_out, write ln_out
+// (algorithmic bytes 4*rows*D*sizeof(T)).  Backward is one pass too (read g_xout, g_ln,
+// branch, x_out; write d_x, d_branch) with per-CTA column partials for d_gamma/d_beta/d_gate
+// reduced by a second small kernel in fixed order (deterministic).
+#include "common.cuh"
+
+namespace unimp {
+
+constexpr int LN_VPT = 4;  // 16-byte vectors held per thread
+
+static inline int ln_threads(int D, int n_per_vec) {
+  const int nvec = D / n_per_vec;
+  int t = (nvec + LN_VPT - 1) / LN_VPT;
+  t = ((t + 31) / 32) * 32;
+  return t;
+}
+
+template <typename T>
+__global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ x,
+                                            const T* __restrict__ gate,
+                                            const T* __restrict__ gamma, const T* __restrict__ beta,
+                                            T* __restrict__ x_out, T* __restrict__ ln_out,
+                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                            int D, float eps) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t row = blockIdx.x;
+  const int nvec = D / N;
+  const T* xr = x + row * D;
+  const T* br = branch ? branch + row * D : nullptr;
+  float v[LN_VPT][N];
+  const float tg = br ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+      Vec16<T> a;
+      a.load(xr + j * N);
+      a.unpack(v[k]);
+      if (br) {
+        Vec16<T> b;
+        float bf[N];
+        b.load_stream(br + j * N);
+        b.unpack(bf);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[k][i] = fmaf(bf[i], tg, v[k][i]);
+        // the residual stream is stored in T: LN must see the rounded value the next
+        // consumer reads, so statistics are taken on the rounded x_out.
+        Vec16<T> o;
+        o.pack(v[k]);
+        o.store(x_out + row * D + j * N);
+        o.unpack(v[k]);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) s += v[k][i];
+    }
+  }
+  if (!gamma) return;
+  __shared__ float sh[32];
+  const float mean = block_sum(s, sh) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float d = v[k][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float var = block_sum(q, sh) / D;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    mean_o[row] = mean;
+    rstd_o[row] = rstd;
+  }
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+      Vec16<T> g, b;
+      float gf[N], bf[N], o[N];
+      g.load(gamma + j * N);
+      g.unpack(gf);
+      b.load(beta + j * N);
+      b.unpack(bf);
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gf[i], bf[i]);
+      Vec16<T> ov;
+      ov.pack(o);
+      ov.store(ln_out + row * D + j * N);
+    }
+  }
+}
+
+// Persistent-style: CTA c handles rows c, c+G, ...; column partials live in registers.
+// partial layout: [G][2*D + 1]: d_gamma cols, d_beta cols, d_gate.
+template <typename T>
+__global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ g_ln,
+                                            const T* __restrict__ branch, const T* __restrict__ x_out,
+                                            const T* __restrict__ gate,
+                                            const T* __restrict__ gamma,
+                                            const float* __restrict__ mean_i,
+                                            const float* __restrict__ rstd_i, T* __restrict__ d_x,
+                                            T* __restrict__ d_branch, float* __restrict__ partial,
+                                            int64_t rows, int D) {
+  constexpr int N = Vec16<T>::N;
+  const int nvec = D / N;
+  const bool has_ln = g_ln != nullptr && gamma != nullptr;
+  const float tg = branch ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
+  float dg[LN_VPT][N], db[LN_VPT][N], gam[LN_VPT][N];
+  float dgate = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f, gam[k][i] = 0.f;
+    const int j = threadIdx.x + k * blockDim.x;
+    if (has_ln && j < nvec) {
+      Vec16<T> g;
+      g.load(gamma + j * N);
+      g.unpack(gam[k]);
+    }
+  }
+  __shared__ float sh[32];
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    float gy[LN_VPT][N], xh[LN_VPT][N];
+    float s1 = 0.f, s2 = 0.f;
+    float mean = 0.f, rstd = 0.f;
+    if (has_ln) {
+      mean = mean_i[row];
+      rstd = rstd_i[row];
+#pragma unroll
+      for (int k = 0; k < LN_VPT; ++k) {
+        const int j = threadIdx.x + k * blockDim.x;
+        if (j < nvec) {
+          Vec16<T> a, b;
+          float gl[N], xo[N];
+          a.load_stream(g_ln + row * D + j * N);
+          a.unpack(gl);
+          b.load_stream(x_out + row * D + j * N);
+          b.unpack(xo);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            xh[k][i] = (xo[i] - mean) * rstd;
+            gy[k][i] = gl[i] * gam[k][i];
+            s1 += gy[k][i];
+            s2 += gy[k][i] * xh[k][i];
+            dg[k][i] += gl[i] * xh[k][i];
+            db[k][i] += gl[i];
+          }
+        }
+      }
+      s1 = block_sum(s1, sh) / D;
+      s2 = block_sum(s2, sh) / D;
+    }
+#pragma unroll
+    for (int k = 0; k < LN_VPT; ++k) {
+      const int j = threadIdx.x + k * blockDim.x;
+      if (j < nvec) {
+        float dx[N];
+        if (g_xout) {
+          Vec16<T> a;
+          a.load_stream(g_xout + row * D + j * N);
+          a.unpack(dx);
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) dx[i] = 0.f;
+        }
+        if (has_ln) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) dx[i] += rstd * (gy[k][i] - s1 - xh[k][i] * s2);
+        }
+        Vec16<T> o;
+        o.pack(dx);
+        o.store(d_x + row * D + j * N);
+        if (branch) {
+          Vec16<T> b;
+          float bf[N], dbr[N];
+          b.load_stream(branch + row * D + j * N);
+          b.unpack(bf);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            dgate += dx[i] * bf[i];
+            dbr[i] = dx[i] * tg;
+          }
+          Vec16<T> ob;
+          ob.pack(dbr);
+          ob.store(d_branch + row * D + j * N);
+        }
+      }
+    }
+  }
+  float* pr = partial + (int64_t)blockIdx.x * (2 * D + 1);
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        pr[j * N + i] = dg[k][i];
+        pr[D + j * N + i] = db[k][i];
+      }
+    }
+  }
+  dgate = block_sum(dgate, sh);
+  if (threadIdx.x == 0) pr[2 * D] = dgate * (1.f - tg * tg);
+}
+
+// Reduce partial[G][2D+1] over G in fixed order. One thread per column.
+template <typename T>
+__global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ partial, int G, int D,
+                                                   T* __restrict__ d_gate, T* __restrict__ d_gamma,
+                                                   T* __restrict__ d_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 2 * D + 1;
+  if (c >= W) return;
+  float s = 0.f;
+  for (int g = 0; g < G; ++g) s += partial[(int64_t)g * W + c];
+  if (c < D) {
+    if (d_gamma) d_gamma[c] = Elem<T>::from_f(s);
+  } else if (c < 2 * D) {
+    if (d_beta) d_beta[c - D] = Elem<T>::from_f(s);
+  } else {
+    if (d_gate) d_gate[0] = Elem<T>::from_f(s);
+  }
+}
+
+static inline int ln_bwd_grid(int64_t rows) {
+  const int64_t g = 2 * UNIMP_NUM_SMS;
+  return (int)(rows < g ? rows : g);
+}
+
+}  // namespace unimp
+
+using namespace unimp;
+
+extern "C" int unimp_gate_residual_ln_fwd(const void* branch, const void* x, const void* gate,
+                                          const void* gamma, const void* beta, void* x_out,
+                                          void* ln_out, float* mean, float* rstd, int64_t rows,
+                                          int D, float eps, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(x, UNIMP_E_NULL, "gate_residual_ln_fwd: x is NULL");
+  UNIMP_CHECK_ARG(!branch || x_out, UNIMP_E_NULL, "gate_residual_ln_fwd: branch given without x_out");
+  UNIMP_CHECK_ARG(!gamma || (beta && ln_out && mean && rstd), UNIMP_E_NULL,
+                  "gate_residual_ln_fwd: gamma given without beta/ln_out/mean/rstd");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE,
+                  "gate_residual_ln_fwd: dtype");
+  const int npv = dtype == UNIMP_BF16 ? 8 : 4;
+  UNIMP_CHECK_ARG(rows >= 0 && D > 0 && D % npv == 0 && D / npv <= 1024 * LN_VPT, UNIMP_E_SHAPE,
+                  "gate_residual_ln_fwd: D=%d must be a multiple of %d and <= %d", D, npv,
+                  1024 * LN_VPT * npv);
+  UNIMP_CHECK_ARG(aligned16(x) && aligned16(branch) && aligned16(gamma) && aligned16(beta) &&
+                      aligned16(x_out) && aligned16(ln_out),
+                  UNIMP_E_ALIGN, "gate_residual_ln_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const int threads = ln_threads(D, npv);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNIMP_BF16)
+    gate_residual_ln_fwd_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, st>>>(
+        (const __nv_bfloat16*)branch, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate,
+        (const __nv_bfloat16*)gamma,
+        (const __nv_bfloat16*)beta, (__nv_bfloat16*)x_out, (__nv_bfloat16*)ln_out, mean, rstd, D,
+        eps);
+  else
+    gate_residual_ln_fwd_kernel<float><<<(unsigned)rows, threads, 0, st>>>(
+        (const float*)branch, (const float*)x, (const float*)gate, (const float*)gamma,
+        (const float*)beta,
+        (float*)x_out, (float*)ln_out, mean, rstd, D, eps);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int64_t unimp_gate_residual_ln_bwd_workspace(int64_t rows, int D) {
+  return (int64_t)ln_bwd_grid(rows > 0 ? rows : 1) * (2 * (int64_t)D + 1) * sizeof(float);
+}
+
+extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void* branch,
+                                          const void* x_out, const void* gate, const void* gamma,
+                                          const float* mean, const float* rstd, void* d_x,
+                                          void* d_branch, void* d_gate, void* d_gamma,
+                                          void* d_beta, void* partial, int64_t rows, int D,
+                                          int dtype, void* stream) {
+  UNIMP_CHECK_ARG(d_x && partial, UNIMP_E_NULL, "gate_residual_ln_bwd: d_x/partial NULL");
+  UNIMP_CHECK_ARG(g_xout || g_ln, UNIMP_E_NULL, "gate_residual_ln_bwd: no incoming gradient");
+  UNIMP_CHECK_ARG(!g_ln || (gamma && x_out && mean && rstd), UNIMP_E_NULL,
+                  "gate_residual_ln_bwd: g_ln given without gamma/x_out/mean/rstd");
+  UNIMP_CHECK_ARG(!branch || d_branch, UNIMP_E_NULL,
+                  "gate_residual_ln_bwd: branch given without d_branch");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE,
+                  "gate_residual_ln_bwd: dtype");
+  const int npv = dtype == UNIMP_BF16 ? 8 : 4;
+  UNIMP_CHECK_ARG(rows > 0 && D > 0 && D % npv == 0 && D / npv <= 1024 * LN_VPT, UNIMP_E_SHAPE,
+                  "gate_residual_ln_bwd: bad rows/D");
+  UNIMP_CHECK_ARG(aligned16(g_xout) && aligned16(g_ln) && aligned16(branch) && aligned16(x_out) &&
+                      aligned16(gamma) && aligned16(d_x) && aligned16(d_branch),
+                  UNIMP_E_ALIGN, "gate_residual_ln_bwd: pointers must be 16-byte aligned");
+  const int threads = ln_threads(D, npv);
+  const int G = ln_bwd_grid(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNIMP_BF16)
+    gate_residual_ln_bwd_kernel<__nv_bfloat16><<<G, threads, 0, st>>>(
+        (const __nv_bfloat16*)g_xout, (const __nv_bfloat16*)g_ln, (const __nv_bfloat16*)branch,
+        (const __nv_bfloat16*)x_out, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)gamma, mean,
+        rstd,
+        (__nv_bfloat16*)d_x, (__nv_bfloat16*)d_branch, (float*)partial, rows, D);
+  else
+    gate_residual_ln_bwd_kernel<float><<<G, threads, 0, st>>>(
+        (const float*)g_xout, (const float*)g_ln, (const float*)branch, (const float*)x_out,
+        (const float*)gate,
+        (const float*)gamma, mean, rstd, (float*)d_x, (float*)d_branch, (float*)partial, rows, D);
+  UNIMP_CHECK_LAUNCH();
+  const int W = 2 * D + 1;
+  if (dtype == UNIMP_BF16)
+    gate_residual_ln_bwd_reduce_kernel<__nv_bfloat16><<<(W + 255) / 256, 256, 0, st>>>(
+        (const float*)partial, G, D, (__nv_bfloat16*)d_gate, (__nv_bfloat16*)d_gamma,
+        (__nv_bfloat16*)d_beta);
+  else
+    gate_residual_ln_bwd_reduce_kernel<float><<<(W + 255) / 256, 256, 0, st>>>(
+        (const float*)partial, G, D, (float*)d_gate, (float*)d_gamma, (float*)d_beta);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}

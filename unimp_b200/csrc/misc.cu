@@ -1,0 +1,210 @@
+// Integer/bookkeeping kernels on either side of the attention path, plus the fused AdamW:
+//   unimp_text_time    (a4)  media_locations -> per-token image index, ballot prefix scan
+//   unimp_mask_labels  (a9)  reference UniMP/mmrec.py:143-168 as a warp scan
+//   unimp_adamw_step   (f1)  reference UniMP/mmrec.py:671 (+ clip 247-248), one HBM pass
+//   unimp_sumsq        grad-norm partial for the clip
+#include "common.cuh"
+
+namespace unimp {
+
+// One warp per sample; 32 tokens per step; running count carried in a register.
+__global__ void text_time_kernel(const int64_t* __restrict__ lang_x, int64_t media_id, int B, int T,
+                                 int use_cached, int T_out, int32_t* __restrict__ text_time) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int64_t* row = lang_x + (int64_t)b * T;
+  int run = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool f = t < T && row[t] == media_id;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (!use_cached && t < T)
+      text_time[(int64_t)b * T_out + t] = run + __popc(m & (0xffffffffu >> (31 - lane)));
+    run += __popc(m);
+  }
+  if (use_cached)
+    for (int t = lane; t < T_out; t += 32) text_time[(int64_t)b * T_out + t] = run;
+}
+
+// State after a token depends only on the LAST event token (<answer> sets, <|endofchunk|>
+// clears), so "in answer span before token j" == last <answer> before j is later than the
+// last <|endofchunk|> before j.  One warp per sample.
+__global__ void mask_labels_kernel(const int64_t* __restrict__ ids, int64_t answer_id,
+                                   int64_t eoc_id, int64_t media_id, int64_t pad_id,
+                                   int64_t* __restrict__ labels, int B, int T) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int64_t* row = ids + (int64_t)b * T;
+  int last_ans = -1, last_eoc = -1;  // positions strictly before the current chunk
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const int64_t tok = t < T ? row[t] : pad_id;
+    const unsigned ma = __ballot_sync(0xffffffffu, t < T && tok == answer_id);
+    const unsigned me = __ballot_sync(0xffffffffu, t < T && tok == eoc_id);
+    const unsigned below = lane ? (0xffffffffu >> (32 - lane)) : 0u;
+    const unsigned pa = ma & below, pe = me & below;
+    const int la = pa ? t0 + 31 - __clz(pa) : last_ans;
+    const int le = pe ? t0 + 31 - __clz(pe) : last_eoc;
+    const bool in_answer = la > le;
+    if (t < T) {
+      int64_t lab = tok;
+      if (!in_answer || tok == eoc_id) lab = -100;     // mmrec.py:149-156
+      if (tok == pad_id) lab = -100;                   // mmrec.py:157
+      if (t == 0) lab = -100;                          // mmrec.py:158
+      if (tok == answer_id || tok == media_id) lab = -100;  // mmrec.py:167-168
+      labels[(int64_t)b * T + t] = lab;
+    }
+    if (ma) last_ans = t0 + 31 - __clz(ma);
+    if (me) last_eoc = t0 + 31 - __clz(me);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const T* __restrict__ g, int64_t n, float* __restrict__ acc) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t nvec = n / N;
+  float s = 0.f;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nvec;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> v;
+    float f[N];
+    v.load_stream(g + j * N);
+    v.unpack(f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += f[i] * f[i];
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * N + threadIdx.x; i < n; i += blockDim.x) {
+      const float f = Elem<T>::to_f(g[i]);
+      s += f * f;
+    }
+  __shared__ float sh[32];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+// One pass: read grad, master, m, v; write master, m, v and the T working copy.
+template <typename T>
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ master, T* __restrict__ param, const T* __restrict__ grad,
+             float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float b1, float b2,
+             float eps, float wd, float bc1, float bc2_sqrt, const float* __restrict__ gnorm_sq,
+             float max_norm, float grad_scale) {
+  float clip = grad_scale;
+  if (gnorm_sq) {
+    // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)
+    const float norm = sqrtf(*gnorm_sq) * grad_scale;
+    clip *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
+    if (i0 + 4 <= n) {
+      float4 p4 = *reinterpret_cast<float4*>(master + i0);
+      float4 m4 = *reinterpret_cast<float4*>(m + i0);
+      float4 v4 = *reinterpret_cast<float4*>(v + i0);
+      float p[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w},
+            vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g = Elem<T>::to_f(grad[i0 + i]) * clip;
+        p[i] *= 1.f - lr * wd;                       // decoupled weight decay
+        mm[i] = b1 * mm[i] + (1.f - b1) * g;
+        vv[i] = b2 * vv[i] + (1.f - b2) * g * g;
+        const float denom = sqrtf(vv[i]) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mm[i] / denom);
+        param[i0 + i] = Elem<T>::from_f(p[i]);
+      }
+      *reinterpret_cast<float4*>(master + i0) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(m + i0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + i0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+      for (int64_t i = i0; i < n; ++i) {
+        const float g = Elem<T>::to_f(grad[i]) * clip;
+        float p = master[i] * (1.f - lr * wd);
+        const float mm = b1 * m[i] + (1.f - b1) * g;
+        const float vv = b2 * v[i] + (1.f - b2) * g * g;
+        p -= (lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        master[i] = p; m[i] = mm; v[i] = vv;
+        param[i] = Elem<T>::from_f(p);
+      }
+    }
+  }
+}
+
+}  // namespace unimp
+
+using namespace unimp;
+
+extern "C" int unimp_text_time(const int64_t* lang_x, int64_t media_token_id, int B, int T,
+                               int use_cached, int T_out, int32_t* text_time, void* stream) {
+  UNIMP_CHECK_ARG(lang_x && text_time, UNIMP_E_NULL, "text_time: NULL pointer");
+  UNIMP_CHECK_ARG(B > 0 && T > 0 && T_out > 0 && (use_cached || T_out == T), UNIMP_E_SHAPE,
+                  "text_time: bad shape B=%d T=%d T_out=%d", B, T, T_out);
+  const int wpb = 4;
+  text_time_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+      lang_x, media_token_id, B, T, use_cached, T_out, text_time);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int unimp_mask_labels(const int64_t* input_ids, int64_t answer_id, int64_t endofchunk_id,
+                                 int64_t media_id, int64_t pad_id, int64_t* labels, int B, int T,
+                                 void* stream) {
+  UNIMP_CHECK_ARG(input_ids && labels, UNIMP_E_NULL, "mask_labels: NULL pointer");
+  UNIMP_CHECK_ARG(B > 0 && T > 0, UNIMP_E_SHAPE, "mask_labels: bad shape");
+  const int wpb = 4;
+  mask_labels_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+      input_ids, answer_id, endofchunk_id, media_id, pad_id, labels, B, T);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(grad && acc, UNIMP_E_NULL, "sumsq: NULL pointer");
+  UNIMP_CHECK_ARG(aligned16(grad), UNIMP_E_ALIGN, "sumsq: grad must be 16-byte aligned");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "sumsq: dtype");
+  if (n <= 0) return 0;
+  const int npv = dtype == UNIMP_BF16 ? 8 : 4;
+  int64_t blocks = (n / npv + 255) / 256;
+  if (blocks > 8 * UNIMP_NUM_SMS) blocks = 8 * UNIMP_NUM_SMS;
+  if (blocks < 1) blocks = 1;
+  if (dtype == UNIMP_BF16)
+    sumsq_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)grad, n, acc);
+  else
+    sumsq_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)grad, n,
+                                                                             acc);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
+                                float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, int step, const float* gnorm_sq,
+                                float max_norm, float grad_scale, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(master && param && grad && exp_avg && exp_avg_sq, UNIMP_E_NULL,
+                  "adamw_step: NULL pointer");
+  UNIMP_CHECK_ARG(step >= 1, UNIMP_E_SHAPE, "adamw_step: step must be >= 1");
+  UNIMP_CHECK_ARG(aligned16(master) && aligned16(exp_avg) && aligned16(exp_avg_sq), UNIMP_E_ALIGN,
+                  "adamw_step: fp32 state must be 16-byte aligned");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "adamw_step: dtype");
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 16 * UNIMP_NUM_SMS) blocks = 16 * UNIMP_NUM_SMS;
+  if (blocks < 1) blocks = 1;
+  if (dtype == UNIMP_BF16)
+    adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, lr,
+        beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_scale);
+  else
+    adamw_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        master, (float*)param, (const float*)grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+        weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_scale);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}

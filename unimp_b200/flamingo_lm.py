@@ -1,0 +1,153 @@
+"""FlamingoLayer / FlamingoLMMixin — the language-model side of the drop-in.
+
+Same names, attributes and conditioning protocol as `open_flamingo/src/flamingo_lm.py`
+v2.0.1: the mixin is grafted onto a HF causal LM *instance*, builds
+`gated_cross_attn_layers`, wraps each decoder layer in a FlamingoLayer, and its forward
+derives media locations from `input_ids == media_token_id`.  New here: the per-token image
+index (`text_time`, int32) is computed ONCE per forward by the `unimp_text_time` kernel and
+handed to every layer, instead of a bool mask being re-cumsum'ed and materialised per layer;
+and `forward(labels=...)` gets its logged mean CE (`out[0]`, reference UniMP/mmrec.py:182)
+from the one-pass focal-CE kernel rather than HF's fp32 upcast + CrossEntropyLoss.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+from . import ops
+from .helpers import GatedCrossAttentionBlock
+
+
+def getattr_recursive(obj, att):
+    if att == "":
+        return obj
+    i = att.find(".")
+    if i < 0:
+        return getattr(obj, att)
+    return getattr_recursive(getattr(obj, att[:i]), att[i + 1:])
+
+
+def setattr_recursive(obj, att, val):
+    if "." in att:
+        obj = getattr_recursive(obj, ".".join(att.split(".")[:-1]))
+    setattr(obj, att.split(".")[-1], val)
+
+
+def extend_instance(obj, mixin):
+    """Apply a mixin to an existing instance (upstream `utils.extend_instance`)."""
+    base_cls = obj.__class__
+    obj.__class__ = type(base_cls.__name__, (mixin, base_cls), {})
+
+
+class FlamingoLayer(nn.Module):
+    def __init__(self, gated_cross_attn_layer, decoder_layer, gradient_checkpointing=False):
+        super().__init__()
+        self.gated_cross_attn_layer = gated_cross_attn_layer
+        self.decoder_layer = decoder_layer
+        self.vis_x = None
+        self.media_locations = None
+        self.text_time = None
+        self.use_cached_media = False
+
+    def is_conditioned(self) -> bool:
+        return self.vis_x is not None and self.media_locations is not None
+
+    def condition_vis_x(self, vis_x):
+        self.vis_x = vis_x
+        if vis_x is None and self.gated_cross_attn_layer is not None:
+            self.gated_cross_attn_layer.attn._kv_cache = None
+
+    def condition_media_locations(self, media_locations, text_time=None):
+        self.media_locations = media_locations
+        self.text_time = text_time
+
+    def condition_use_cached_media(self, use_cached_media):
+        self.use_cached_media = use_cached_media
+
+    def forward(self, lang_x, attention_mask=None, **decoder_layer_kwargs):
+        if self.gated_cross_attn_layer is not None:
+            if self.vis_x is None:
+                raise ValueError("vis_x must be conditioned before forward pass")
+            if self.media_locations is None:
+                raise ValueError("media_locations must be conditioned before forward pass")
+            tt = self.text_time
+            if tt is not None and tt.shape[1] != lang_x.shape[1]:
+                tt = None  # stale (e.g. cached prompt length): let the block derive it
+            lang_x = self.gated_cross_attn_layer(
+                lang_x, self.vis_x, media_locations=self.media_locations,
+                use_cached_media=self.use_cached_media, text_time=tt)
+        return self.decoder_layer(lang_x, attention_mask=attention_mask, **decoder_layer_kwargs)
+
+
+class FlamingoLMMixin(nn.Module):
+    """Mixin adding gated cross-attention to a HF causal LM instance."""
+
+    def set_decoder_layers_attr_name(self, name):
+        self.decoder_layers_attr_name = name
+
+    def _get_decoder_layers(self):
+        return getattr_recursive(self, self.decoder_layers_attr_name)
+
+    def _set_decoder_layers(self, value):
+        setattr_recursive(self, self.decoder_layers_attr_name, value)
+
+    def init_flamingo(self, media_token_id, lang_hidden_size, vis_hidden_size,
+                      cross_attn_every_n_layers, gradient_checkpointing=False):
+        self.old_decoder_blocks = self._get_decoder_layers()
+        self.gated_cross_attn_layers = nn.ModuleList([
+            GatedCrossAttentionBlock(dim=lang_hidden_size, dim_visual=vis_hidden_size)
+            if (i + 1) % cross_attn_every_n_layers == 0 else None
+            for i, _ in enumerate(self._get_decoder_layers())
+        ])
+        self.init_flamingo_layers(gradient_checkpointing)
+        self.media_token_id = media_token_id
+        self.initialized_flamingo = True
+        self._use_cached_vision_x = False
+
+    def init_flamingo_layers(self, gradient_checkpointing=False):
+        self._set_decoder_layers(nn.ModuleList([
+            FlamingoLayer(g, d, gradient_checkpointing)
+            for g, d in zip(self.gated_cross_attn_layers, self.old_decoder_blocks)
+        ]))
+
+    def forward(self, input_ids=None, attention_mask=None, labels=None, **kwargs):
+        if not self.initialized_flamingo:
+            raise ValueError("Flamingo layers are not initialized. Call `init_flamingo` first.")
+        media_locations = input_ids == self.media_token_id
+        # single host sync per forward only on the decode path, exactly where upstream has it
+        use_cached = bool(self._use_cached_vision_x and self.is_conditioned()
+                          and not media_locations.any())
+        layers = self._get_decoder_layers()
+        if use_cached:
+            cached = layers[0].media_locations
+            tt = ops.text_time(cached.to(torch.int64), 1, use_cached=True,
+                               T_out=input_ids.shape[1])
+            for layer in layers:
+                layer.text_time = tt
+                layer.condition_use_cached_media(True)
+        else:
+            tt = ops.text_time(input_ids, self.media_token_id)
+            for layer in layers:
+                layer.condition_media_locations(media_locations, tt)
+                layer.condition_use_cached_media(False)
+        kwargs["input_ids"] = input_ids
+        kwargs["attention_mask"] = attention_mask
+        out = super().forward(**kwargs)  # HF forward without labels: no fp32 logits copy
+        if labels is None:
+            return out
+        logits = out.logits
+        ones = torch.ones(logits.shape[0], dtype=torch.float32, device=logits.device)
+        loss = ops.focal_ce(logits, labels, ones, gamma=0.0, use_focal=False)  # HF mean CE
+        return CausalLMOutputWithPast(loss=loss, logits=logits,
+                                      past_key_values=out.past_key_values,
+                                      hidden_states=out.hidden_states, attentions=out.attentions)
+
+    def is_conditioned(self) -> bool:
+        return all(l.is_conditioned() for l in self._get_decoder_layers())
+
+    def clear_conditioned_layers(self):
+        for layer in self._get_decoder_layers():
+            layer.condition_vis_x(None)
+            layer.condition_media_locations(None)
+            layer.condition_use_cached_media(None)

@@ -1,0 +1,320 @@
+"""torch.autograd wrappers over the C ABI (include/unimp_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op below launches
+hand-written sm_100a kernels through ctypes.  No CPU path, no fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, View, check
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise _lib.UnimpError("unimp_b200 ops need CUDA tensors (there is no CPU fallback)")
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.UnimpError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _view3(t: torch.Tensor) -> View:
+    """(B, L, H*dh) tensor with unit inner stride -> unimp_view_t (strides in elements)."""
+    assert t.dim() == 3 and t.stride(2) == 1, (t.shape, t.stride())
+    return View(t.data_ptr(), t.stride(0), t.stride(1))
+
+
+def _inner_contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+# --------------------------------------------------------------------------- text_time
+
+def text_time(lang_x: torch.Tensor, media_token_id: int, *, use_cached: bool = False,
+              T_out: int | None = None) -> torch.Tensor:
+    """int32 (B, T_out): cumsum of `lang_x == media_token_id` (or its total, broadcast, when
+    `use_cached`) — MaskedCrossAttention's text_time."""
+    assert lang_x.dtype == torch.int64 and lang_x.dim() == 2 and lang_x.is_cuda
+    lang_x = lang_x.contiguous()
+    B, T = lang_x.shape
+    T_out = T if T_out is None else T_out
+    out = torch.empty((B, T_out), dtype=torch.int32, device=lang_x.device)
+    check(_lib.load().unimp_text_time(lang_x.data_ptr(), int(media_token_id), B, T,
+                                      int(use_cached), T_out, out.data_ptr(), _stream()),
+          "unimp_text_time")
+    return out
+
+
+def mask_labels(input_ids, *, answer_token_id, endofchunk_token_id, media_token_id, pad_token_id):
+    """GPU form of reference UniMP/mmrec.py:143-168."""
+    assert input_ids.dtype == torch.int64 and input_ids.dim() == 2 and input_ids.is_cuda
+    input_ids = input_ids.contiguous()
+    B, T = input_ids.shape
+    out = torch.empty_like(input_ids)
+    check(_lib.load().unimp_mask_labels(input_ids.data_ptr(), int(answer_token_id),
+                                        int(endofchunk_token_id), int(media_token_id),
+                                        int(pad_token_id), out.data_ptr(), B, T, _stream()),
+          "unimp_mask_labels")
+    return out
+
+
+# --------------------------------------------------------------------------- attention
+
+class _Attention(torch.autograd.Function):
+    """q (B,Lq,H*64); kv (B,Lk,2*H*64) packed [k | v]; text_time int32 (B,Lq) or None."""
+
+    @staticmethod
+    def forward(ctx, q, kv, tt, heads, n, Ti, scale, force_simt):
+        dt = _dt(q)
+        assert kv.dtype == q.dtype
+        q = _inner_contig(q)
+        kv = _inner_contig(kv)
+        B, Lq, inner = q.shape
+        Lk = kv.shape[1]
+        dh = inner // heads
+        assert kv.shape[2] == 2 * inner and kv.shape[0] == B
+        k, v = kv[..., :inner], kv[..., inner:]
+        o = torch.empty((B, Lq, inner), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B, heads, Lq), dtype=torch.float32, device=q.device)
+        lib = _lib.load()
+        if tt is not None:
+            assert tt.dtype == torch.int32 and tt.shape == (B, Lq) and tt.is_contiguous()
+        if force_simt:
+            rc = lib.unimp__attn_fwd_simt(_view3(q), _view3(k), _view3(v), _ptr(tt), _view3(o),
+                                          lse.data_ptr(), B, Lq, Lk, heads, n, Ti, dh, scale, dt,
+                                          _stream())
+        elif tt is not None:
+            assert Lk == Ti * n
+            rc = lib.unimp_xattn_fwd(_view3(q), _view3(k), _view3(v), tt.data_ptr(), _view3(o),
+                                     lse.data_ptr(), B, Lq, Ti, n, heads, dh, scale, dt, _stream())
+        else:
+            rc = lib.unimp_attn_fwd(_view3(q), _view3(k), _view3(v), _view3(o), lse.data_ptr(), B,
+                                    Lq, Lk, heads, dh, scale, dt, _stream())
+        check(rc, "attention forward")
+        ctx.save_for_backward(q, kv, o, lse, tt)
+        ctx.cfg = (heads, n, Ti, scale, force_simt, dt)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse, tt = ctx.saved_tensors
+        heads, n, Ti, scale, force_simt, dt = ctx.cfg
+        B, Lq, inner = q.shape
+        Lk = kv.shape[1]
+        dh = inner // heads
+        d_o = _inner_contig(d_o)
+        k, v = kv[..., :inner], kv[..., inner:]
+        dq = torch.empty_like(q, memory_format=torch.contiguous_format)
+        dkv = torch.empty((B, Lk, 2 * inner), dtype=kv.dtype, device=kv.device)
+        dk, dv = dkv[..., :inner], dkv[..., inner:]
+        lib = _lib.load()
+        ws = torch.empty(lib.unimp_attn_bwd_workspace(B, Lq, Lk, heads, dh), dtype=torch.uint8,
+                         device=q.device)
+        if force_simt:
+            rc = lib.unimp__attn_bwd_simt(_view3(q), _view3(k), _view3(v), _ptr(tt), _view3(o),
+                                          _view3(d_o), lse.data_ptr(), ws.data_ptr(), _view3(dq),
+                                          _view3(dk), _view3(dv), B, Lq, Lk, heads, n, Ti, dh,
+                                          scale, dt, _stream())
+        elif tt is not None:
+            rc = lib.unimp_xattn_bwd(_view3(q), _view3(k), _view3(v), tt.data_ptr(), _view3(o),
+                                     _view3(d_o), lse.data_ptr(), ws.data_ptr(), _view3(dq),
+                                     _view3(dk), _view3(dv), B, Lq, Ti, n, heads, dh, scale, dt,
+                                     _stream())
+        else:
+            rc = lib.unimp_attn_bwd(_view3(q), _view3(k), _view3(v), _view3(o), _view3(d_o),
+                                    lse.data_ptr(), ws.data_ptr(), _view3(dq), _view3(dk),
+                                    _view3(dv), B, Lq, Lk, heads, dh, scale, dt, _stream())
+        check(rc, "attention backward")
+        return dq, dkv, None, None, None, None, None, None
+
+
+def masked_cross_attention(q, kv, text_time_i32, *, heads: int, n_latents: int, scale: float,
+                           force_simt: bool = False):
+    """K1: each query row attends the `n_latents` keys of image text_time-1 (0 -> zero row)."""
+    Lk = kv.shape[1]
+    assert Lk % n_latents == 0
+    return _Attention.apply(q, kv, text_time_i32, heads, n_latents, Lk // n_latents, float(scale),
+                            force_simt)
+
+
+def attention(q, kv, *, heads: int, scale: float, force_simt: bool = False):
+    """K2/K3: unmasked softmax(scale * q k^T) v, packed kv."""
+    return _Attention.apply(q, kv, None, heads, kv.shape[1], 1, float(scale), force_simt)
+
+
+def xattn_decode(q, kv, n_media_i32, *, heads: int, n_latents: int, scale: float):
+    """a12: single-token decode against cached packed K/V. q (B,1,H*64)."""
+    dt = _dt(q)
+    q = _inner_contig(q)
+    kv = _inner_contig(kv)
+    B, one, inner = q.shape
+    assert one == 1
+    Lk = kv.shape[1]
+    k, v = kv[..., :inner], kv[..., inner:]
+    o = torch.empty_like(q, memory_format=torch.contiguous_format)
+    check(_lib.load().unimp_xattn_decode(_view3(q), _view3(k), _view3(v), n_media_i32.data_ptr(),
+                                         _view3(o), B, Lk // n_latents, n_latents, heads,
+                                         inner // heads, float(scale), dt, _stream()),
+          "unimp_xattn_decode")
+    return o
+
+
+# --------------------------------------------------------------------------- gate + residual + LN
+
+class _GateResidualLN(torch.autograd.Function):
+    """mode bits: 1 = has branch (gate+residual), 2 = has LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, branch, x, gate, gamma, beta, eps):
+        dt = _dt(x)
+        x = x.contiguous()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        has_b, has_ln = branch is not None, gamma is not None
+        if has_b:
+            branch = branch.contiguous()
+            assert branch.shape == x.shape and branch.dtype == x.dtype
+            assert gate is None or (gate.dtype == x.dtype and gate.numel() == 1)
+        x_out = torch.empty_like(x) if has_b else None
+        ln_out = torch.empty_like(x) if has_ln else None
+        mean = rstd = None
+        if has_ln:
+            assert gamma.dtype == x.dtype and beta.dtype == x.dtype
+            gamma, beta = gamma.contiguous(), beta.contiguous()
+            mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+            rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(_lib.load().unimp_gate_residual_ln_fwd(
+            _ptr(branch), x.data_ptr(), _ptr(gate), _ptr(gamma), _ptr(beta), _ptr(x_out),
+            _ptr(ln_out), _ptr(mean), _ptr(rstd), rows, D, float(eps), dt, _stream()),
+            "unimp_gate_residual_ln_fwd")
+        ctx.save_for_backward(branch, x_out if has_b else x, gate, gamma, mean, rstd)
+        ctx.cfg = (has_b, has_ln, rows, D, dt)
+        if has_b and has_ln:
+            return x_out, ln_out
+        return x_out if has_b else ln_out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        branch, xo, gate, gamma, mean, rstd = ctx.saved_tensors
+        has_b, has_ln, rows, D, dt = ctx.cfg
+        if has_b and has_ln:
+            g_xout, g_ln = grads
+        elif has_b:
+            g_xout, g_ln = grads[0], None
+        else:
+            g_xout, g_ln = None, grads[0]
+        if g_xout is not None:
+            g_xout = g_xout.contiguous()
+        if g_ln is not None:
+            g_ln = g_ln.contiguous()
+        lib = _lib.load()
+        d_x = torch.empty_like(xo)
+        d_branch = torch.empty_like(xo) if has_b else None
+        d_gate = torch.empty_like(gate) if (has_b and gate is not None) else None
+        d_gamma = torch.empty_like(gamma) if (has_ln and g_ln is not None) else None
+        d_beta = torch.empty_like(gamma) if (has_ln and g_ln is not None) else None
+        ws = torch.empty(lib.unimp_gate_residual_ln_bwd_workspace(rows, D), dtype=torch.uint8,
+                         device=xo.device)
+        use_ln = has_ln and g_ln is not None
+        check(lib.unimp_gate_residual_ln_bwd(
+            _ptr(g_xout), _ptr(g_ln) if use_ln else None, _ptr(branch), xo.data_ptr(),
+            _ptr(gate), _ptr(gamma) if use_ln else None, _ptr(mean), _ptr(rstd), d_x.data_ptr(),
+            _ptr(d_branch), _ptr(d_gate), _ptr(d_gamma), _ptr(d_beta), ws.data_ptr(), rows, D, dt,
+            _stream()), "unimp_gate_residual_ln_bwd")
+        if has_ln and d_gamma is None:
+            d_gamma = torch.zeros_like(gamma)
+            d_beta = torch.zeros_like(gamma)
+        return d_branch, d_x, d_gate, d_gamma, d_beta, None
+
+
+def gate_residual_ln(branch, x, gate, gamma, beta, eps: float = 1e-5):
+    """K5: x_out = branch*tanh(gate) + x ; ln_out = LN(x_out)*gamma+beta -> (x_out, ln_out)."""
+    return _GateResidualLN.apply(branch, x, gate, gamma, beta, eps)
+
+
+def gate_residual(branch, x, gate):
+    """K5 without the LayerNorm: branch*tanh(gate) + x (gate None: branch + x)."""
+    return _GateResidualLN.apply(branch, x, gate, None, None, 0.0)
+
+
+def layer_norm(x, gamma, beta, eps: float = 1e-5):
+    """K5 without the gate: LN(x)*gamma+beta (MaskedCrossAttention.norm, perceiver norms)."""
+    return _GateResidualLN.apply(None, x, None, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------- focal CE
+
+class _FocalCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, weights, gamma, use_focal):
+        dt = _dt(logits)
+        assert logits.dim() == 3 and labels.shape == logits.shape[:2]
+        B, T, V = logits.shape
+        if logits.stride(2) != 1 or logits.stride(0) != T * logits.stride(1):
+            logits = logits.contiguous()
+        ld = logits.stride(1)
+        labels = labels.to(device=logits.device, dtype=torch.int64).contiguous()
+        weights = weights.to(device=logits.device, dtype=torch.float32).contiguous()
+        dev = logits.device
+        lib = _lib.load()
+        row_lse = torch.empty(B * T, dtype=torch.float32, device=dev)
+        row_pt = torch.empty(B * T, dtype=torch.float32, device=dev)
+        acc = torch.empty(2, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.unimp_focal_ce_workspace(B, T, V, dt), dtype=torch.uint8, device=dev)
+        check(lib.unimp_focal_ce_fwd(logits.data_ptr(), ld, labels.data_ptr(), weights.data_ptr(),
+                                     float(gamma), int(use_focal), row_lse.data_ptr(),
+                                     row_pt.data_ptr(), acc.data_ptr(), loss.data_ptr(),
+                                     ws.data_ptr(), B, T, V, dt, _stream()), "unimp_focal_ce_fwd")
+        ctx.save_for_backward(logits, labels, weights, row_lse, row_pt, acc)
+        ctx.cfg = (float(gamma), int(use_focal), ld, dt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        logits, labels, weights, row_lse, row_pt, acc = ctx.saved_tensors
+        gamma, use_focal, ld, dt = ctx.cfg
+        B, T, V = logits.shape
+        g = g_loss.to(torch.float32).contiguous()
+        buf = torch.empty((B, T, ld), dtype=logits.dtype, device=logits.device)
+        check(_lib.load().unimp_focal_ce_bwd(logits.data_ptr(), ld, labels.data_ptr(),
+                                             weights.data_ptr(), gamma, use_focal,
+                                             row_lse.data_ptr(), row_pt.data_ptr(), acc.data_ptr(),
+                                             g.data_ptr(), buf.data_ptr(), ld, B, T, V, dt,
+                                             _stream()), "unimp_focal_ce_bwd")
+        return (buf[..., :V] if ld != V else buf), None, None, None, None
+
+
+def focal_ce(logits, labels, weights, *, gamma: float = 2.0, use_focal: bool = True):
+    """K6: reference UniMP/mmrec.py:190-213 on (B,T,V) logits, (B,T) labels, (B,) weights."""
+    return _FocalCE.apply(logits, labels, weights, gamma, use_focal)
+
+
+# --------------------------------------------------------------------------- optimizer pieces
+
+def sumsq_(grad: torch.Tensor, acc: torch.Tensor):
+    """acc[0] += sum(grad^2)."""
+    check(_lib.load().unimp_sumsq(grad.data_ptr(), grad.numel(), acc.data_ptr(), _dt(grad),
+                                  _stream()), "unimp_sumsq")
+
+
+def adamw_step_(master, param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay,
+                step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    check(_lib.load().unimp_adamw_step(master.data_ptr(), param.data_ptr(), grad.data_ptr(),
+                                       exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                       float(lr), float(beta1), float(beta2), float(eps),
+                                       float(weight_decay), int(step), _ptr(gnorm_sq),
+                                       float(max_norm), float(grad_scale), _dt(param), _stream()),
+          "unimp_adamw_step")
