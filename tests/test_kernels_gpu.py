@@ -1,0 +1,269 @@
+"""Per-kernel parity on the GPU: CUDA path (through the C ABI) vs the oracle arithmetic on the
+same seeded inputs.  Tolerances: fp32 rel 1e-4; bf16 rel 2e-2 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from util import max_rel, rel_err
+
+from oracle.flamingo_oracle import MaskedCrossAttention as OracleMCA
+from oracle.loss_oracle import focal_loss, mask_labels as oracle_mask_labels
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def ops():
+    from unimp_b200 import ops as o
+    return o
+
+
+# ------------------------------------------------------------------ text_time / labels (bit-exact)
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 33), (4, 256), (2, 1000)])
+def test_text_time_bit_exact(B, T):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    ids = torch.randint(0, 6, (B, T), generator=g)
+    tt = ops().text_time(ids.to(DEV), 3)
+    assert torch.equal(tt.cpu().long(), (ids == 3).cumsum(-1))
+    cached = ops().text_time(ids.to(DEV), 3, use_cached=True, T_out=5)
+    assert torch.equal(cached.cpu().long(), (ids == 3).sum(-1, keepdim=True).expand(B, 5))
+
+
+@pytest.mark.parametrize("B,T", [(2, 16), (3, 100), (2, 257)])
+def test_mask_labels_bit_exact_vs_reference_loop(B, T):
+    g = torch.Generator().manual_seed(T)
+    A, E, M, P = 7, 8, 9, 10
+    ids = torch.randint(0, 12, (B, T), generator=g)  # dense in special tokens: hits every branch
+    want = oracle_mask_labels(ids, answer_token_id=A, endofchunk_token_id=E, media_token_id=M, pad_token_id=P)
+    got = ops().mask_labels(ids.to(DEV), answer_token_id=A, endofchunk_token_id=E, media_token_id=M, pad_token_id=P)
+    assert torch.equal(got.cpu(), want)
+
+
+# ------------------------------------------------------------------ attention cores
+
+def _dense_attn_ref(q, kv, tt, heads, n, scale):
+    """fp64 dense restatement with upstream's masking semantics (oracle MaskedCrossAttention core)."""
+    B, Lq, inner = q.shape
+    Lk = kv.shape[1]
+    dh = inner // heads
+    k, v = kv[..., :inner], kv[..., inner:]
+    qh = q.view(B, Lq, heads, dh).transpose(1, 2) * scale
+    kh = k.view(B, Lk, heads, dh).transpose(1, 2)
+    vh = v.view(B, Lk, heads, dh).transpose(1, 2)
+    sim = qh @ kh.transpose(-1, -2)
+    if tt is not None:
+        Ti = Lk // n
+        media_time = (torch.arange(Ti, device=q.device) + 1).repeat_interleave(n)
+        mask = tt[:, None, :, None] == media_time[None, None, None, :]
+        sim = sim.masked_fill(~mask, -torch.finfo(sim.dtype).max)
+    sim = sim - sim.amax(-1, keepdim=True).detach()
+    attn = sim.softmax(-1)
+    if tt is not None:
+        attn = attn.masked_fill((tt == 0)[:, None, :, None], 0.0)
+    out = attn @ vh
+    return out.transpose(1, 2).reshape(B, Lq, inner)
+
+
+def _mk_tt(B, T, Ti, seed, overflow=False):
+    g = torch.Generator().manual_seed(seed)
+    loc = torch.zeros(B, T, dtype=torch.bool)
+    for b in range(B):
+        k = Ti if b % 2 == 0 else max(1, Ti - 1)
+        if overflow and b == 0:
+            k = Ti + 1
+        pos = torch.randperm(T - 2, generator=g)[:k] + (2 if b % 2 else 0)
+        loc[b, pos] = True
+    return loc.cumsum(-1).to(torch.int32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,T,Ti,overflow", [(2, 32, 2, False), (3, 256, 2, False), (2, 100, 5, False),
+                                             (2, 48, 2, True), (1, 513, 8, False)])
+@pytest.mark.parametrize("simt", [True, False])
+def test_masked_cross_attention_fwd_bwd(dtype, tol, B, T, Ti, overflow, simt):
+    H, dh, n = 8, 64, 64
+    torch.manual_seed(B * T + Ti)
+    q = torch.randn(B, T, H * dh, dtype=torch.float64)
+    kv = torch.randn(B, Ti * n, 2 * H * dh, dtype=torch.float64)
+    tt = _mk_tt(B, T, Ti, seed=T, overflow=overflow)
+    go = torch.randn(B, T, H * dh, dtype=torch.float64)
+    # quantise inputs to the storage dtype first so both sides see identical numbers
+    q, kv, go = (t.to(dtype).double() for t in (q, kv, go))
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    ref = _dense_attn_ref(qr, kvr, tt.long(), H, n, dh ** -0.5)
+    ref.backward(go)
+    qd = q.to(DEV, dtype).requires_grad_(True)
+    kvd = kv.to(DEV, dtype).requires_grad_(True)
+    out = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=dh ** -0.5,
+                                       force_simt=simt)
+    out.backward(go.to(DEV, dtype))
+    assert rel_err(out, ref) < tol
+    assert rel_err(qd.grad, qr.grad) < tol
+    assert rel_err(kvd.grad, kvr.grad) < tol
+    zero_rows = (tt == 0)
+    assert out.detach().cpu()[zero_rows].abs().max() == 0 if zero_rows.any() else True
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("Bt,Lq,Lk,H", [(4, 64, 320, 8), (2, 257, 257, 16), (3, 17, 17, 1), (1, 64, 80, 8)])
+@pytest.mark.parametrize("simt", [True, False])
+def test_unmasked_attention_fwd_bwd(dtype, tol, Bt, Lq, Lk, H, simt):
+    """Perceiver (64x320) and ViT (257x257) shapes plus ragged tails; q/kv as strided views of a
+    packed qkv projection (no copies), like the model calls it."""
+    dh = 64
+    torch.manual_seed(Lq * Lk)
+    inner = H * dh
+    qkv = torch.randn(Bt, max(Lq, Lk), 3 * inner, dtype=torch.float64).to(dtype).double()
+    go = torch.randn(Bt, Lq, inner, dtype=torch.float64).to(dtype).double()
+    r = qkv.clone().requires_grad_(True)
+    ref = _dense_attn_ref(r[:, :Lq, :inner], r[:, :Lk, inner:], None, H, Lk, 0.125)
+    ref.backward(go)
+    d = qkv.to(DEV, dtype).requires_grad_(True)
+    out = ops().attention(d[:, :Lq, :inner], d[:, :Lk, inner:], heads=H, scale=0.125, force_simt=simt)
+    out.backward(go.to(DEV, dtype))
+    assert rel_err(out, ref) < tol
+    assert rel_err(d.grad, r.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_xattn_decode_matches_full(dtype, tol):
+    B, Ti, n, H, dh = 5, 3, 64, 8, 64
+    torch.manual_seed(0)
+    q = torch.randn(B, 1, H * dh).to(dtype).double()
+    kv = torch.randn(B, Ti * n, 2 * H * dh).to(dtype).double()
+    nm = torch.tensor([1, 3, 0, 2, 4], dtype=torch.int32)  # 0 -> zeros, 4 > Ti -> uniform
+    ref = _dense_attn_ref(q, kv, nm.long()[:, None], H, n, 0.125)
+    out = ops().xattn_decode(q.to(DEV, dtype), kv.to(DEV, dtype), nm.to(DEV), heads=H, n_latents=n, scale=0.125)
+    assert rel_err(out, ref) < tol
+    assert out[2].abs().max() == 0
+
+
+# ------------------------------------------------------------------ gate + residual + LN
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("rows,D", [(7, 128), (768, 2560), (33, 1024), (5, 64)])
+@pytest.mark.parametrize("mode", ["gate_ln", "gate", "ln", "resid_ln"])
+def test_gate_residual_ln(dtype, tol, rows, D, mode):
+    torch.manual_seed(rows + D)
+    f64 = torch.float64
+    branch = torch.randn(rows, D).to(dtype).to(f64)
+    x = torch.randn(rows, D).to(dtype).to(f64)
+    gate = torch.tensor([0.5], dtype=f64)
+    gamma = (1 + 0.1 * torch.randn(D)).to(dtype).to(f64)
+    beta = (0.1 * torch.randn(D)).to(dtype).to(f64)
+    g1 = torch.randn(rows, D).to(dtype).to(f64)
+    g2 = torch.randn(rows, D).to(dtype).to(f64)
+    leaves = [t.clone().requires_grad_(True) for t in (branch, x, gate, gamma, beta)]
+    b_, x_, gt_, ga_, be_ = leaves
+    dl = [t.detach().to(DEV, dtype).requires_grad_(True) for t in (branch, x, gate, gamma, beta)]
+    db, dx, dgt, dga, dbe = dl
+    o = ops()
+    if mode == "gate_ln":
+        xo = b_ * gt_.tanh() + x_
+        ln = torch.nn.functional.layer_norm(xo, (D,), ga_, be_, 1e-5)
+        (xo * g1 + ln * g2).sum().backward()
+        xo_d, ln_d = o.gate_residual_ln(db, dx, dgt, dga, dbe, 1e-5)
+        (xo_d * g1.to(DEV, dtype) + ln_d * g2.to(DEV, dtype)).sum().backward()
+        pairs = [(xo_d, xo), (ln_d, ln), (db.grad, b_.grad), (dx.grad, x_.grad), (dgt.grad, gt_.grad),
+                 (dga.grad, ga_.grad), (dbe.grad, be_.grad)]
+    elif mode == "resid_ln":
+        xo = b_ + x_
+        ln = torch.nn.functional.layer_norm(xo, (D,), ga_, be_, 1e-5)
+        (xo * g1 + ln * g2).sum().backward()
+        xo_d, ln_d = o.gate_residual_ln(db, dx, None, dga, dbe, 1e-5)
+        (xo_d * g1.to(DEV, dtype) + ln_d * g2.to(DEV, dtype)).sum().backward()
+        pairs = [(xo_d, xo), (ln_d, ln), (db.grad, b_.grad), (dx.grad, x_.grad), (dga.grad, ga_.grad),
+                 (dbe.grad, be_.grad)]
+    elif mode == "gate":
+        xo = b_ * gt_.tanh() + x_
+        (xo * g1).sum().backward()
+        xo_d = o.gate_residual(db, dx, dgt)
+        (xo_d * g1.to(DEV, dtype)).sum().backward()
+        pairs = [(xo_d, xo), (db.grad, b_.grad), (dx.grad, x_.grad), (dgt.grad, gt_.grad)]
+    else:
+        ln = torch.nn.functional.layer_norm(x_, (D,), ga_, be_, 1e-5)
+        (ln * g2).sum().backward()
+        ln_d = o.layer_norm(dx, dga, dbe, 1e-5)
+        (ln_d * g2.to(DEV, dtype)).sum().backward()
+        pairs = [(ln_d, ln), (dx.grad, x_.grad), (dga.grad, ga_.grad), (dbe.grad, be_.grad)]
+    for got, want in pairs:
+        assert rel_err(got, want) < tol, mode
+
+
+# ------------------------------------------------------------------ focal CE
+
+@pytest.mark.parametrize("dtype,tol_l,tol_g", [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1e-3, 2e-2)])
+@pytest.mark.parametrize("B,T,V", [(2, 8, 128), (3, 33, 1001), (2, 16, 74053), (1, 2, 100)])
+@pytest.mark.parametrize("gamma,use", [(2.0, True), (0.0, False), (0.5, True)])
+def test_focal_ce_fwd_bwd(dtype, tol_l, tol_g, B, T, V, gamma, use):
+    torch.manual_seed(B * T + V)
+    z = (3 * torch.randn(B, T, V)).to(dtype)
+    y = torch.randint(0, V, (B, T))
+    y[:, 0] = -100
+    if B > 1:
+        y[0, T // 2:] = -100
+    if B * T > 4:
+        y[-1, 1] = V - 1
+    w = torch.tensor([2.0, 1.0, 1.0][:B])
+    zr = z.double().requires_grad_(True)
+    ref = focal_loss(zr, y, w.double(), gamma=gamma, use_reweight=use)
+    ref.backward()
+    zd = z.to(DEV).requires_grad_(True)
+    loss = ops().focal_ce(zd, y.to(DEV), w.to(DEV), gamma=gamma, use_focal=use)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol_l
+    assert rel_err(zd.grad, zr.grad) < tol_g
+    # rows that carry no label get an exactly-zero gradient, and so does the last step
+    assert zd.grad[:, -1].abs().max() == 0
+    if B > 1:
+        assert zd.grad[0, T // 2 - 1:].abs().max() == 0
+
+
+def test_focal_ce_padded_row_stride_and_determinism():
+    """logits as a view of a padded buffer (ld > V); two runs give the identical loss bits."""
+    B, T, V, ld = 2, 12, 1003, 1008
+    torch.manual_seed(0)
+    buf = torch.randn(B, T, ld, device=DEV, dtype=torch.bfloat16)
+    z = buf[..., :V]
+    y = torch.randint(0, V, (B, T), device=DEV)
+    w = torch.ones(B, device=DEV)
+    a = ops().focal_ce(z, y, w)
+    b = ops().focal_ce(z.contiguous(), y, w)
+    c = ops().focal_ce(z, y, w)
+    assert torch.equal(a, c)
+    assert abs(float(a) - float(b)) < 1e-6 * abs(float(b))
+
+
+def test_focal_ce_all_ignored_is_nan_like_reference():
+    z = torch.randn(1, 4, 128, device=DEV)
+    y = torch.full((1, 4), -100, device=DEV)
+    assert torch.isnan(ops().focal_ce(z, y, torch.ones(1, device=DEV)))
+
+
+# ------------------------------------------------------------------ optimizer kernels
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_adamw_matches_torch(dtype):
+    torch.manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    master = p0.clone().to(DEV)
+    param = p0.to(DEV, dtype)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        g = torch.randn(n).to(dtype)
+        ref_p.grad = g.float().clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        acc = torch.zeros(1, device=DEV)
+        gd = g.to(DEV)
+        ops().sumsq_(gd, acc)
+        assert abs(float(acc) - float(g.float().pow(2).sum())) / float(acc) < 1e-5
+        ops().adamw_step_(master, param, gd, m, v, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8,
+                          weight_decay=0.1, step=step, gnorm_sq=acc, max_norm=1.0)
+    assert max_rel(master, ref_p.detach(), floor=1e-3) < 1e-4
+    assert rel_err(param, ref_p.detach()) < (1e-6 if dtype == torch.float32 else 4e-3)

@@ -60,7 +60,7 @@ def copy_oracle_weights(oracle, product):
 
 
 def rel_err(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
