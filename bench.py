@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — train samples/s of the UniMP hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 8 --warmup 3            # ours, N=1
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # ours, N>1 (one rank per GPU)
+    python bench.py --impl reference --steps 2 --warmup 1    # reference arithmetic on host CPU
+
+One "step" = one optimizer step of the reference's canonical launch (README.md:56-57,
+UniMP/unimp_task.sh:2-9): `accum` micro-batches of B samples per GPU, each = Flamingo forward +
+focal loss + backward; then gradient all-reduce, clip 1.0, AdamW.  samples/s follows the
+reference's definition `accum * B * world / step_time` (UniMP/mmrec.py:267-275).
+Workload = BASELINE.json configs[1]: OpenFlamingo-4B-instruct, bf16, synthetic 2-image histories.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2-rec")
+    ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU micro-batch (default: workload's)")
+    ap.add_argument("--accum", type=int, default=2, help="gradient accumulation (reference: 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference / cpu_baseline arm: the oracle (restated reference arithmetic) on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_oracle_samples_per_s(cfg, wl, *, batch, steps, warmup, accum=1):
+    """Times the oracle train step (fwd + focal loss + bwd + clip + AdamW, fp32) on all host
+    cores.  `batch` samples per step is the bounded sample of the workload."""
+    import copy
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import hf_configs
+
+    from oracle.flamingo_oracle import Flamingo as OracleFlamingo
+    from oracle.loss_oracle import focal_loss, mask_labels
+    from unimp_b200.synth import make_batch
+    from unimp_b200.train import apply_decay
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from transformers import CLIPVisionModel, GPTNeoXForCausalLM
+
+    vc, lc = hf_configs(cfg)
+    t0 = time.time()
+    with torch.device("meta"):
+        vis = CLIPVisionModel(vc)
+        lm = GPTNeoXForCausalLM(lc)
+        model = OracleFlamingo(vis, lm, cfg.tokens.endofchunk, cfg.tokens.media,
+                               vis_dim=cfg.vis_width,
+                               cross_attn_every_n_layers=cfg.cross_attn_every_n_layers)
+    model.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.uniform_(-0.02, 0.02, generator=g)
+            elif "norm" in n.lower() and n.endswith("weight") or n.endswith(".0.weight"):
+                p.fill_(1.0)
+            else:
+                p.zero_()
+        for n, b in model.named_buffers():
+            if "inv_freq" in n:
+                dim = b.numel() * 2
+                b.copy_(1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim)))
+            elif "position_ids" in n:
+                b.copy_(torch.arange(b.numel()).view_as(b))
+        for blk in model.lang_encoder.gated_cross_attn_layers:
+            if blk is not None:
+                blk.attn_gate.fill_(0.5)
+                blk.ff_gate.fill_(0.5)
+    model.requires_grad_(False)
+    model.perceiver.requires_grad_(True)
+    model.lang_encoder.gated_cross_attn_layers.requires_grad_(True)
+    model.lang_encoder.lm.get_input_embeddings().requires_grad_(True)
+    wd, no_wd = [], []
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            (wd if apply_decay(n) else no_wd).append(p)
+    opt = torch.optim.AdamW([{"params": wd, "weight_decay": 0.1},
+                             {"params": no_wd, "weight_decay": 0.0}], lr=2e-4)
+    init_s = time.time() - t0
+    wl2 = copy.copy(wl)
+    wl2.B = batch
+    tk = cfg.tokens
+    times = []
+    for it in range(warmup + steps):
+        mbs = [make_batch(cfg, wl2, seed=1234 + it * accum + a) for a in range(accum)]
+        t1 = time.time()
+        opt.zero_grad(set_to_none=True)
+        for b in mbs:
+            labels = mask_labels(b["input_ids"], answer_token_id=tk.answer,
+                                 endofchunk_token_id=tk.endofchunk, media_token_id=tk.media,
+                                 pad_token_id=tk.pad)
+            out = model(vision_x=b["patch_images"].unsqueeze(2), lang_x=b["input_ids"],
+                        attention_mask=b["attention_masks"], labels=labels)
+            loss = focal_loss(out["logits"], labels, b["weights"], gamma=wl.gamma)
+            (loss / accum).backward()
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 1.0)
+        opt.step()
+        dt = time.time() - t1
+        if it >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    return {"value": accum * batch / per_step, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} optimizer steps of {accum} x {batch} sample(s) of {wl.name} "
+                      f"(T={wl.T}, Ti={wl.Ti}), fp32 eager PyTorch oracle, {warmup} warm-up; "
+                      f"model init {init_s:.0f}s not timed",
+            "ms_per_step": per_step * 1e3}
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel profile (roofline): CUDA events around every launch of OUR kernels inside real steps
+# ---------------------------------------------------------------------------------------------
+
+class KernelProfile:
+    """Wraps the C-ABI entry points with CUDA events on the launching stream (torch's current
+    stream) and accumulates algorithmic bytes / FLOPs per call from the call's own shapes
+    (DESIGN.md "roofline accounting")."""
+
+    def __init__(self):
+        self.rec = {}
+        self.launches = 0
+
+    def install(self):
+        from unimp_b200 import _lib
+        lib = _lib.load()
+        self.lib, self.orig = lib, {}
+        for name in _lib.SIGNATURES:
+            if name in ("unimp_version", "unimp_last_error_string", "unimp_device_ok") or \
+               name.endswith("_workspace"):
+                continue
+            fn = getattr(lib, name)
+            self.orig[name] = fn
+            setattr(lib, name, self._wrap(name, fn))
+
+    def uninstall(self):
+        for n, f in self.orig.items():
+            setattr(self.lib, n, f)
+
+    def _wrap(self, name, fn):
+        def w(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*a)
+            e.record()
+            self.rec.setdefault(name, []).append((s, e, self._work(name, a)))
+            return rc
+        return w
+
+    @staticmethod
+    def _work(name, a):
+        """(algorithmic bytes, algorithmic flops) of this call."""
+        es = lambda dt: 2 if dt == 1 else 4
+        if name in ("unimp_xattn_fwd", "unimp_xattn_bwd"):
+            if name == "unimp_xattn_fwd":
+                B, T, Ti, n, H, dh, dt = a[6], a[7], a[8], a[9], a[10], a[11], a[13]
+                mul_b, mul_f = 1.0, 1.0
+            else:
+                B, T, Ti, n, H, dh, dt = a[11], a[12], a[13], a[14], a[15], a[16], a[18]
+                mul_b, mul_f = 2.5, 2.5
+            inner = H * dh
+            byts = es(dt) * (2 * B * T * inner + 2 * B * Ti * n * inner) + 4 * B * T * H
+            fl = 4.0 * H * dh * n * B * T  # upper bound: every token attends one block
+            return byts * mul_b, fl * mul_f
+        if name in ("unimp_attn_fwd", "unimp_attn_bwd"):
+            if name == "unimp_attn_fwd":
+                Bt, Lq, Lk, H, dh, dt = a[5], a[6], a[7], a[8], a[9], a[11]
+                mul = 1.0
+            else:
+                Bt, Lq, Lk, H, dh, dt = a[10], a[11], a[12], a[13], a[14], a[16]
+                mul = 2.5
+            inner = H * dh
+            byts = es(dt) * (2 * Bt * Lq * inner + 2 * Bt * Lk * inner) + 4 * Bt * Lq * H
+            return byts * mul, 4.0 * Bt * H * Lq * Lk * dh * mul
+        if name == "unimp_gate_residual_ln_fwd":
+            rows, D, dt = a[9], a[10], a[12]
+            n_t = 1 + (a[0] is not None) * 2 + (a[3] is not None)
+            return es(dt) * rows * D * n_t, 0.0
+        if name == "unimp_gate_residual_ln_bwd":
+            rows, D, dt = a[14], a[15], a[16]
+            n_t = 1 + (a[0] is not None) + (a[1] is not None) * 2 + (a[2] is not None) * 2
+            return es(dt) * rows * D * n_t, 0.0
+        if name == "unimp_focal_ce_fwd":
+            B, T, V, dt = a[11], a[12], a[13], a[14]
+            return None, 0.0  # bytes depend on n_valid: filled in by the caller
+        if name == "unimp_focal_ce_bwd":
+            B, T, V, dt = a[12], a[13], a[14], a[15]
+            return es(dt) * B * T * V, 0.0  # dense d_logits write (+ n_valid rows read)
+        if name == "unimp_adamw_step":
+            n, dt = a[5], a[15]
+            return n * (es(dt) * 2 + 4 * 6), 0.0
+        if name == "unimp_sumsq":
+            return a[1] * es(a[3]), 0.0
+        return 0.0, 0.0
+
+    def summary(self, peaks, n_valid_rows=None, V=None, es=2, steps=1):
+        torch.cuda.synchronize()
+        out = {}
+        for name, calls in self.rec.items():
+            ms = sum(s.elapsed_time(e) for s, e, _ in calls)
+            byts = sum((w[0] if w[0] is not None else (n_valid_rows or 0) * (V or 0) * es)
+                       for _, _, w in calls)
+            fl = sum(w[1] for _, _, w in calls)
+            if name == "unimp_focal_ce_bwd" and n_valid_rows:
+                byts += len(calls) * n_valid_rows * V * es
+            d = {"launches_per_step": len(calls) / steps, "ms_per_step": ms / steps,
+                 "avg_us": 1e3 * ms / len(calls), "GB/s": byts / (ms * 1e-3) / 1e9 if ms else 0.0}
+            if fl:
+                d["TFLOP/s"] = fl / (ms * 1e-3) / 1e12
+                d["frac_of_bf16_peak"] = d["TFLOP/s"] / peaks["bf16_tflops_sustained"]
+            d["frac_of_hbm_peak"] = d["GB/s"] / peaks["hbm_gbs"]
+            d["alg_bytes_per_launch"] = byts / len(calls)
+            out[name] = d
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+
+def main():
+    args = parse()
+    from unimp_b200 import openflamingo_4b_config, tiny_config
+    from unimp_b200.config import WORKLOADS
+    import copy
+
+    cfg = openflamingo_4b_config() if args.model == "4b" else tiny_config()
+    wl = copy.copy(WORKLOADS[args.workload])
+    if args.batch:
+        wl.B = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "train samples/s"
+    config = {"workload": f"{wl.name}: {cfg.name}, per-GPU micro-batch {wl.B} x accum {args.accum}, "
+                          f"Ti={wl.Ti} images/sample, T={wl.T} tokens, V={cfg.vocab}, gamma={wl.gamma}, "
+                          f"fwd+focal loss+bwd+allreduce+clip+AdamW",
+              "per_gpu_batch": wl.B, "accum": args.accum, "seq_len": wl.T, "images_per_sample": wl.Ti,
+              "parallelism": f"dp{world}",
+              "l2_policy": "per-step working set (weights 8 GB + activations) far exceeds the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_oracle_samples_per_s(cfg, wl, batch=args.cpu_batch, steps=max(1, args.steps),
+                                     warmup=args.warmup, accum=1)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from unimp_b200 import _lib
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.synth import make_batch
+    from unimp_b200.train import BucketedAllReduce, FlatAdamW, get_grouped_params, train_step
+
+    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert _lib.load().unimp_device_ok() == 1
+    torch.backends.cuda.matmul.allow_tf32 = True
+    peaks = load_peaks()
+
+    model = build_flamingo(cfg, dtype=torch.bfloat16, device="cuda", seed=0, gate=0.5)
+    model.train()
+    opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4)
+    reducer = BucketedAllReduce(opt) if world > 1 else None
+    tk = cfg.tokens
+
+    n_batches = args.accum * 4
+    host = [make_batch(cfg, wl, seed=1234 + rank * 1000 + i) for i in range(n_batches)]
+    for b in host:
+        for k in b:
+            b[k] = b[k].pin_memory()
+    dev = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * args.accum
+
+    def step_resident(i):
+        mbs = [dev[(i * args.accum + a) % n_batches] for a in range(args.accum)]
+        return train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
+                          micro_batches=mbs)
+
+    def step_e2e(i):
+        mbs = [{k: v.cuda(non_blocking=True) for k, v in host[(i * args.accum + a) % n_batches].items()}
+               for a in range(args.accum)]
+        loss = train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
+                          micro_batches=mbs)
+        return loss.item()  # device -> host read of the step's result
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    samples_per_step = args.accum * wl.B * world
+    value = samples_per_step * args.steps / (ms * 1e-3)
+    e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
+
+    kernels, roofline, launches = {}, None, None
+    if not args.no_kernel_profile:
+        prof = KernelProfile()
+        prof.install()
+        ksteps = 2
+        for i in range(ksteps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        prof.uninstall()
+        from unimp_b200 import ops
+        lab = ops.mask_labels(dev[0]["input_ids"], answer_token_id=tk.answer,
+                              endofchunk_token_id=tk.endofchunk, media_token_id=tk.media,
+                              pad_token_id=tk.pad)
+        n_valid = int((lab[:, 1:] != -100).sum())
+        kernels = prof.summary(peaks, n_valid_rows=n_valid, V=cfg.vocab, es=2, steps=ksteps)
+        launches = int(sum(k["launches_per_step"] for k in kernels.values()) * args.steps)
+        # headline kernel of the metric: the masked cross-attention core (fwd)
+        kx = kernels.get("unimp_xattn_fwd")
+        if kx:
+            bound = "hbm"
+            roofline = {"kernel": "unimp_xattn_fwd (masked media-located cross-attention core, fwd)",
+                        "bound": bound, "achieved": kx["GB/s"], "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": kx["GB/s"] / peaks["hbm_gbs"], "traffic": None,
+                        "tflops": kx.get("TFLOP/s"), "frac_of_bf16_peak": kx.get("frac_of_bf16_peak"),
+                        "avg_us": kx["avg_us"], "peak_source": peaks["source"],
+                        "alg_bytes_per_launch": kx["alg_bytes_per_launch"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_baseline = cpu_oracle_samples_per_s(cfg, wl, batch=args.cpu_batch, steps=2, warmup=1)
+            cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": "samples/s", "cores": os.cpu_count(),
+                            "kind": "port", "sample": f"failed: {ex!r}"}
+
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "kernels": kernels}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
