@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU micro-batch (default: workload's)")
     ap.add_argument("--accum", type=int, default=2, help="gradient accumulation (reference: 2)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -342,7 +343,8 @@ def main():
     from unimp_b200 import _lib
     from unimp_b200.factory import build_flamingo
     from unimp_b200.synth import make_batch
-    from unimp_b200.train import BucketedAllReduce, FlatAdamW, get_grouped_params, train_step
+    from unimp_b200.train import (BucketedAllReduce, FlatAdamW, GraphedTrainStep, get_grouped_params,
+                                  train_step)
 
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -366,17 +368,34 @@ def main():
     dev = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * args.accum
 
-    def step_resident(i):
-        mbs = [dev[(i * args.accum + a) % n_batches] for a in range(args.accum)]
+    use_graph = not args.no_graph
+    graphed = None
+    if use_graph:
+        # whole optimizer step captured once (DESIGN.md "launch overhead"); replays read the
+        # step's inputs from static device buffers that are refilled before every replay
+        graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma)
+    config["launch"] = "cuda-graph replay of the whole step" if use_graph else "eager"
+
+    def run_step(mbs):
+        if graphed is not None:
+            return graphed(mbs)
         return train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
                           micro_batches=mbs)
 
+    def step_resident(i):
+        # inputs already resident in HBM (the graphed path copies them device->device into its
+        # static buffers: 7 MB, inside the timed region)
+        return run_step([dev[(i * args.accum + a) % n_batches] for a in range(args.accum)])
+
     def step_e2e(i):
-        mbs = [{k: v.cuda(non_blocking=True) for k, v in host[(i * args.accum + a) % n_batches].items()}
-               for a in range(args.accum)]
-        loss = train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
-                          micro_batches=mbs)
-        return loss.item()  # device -> host read of the step's result
+        # host (pinned) -> device copy of this step's inputs, then device -> host read of the loss
+        if graphed is not None:
+            loss = graphed([host[(i * args.accum + a) % n_batches] for a in range(args.accum)])
+        else:
+            mbs = [{k: v.cuda(non_blocking=True) for k, v in host[(i * args.accum + a) % n_batches].items()}
+                   for a in range(args.accum)]
+            loss = run_step(mbs)
+        return loss.item()
 
     def timed(fn, steps):
         if world > 1:
@@ -414,8 +433,9 @@ def main():
         prof = KernelProfile()
         prof.install()
         ksteps = 2
-        for i in range(ksteps):
-            step_resident(i)
+        for i in range(ksteps):  # eager on purpose: events around each of OUR launches
+            train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
+                       micro_batches=[dev[(i * args.accum + a) % n_batches] for a in range(args.accum)])
         torch.cuda.synchronize()
         prof.uninstall()
         from unimp_b200 import ops

@@ -175,11 +175,13 @@ int unimp_mask_labels(const int64_t* input_ids, int64_t answer_id, int64_t endof
  * Replaces torch.optim.AdamW.step for one param group (reference UniMP/mmrec.py:671) with
  * grad-clip scaling folded in (clip coefficient = min(1, max_norm/(norm+1e-6)),
  * UniMP/mmrec.py:247-248).  master/m/v fp32, grad `dtype`; writes the `dtype` working
- * copy `param`.  gnorm_sq: device scalar, sum of squared grads (NULL = no clipping). */
+ * copy `param`.  gnorm_sq: device scalar, sum of squared grads (NULL = no clipping).
+ * hyper: DEVICE float[3] = {lr, 1-beta1^t, sqrt(1-beta2^t)} — step-dependent scalars live in
+ * device memory so that a captured CUDA graph of the step stays valid across steps. */
 int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
-                     float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, int step, const float* gnorm_sq,
-                     float max_norm, float grad_scale, int dtype, void* stream);
+                     float* exp_avg_sq, int64_t n, const float* hyper, float beta1, float beta2,
+                     float eps, float weight_decay, const float* gnorm_sq, float max_norm,
+                     float grad_scale, int dtype, void* stream);
 /* acc[0] += sum(grad^2) (fp32). */
 int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, void* stream);
 

@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: synthetic batch layout, weight-decay rule, LR schedule, and the
+N>1 data-parallel path (bucketed all-reduce) with world_size 2 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.loss_oracle import mask_labels
+from unimp_b200 import openflamingo_4b_config, tiny_config
+from unimp_b200.config import WORKLOADS
+from unimp_b200.synth import make_batch
+from unimp_b200.train import BucketedAllReduce, FlatAdamW, apply_decay, cosine_with_warmup
+
+
+def test_vocab_layout_matches_reference_token_growth():
+    cfg = openflamingo_4b_config()
+    t = cfg.tokens
+    # reference UniMP/mmrec.py:538-581: <answer>, 5 rate_*, 5 s_*, 22738 item_*, 1024 img_*
+    assert cfg.vocab == 50277 + 3 + 1 + 5 + 5 + 22738 + 1024 == 74053
+    assert t.first_item - t.answer - 1 == 10 and t.first_img == t.first_item + 22738
+
+
+@pytest.mark.parametrize("name", ["C1-tiny", "C2-rec", "C5-imggen"])
+def test_synthetic_batch_has_the_reference_prompt_structure(name):
+    cfg = tiny_config() if name == "C1-tiny" else openflamingo_4b_config()
+    wl = WORKLOADS[name]
+    b = make_batch(cfg, wl, seed=3, ragged=True)
+    ids, am = b["input_ids"], b["attention_masks"]
+    assert ids.shape == (wl.B, wl.T) and b["patch_images"].shape[:2] == (wl.B, wl.Ti)
+    t = cfg.tokens
+    for i in range(wl.B):
+        L = int(am[i].sum())
+        assert (ids[i, L:] == t.pad).all() and (am[i, :L] == 1).all()      # right padding
+        n_img = int((ids[i] == t.media).sum())
+        assert n_img == (max(1, wl.Ti - 1) if i == 0 else wl.Ti)           # ragged sample 0
+        assert int((ids[i] == t.answer).sum()) == n_img + 1                # one answer per chunk + final
+        assert int((ids[i] == t.endofchunk).sum()) == n_img
+    lab = mask_labels(ids, answer_token_id=t.answer, endofchunk_token_id=t.endofchunk,
+                      media_token_id=t.media, pad_token_id=t.pad)
+    valid = lab != -100
+    assert valid.any()
+    kept = ids[valid]
+    lo, hi = t.first_item, t.first_img + t.n_img
+    assert (((kept >= lo) & (kept < hi)) | (kept == t.eos)).all()          # answers (+ trailing EOS) only
+
+
+def test_weight_decay_rule_is_the_reference_rule():
+    # reference UniMP/mmrec.py:612-619
+    assert apply_decay("lang_encoder.gated_cross_attn_layers.3.attn.to_q.weight")
+    assert apply_decay("lang_encoder.gpt_neox.layers.1.gated_cross_attn_layer.ff.1.weight")
+    assert not apply_decay("lang_encoder.gated_cross_attn_layers.3.attn_gate")
+    assert not apply_decay("lang_encoder.gated_cross_attn_layers.3.ff_gate")
+    assert not apply_decay("lang_encoder.gated_cross_attn_layers.3.attn.norm.weight")
+    assert not apply_decay("perceiver.layers.0.0.to_q.weight")
+    assert not apply_decay("lang_encoder.gpt_neox.embed_in.weight")
+
+
+def test_cosine_schedule_matches_transformers():
+    from transformers import get_cosine_schedule_with_warmup
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sch = get_cosine_schedule_with_warmup(opt, num_warmup_steps=5, num_training_steps=40)
+    for s in range(40):
+        assert abs(opt.param_groups[0]["lr"] - cosine_with_warmup(s, 5, 40)) < 1e-7
+        opt.step()
+        sch.step()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dp_worker(rank, world, port, accum, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # identical weights on every rank (bench: weights seed 0)
+    net = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.Tanh(), torch.nn.Linear(40, 8))
+    groups = [{"params": [(n, p) for n, p in net.named_parameters() if "weight" in n], "weight_decay": 0.1},
+              {"params": [(n, p) for n, p in net.named_parameters() if "bias" in n], "weight_decay": 0.0}]
+    opt = FlatAdamW(groups, lr=1e-3)
+    red = BucketedAllReduce(opt, bucket_bytes=1024)  # several buckets
+    assert len(red.buckets) >= 3
+    opt.zero_grad()
+    g = torch.Generator().manual_seed(100 + rank)   # per-rank data (reference: seed + rank)
+    xs = [torch.randn(5, 24, generator=g) for _ in range(accum)]
+    for i, x in enumerate(xs):
+        red.armed = i == accum - 1
+        (net(x).pow(2).mean() / accum).backward()
+    red.finish()
+    flat = torch.cat([grp["flat_g"] for grp in opt.groups]) * red.grad_scale
+    q.put((rank, flat.clone(), [x.clone() for x in xs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_bucketed_allreduce_world2_equals_single_process_mean(accum):
+    """N-GPU == 1-GPU gradient equality on the same global batch, over gloo."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, accum, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.allclose(res[0][1], res[1][1], atol=0, rtol=0)  # every rank holds the same mean
+    # single-process reference: average of the per-rank losses (DeepSpeed DP semantics)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.Tanh(), torch.nn.Linear(40, 8))
+    groups = [{"params": [(n, p) for n, p in net.named_parameters() if "weight" in n], "weight_decay": 0.1},
+              {"params": [(n, p) for n, p in net.named_parameters() if "bias" in n], "weight_decay": 0.0}]
+    opt = FlatAdamW(groups, lr=1e-3)
+    opt.zero_grad()
+    for r in range(world):
+        for x in res[r][2]:
+            (net(x).pow(2).mean() / accum / world).backward()
+    want = torch.cat([grp["flat_g"] for grp in opt.groups])
+    assert torch.allclose(res[0][1], want, atol=1e-7, rtol=1e-5)

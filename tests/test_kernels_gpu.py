@@ -263,7 +263,8 @@ def test_fused_adamw_matches_torch(dtype):
         gd = g.to(DEV)
         ops().sumsq_(gd, acc)
         assert abs(float(acc) - float(g.float().pow(2).sum())) / float(acc) < 1e-5
-        ops().adamw_step_(master, param, gd, m, v, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8,
-                          weight_decay=0.1, step=step, gnorm_sq=acc, max_norm=1.0)
-    assert max_rel(master, ref_p.detach(), floor=1e-3) < 1e-4
+        hyper = torch.tensor(ops().adamw_hyper(1e-2, 0.9, 0.999, step), device=DEV)
+        ops().adamw_step_(master, param, gd, m, v, hyper=hyper, beta1=0.9, beta2=0.999, eps=1e-8,
+                          weight_decay=0.1, gnorm_sq=acc, max_norm=1.0)
+    assert torch.allclose(master.cpu(), ref_p.detach(), rtol=1e-5, atol=2e-6)
     assert rel_err(param, ref_p.detach()) < (1e-6 if dtype == torch.float32 else 4e-3)

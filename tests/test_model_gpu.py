@@ -67,7 +67,11 @@ def test_forward_loss_backward_vs_oracle(dtype, ragged):
          oracle.lang_encoder.lm.get_input_embeddings().weight.grad),
     ]
     for i, (got, want) in enumerate(pairs):
-        assert rel_err(got, want) < tol["grad"], (i, rel_err(got, want))
+        if got.numel() == 1 and dtype == torch.bfloat16:
+            # a scalar gate gradient is one long cancellation-prone sum of bf16 products
+            assert abs(float(got) - float(want)) < 5e-3 + 0.1 * abs(float(want)), (i, got, want)
+        else:
+            assert rel_err(got, want) < tol["grad"], (i, rel_err(got, want))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -130,6 +134,29 @@ def test_generate_with_cached_media_matches_oracle_greedy():
                          attention_mask=torch.ones_like(ids).cuda(), max_new_tokens=new,
                          num_beams=1, do_sample=False, eos_token_id=-1, pad_token_id=cfg.tokens.pad)
     assert out.cpu().tolist() == cur.tolist()
+
+
+def test_graphed_train_step_matches_eager():
+    """The CUDA-graph replay of the whole step follows the eager step's loss trajectory."""
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import FlatAdamW, GraphedTrainStep, get_grouped_params, train_step
+
+    cfg = tiny_config()
+    mbs = [{k: v.cuda() for k, v in make_batch(cfg, WORKLOADS["C1-tiny"], seed=i).items()} for i in range(2)]
+
+    def fresh():
+        m = build_flamingo(cfg, dtype=torch.float32, device="cuda", gate=0.5)
+        return m, FlatAdamW(get_grouped_params(m, 0.1), lr=1e-3)
+
+    model, opt = fresh()
+    eager = [float(train_step(model, None, cfg.tokens, opt, None, accum_steps=2, micro_batches=mbs))
+             for _ in range(6)]
+    model, opt = fresh()
+    g = GraphedTrainStep(model, cfg.tokens, opt, None, mbs, warmup_iters=3)  # steps 1-3 run eagerly
+    got = [float(g(mbs)) for _ in range(3)]                                  # steps 4, 5, 6
+    assert opt.step_count == 6
+    for a, b in zip(got, eager[3:]):
+        assert abs(a - b) < 2e-3 * abs(b)
 
 
 def test_train_step_reduces_loss_and_updates_only_trainables():

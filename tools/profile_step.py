@@ -1,4 +1,4 @@
-"""torch.profiler breakdown of one 4B train step (dev tool; numbers under a profiler are never bench values)."""
+"""torch.profiler breakdown of one 4B train step (eager) (dev tool; numbers under a profiler are never bench values)."""
 import os, sys, copy
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -60,6 +60,16 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
     }
   }
   if (!gamma) return;
+  // issue the affine-parameter loads now so their latency hides under the two reductions
+  Vec16<T> gv[LN_VPT], bv[LN_VPT];
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+      gv[k].load(gamma + j * N);
+      bv[k].load(beta + j * N);
+    }
+  }
   __shared__ float sh[32];
   const float mean = block_sum(s, sh) / D;
   float q = 0.f;
@@ -84,12 +94,9 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
   for (int k = 0; k < LN_VPT; ++k) {
     const int j = threadIdx.x + k * blockDim.x;
     if (j < nvec) {
-      Vec16<T> g, b;
       float gf[N], bf[N], o[N];
-      g.load(gamma + j * N);
-      g.unpack(gf);
-      b.load(beta + j * N);
-      b.unpack(bf);
+      gv[k].unpack(gf);
+      bv[k].unpack(bf);
 #pragma unroll
       for (int i = 0; i < N; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gf[i], bf[i]);
       Vec16<T> ov;
@@ -99,8 +106,23 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
   }
 }
 
-// Persistent-style: CTA c handles rows c, c+G, ...; column partials live in registers.
-// partial layout: [G][2*D + 1]: d_gamma cols, d_beta cols, d_gate.
+// R row-groups of TG threads per CTA, each group walking its own rows, so that (nearly) every row
+// of a 768-row activation is in flight at once; column partials (d_gamma, d_beta) live in
+// registers per thread, are folded across the R groups through shared memory in a fixed order,
+// and leave the CTA as one partial row: partial[G][2*D + 1] (last = d_gate).
+constexpr int LN_BWD_MAX_R = 12;       // row-groups per CTA: R = clamp(384 / TG, 1, 12)
+static inline int ln_bwd_r(int TG) { int r = 384 / TG; return r < 1 ? 1 : (r > LN_BWD_MAX_R ? LN_BWD_MAX_R : r); }
+
+__device__ __forceinline__ float group_sum(float v, float* sh, int rg, int tg_threads, int t) {
+  const int lane = t & 31, w = t >> 5, nw = tg_threads >> 5;
+  v = warp_sum(v);
+  asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
+  if (lane == 0) sh[w] = v;
+  asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  return warp_sum(r);
+}
+
 template <typename T>
 __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ g_ln,
                                             const T* __restrict__ branch, const T* __restrict__ x_out,
@@ -109,59 +131,63 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
                                             const float* __restrict__ mean_i,
                                             const float* __restrict__ rstd_i, T* __restrict__ d_x,
                                             T* __restrict__ d_branch, float* __restrict__ partial,
-                                            int64_t rows, int D) {
+                                            int64_t rows, int D, int TG, int R) {
   constexpr int N = Vec16<T>::N;
+  extern __shared__ float sdyn[];          // [2*D] column sums, then LN_BWD_R*32 scratch, then R
   const int nvec = D / N;
+  const int rg = threadIdx.x / TG, t = threadIdx.x - rg * TG;
+  float* sh = sdyn + 2 * D + rg * 32;
+  float* sgate = sdyn + 2 * D + LN_BWD_MAX_R * 32;
   const bool has_ln = g_ln != nullptr && gamma != nullptr;
   const float tg = branch ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
-  float dg[LN_VPT][N], db[LN_VPT][N], gam[LN_VPT][N];
+  float dg[LN_VPT][N], db[LN_VPT][N];
   float dgate = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_VPT; ++k) {
+  for (int k = 0; k < LN_VPT; ++k)
 #pragma unroll
-    for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f, gam[k][i] = 0.f;
-    const int j = threadIdx.x + k * blockDim.x;
-    if (has_ln && j < nvec) {
-      Vec16<T> g;
-      g.load(gamma + j * N);
-      g.unpack(gam[k]);
-    }
-  }
-  __shared__ float sh[32];
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    float gy[LN_VPT][N], xh[LN_VPT][N];
-    float s1 = 0.f, s2 = 0.f;
-    float mean = 0.f, rstd = 0.f;
+    for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sdyn[i] = 0.f;
+
+  for (int64_t row = (int64_t)blockIdx.x * R + rg; row < rows; row += (int64_t)gridDim.x * R) {
+    Vec16<T> gl_raw[LN_VPT], xo_raw[LN_VPT];
+    float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
     if (has_ln) {
       mean = mean_i[row];
       rstd = rstd_i[row];
 #pragma unroll
       for (int k = 0; k < LN_VPT; ++k) {
-        const int j = threadIdx.x + k * blockDim.x;
+        const int j = t + k * TG;
         if (j < nvec) {
-          Vec16<T> a, b;
-          float gl[N], xo[N];
-          a.load_stream(g_ln + row * D + j * N);
-          a.unpack(gl);
-          b.load_stream(x_out + row * D + j * N);
-          b.unpack(xo);
+          gl_raw[k].load_stream(g_ln + row * D + j * N);
+          xo_raw[k].load_stream(x_out + row * D + j * N);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < LN_VPT; ++k) {
+        const int j = t + k * TG;
+        if (j < nvec) {
+          Vec16<T> gmv;
+          float gl[N], xo[N], gm[N];
+          gmv.load(gamma + j * N);
+          gmv.unpack(gm);
+          gl_raw[k].unpack(gl);
+          xo_raw[k].unpack(xo);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            xh[k][i] = (xo[i] - mean) * rstd;
-            gy[k][i] = gl[i] * gam[k][i];
-            s1 += gy[k][i];
-            s2 += gy[k][i] * xh[k][i];
-            dg[k][i] += gl[i] * xh[k][i];
+            const float xh = (xo[i] - mean) * rstd, gy = gl[i] * gm[i];
+            s1 += gy;
+            s2 += gy * xh;
+            dg[k][i] += gl[i] * xh;
             db[k][i] += gl[i];
           }
         }
       }
-      s1 = block_sum(s1, sh) / D;
-      s2 = block_sum(s2, sh) / D;
+      s1 = group_sum(s1, sh, rg, TG, t) / D;
+      s2 = group_sum(s2, sh, rg, TG, t) / D;
     }
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
-      const int j = threadIdx.x + k * blockDim.x;
+      const int j = t + k * TG;
       if (j < nvec) {
         float dx[N];
         if (g_xout) {
@@ -173,8 +199,17 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
           for (int i = 0; i < N; ++i) dx[i] = 0.f;
         }
         if (has_ln) {
+          Vec16<T> gmv;
+          float gl[N], xo[N], gm[N];
+          gmv.load(gamma + j * N);
+          gmv.unpack(gm);
+          gl_raw[k].unpack(gl);
+          xo_raw[k].unpack(xo);
 #pragma unroll
-          for (int i = 0; i < N; ++i) dx[i] += rstd * (gy[k][i] - s1 - xh[k][i] * s2);
+          for (int i = 0; i < N; ++i) {
+            const float xh = (xo[i] - mean) * rstd;
+            dx[i] += rstd * (gl[i] * gm[i] - s1 - xh * s2);
+          }
         }
         Vec16<T> o;
         o.pack(dx);
@@ -196,44 +231,67 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
       }
     }
   }
-  float* pr = partial + (int64_t)blockIdx.x * (2 * D + 1);
+  // fold the R groups' column partials in a fixed order (deterministic), then emit one row
+  dgate = group_sum(dgate, sh, rg, TG, t);
+  if (t == 0) sgate[rg] = dgate;
+  __syncthreads();
+  for (int g = 0; g < R; ++g) {
+    if (rg == g && has_ln) {
 #pragma unroll
-  for (int k = 0; k < LN_VPT; ++k) {
-    const int j = threadIdx.x + k * blockDim.x;
-    if (j < nvec) {
+      for (int k = 0; k < LN_VPT; ++k) {
+        const int j = t + k * TG;
+        if (j < nvec) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        pr[j * N + i] = dg[k][i];
-        pr[D + j * N + i] = db[k][i];
+          for (int i = 0; i < N; ++i) {
+            sdyn[j * N + i] += dg[k][i];
+            sdyn[D + j * N + i] += db[k][i];
+          }
+        }
       }
     }
+    __syncthreads();
   }
-  dgate = block_sum(dgate, sh);
-  if (threadIdx.x == 0) pr[2 * D] = dgate * (1.f - tg * tg);
+  float* pr = partial + (int64_t)blockIdx.x * (2 * D + 1);
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) pr[i] = sdyn[i];
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int g = 0; g < R; ++g) s += sgate[g];
+    pr[2 * D] = s * (1.f - tg * tg);
+  }
 }
 
-// Reduce partial[G][2D+1] over G in fixed order. One thread per column.
+// Reduce partial[G][2D+1] over G in a fixed order: block = 32 columns x 8 g-lanes.
 template <typename T>
 __global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ partial, int G, int D,
                                                    T* __restrict__ d_gate, T* __restrict__ d_gamma,
                                                    T* __restrict__ d_beta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   const int W = 2 * D + 1;
-  if (c >= W) return;
   float s = 0.f;
-  for (int g = 0; g < G; ++g) s += partial[(int64_t)g * W + c];
-  if (c < D) {
-    if (d_gamma) d_gamma[c] = Elem<T>::from_f(s);
-  } else if (c < 2 * D) {
-    if (d_beta) d_beta[c - D] = Elem<T>::from_f(s);
-  } else {
-    if (d_gate) d_gate[0] = Elem<T>::from_f(s);
+  if (c < W)
+    for (int g = gy; g < G; g += 8) s += partial[(int64_t)g * W + c];
+  sh[gy][cx] = s;
+  __syncthreads();
+  if (gy == 0 && c < W) {
+    s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += sh[g][cx];
+    if (c < D) {
+      if (d_gamma) d_gamma[c] = Elem<T>::from_f(s);
+    } else if (c < 2 * D) {
+      if (d_beta) d_beta[c - D] = Elem<T>::from_f(s);
+    } else {
+      if (d_gate) d_gate[0] = Elem<T>::from_f(s);
+    }
   }
 }
 
-static inline int ln_bwd_grid(int64_t rows) {
-  const int64_t g = 2 * UNIMP_NUM_SMS;
-  return (int)(rows < g ? rows : g);
+static inline int ln_bwd_grid(int64_t rows, int R) {
+  const int64_t need = (rows + R - 1) / R;
+  const int64_t g = UNIMP_NUM_SMS;  // one CTA (R row-groups) per SM
+  return (int)(need < g ? need : g);
 }
 
 }  // namespace unimp
@@ -276,7 +334,8 @@ extern "C" int unimp_gate_residual_ln_fwd(const void* branch, const void* x, con
 }
 
 extern "C" int64_t unimp_gate_residual_ln_bwd_workspace(int64_t rows, int D) {
-  return (int64_t)ln_bwd_grid(rows > 0 ? rows : 1) * (2 * (int64_t)D + 1) * sizeof(float);
+  (void)rows;
+  return (int64_t)UNIMP_NUM_SMS * (2 * (int64_t)D + 1) * sizeof(float);
 }
 
 extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void* branch,
@@ -299,28 +358,42 @@ extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, 
   UNIMP_CHECK_ARG(aligned16(g_xout) && aligned16(g_ln) && aligned16(branch) && aligned16(x_out) &&
                       aligned16(gamma) && aligned16(d_x) && aligned16(d_branch),
                   UNIMP_E_ALIGN, "gate_residual_ln_bwd: pointers must be 16-byte aligned");
-  const int threads = ln_threads(D, npv);
-  const int G = ln_bwd_grid(rows);
+  const int TG = ln_threads(D, npv);
+  const int R = ln_bwd_r(TG);
+  UNIMP_CHECK_ARG(TG * R <= 384 || (R == 1 && TG <= 384), UNIMP_E_SHAPE,
+                  "gate_residual_ln_bwd: D=%d too large for the register budget", D);
+  const int threads = TG * R;
+  const int G = ln_bwd_grid(rows, R);
+  const int smem = (2 * D + LN_BWD_MAX_R * 32 + LN_BWD_MAX_R) * (int)sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
   if (dtype == UNIMP_BF16)
-    gate_residual_ln_bwd_kernel<__nv_bfloat16><<<G, threads, 0, st>>>(
+    gate_residual_ln_bwd_kernel<__nv_bfloat16><<<G, threads, smem, st>>>(
         (const __nv_bfloat16*)g_xout, (const __nv_bfloat16*)g_ln, (const __nv_bfloat16*)branch,
         (const __nv_bfloat16*)x_out, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)gamma, mean,
         rstd,
-        (__nv_bfloat16*)d_x, (__nv_bfloat16*)d_branch, (float*)partial, rows, D);
+        (__nv_bfloat16*)d_x, (__nv_bfloat16*)d_branch, (float*)partial, rows, D, TG, R);
   else
-    gate_residual_ln_bwd_kernel<float><<<G, threads, 0, st>>>(
+    gate_residual_ln_bwd_kernel<float><<<G, threads, smem, st>>>(
         (const float*)g_xout, (const float*)g_ln, (const float*)branch, (const float*)x_out,
         (const float*)gate,
-        (const float*)gamma, mean, rstd, (float*)d_x, (float*)d_branch, (float*)partial, rows, D);
+        (const float*)gamma, mean, rstd, (float*)d_x, (float*)d_branch, (float*)partial, rows, D,
+        TG, R);
   UNIMP_CHECK_LAUNCH();
   const int W = 2 * D + 1;
   if (dtype == UNIMP_BF16)
-    gate_residual_ln_bwd_reduce_kernel<__nv_bfloat16><<<(W + 255) / 256, 256, 0, st>>>(
+    gate_residual_ln_bwd_reduce_kernel<__nv_bfloat16><<<(W + 31) / 32, 256, 0, st>>>(
         (const float*)partial, G, D, (__nv_bfloat16*)d_gate, (__nv_bfloat16*)d_gamma,
         (__nv_bfloat16*)d_beta);
   else
-    gate_residual_ln_bwd_reduce_kernel<float><<<(W + 255) / 256, 256, 0, st>>>(
+    gate_residual_ln_bwd_reduce_kernel<float><<<(W + 31) / 32, 256, 0, st>>>(
         (const float*)partial, G, D, (float*)d_gate, (float*)d_gamma, (float*)d_beta);
   UNIMP_CHECK_LAUNCH();
   return 0;

@@ -90,9 +90,10 @@ sumsq_kernel(const T* __restrict__ g, int64_t n, float* __restrict__ acc) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ master, T* __restrict__ param, const T* __restrict__ grad,
-             float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float b1, float b2,
-             float eps, float wd, float bc1, float bc2_sqrt, const float* __restrict__ gnorm_sq,
+             float* __restrict__ m, float* __restrict__ v, int64_t n, const float* __restrict__ hyper,
+             float b1, float b2, float eps, float wd, const float* __restrict__ gnorm_sq,
              float max_norm, float grad_scale) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2_sqrt = hyper[2];
   float clip = grad_scale;
   if (gnorm_sq) {
     // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)
@@ -182,29 +183,26 @@ extern "C" int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, v
 }
 
 extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
-                                float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                                float eps, float weight_decay, int step, const float* gnorm_sq,
+                                float* exp_avg_sq, int64_t n, const float* hyper, float beta1,
+                                float beta2, float eps, float weight_decay, const float* gnorm_sq,
                                 float max_norm, float grad_scale, int dtype, void* stream) {
-  UNIMP_CHECK_ARG(master && param && grad && exp_avg && exp_avg_sq, UNIMP_E_NULL,
+  UNIMP_CHECK_ARG(master && param && grad && exp_avg && exp_avg_sq && hyper, UNIMP_E_NULL,
                   "adamw_step: NULL pointer");
-  UNIMP_CHECK_ARG(step >= 1, UNIMP_E_SHAPE, "adamw_step: step must be >= 1");
   UNIMP_CHECK_ARG(aligned16(master) && aligned16(exp_avg) && aligned16(exp_avg_sq), UNIMP_E_ALIGN,
                   "adamw_step: fp32 state must be 16-byte aligned");
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "adamw_step: dtype");
   if (n <= 0) return 0;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * UNIMP_NUM_SMS) blocks = 16 * UNIMP_NUM_SMS;
   if (blocks < 1) blocks = 1;
   if (dtype == UNIMP_BF16)
     adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, lr,
-        beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_scale);
+        master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, hyper,
+        beta1, beta2, eps, weight_decay, gnorm_sq, max_norm, grad_scale);
   else
     adamw_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        master, (float*)param, (const float*)grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-        weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_scale);
+        master, (float*)param, (const float*)grad, exp_avg, exp_avg_sq, n, hyper, beta1, beta2, eps,
+        weight_decay, gnorm_sq, max_norm, grad_scale);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }

@@ -40,6 +40,69 @@ def extend_instance(obj, mixin):
     obj.__class__ = type(base_cls.__name__, (mixin, base_cls), {})
 
 
+class _PaddedHeadFn(torch.autograd.Function):
+    """logits = h @ W^T with W zero-padded to a multiple of 128 rows, returned as the [:V] view.
+
+    V = 74 053 is odd: an unaligned N sends cuBLAS to a legacy kernel (measured 2.5 ms vs 0.4 ms
+    per call on B200).  The pad columns never leave this function: the focal-CE kernels take the
+    padded row stride as `ld`, and their d_logits comes back as the [:V] view of a buffer with the
+    same padded stride, which backward re-expands in place (no copy) for dH = dlogits @ W."""
+
+    @staticmethod
+    def forward(ctx, h, w_pad, V):
+        ctx.save_for_backward(w_pad)
+        ctx.V = V
+        return torch.nn.functional.linear(h, w_pad)[..., :V]
+
+    @staticmethod
+    def backward(ctx, g):
+        (w_pad,) = ctx.saved_tensors
+        V, Vp = ctx.V, w_pad.shape[0]
+        lead = g.shape[:-1]
+        n_lead = 1
+        for d in lead:
+            n_lead *= d
+        need = (g.storage_offset() + n_lead * Vp) * g.element_size()
+        dense_prefix = g.dim() >= 2 and g.stride(-1) == 1 and g.stride(-2) == Vp and all(
+            g.stride(i) == g.stride(i + 1) * g.shape[i + 1] for i in range(g.dim() - 2))
+        if dense_prefix and g.untyped_storage().nbytes() >= need:
+            gp = g.as_strided(tuple(lead) + (Vp,), tuple(g.stride()[:-1]) + (1,), g.storage_offset())
+            gp[..., V:].zero_()
+        else:
+            gp = torch.nn.functional.pad(g, (0, Vp - V))
+        return (gp.reshape(-1, Vp) @ w_pad).reshape(*lead, w_pad.shape[1]), None, None
+
+
+class PaddedOutputHead(nn.Module):
+    """Drop-in for the frozen, bias-free `embed_out` Linear (state-dict key `weight`, shape (V, D)
+    unchanged); see _PaddedHeadFn."""
+
+    def __init__(self, linear: nn.Linear, multiple: int = 128):
+        super().__init__()
+        assert linear.bias is None
+        self.weight = linear.weight
+        self.in_features, self.out_features = linear.in_features, linear.out_features
+        self.multiple = multiple
+        self._wp = None
+
+    def _padded(self):
+        w = self.weight
+        V = w.shape[0]
+        Vp = (V + self.multiple - 1) // self.multiple * self.multiple
+        wp = self._wp
+        if wp is None or wp.dtype != w.dtype or wp.device != w.device or wp.data_ptr() != w.data_ptr():
+            wp = torch.zeros((Vp, w.shape[1]), dtype=w.dtype, device=w.device)
+            wp[:V].copy_(w.data)
+            w.data = wp[:V]          # the parameter now aliases the padded buffer: no second copy
+            self._wp = wp
+        return wp
+
+    def forward(self, h):
+        if self.weight.requires_grad or not h.is_cuda:
+            return torch.nn.functional.linear(h, self.weight)
+        return _PaddedHeadFn.apply(h, self._padded(), self.out_features)
+
+
 class FlamingoLayer(nn.Module):
     def __init__(self, gated_cross_attn_layer, decoder_layer, gradient_checkpointing=False):
         super().__init__()

@@ -310,11 +310,17 @@ def sumsq_(grad: torch.Tensor, acc: torch.Tensor):
                                   _stream()), "unimp_sumsq")
 
 
-def adamw_step_(master, param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay,
-                step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+def adamw_step_(master, param, grad, exp_avg, exp_avg_sq, *, hyper, beta1, beta2, eps, weight_decay,
+                gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    """hyper: device float32[3] = (lr, 1-beta1^t, sqrt(1-beta2^t)); see adamw_hyper()."""
     check(_lib.load().unimp_adamw_step(master.data_ptr(), param.data_ptr(), grad.data_ptr(),
                                        exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
-                                       float(lr), float(beta1), float(beta2), float(eps),
-                                       float(weight_decay), int(step), _ptr(gnorm_sq),
-                                       float(max_norm), float(grad_scale), _dt(param), _stream()),
+                                       hyper.data_ptr(), float(beta1), float(beta2), float(eps),
+                                       float(weight_decay), _ptr(gnorm_sq), float(max_norm),
+                                       float(grad_scale), _dt(param), _stream()),
           "unimp_adamw_step")
+
+
+def adamw_hyper(lr: float, beta1: float, beta2: float, step: int):
+    """Host-side values of the `hyper` vector for optimizer step `step` (1-based)."""
+    return [float(lr), 1.0 - beta1 ** step, (1.0 - beta2 ** step) ** 0.5]

@@ -84,6 +84,12 @@ class FlatAdamW:
             })
         dev = self.groups[0]["flat_p"].device
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        # step-dependent scalars (lr, bias corrections) live in device memory so that a captured
+        # CUDA graph of the whole step stays valid from step to step
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(3, dtype=torch.float32)
+        if dev.type == "cuda":
+            self._hyper_host = self._hyper_host.pin_memory()
 
     def zero_grad(self):
         for g in self.groups:
@@ -92,19 +98,31 @@ class FlatAdamW:
     def grad_norm(self) -> torch.Tensor:
         return self.gnorm_sq.sqrt()
 
-    @torch.no_grad()
-    def step(self, *, lr_scale: float = 1.0, grad_scale: float = 1.0):
-        """clip_grad_norm_(max_grad_norm) over ALL groups, then AdamW; no host sync."""
+    def prepare_step(self, lr_scale: float = 1.0):
+        """Host side of a step: advance the step count and upload (lr, bias corrections).
+        Call BEFORE replaying a captured step (step() calls it itself)."""
         self.step_count += 1
+        h = ops.adamw_hyper(self.lr * lr_scale, self.betas[0], self.betas[1], self.step_count)
+        self._hyper_host.copy_(torch.tensor(h))
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    @torch.no_grad()
+    def step_kernels(self, grad_scale: float = 1.0):
+        """Device side of a step (capturable): grad-norm, clip, AdamW. No host sync."""
         self.gnorm_sq.zero_()
         for g in self.groups:
             ops.sumsq_(g["flat_g"], self.gnorm_sq)
         for g in self.groups:
             ops.adamw_step_(g["master"], g["flat_p"], g["flat_g"], g["m"], g["v"],
-                            lr=self.lr * lr_scale, beta1=self.betas[0], beta2=self.betas[1],
-                            eps=self.eps, weight_decay=g["weight_decay"], step=self.step_count,
+                            hyper=self.hyper, beta1=self.betas[0], beta2=self.betas[1],
+                            eps=self.eps, weight_decay=g["weight_decay"],
                             gnorm_sq=self.gnorm_sq if self.max_grad_norm > 0 else None,
                             max_norm=self.max_grad_norm, grad_scale=grad_scale)
+
+    def step(self, *, lr_scale: float = 1.0, grad_scale: float = 1.0):
+        """clip_grad_norm_(max_grad_norm) over ALL groups, then AdamW."""
+        self.prepare_step(lr_scale)
+        self.step_kernels(grad_scale)
 
 
 class BucketedAllReduce:
@@ -206,3 +224,55 @@ def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce 
         reducer.finish()
     opt.step(lr_scale=lr_scale, grad_scale=reducer.grad_scale if reducer is not None else 1.0)
     return loss
+
+
+class GraphedTrainStep:
+    """The whole optimizer step (accum x [fwd + loss + bwd], all-reduce, clip, AdamW) captured
+    once into a CUDA graph and replayed: ~5000 launches per step stop costing CPU time.
+
+    Shapes are static (the synthetic workloads are; a real loader pads to the batch max,
+    collate_rec.py:51-55, so one graph per (B, T) bucket).  Inputs are copied into static device
+    buffers before each replay — from pinned host memory on the end-to-end path.
+    """
+
+    def __init__(self, model, tokens, opt: FlatAdamW, reducer, example_mbs, *, gamma=2.0,
+                 use_reweight=True, warmup_iters=3):
+        self.model, self.tokens, self.opt, self.reducer = model, tokens, opt, reducer
+        self.gamma, self.use_reweight = gamma, use_reweight
+        self.static = [{k: v.clone() for k, v in mb.items()} for mb in example_mbs]
+        self.accum = len(self.static)
+        self.grad_scale = reducer.grad_scale if reducer is not None else 1.0
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_iters):
+                self.opt.prepare_step()
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # capture records the launches without running them: no step is consumed here
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        self.opt.zero_grad()
+        loss = None
+        for i, mb in enumerate(self.static):
+            if self.reducer is not None:
+                self.reducer.armed = i == self.accum - 1
+            loss, _, _ = unimp_loss(self.model, mb, self.tokens, gamma=self.gamma,
+                                    use_reweight=self.use_reweight)
+            (loss / self.accum if self.accum > 1 else loss).backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step_kernels(self.grad_scale)
+        return loss.detach()
+
+    def __call__(self, mbs, lr_scale: float = 1.0):
+        for st, mb in zip(self.static, mbs):
+            for k, v in mb.items():
+                st[k].copy_(v, non_blocking=True)
+        self.opt.prepare_step(lr_scale)
+        self.graph.replay()
+        return self.loss
