@@ -379,15 +379,327 @@ int launch_attn_fwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int
   return launch_fwd<false>(q, k, v, nullptr, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
 }
 
-bool attn_bwd_tc_supported(unimp_view_t, unimp_view_t, unimp_view_t, unimp_view_t, unimp_mview_t,
-                           unimp_mview_t, unimp_mview_t, const int32_t*, int, int, int, int) {
-  return false;
+// ---------------------------------------------------------------------------------------------
+// Backward.  For a (128-query tile i, 64-key block j) pair, five tensor-core products:
+//     S  = Q_i K_j^T            dP = dO_i V_j^T                      (128 x 64, K = dh)
+//     P  = exp(scale*S - lse),  dS = scale * P o (dP - delta)        (threads, registers)
+//     [dV_j | dK_j] += [P | dS]^T [dO_i | Q_i]   one M=128,N=128 MMA; the diagonal blocks are
+//                                                 dV (lanes 0-63, cols 0-63) and dK (64-127)
+//     dQ_i (+)= dS K_j                                                (128 x 64, K = 64 keys)
+// MASKED  : CTA = (key block j, head, batch); walks the query tiles that reference image j;
+//           dV/dK accumulate in TMEM across tiles; every query row has exactly one block, so
+//           dQ rows are written once, straight from TMEM (no atomics, no fp32 scratch).
+// UNMASKED: CTA = (head, batch) with Lq <= 128 (Perceiver latents); walks the key blocks;
+//           dQ accumulates in TMEM across blocks; dV/dK are flushed per block.
+// delta = rowsum(dO o O) is computed inline by the thread that owns the row.
+struct BwdArgs {
+  const __nv_bfloat16 *o, *d_o;
+  int64_t o_bs, o_rs, do_bs, do_rs;
+  __nv_bfloat16 *dq, *dk, *dv;
+  int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  const float* lse;
+  const int32_t* tt;
+  int Lq, Lk, H, n, Ti;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t* r, float mul) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v;
+    v.x = pack_bf16(__uint_as_float(r[8 * c + 0]) * mul, __uint_as_float(r[8 * c + 1]) * mul);
+    v.y = pack_bf16(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul);
+    v.z = pack_bf16(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul);
+    v.w = pack_bf16(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul);
+    *reinterpret_cast<uint4*>(dst + c * 8) = v;
+  }
 }
-int launch_attn_bwd_tc(unimp_view_t, unimp_view_t, unimp_view_t, const int32_t*, unimp_view_t, unimp_view_t,
-                       const float*, void*, unimp_mview_t, unimp_mview_t, unimp_mview_t, int, int, int, int,
-                       int, int, float, cudaStream_t) {
-  set_error("attn_bwd_tc: not built");
-  return UNIMP_E_SHAPE;
+
+template <bool MASKED>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
+                   const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                   const BwdArgs a) {
+  constexpr uint32_t S_COL = 0, DP_COL = 64, DQ_COL = 128, DKV_COL = 192, TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sdO = smem;                 // [128 q][64]   \  contiguous: B operand [dO | Q], N = 128
+  uint8_t* sQ = sdO + Q_BYTES;         // [128 q][64]   /
+  uint8_t* sP = sQ + Q_BYTES;          // [128 q][64 keys]  \  contiguous: A operand [P | dS]^T, M = 128
+  uint8_t* sdS = sP + P_BYTES;         // [128 q][64 keys]  /
+  uint8_t* sK = sdS + P_BYTES;         // [64 keys][64]
+  uint8_t* sV = sK + KV_BYTES;         // [64 keys][64]
+  __shared__ uint64_t bar_qdo, bar_kv, bar_s, bar_g;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer = tid == TQ, worker = tid < TQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+
+  if (issuer) {
+    mbar_init(&bar_qdo, 1); mbar_init(&bar_kv, 1); mbar_init(&bar_s, 1); mbar_init(&bar_g, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tdo); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+
+  const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);      // S, dP
+  const uint32_t idesc_dq = make_idesc(TQ, DH, 0, 1);     // dQ = dS K      (B = K tile, MN-major)
+  const uint32_t idesc_dkv = make_idesc(128, 128, 1, 1);  // [P|dS]^T [dO|Q] (both MN-major)
+  const float l2e = 1.4426950408889634f;
+
+  const int n_qt = (a.Lq + TQ - 1) / TQ;
+  const int n_kb = (a.Lk + KB - 1) / KB;
+  const int n_pairs = MASKED ? n_qt : n_kb;
+  uint32_t ph_qdo = 0, ph_kv = 0, ph_s = 0, ph_g = 0;
+  bool kv_loaded = false, qdo_loaded = false, acc_started = false;
+  uint32_t r[32];
+
+  for (int pidx = 0; pidx < n_pairs; ++pidx) {
+    const int qt = MASKED ? pidx : 0;
+    const int kb = MASKED ? (int)blockIdx.x : pidx;
+    const int row = qt * TQ + tid;
+    const bool valid = worker && row < a.Lq;
+    int ttr = 0;
+    bool mine = valid, uniform = false;
+    if (MASKED) {
+      if (valid) ttr = a.tt[(int64_t)b * a.Lq + row];
+      uniform = ttr > a.Ti;
+      mine = valid && (uniform || ttr == kb + 1);
+      const bool zero_row = valid && ttr <= 0 && kb == 0;  // rows nobody attends: dq = 0, by block 0
+      const int any_mine = __syncthreads_or(mine ? 1 : 0);
+      if (zero_row) {
+        __nv_bfloat16* dst = a.dq + (int64_t)b * a.dq_bs + (int64_t)row * a.dq_rs + h * DH;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+      if (!any_mine) continue;  // CTA-uniform
+    }
+    // ---- loads + S / dP ---------------------------------------------------------------
+    if (issuer) {
+      const bool need_qdo = MASKED || !qdo_loaded, need_kv = !MASKED || !kv_loaded;
+      if (need_qdo) {
+        mbar_arrive_expect_tx(&bar_qdo, 2 * Q_BYTES);
+        tma_load_4d(sdO, &tdo, &bar_qdo, 0, h, qt * TQ, b);
+        tma_load_4d(sQ, &tq, &bar_qdo, 0, h, qt * TQ, b);
+      }
+      if (need_kv) {
+        mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
+        tma_load_4d(sK, &tk, &bar_kv, 0, h, kb * KB, b);
+        tma_load_4d(sV, &tv, &bar_kv, 0, h, kb * KB, b);
+      }
+      if (need_qdo) mbar_wait(&bar_qdo, ph_qdo);
+      if (need_kv) mbar_wait(&bar_kv, ph_kv);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k4 = 0; k4 < DH / 16; ++k4)
+        umma_ss(tmem + S_COL, make_smem_desc(smem_u32(sQ) + k4 * 32, 16, 1024),
+                make_smem_desc(smem_u32(sK) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+#pragma unroll
+      for (int k4 = 0; k4 < DH / 16; ++k4)
+        umma_ss(tmem + DP_COL, make_smem_desc(smem_u32(sdO) + k4 * 32, 16, 1024),
+                make_smem_desc(smem_u32(sV) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      umma_commit(&bar_s);
+    }
+    if (MASKED || !qdo_loaded) { ph_qdo ^= 1; qdo_loaded = true; }
+    if (!MASKED || !kv_loaded) { ph_kv ^= 1; kv_loaded = true; }
+
+    if (worker) {
+      // delta and lse for this row while the MMAs run
+      float delta = 0.f, lse_l2 = 0.f;
+      if (valid) {
+        const __nv_bfloat16* op = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
+        const __nv_bfloat16* gp = a.d_o + (int64_t)b * a.do_bs + (int64_t)row * a.do_rs + h * DH;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          Vec16<__nv_bfloat16> ov, gv;
+          float of[8], gf[8];
+          ov.load(op + c * 8); gv.load(gp + c * 8);
+          ov.unpack(of); gv.unpack(gf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) delta = fmaf(of[e], gf[e], delta);
+        }
+        const float lse = a.lse[((int64_t)b * a.H + h) * a.Lq + row];
+        lse_l2 = lse * l2e;
+        if (!(lse > -INFINITY)) mine = false;
+      }
+      mbar_wait(&bar_s, ph_s);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t rp[32];
+        tmem_ld32(lane_addr + S_COL + half * 32, r);
+        tmem_ld32(lane_addr + DP_COL + half * 32, rp);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int key = kb * KB + half * 32 + c;
+          float p = 0.f, ds = 0.f;
+          if (mine && key < a.Lk) {
+            if (uniform) {
+              p = exp2f(-lse_l2);
+            } else {
+              p = exp2f(__uint_as_float(r[c]) * a.scale_log2 - lse_l2);
+              ds = p * (__uint_as_float(rp[c]) - delta) * a.scale;
+            }
+          }
+          pv[c] = p;
+          dsv[c] = ds;
+        }
+        store_p_half(sP, tid, half, pv);
+        store_p_half(sdS, tid, half, dsv);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+    }
+    ph_s ^= 1;
+    __syncthreads();
+    // ---- [dV|dK] += [P|dS]^T [dO|Q]  and  dQ (+)= dS K -------------------------------------
+    if (issuer) {
+      tcgen05_fence_after();
+      const bool kv_acc = MASKED ? acc_started : false;   // MASKED: accumulate across tiles
+      const bool dq_acc = MASKED ? false : acc_started;   // UNMASKED: accumulate across blocks
+#pragma unroll
+      for (int k8 = 0; k8 < TQ / 16; ++k8)
+        umma_ss(tmem + DKV_COL, make_smem_desc(smem_u32(sP) + k8 * 2048, P_BYTES, 1024),
+                make_smem_desc(smem_u32(sdO) + k8 * 2048, Q_BYTES, 1024), idesc_dkv,
+                (kv_acc || k8 > 0));
+#pragma unroll
+      for (int k4 = 0; k4 < KB / 16; ++k4)
+        umma_ss(tmem + DQ_COL, make_smem_desc(smem_u32(sdS) + k4 * 32, 16, 1024),
+                make_smem_desc(smem_u32(sK) + k4 * 2048, 1024, 1024), idesc_dq, (dq_acc || k4 > 0));
+      umma_commit(&bar_g);
+    }
+    acc_started = true;
+    mbar_wait(&bar_g, ph_g);   // everyone: smem tiles and S/dP columns are free again
+    ph_g ^= 1;
+    tcgen05_fence_after();
+    if (worker) {
+      if (MASKED) {
+        // dQ rows of this tile that belong to block kb (uniform rows: dS = 0 -> zeros, written by
+        // every block alike)
+        tmem_ld32(lane_addr + DQ_COL, r);
+        tmem_ld_wait();
+        __nv_bfloat16* dst = a.dq + (int64_t)b * a.dq_bs + (int64_t)row * a.dq_rs + h * DH;
+        if (mine) store_row_bf16(dst, r, 1.f);
+        tmem_ld32(lane_addr + DQ_COL + 32, r);
+        tmem_ld_wait();
+        if (mine) store_row_bf16(dst + 32, r, 1.f);
+      } else {
+        // flush this key block's dV (lanes 0-63, cols 0-63) and dK (lanes 64-127, cols 64-127)
+        const int key = kb * KB + (tid & 63);
+        const bool is_k = tid >= 64;
+        const uint32_t col = DKV_COL + (is_k ? 64 : 0);
+        __nv_bfloat16* dst = is_k ? a.dk + (int64_t)b * a.dk_bs + (int64_t)key * a.dk_rs + h * DH
+                                  : a.dv + (int64_t)b * a.dv_bs + (int64_t)key * a.dv_rs + h * DH;
+        tmem_ld32(lane_addr + col, r);
+        tmem_ld_wait();
+        if (key < a.Lk) store_row_bf16(dst, r, 1.f);
+        tmem_ld32(lane_addr + col + 32, r);
+        tmem_ld_wait();
+        if (key < a.Lk) store_row_bf16(dst + 32, r, 1.f);
+      }
+      tcgen05_fence_before();
+    }
+    __syncthreads();  // TMEM reads done before the next pair's MMAs overwrite the columns
+    tcgen05_fence_after();
+  }
+
+  // ---- final flush -------------------------------------------------------------------------
+  if (worker) {
+    if (MASKED) {
+      const int key = (int)blockIdx.x * KB + (tid & 63);
+      const bool is_k = tid >= 64;
+      const uint32_t col = DKV_COL + (is_k ? 64 : 0);
+      __nv_bfloat16* dst = is_k ? a.dk + (int64_t)b * a.dk_bs + (int64_t)key * a.dk_rs + h * DH
+                                : a.dv + (int64_t)b * a.dv_bs + (int64_t)key * a.dv_rs + h * DH;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (acc_started) {
+          tmem_ld32(lane_addr + col + half * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = 0u;
+        }
+        if (key < a.Lk) store_row_bf16(dst + half * 32, r, 1.f);
+      }
+    } else {
+      const int row = tid;
+      __nv_bfloat16* dst = a.dq + (int64_t)b * a.dq_bs + (int64_t)row * a.dq_rs + h * DH;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(lane_addr + DQ_COL + half * 32, r);
+        tmem_ld_wait();
+        if (row < a.Lq) store_row_bf16(dst + half * 32, r, 1.f);
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+bool attn_bwd_tc_supported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t d_o,
+                           unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, const int32_t* tt,
+                           int Lq, int Lk, int n, int dh) {
+  (void)Lk;
+  if (dh != DH) return false;
+  if (!view_ok(q.ptr, q.batch_stride, q.row_stride) || !view_ok(k.ptr, k.batch_stride, k.row_stride) ||
+      !view_ok(v.ptr, v.batch_stride, v.row_stride) || !view_ok(d_o.ptr, d_o.batch_stride, d_o.row_stride) ||
+      !view_ok(dq.ptr, dq.batch_stride, dq.row_stride) || !view_ok(dk.ptr, dk.batch_stride, dk.row_stride) ||
+      !view_ok(dv.ptr, dv.batch_stride, dv.row_stride))
+    return false;
+  if (tt) return n == KB;
+  return Lq <= TQ;
+}
+
+template <bool MASKED>
+static int launch_bwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt, unimp_view_t o,
+                      unimp_view_t d_o, const float* lse, unimp_mview_t dq, unimp_mview_t dk,
+                      unimp_mview_t dv, int B, int Lq, int Lk, int H, int n, int Ti, float scale,
+                      cudaStream_t st) {
+  CUtensorMap tq, tdo, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bhld(&tq, q.ptr, q.batch_stride, q.row_stride, B, Lq, H, TQ))) return rc;
+  if ((rc = make_tmap_bhld(&tdo, d_o.ptr, d_o.batch_stride, d_o.row_stride, B, Lq, H, TQ))) return rc;
+  if ((rc = make_tmap_bhld(&tk, k.ptr, k.batch_stride, k.row_stride, B, Lk, H, KB))) return rc;
+  if ((rc = make_tmap_bhld(&tv, v.ptr, v.batch_stride, v.row_stride, B, Lk, H, KB))) return rc;
+  const int smem = 1024 + 2 * Q_BYTES + 2 * P_BYTES + 2 * KV_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MASKED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("attn_bwd_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr = true;
+  }
+  BwdArgs a;
+  a.o = (const __nv_bfloat16*)o.ptr; a.o_bs = o.batch_stride; a.o_rs = o.row_stride;
+  a.d_o = (const __nv_bfloat16*)d_o.ptr; a.do_bs = d_o.batch_stride; a.do_rs = d_o.row_stride;
+  a.dq = (__nv_bfloat16*)dq.ptr; a.dq_bs = dq.batch_stride; a.dq_rs = dq.row_stride;
+  a.dk = (__nv_bfloat16*)dk.ptr; a.dk_bs = dk.batch_stride; a.dk_rs = dk.row_stride;
+  a.dv = (__nv_bfloat16*)dv.ptr; a.dv_bs = dv.batch_stride; a.dv_rs = dv.row_stride;
+  a.lse = lse; a.tt = tt; a.Lq = Lq; a.Lk = Lk; a.H = H; a.n = n; a.Ti = Ti;
+  a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(MASKED ? (Lk + KB - 1) / KB : 1, H, B);
+  attn_bwd_tc_kernel<MASKED><<<grid, FWD_THREADS, smem, st>>>(tq, tdo, tk, tv, a);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_attn_bwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt, unimp_view_t o,
+                       unimp_view_t d_o, const float* lse, void* workspace, unimp_mview_t dq,
+                       unimp_mview_t dk, unimp_mview_t dv, int B, int Lq, int Lk, int H, int n, int Ti,
+                       float scale, cudaStream_t st) {
+  (void)workspace;
+  if (tt) return launch_bwd<true>(q, k, v, tt, o, d_o, lse, dq, dk, dv, B, Lq, Lk, H, n, Ti, scale, st);
+  return launch_bwd<false>(q, k, v, nullptr, o, d_o, lse, dq, dk, dv, B, Lq, Lk, H, n, Ti, scale, st);
 }
 
 }  // namespace unimp
