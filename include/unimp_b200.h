@@ -171,6 +171,20 @@ int unimp_mask_labels(const int64_t* input_ids, int64_t answer_id, int64_t endof
                       int64_t media_id, int64_t pad_id, int64_t* labels, int B, int T,
                       void* stream);
 
+/* ---- f3: elementwise fusions around the frozen towers -------------------------------
+ * GPT-NeoX rotary embedding (HF `apply_rotary_pos_emb`, transformers gpt_neox) over the packed
+ * (B,T,H,3*dh) output of `query_key_value` into `out` (same layout, out != qkv; v and the
+ * non-rotary tail are copied); cos/sin are (1 or B, T, rot) in `dtype` (cs_batch_stride = 0 when
+ * shared across the batch).  q/k/v then go to SDPA as strided views of `out`.  Backward un-rotates dq/dk and packs dq|dk|dv ((B,H,T,dh) views; strides9 is a HOST
+ * array {q_sb,q_sh,q_st,k_sb,k_sh,k_st,v_sb,v_sh,v_st} in elements) into d_qkv (B,T,H,3*dh). */
+int unimp_rotary_qkv_fwd(const void* qkv, void* out, const void* cos, const void* sin, int B, int T,
+                         int H, int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream);
+int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const int64_t* strides9,
+                         const void* cos, const void* sin, void* d_qkv, int B, int T, int H, int dh,
+                         int rot, int64_t cs_batch_stride, int dtype, void* stream);
+/* CLIP QuickGELU x*sigmoid(1.702x), in place (ViT MLP; forward only: the tower is frozen). */
+int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream);
+
 /* ---- f1: fused AdamW over a flat parameter group --------------------------------------
  * Replaces torch.optim.AdamW.step for one param group (reference UniMP/mmrec.py:671) with
  * grad-clip scaling folded in (clip coefficient = min(1, max_norm/(norm+1e-6)),

@@ -268,3 +268,65 @@ def test_fused_adamw_matches_torch(dtype):
                           weight_decay=0.1, gnorm_sq=acc, max_norm=1.0)
     assert torch.allclose(master.cpu(), ref_p.detach(), rtol=1e-5, atol=2e-6)
     assert rel_err(param, ref_p.detach()) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+# ------------------------------------------------------------------ LM / ViT elementwise fusions
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,T,H,dh,rot,cb", [(2, 9, 4, 32, 32, 1), (3, 64, 32, 80, 80, 1), (2, 5, 2, 64, 32, 2)])
+def test_rotary_qkv_matches_hf_apply_rotary(dtype, tol, B, T, H, dh, rot, cb):
+    from transformers.models.gpt_neox.modeling_gpt_neox import apply_rotary_pos_emb
+
+    torch.manual_seed(T)
+    qkv = torch.randn(B, T, H * 3 * dh).to(dtype).double()
+    ang = torch.rand(cb, T, rot // 2) * 6.28
+    emb = torch.cat([ang, ang], -1)
+    cos, sin = emb.cos().to(dtype).double(), emb.sin().to(dtype).double()
+    gq, gk, gv = (torch.randn(B, H, T, dh).to(dtype).double() for _ in range(3))
+    r = qkv.clone().requires_grad_(True)
+    q0, k0, v0 = r.view(B, T, H, 3 * dh).transpose(1, 2).chunk(3, dim=-1)
+    qe, ke = apply_rotary_pos_emb(q0, k0, cos, sin)
+    (qe * gq + ke * gk + v0 * gv).sum().backward()
+    d = qkv.to(DEV, dtype).requires_grad_(True)
+    proj = d * 1.0  # a non-leaf, like the output of query_key_value
+    q, k, v = ops().rotary_qkv(proj, cos.to(DEV, dtype), sin.to(DEV, dtype), heads=H, head_dim=dh, rotary_dim=rot)
+    assert rel_err(q, qe) < tol and rel_err(k, ke) < tol and rel_err(v, v0) < tol
+    (q * gq.to(DEV, dtype) + k * gk.to(DEV, dtype) + v * gv.to(DEV, dtype)).sum().backward()
+    assert rel_err(d.grad, r.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_quick_gelu(dtype, tol):
+    x = torch.randn(37, 256).to(dtype)
+    want = x.double() * torch.sigmoid(1.702 * x.double())
+    got = ops().quick_gelu_(x.to(DEV).clone())
+    assert rel_err(got, want) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("parallel", [False, True])
+def test_fused_neox_layer_matches_hf_layer(dtype, tol, parallel):
+    """The fused decoder-layer path == HF GPTNeoXLayer.forward (fwd and input gradient)."""
+    from transformers import GPTNeoXConfig
+    from transformers.models.gpt_neox.modeling_gpt_neox import GPTNeoXLayer, GPTNeoXRotaryEmbedding
+
+    from unimp_b200.flamingo_lm import fused_neox_layer
+
+    torch.manual_seed(0)
+    cfg = GPTNeoXConfig(hidden_size=256, num_hidden_layers=1, num_attention_heads=4, intermediate_size=512,
+                        vocab_size=128, use_parallel_residual=parallel, hidden_dropout=0.0, attention_dropout=0.0)
+    cfg._attn_implementation = "sdpa"
+    layer = GPTNeoXLayer(cfg, 0).to(DEV, dtype)
+    rope = GPTNeoXRotaryEmbedding(cfg).to(DEV)
+    B, T = 2, 24
+    x = torch.randn(B, T, 256, device=DEV, dtype=dtype)
+    pe = rope(x, torch.arange(T, device=DEV)[None])
+    g = torch.randn_like(x)
+    xa = x.clone().requires_grad_(True)
+    ya = layer(xa, attention_mask=None, position_embeddings=pe)
+    ya.backward(g)
+    xb = x.clone().requires_grad_(True)
+    yb = fused_neox_layer(layer, xb, None, pe)
+    yb.backward(g)
+    assert rel_err(yb, ya) < tol
+    assert rel_err(xb.grad, xa.grad) < tol

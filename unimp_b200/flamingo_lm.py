@@ -103,6 +103,61 @@ class PaddedOutputHead(nn.Module):
         return _PaddedHeadFn.apply(h, self._padded(), self.out_features)
 
 
+def _neox_fusable(layer, x, kw) -> bool:
+    """Can this (frozen) HF GPT-NeoX decoder layer run on the fused path? (no KV cache, SDPA,
+    no active dropout, vectorisable rotary dims)"""
+    from transformers.models.gpt_neox.modeling_gpt_neox import GPTNeoXLayer
+
+    if not isinstance(layer, GPTNeoXLayer) or not x.is_cuda:
+        return False
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        return False
+    if kw.get("layer_past") is not None or kw.get("position_embeddings") is None:
+        return False
+    att = layer.attention
+    if getattr(att.config, "_attn_implementation", "sdpa") != "sdpa":
+        return False
+    if layer.training and (layer.post_attention_dropout.p > 0 or layer.post_mlp_dropout.p > 0
+                           or att.attention_dropout > 0):
+        return False
+    npv = 8 if x.dtype == torch.bfloat16 else 4
+    return att.rotary_ndims % 2 == 0 and (att.rotary_ndims // 2) % npv == 0 and att.head_size % npv == 0
+
+
+def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None):
+    """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
+    our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
+    qkv projection (`unimp_rotary_qkv_*`), q/k/v reach SDPA as strided views.  GEMMs stay on
+    cuBLAS and the causal attention core on cuDNN SDPA (K4: not in the north star).  Same
+    parameters, same arithmetic; ~11 launches instead of ~30 per layer.
+    `h1`: input_layernorm(x) if the caller already produced it in a fused epilogue."""
+    F = torch.nn.functional
+    att = layer.attention
+    B, T, D = x.shape
+    H, dh, rot = att.config.num_attention_heads, att.head_size, att.rotary_ndims
+    ln1, ln2 = layer.input_layernorm, layer.post_attention_layernorm
+    if h1 is None:
+        h1 = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
+    qkv = F.linear(h1, att.query_key_value.weight, att.query_key_value.bias)
+    cos, sin = position_embeddings
+    q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
+                             rotary_dim=rot)
+    a = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0,
+                                       is_causal=attention_mask is None and T > 1,
+                                       scale=att.scaling)
+    o = F.linear(a.transpose(1, 2).reshape(B, T, D), att.dense.weight, att.dense.bias)
+    mlp = layer.mlp
+    if layer.use_parallel_residual:
+        h2 = ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps)
+        m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+                     mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+        return ops.gate_residual(m, ops.gate_residual(o, x, None), None)
+    x1, h2 = ops.gate_residual_ln(o, x, None, ln2.weight, ln2.bias, ln2.eps)
+    m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+                 mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+    return ops.gate_residual(m, x1, None)
+
+
 class FlamingoLayer(nn.Module):
     def __init__(self, gated_cross_attn_layer, decoder_layer, gradient_checkpointing=False):
         super().__init__()
@@ -129,6 +184,8 @@ class FlamingoLayer(nn.Module):
         self.use_cached_media = use_cached_media
 
     def forward(self, lang_x, attention_mask=None, **decoder_layer_kwargs):
+        fuse = _neox_fusable(self.decoder_layer, lang_x, decoder_layer_kwargs)
+        h1 = None
         if self.gated_cross_attn_layer is not None:
             if self.vis_x is None:
                 raise ValueError("vis_x must be conditioned before forward pass")
@@ -137,9 +194,14 @@ class FlamingoLayer(nn.Module):
             tt = self.text_time
             if tt is not None and tt.shape[1] != lang_x.shape[1]:
                 tt = None  # stale (e.g. cached prompt length): let the block derive it
-            lang_x = self.gated_cross_attn_layer(
+            out = self.gated_cross_attn_layer(
                 lang_x, self.vis_x, media_locations=self.media_locations,
-                use_cached_media=self.use_cached_media, text_time=tt)
+                use_cached_media=self.use_cached_media, text_time=tt,
+                next_ln=self.decoder_layer.input_layernorm if fuse else None)
+            lang_x, h1 = out if fuse else (out, None)
+        if fuse:
+            return fused_neox_layer(self.decoder_layer, lang_x, attention_mask,
+                                    decoder_layer_kwargs["position_embeddings"], h1)
         return self.decoder_layer(lang_x, attention_mask=attention_mask, **decoder_layer_kwargs)
 
 

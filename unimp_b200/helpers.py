@@ -167,7 +167,11 @@ class GatedCrossAttentionBlock(nn.Module):
         self.ff = FeedForward(dim, mult=ff_mult)
         self.ff_gate = nn.Parameter(torch.tensor([0.0]))
 
-    def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None):
+    def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None,
+                next_ln=None):
+        """`next_ln`: the LayerNorm module that consumes the block's output next (the decoder
+        layer's input_layernorm); if given, its output is produced by the same K5 launch as the
+        last gated residual and the call returns (x, next_ln(x))."""
         a = self.attn(x, media, media_locations=media_locations,
                       use_cached_media=use_cached_media, text_time=text_time)
         # x = a*tanh(attn_gate) + x, fused with ff's LayerNorm                     (K5)
@@ -175,4 +179,6 @@ class GatedCrossAttentionBlock(nn.Module):
                                     self.ff[0].eps)
         h = _ff_tail(self.ff, h)
         # x = ff*tanh(ff_gate) + x                                                 (K5)
+        if next_ln is not None:
+            return ops.gate_residual_ln(h, x, self.ff_gate, next_ln.weight, next_ln.bias, next_ln.eps)
         return ops.gate_residual(h, x, self.ff_gate)

@@ -302,6 +302,62 @@ def focal_ce(logits, labels, weights, *, gamma: float = 2.0, use_focal: bool = T
     return _FocalCE.apply(logits, labels, weights, gamma, use_focal)
 
 
+# --------------------------------------------------------------------------- LM / ViT fusions
+
+class _RotaryQKV(torch.autograd.Function):
+    """GPT-NeoX rotary on the packed qkv projection; returns q,k,v (B,H,T,dh) views of ONE packed
+    output buffer (no chunk/cat temporaries)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, H, dh, rot):
+        dt = _dt(qkv)
+        B, T, _ = qkv.shape
+        assert qkv.is_contiguous() and qkv.shape[2] == 3 * H * dh
+        cos, sin = cos.contiguous(), sin.contiguous()
+        assert cos.dtype == qkv.dtype and cos.shape[-1] == rot and cos.shape[-2] == T
+        cb = cos.shape[0] if cos.dim() == 3 else 1
+        cs_bs = T * rot if cb > 1 else 0
+        out = torch.empty_like(qkv)
+        check(_lib.load().unimp_rotary_qkv_fwd(qkv.data_ptr(), out.data_ptr(), cos.data_ptr(),
+                                               sin.data_ptr(), B, T, H, dh, rot, cs_bs, dt,
+                                               _stream()), "unimp_rotary_qkv_fwd")
+        ctx.save_for_backward(cos, sin)
+        ctx.cfg = (B, T, H, dh, rot, cs_bs, dt)
+        v5 = out.view(B, T, H, 3, dh)
+        q, k, v = (v5[:, :, :, i].transpose(1, 2) for i in range(3))
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        import ctypes
+        cos, sin = ctx.saved_tensors
+        B, T, H, dh, rot, cs_bs, dt = ctx.cfg
+        gs = []
+        for g in (dq, dk, dv):
+            if g.stride(-1) != 1:
+                g = g.contiguous()
+            gs.append(g)
+        strides = (ctypes.c_int64 * 9)(*[s for g in gs for s in (g.stride(0), g.stride(1), g.stride(2))])
+        d_qkv = torch.empty((B, T, 3 * H * dh), dtype=gs[0].dtype, device=gs[0].device)
+        check(_lib.load().unimp_rotary_qkv_bwd(gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr(),
+                                               strides, cos.data_ptr(), sin.data_ptr(),
+                                               d_qkv.data_ptr(), B, T, H, dh, rot, cs_bs, dt,
+                                               _stream()), "unimp_rotary_qkv_bwd")
+        return d_qkv, None, None, None, None, None
+
+
+def rotary_qkv(qkv, cos, sin, *, heads: int, head_dim: int, rotary_dim: int):
+    """qkv (B,T,H*3*dh) projection output -> rotated q, k and v as (B,H,T,dh) views."""
+    return _RotaryQKV.apply(qkv, cos, sin, heads, head_dim, rotary_dim)
+
+
+def quick_gelu_(x):
+    """In-place CLIP QuickGELU (no autograd: used inside the frozen, no_grad vision tower)."""
+    assert x.is_contiguous()
+    check(_lib.load().unimp_quick_gelu(x.data_ptr(), x.numel(), _dt(x), _stream()), "unimp_quick_gelu")
+    return x
+
+
 # --------------------------------------------------------------------------- optimizer pieces
 
 def sumsq_(grad: torch.Tensor, acc: torch.Tensor):

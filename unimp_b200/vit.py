@@ -70,7 +70,7 @@ class VisionTransformer(nn.Module):
             nn.init.normal_(blk.attn.in_proj_weight, std=scale)
 
     def _act(self, h):
-        return h * torch.sigmoid(1.702 * h) if self.quick_gelu else F.gelu(h)
+        return ops.quick_gelu_(h) if self.quick_gelu else F.gelu(h)
 
     @torch.no_grad()
     def forward(self, x):
