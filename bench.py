@@ -350,6 +350,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # everything (model build, warm-up, capture, replay, timing events) runs on ONE non-default
+    # stream: the legacy default stream cannot take part in a graph capture that contains NCCL
+    torch.cuda.set_stream(torch.cuda.Stream())
     assert _lib.load().unimp_device_ok() == 1
     torch.backends.cuda.matmul.allow_tf32 = True
     peaks = load_peaks()
@@ -456,9 +459,17 @@ def main():
                         "avg_us": kx["avg_us"], "peak_source": peaks["source"],
                         "alg_bytes_per_launch": kx["alg_bytes_per_launch"]}
 
-    if rank != 0:
+    def finish():
+        # a process group cannot be torn down cleanly while a captured graph still references its
+        # communicator: flush, meet at a barrier, and leave
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     cpu_baseline = None
@@ -479,8 +490,7 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "kernels": kernels}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -236,7 +236,13 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, tokens, opt: FlatAdamW, reducer, example_mbs, *, gamma=2.0,
-                 use_reweight=True, warmup_iters=3):
+                 use_reweight=True, warmup_iters=3, capture_error_mode=None):
+        # NOTE: with NCCL in the graph, run the whole process on a NON-default stream
+        # (`torch.cuda.set_stream(torch.cuda.Stream())` before building the model): gradient
+        # accumulators remember the stream they were created on, and the legacy default stream
+        # may not depend on a capturing stream (cudaErrorStreamCaptureImplicit).
+        if capture_error_mode is None:
+            capture_error_mode = "thread_local" if reducer is not None and reducer.world > 1 else "global"
         self.model, self.tokens, self.opt, self.reducer = model, tokens, opt, reducer
         self.gamma, self.use_reweight = gamma, use_reweight
         self.static = [{k: v.clone() for k, v in mb.items()} for mb in example_mbs]
@@ -252,7 +258,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         # capture records the launches without running them: no step is consumed here
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = self._body()
 
     def _body(self):
