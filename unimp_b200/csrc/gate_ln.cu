@@ -110,8 +110,9 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
 // of a 768-row activation is in flight at once; column partials (d_gamma, d_beta) live in
 // registers per thread, are folded across the R groups through shared memory in a fixed order,
 // and leave the CTA as one partial row: partial[G][2*D + 1] (last = d_gate).
-constexpr int LN_BWD_MAX_R = 12;       // row-groups per CTA: R = clamp(384 / TG, 1, 12)
-static inline int ln_bwd_r(int TG) { int r = 384 / TG; return r < 1 ? 1 : (r > LN_BWD_MAX_R ? LN_BWD_MAX_R : r); }
+constexpr int LN_BWD_MAX_R = 12;       // row-groups per CTA: R = clamp(192 / TG, 1, 12): small CTAs,
+                                       // so 2-3 of them fit the register file of an SM
+static inline int ln_bwd_r(int TG) { int r = 192 / TG; return r < 1 ? 1 : (r > LN_BWD_MAX_R ? LN_BWD_MAX_R : r); }
 
 __device__ __forceinline__ float group_sum(float v, float* sh, int rg, int tg_threads, int t) {
   const int lane = t & 31, w = t >> 5, nw = tg_threads >> 5;
@@ -123,7 +124,22 @@ __device__ __forceinline__ float group_sum(float v, float* sh, int rg, int tg_th
   return warp_sum(r);
 }
 
-template <typename T>
+// COLS = false: the LayerNorm's affine parameters are frozen (the LM / ViT towers): no column
+// partials are kept, which frees 64 registers per thread and the final fold.
+// two sums with one pair of barriers
+__device__ __forceinline__ void group_sum2(float& a, float& b, float* sh, int rg, int tg_threads, int t) {
+  const int lane = t & 31, w = t >> 5, nw = tg_threads >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
+  if (lane == 0) { sh[w] = a; sh[16 + w] = b; }
+  asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
+  float ra = (lane < nw) ? sh[lane] : 0.f, rb = (lane < nw) ? sh[16 + lane] : 0.f;
+  a = warp_sum(ra);
+  b = warp_sum(rb);
+}
+
+template <typename T, bool COLS>
 __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ g_ln,
                                             const T* __restrict__ branch, const T* __restrict__ x_out,
                                             const T* __restrict__ gate,
@@ -140,13 +156,15 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
   float* sgate = sdyn + 2 * D + LN_BWD_MAX_R * 32;
   const bool has_ln = g_ln != nullptr && gamma != nullptr;
   const float tg = branch ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
-  float dg[LN_VPT][N], db[LN_VPT][N];
+  float dg[COLS ? LN_VPT : 1][N], db[COLS ? LN_VPT : 1][N];
   float dgate = 0.f;
+  if (COLS) {
 #pragma unroll
-  for (int k = 0; k < LN_VPT; ++k)
+    for (int k = 0; k < LN_VPT; ++k)
 #pragma unroll
-    for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sdyn[i] = 0.f;
+      for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sdyn[i] = 0.f;
+  }
 
   for (int64_t row = (int64_t)blockIdx.x * R + rg; row < rows; row += (int64_t)gridDim.x * R) {
     Vec16<T> gl_raw[LN_VPT], xo_raw[LN_VPT];
@@ -177,13 +195,16 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
             const float xh = (xo[i] - mean) * rstd, gy = gl[i] * gm[i];
             s1 += gy;
             s2 += gy * xh;
-            dg[k][i] += gl[i] * xh;
-            db[k][i] += gl[i];
+            if (COLS) {
+              dg[k][i] += gl[i] * xh;
+              db[k][i] += gl[i];
+            }
           }
         }
       }
-      s1 = group_sum(s1, sh, rg, TG, t) / D;
-      s2 = group_sum(s2, sh, rg, TG, t) / D;
+      group_sum2(s1, s2, sh, rg, TG, t);
+      s1 /= D;
+      s2 /= D;
     }
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
@@ -235,7 +256,7 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
   dgate = group_sum(dgate, sh, rg, TG, t);
   if (t == 0) sgate[rg] = dgate;
   __syncthreads();
-  for (int g = 0; g < R; ++g) {
+  for (int g = 0; COLS && g < R; ++g) {
     if (rg == g && has_ln) {
 #pragma unroll
       for (int k = 0; k < LN_VPT; ++k) {
@@ -252,7 +273,8 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
     __syncthreads();
   }
   float* pr = partial + (int64_t)blockIdx.x * (2 * D + 1);
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) pr[i] = sdyn[i];
+  if (COLS)
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) pr[i] = sdyn[i];
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int g = 0; g < R; ++g) s += sgate[g];
@@ -288,9 +310,10 @@ __global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ par
   }
 }
 
-static inline int ln_bwd_grid(int64_t rows, int R) {
+static inline int ln_bwd_grid(int64_t rows, int R, bool cols) {
   const int64_t need = (rows + R - 1) / R;
-  const int64_t g = UNIMP_NUM_SMS;  // one CTA (R row-groups) per SM
+  // 192-thread CTAs: ~150 registers with column partials (2 CTAs/SM), ~96 without (3 CTAs/SM)
+  const int64_t g = cols ? 2 * UNIMP_NUM_SMS : 3 * UNIMP_NUM_SMS;
   return (int)(need < g ? need : g);
 }
 
@@ -335,7 +358,7 @@ extern "C" int unimp_gate_residual_ln_fwd(const void* branch, const void* x, con
 
 extern "C" int64_t unimp_gate_residual_ln_bwd_workspace(int64_t rows, int D) {
   (void)rows;
-  return (int64_t)UNIMP_NUM_SMS * (2 * (int64_t)D + 1) * sizeof(float);
+  return 3 * (int64_t)UNIMP_NUM_SMS * (2 * (int64_t)D + 1) * sizeof(float);
 }
 
 extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void* branch,
@@ -360,33 +383,39 @@ extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, 
                   UNIMP_E_ALIGN, "gate_residual_ln_bwd: pointers must be 16-byte aligned");
   const int TG = ln_threads(D, npv);
   const int R = ln_bwd_r(TG);
-  UNIMP_CHECK_ARG(TG * R <= 384 || (R == 1 && TG <= 384), UNIMP_E_SHAPE,
+  UNIMP_CHECK_ARG(TG * R <= 384, UNIMP_E_SHAPE,
                   "gate_residual_ln_bwd: D=%d too large for the register budget", D);
   const int threads = TG * R;
-  const int G = ln_bwd_grid(rows, R);
   const int smem = (2 * D + LN_BWD_MAX_R * 32 + LN_BWD_MAX_R) * (int)sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool cols = (d_gamma || d_beta) && g_ln;
+  const int G = ln_bwd_grid(rows, R, cols);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16>,
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16, true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float>,
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float, false>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  if (dtype == UNIMP_BF16)
-    gate_residual_ln_bwd_kernel<__nv_bfloat16><<<G, threads, smem, st>>>(
-        (const __nv_bfloat16*)g_xout, (const __nv_bfloat16*)g_ln, (const __nv_bfloat16*)branch,
-        (const __nv_bfloat16*)x_out, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)gamma, mean,
-        rstd,
-        (__nv_bfloat16*)d_x, (__nv_bfloat16*)d_branch, (float*)partial, rows, D, TG, R);
-  else
-    gate_residual_ln_bwd_kernel<float><<<G, threads, smem, st>>>(
-        (const float*)g_xout, (const float*)g_ln, (const float*)branch, (const float*)x_out,
-        (const float*)gate,
-        (const float*)gamma, mean, rstd, (float*)d_x, (float*)d_branch, (float*)partial, rows, D,
-        TG, R);
+#define UNIMP_LN_BWD_LAUNCH(TT, CC)                                                                  \
+  gate_residual_ln_bwd_kernel<TT, CC><<<G, threads, smem, st>>>(                                      \
+      (const TT*)g_xout, (const TT*)g_ln, (const TT*)branch, (const TT*)x_out, (const TT*)gate,       \
+      (const TT*)gamma, mean, rstd, (TT*)d_x, (TT*)d_branch, (float*)partial, rows, D, TG, R)
+  if (dtype == UNIMP_BF16) {
+    if (cols) UNIMP_LN_BWD_LAUNCH(__nv_bfloat16, true);
+    else UNIMP_LN_BWD_LAUNCH(__nv_bfloat16, false);
+  } else {
+    if (cols) UNIMP_LN_BWD_LAUNCH(float, true);
+    else UNIMP_LN_BWD_LAUNCH(float, false);
+  }
+#undef UNIMP_LN_BWD_LAUNCH
   UNIMP_CHECK_LAUNCH();
+  if (!cols && !d_gate) return 0;
   const int W = 2 * D + 1;
   if (dtype == UNIMP_BF16)
     gate_residual_ln_bwd_reduce_kernel<__nv_bfloat16><<<(W + 31) / 32, 256, 0, st>>>(

@@ -222,9 +222,11 @@ class _GateResidualLN(torch.autograd.Function):
         lib = _lib.load()
         d_x = torch.empty_like(xo)
         d_branch = torch.empty_like(xo) if has_b else None
-        d_gate = torch.empty_like(gate) if (has_b and gate is not None) else None
-        d_gamma = torch.empty_like(gamma) if (has_ln and g_ln is not None) else None
-        d_beta = torch.empty_like(gamma) if (has_ln and g_ln is not None) else None
+        need_gate = has_b and gate is not None and ctx.needs_input_grad[2]
+        need_affine = has_ln and g_ln is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        d_gate = torch.empty_like(gate) if need_gate else None
+        d_gamma = torch.empty_like(gamma) if need_affine else None   # frozen LN: no column sums
+        d_beta = torch.empty_like(gamma) if need_affine else None
         ws = torch.empty(lib.unimp_gate_residual_ln_bwd_workspace(rows, D), dtype=torch.uint8,
                          device=xo.device)
         use_ln = has_ln and g_ln is not None
@@ -233,7 +235,7 @@ class _GateResidualLN(torch.autograd.Function):
             _ptr(gate), _ptr(gamma) if use_ln else None, _ptr(mean), _ptr(rstd), d_x.data_ptr(),
             _ptr(d_branch), _ptr(d_gate), _ptr(d_gamma), _ptr(d_beta), ws.data_ptr(), rows, D, dt,
             _stream()), "unimp_gate_residual_ln_bwd")
-        if has_ln and d_gamma is None:
+        if has_ln and d_gamma is None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
             d_gamma = torch.zeros_like(gamma)
             d_beta = torch.zeros_like(gamma)
         return d_branch, d_x, d_gate, d_gamma, d_beta, None
