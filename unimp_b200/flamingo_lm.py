@@ -256,7 +256,14 @@ class FlamingoLMMixin(nn.Module):
             for layer in layers:
                 layer.condition_media_locations(media_locations, tt)
                 layer.condition_use_cached_media(False)
-        kwargs["input_ids"] = input_ids
+        emb = self.get_input_embeddings()
+        if (torch.is_grad_enabled() and emb.weight.requires_grad and input_ids.is_cuda
+                and kwargs.get("inputs_embeds") is None and type(emb) is nn.Embedding
+                and emb.padding_idx is None and emb.max_norm is None):
+            # trainable input embeddings: gradient rows go straight into the flat grad buffer
+            kwargs["inputs_embeds"] = ops.embedding_acc(input_ids, emb.weight)
+        else:
+            kwargs["input_ids"] = input_ids
         kwargs["attention_mask"] = attention_mask
         out = super().forward(**kwargs)  # HF forward without labels: no fp32 logits copy
         if labels is None:

@@ -32,9 +32,9 @@ def FeedForward(dim: int, mult: int = 4) -> nn.Sequential:
 
 def _ff_tail(ff: nn.Sequential, ln_out: torch.Tensor) -> torch.Tensor:
     """Linear -> GELU -> Linear of a FeedForward whose LayerNorm was already applied (fused)."""
-    h = F.linear(ln_out, ff[1].weight)
+    h = ops.linear_acc(ln_out, ff[1].weight)
     h = F.gelu(h)
-    return F.linear(h, ff[3].weight)
+    return ops.linear_acc(h, ff[3].weight)
 
 
 class PerceiverAttention(nn.Module):
@@ -58,11 +58,11 @@ class PerceiverAttention(nn.Module):
         if latents_ln is None:
             latents_ln = ops.layer_norm(latents, self.norm_latents.weight, self.norm_latents.bias,
                                         self.norm_latents.eps)
-        q = F.linear(latents_ln, self.to_q.weight).view(b * T, n2, -1)
+        q = ops.linear_acc(latents_ln, self.to_q.weight).view(b * T, n2, -1)
         kv_in = torch.cat((x_ln, latents_ln), dim=-2)
-        kv = F.linear(kv_in, self.to_kv.weight).view(b * T, n1 + n2, -1)
+        kv = ops.linear_acc(kv_in, self.to_kv.weight).view(b * T, n1 + n2, -1)
         out = ops.attention(q, kv, heads=self.heads, scale=self.scale)      # K2
-        return F.linear(out, self.to_out.weight).view(b, T, n2, D)
+        return ops.linear_acc(out, self.to_out.weight).view(b, T, n2, D)
 
 
 class PerceiverResampler(nn.Module):
@@ -122,7 +122,7 @@ class MaskedCrossAttention(nn.Module):
     def project_media(self, media):
         """to_kv over (B, Ti*n, Dv) -> packed (B, Ti*n, 2*inner)."""
         B, Ti, n, Dv = media.shape
-        return F.linear(media.reshape(B, Ti * n, Dv), self.to_kv.weight)
+        return ops.linear_acc(media.reshape(B, Ti * n, Dv), self.to_kv.weight)
 
     def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None):
         """x (B,T,D); media (B,Ti,n,Dv); `text_time` int32 (B,T) may be passed precomputed
@@ -139,7 +139,7 @@ class MaskedCrossAttention(nn.Module):
             text_time = ops.text_time(media_locations.to(torch.int64), 1,
                                       use_cached=use_cached_media, T_out=T)
         x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
-        q = F.linear(x_ln, self.to_q.weight)
+        q = ops.linear_acc(x_ln, self.to_q.weight)
         if use_cached_media and not torch.is_grad_enabled():
             if self._kv_cache is None or self._kv_cache.shape[0] != B:
                 self._kv_cache = self.project_media(media)
@@ -147,13 +147,13 @@ class MaskedCrossAttention(nn.Module):
             if T == 1:
                 out = ops.xattn_decode(q, kv, text_time[:, 0].contiguous(), heads=self.heads,
                                        n_latents=n, scale=self.scale)
-                return F.linear(out, self.to_out.weight)
+                return ops.linear_acc(out, self.to_out.weight)
         else:
             self._kv_cache = None
             kv = self.project_media(media)
         out = ops.masked_cross_attention(q, kv, text_time, heads=self.heads, n_latents=n,
                                          scale=self.scale)                  # K1
-        return F.linear(out, self.to_out.weight)
+        return ops.linear_acc(out, self.to_out.weight)
 
 
 class GatedCrossAttentionBlock(nn.Module):

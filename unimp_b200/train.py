@@ -43,6 +43,12 @@ def cosine_with_warmup(step: int, warmup: int, total: int) -> float:
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
 
+# parameters whose forward goes through ops.linear_acc / ops.embedding_acc (helpers.py,
+# flamingo_lm.py): their gradient is written by the backward GEMM / scatter itself
+DIRECT_GRAD_SUFFIXES = ("to_q.weight", "to_kv.weight", "to_out.weight", "ff.1.weight", "ff.3.weight",
+                        ".1.1.weight", ".1.3.weight", "embed_in.weight")
+
+
 class FlatAdamW:
     """AdamW over flat buffers: one `unimp_sumsq` + one `unimp_adamw_step` launch per group.
 
@@ -53,7 +59,8 @@ class FlatAdamW:
     (mixed precision as DeepSpeed-bf16 does: `accelerate_config_zero2.yaml:2-8,21`).
     """
 
-    def __init__(self, groups, *, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0):
+    def __init__(self, groups, *, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0,
+                 direct_grads=True):
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
         self.step_count = 0
         self.groups = []
@@ -61,6 +68,12 @@ class FlatAdamW:
             named = list(reversed(g["params"]))
             if not named:
                 continue
+            # direct-accumulation parameters first, everything else (LN affine, gates, latents)
+            # in one tail that zero_grad memsets
+            is_direct = lambda n, p: (direct_grads and p.dim() == 2 and p.is_cuda
+                                      and n.endswith(DIRECT_GRAD_SUFFIXES))
+            named = [np for np in named if is_direct(*np)] + [np for np in named if not is_direct(*np)]
+            n_direct = sum(1 for np in named if is_direct(*np))
             p0 = named[0][1]
             dev, dt = p0.device, p0.dtype
             sizes = [((p.numel() + 7) // 8) * 8 for _, p in named]  # keep 16-byte alignment
@@ -75,12 +88,19 @@ class FlatAdamW:
                 v.copy_(p.data)
                 p.data = v
                 p.grad = flat_g[off:off + p.numel()].view_as(p)
+                if len(spans) < n_direct:
+                    p._unimp_direct, p._unimp_fresh = True, True
                 spans.append((n, p, off, p.numel()))
                 off += sz
+                if len(spans) == n_direct:
+                    tail_start = off
+            if n_direct == 0:
+                tail_start = 0
             self.groups.append({
                 "weight_decay": g["weight_decay"], "flat_p": flat_p, "flat_g": flat_g,
                 "master": flat_p.float(), "m": torch.zeros(total, dtype=torch.float32, device=dev),
                 "v": torch.zeros(total, dtype=torch.float32, device=dev), "spans": spans,
+                "n_direct": n_direct, "tail": flat_g[tail_start:],
             })
         dev = self.groups[0]["flat_p"].device
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -92,8 +112,20 @@ class FlatAdamW:
             self._hyper_host = self._hyper_host.pin_memory()
 
     def zero_grad(self):
+        """Non-direct gradients are memset; direct ones are only flagged: their first backward
+        GEMM of the step overwrites (beta = 0) instead of accumulating."""
         for g in self.groups:
-            g["flat_g"].zero_()
+            if g["tail"].numel():
+                g["tail"].zero_()
+            for (_, p, _, _) in g["spans"][:g["n_direct"]]:
+                p._unimp_fresh = True
+
+    def _zero_unwritten(self):
+        # a direct parameter that received no gradient this step still holds last step's: zero it
+        for g in self.groups:
+            for (_, p, _, _) in g["spans"][:g["n_direct"]]:
+                if p._unimp_fresh:
+                    p.grad.zero_()
 
     def grad_norm(self) -> torch.Tensor:
         return self.gnorm_sq.sqrt()
@@ -109,6 +141,7 @@ class FlatAdamW:
     @torch.no_grad()
     def step_kernels(self, grad_scale: float = 1.0):
         """Device side of a step (capturable): grad-norm, clip, AdamW. No host sync."""
+        self._zero_unwritten()
         self.gnorm_sq.zero_()
         for g in self.groups:
             ops.sumsq_(g["flat_g"], self.gnorm_sq)
@@ -156,13 +189,22 @@ class BucketedAllReduce:
                 bidx = len(self.buckets)
                 cur_n += 1
                 end = off + ((numel + 7) // 8) * 8
-                self.handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bidx)))
+                hook = self._make_hook(bidx)
+                self.handles.append(p.register_post_accumulate_grad_hook(hook))
+                p._unimp_grad_ready = self._make_direct_hook(hook, p)
                 if (end - cur_start) * esz >= bucket_bytes:
                     self.buckets.append((g["flat_g"][cur_start:end], cur_n))
                     cur_start = None
             if cur_start is not None:
                 self.buckets.append((g["flat_g"][cur_start:g["flat_g"].numel()], cur_n))
         self.pending = [n for _, n in self.buckets]
+
+    def _make_direct_hook(self, hook, p):
+        # direct-accumulation parameters never run AccumulateGrad: their backward calls this
+        # after EVERY write; only the last micro-batch's write counts
+        def ready(_p):
+            hook(_p)
+        return ready
 
     def _make_hook(self, bidx):
         def hook(_p):
