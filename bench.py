@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU micro-batch (default: workload's)")
     ap.add_argument("--accum", type=int, default=2, help="gradient accumulation (reference: 2)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -194,17 +196,16 @@ def cpu_oracle_samples_per_s(cfg, wl, *, batch, steps, warmup, accum=1):
 
 
 # ---------------------------------------------------------------------------------------------
-# kernel profile (roofline): CUDA events around every launch of OUR kernels inside real steps
+# launch counting: how many of OUR kernels one step launches
 # ---------------------------------------------------------------------------------------------
 
-class KernelProfile:
-    """Wraps the C-ABI entry points with CUDA events on the launching stream (torch's current
-    stream) and accumulates algorithmic bytes / FLOPs per call from the call's own shapes
-    (DESIGN.md "roofline accounting")."""
+class LaunchCounter:
+    """Counts the kernels launched through the C ABI during one eager step (the graph replays the
+    same launches).  Kernels per C-ABI call are the launch lists of the .cu files."""
+    PER_CALL = {"unimp_focal_ce_fwd": 2, "unimp_gate_residual_ln_bwd": 2}
 
     def __init__(self):
-        self.rec = {}
-        self.launches = 0
+        self.calls = {}
 
     def install(self):
         from unimp_b200 import _lib
@@ -224,79 +225,12 @@ class KernelProfile:
 
     def _wrap(self, name, fn):
         def w(*a):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            rc = fn(*a)
-            e.record()
-            self.rec.setdefault(name, []).append((s, e, self._work(name, a)))
-            return rc
+            self.calls[name] = self.calls.get(name, 0) + 1
+            return fn(*a)
         return w
 
-    @staticmethod
-    def _work(name, a):
-        """(algorithmic bytes, algorithmic flops) of this call."""
-        es = lambda dt: 2 if dt == 1 else 4
-        if name in ("unimp_xattn_fwd", "unimp_xattn_bwd"):
-            if name == "unimp_xattn_fwd":
-                B, T, Ti, n, H, dh, dt = a[6], a[7], a[8], a[9], a[10], a[11], a[13]
-                mul_b, mul_f = 1.0, 1.0
-            else:
-                B, T, Ti, n, H, dh, dt = a[11], a[12], a[13], a[14], a[15], a[16], a[18]
-                mul_b, mul_f = 2.5, 2.5
-            inner = H * dh
-            byts = es(dt) * (2 * B * T * inner + 2 * B * Ti * n * inner) + 4 * B * T * H
-            fl = 4.0 * H * dh * n * B * T  # upper bound: every token attends one block
-            return byts * mul_b, fl * mul_f
-        if name in ("unimp_attn_fwd", "unimp_attn_bwd"):
-            if name == "unimp_attn_fwd":
-                Bt, Lq, Lk, H, dh, dt = a[5], a[6], a[7], a[8], a[9], a[11]
-                mul = 1.0
-            else:
-                Bt, Lq, Lk, H, dh, dt = a[10], a[11], a[12], a[13], a[14], a[16]
-                mul = 2.5
-            inner = H * dh
-            byts = es(dt) * (2 * Bt * Lq * inner + 2 * Bt * Lk * inner) + 4 * Bt * Lq * H
-            return byts * mul, 4.0 * Bt * H * Lq * Lk * dh * mul
-        if name == "unimp_gate_residual_ln_fwd":
-            rows, D, dt = a[9], a[10], a[12]
-            n_t = 1 + (a[0] is not None) * 2 + (a[3] is not None)
-            return es(dt) * rows * D * n_t, 0.0
-        if name == "unimp_gate_residual_ln_bwd":
-            rows, D, dt = a[14], a[15], a[16]
-            n_t = 1 + (a[0] is not None) + (a[1] is not None) * 2 + (a[2] is not None) * 2
-            return es(dt) * rows * D * n_t, 0.0
-        if name == "unimp_focal_ce_fwd":
-            B, T, V, dt = a[11], a[12], a[13], a[14]
-            return None, 0.0  # bytes depend on n_valid: filled in by the caller
-        if name == "unimp_focal_ce_bwd":
-            B, T, V, dt = a[12], a[13], a[14], a[15]
-            return es(dt) * B * T * V, 0.0  # dense d_logits write (+ n_valid rows read)
-        if name == "unimp_adamw_step":
-            n, dt = a[5], a[15]
-            return n * (es(dt) * 2 + 4 * 6), 0.0
-        if name == "unimp_sumsq":
-            return a[1] * es(a[3]), 0.0
-        return 0.0, 0.0
-
-    def summary(self, peaks, n_valid_rows=None, V=None, es=2, steps=1):
-        torch.cuda.synchronize()
-        out = {}
-        for name, calls in self.rec.items():
-            ms = sum(s.elapsed_time(e) for s, e, _ in calls)
-            byts = sum((w[0] if w[0] is not None else (n_valid_rows or 0) * (V or 0) * es)
-                       for _, _, w in calls)
-            fl = sum(w[1] for _, _, w in calls)
-            if name == "unimp_focal_ce_bwd" and n_valid_rows:
-                byts += len(calls) * n_valid_rows * V * es
-            d = {"launches_per_step": len(calls) / steps, "ms_per_step": ms / steps,
-                 "avg_us": 1e3 * ms / len(calls), "GB/s": byts / (ms * 1e-3) / 1e9 if ms else 0.0}
-            if fl:
-                d["TFLOP/s"] = fl / (ms * 1e-3) / 1e12
-                d["frac_of_bf16_peak"] = d["TFLOP/s"] / peaks["bf16_tflops_sustained"]
-            d["frac_of_hbm_peak"] = d["GB/s"] / peaks["hbm_gbs"]
-            d["alg_bytes_per_launch"] = byts / len(calls)
-            out[name] = d
-        return out
+    def kernels(self):
+        return {n: c * self.PER_CALL.get(n, 1) for n, c in self.calls.items()}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -421,7 +355,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    if args.ncu_range:
+        torch.cuda.profiler.start()
     ms = timed(step_resident, args.steps)
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         step_e2e(i)
@@ -431,33 +369,39 @@ def main():
     value = samples_per_step * args.steps / (ms * 1e-3)
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
 
-    kernels, roofline, launches = {}, None, None
+    kernels, roofline, launches, per_step = {}, None, None, None
     if not args.no_kernel_profile:
-        prof = KernelProfile()
-        prof.install()
-        ksteps = 2
-        for i in range(ksteps):  # eager on purpose: events around each of OUR launches
-            train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
-                       micro_batches=[dev[(i * args.accum + a) % n_batches] for a in range(args.accum)])
+        cnt = LaunchCounter()
+        cnt.install()
+        train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
+                   micro_batches=[dev[a % n_batches] for a in range(args.accum)])
         torch.cuda.synchronize()
-        prof.uninstall()
-        from unimp_b200 import ops
-        lab = ops.mask_labels(dev[0]["input_ids"], answer_token_id=tk.answer,
-                              endofchunk_token_id=tk.endofchunk, media_token_id=tk.media,
-                              pad_token_id=tk.pad)
-        n_valid = int((lab[:, 1:] != -100).sum())
-        kernels = prof.summary(peaks, n_valid_rows=n_valid, V=cfg.vocab, es=2, steps=ksteps)
-        launches = int(sum(k["launches_per_step"] for k in kernels.values()) * args.steps)
-        # headline kernel of the metric: the masked cross-attention core (fwd)
-        kx = kernels.get("unimp_xattn_fwd")
-        if kx:
-            bound = "hbm"
-            roofline = {"kernel": "unimp_xattn_fwd (masked media-located cross-attention core, fwd)",
-                        "bound": bound, "achieved": kx["GB/s"], "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": kx["GB/s"] / peaks["hbm_gbs"], "traffic": None,
-                        "tflops": kx.get("TFLOP/s"), "frac_of_bf16_peak": kx.get("frac_of_bf16_peak"),
-                        "avg_us": kx["avg_us"], "peak_source": peaks["source"],
-                        "alg_bytes_per_launch": kx["alg_bytes_per_launch"]}
+        cnt.uninstall()
+        per_step = cnt.kernels()
+        launches = int(sum(per_step.values()) * args.steps)
+        if rank == 0:
+            from unimp_b200 import kbench, ops
+            lab = ops.mask_labels(dev[0]["input_ids"], answer_token_id=tk.answer,
+                                  endofchunk_token_id=tk.endofchunk, media_token_id=tk.media,
+                                  pad_token_id=tk.pad)
+            n_valid = int((lab[:, 1:] != -100).sum())
+            kernels = kbench.run(cfg, wl, peaks, n_valid_rows=n_valid)
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("xattn_fwd")
+            kx = kernels["xattn_fwd"]
+            # the kernel the metric names; at this workload (2.4 MB, 100 MFLOP per launch) it is
+            # latency-bound: AI = 42 FLOP/B is left of the ridge (~210), so the bound is HBM
+            roofline = {"kernel": "attn_fwd_tc_kernel<MASKED> (unimp_xattn_fwd: masked media-located "
+                                  "cross-attention core, tcgen05+TMEM+TMA)",
+                        "bound": "hbm", "achieved": kx["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": kx["frac_of_hbm_peak"], "traffic": traffic,
+                        "alg_bytes_per_launch": kx["alg_bytes_per_launch"], "avg_us": kx["avg_us"],
+                        "tflops": kx["TFLOP/s"], "frac_of_bf16_peak": kx["frac_of_bf16_peak"],
+                        "peak_source": peaks["source"],
+                        "how": "K cold input sets (> L2) launched back to back from one CUDA graph, "
+                               "CUDA events around the replay, avg = elapsed / K"}
 
     def finish():
         # a process group cannot be torn down cleanly while a captured graph still references its
@@ -487,8 +431,8 @@ def main():
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "kernels": kernels}
+            "gpu_launches": launches, "gpu_launches_per_step": per_step, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels}
     print(json.dumps(line))
     finish()
 

@@ -1,0 +1,141 @@
+"""Isolated, cold-cache timings of the hand-written kernels at a workload's shapes.
+
+Each kernel is launched over K independent input sets whose combined footprint exceeds the
+126 MB L2 (so every launch reads cold data, no flush kernel in the timed region), the K launches
+are captured in a CUDA graph (no Python/launch latency between them) and the graph replay is
+timed with CUDA events on the launching stream: avg = elapsed / K.  Algorithmic bytes / FLOPs per
+launch are the figures of DESIGN.md §4.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+L2_BYTES = 126 << 20
+
+
+def _time_graph(fns, reps=3):
+    """fns: list of zero-arg callables (one per input set). Returns average microseconds per call."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for f in fns:
+            f()
+    g.replay()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e3 / len(fns)
+        best = t if best is None else min(best, t)
+    del g
+    return best
+
+
+def _k(bytes_per_set, cap=48):
+    return max(2, min(cap, (int(1.3 * L2_BYTES) + bytes_per_set - 1) // bytes_per_set))
+
+
+def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
+    """Returns {kernel: {avg_us, alg_bytes, flops, GB/s, TFLOP/s, frac_hbm, frac_tensor, sets}}."""
+    dev = "cuda"
+    es = 2 if dtype == torch.bfloat16 else 4
+    B, T, Ti, n, H, dh, D, V = wl.B, wl.T, wl.Ti, cfg.n_latents, cfg.xattn_heads, cfg.xattn_dim_head, cfg.lm_hidden, cfg.vocab
+    inner = H * dh
+    out = {}
+
+    def rec(name, us, byts, fl, sets):
+        d = {"avg_us": us, "alg_bytes_per_launch": byts, "flops_per_launch": fl, "sets": sets,
+             "GB/s": byts / us / 1e3, "frac_of_hbm_peak": byts / us / 1e3 / peaks["hbm_gbs"]}
+        if fl:
+            d["TFLOP/s"] = fl / us / 1e6
+            d["frac_of_bf16_peak"] = d["TFLOP/s"] / peaks["bf16_tflops"]
+        out[name] = d
+
+    torch.manual_seed(0)
+    # ---- K1 masked x-attn ------------------------------------------------------------------
+    xb = es * (2 * B * T * inner + 2 * B * Ti * n * inner) + 4 * B * T * H
+    xf = 4.0 * H * dh * n * B * T
+    K = _k(xb)
+    loc = torch.zeros(B, T, dtype=torch.bool)
+    for b in range(B):
+        for j in range(Ti):
+            loc[b, 1 + j * (T // Ti)] = True
+    tt = loc.cumsum(-1).to(torch.int32).to(dev)
+    qs = [torch.randn(B, T, inner, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    kvs = [torch.randn(B, Ti * n, 2 * inner, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    gos = [torch.randn(B, T, inner, device=dev, dtype=dtype) for _ in range(K)]
+    fwd = [lambda q=q, kv=kv: ops.masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=dh ** -0.5)
+           for q, kv in zip(qs, kvs)]
+    rec("xattn_fwd", _time_graph(fwd), xb, xf, K)
+    os_ = [f() for f in fwd]
+    bwd = [lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
+           for o, q, kv, g in zip(os_, qs, kvs, gos)]
+    rec("xattn_bwd", _time_graph(bwd), 2.5 * xb, 2.5 * xf, K)
+    del qs, kvs, gos, os_, fwd, bwd
+    # ---- K3 ViT self-attention ----------------------------------------------------------------
+    N, L, Hv = B * Ti, cfg.n_patches + 1, cfg.vis_heads
+    vb = es * 4 * N * L * Hv * 64 + 4 * N * L * Hv
+    vf = 4.0 * N * Hv * L * L * 64
+    K = _k(vb)
+    qkvs = [torch.randn(N, L, 3 * Hv * 64, device=dev, dtype=dtype) for _ in range(K)]
+    rec("vit_attn_fwd", _time_graph([lambda x=x: ops.attention(x[..., :Hv * 64], x[..., Hv * 64:], heads=Hv, scale=0.125)
+                                     for x in qkvs]), vb, vf, K)
+    del qkvs
+    # ---- K2 perceiver attention -----------------------------------------------------------------
+    Lk = cfg.n_patches + n
+    pb = es * (2 * N * n * inner + 2 * N * Lk * inner) + 4 * N * n * H
+    pf = 4.0 * N * H * n * Lk * dh
+    K = _k(pb)
+    pqs = [torch.randn(N, n, inner, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    pkvs = [torch.randn(N, Lk, 2 * inner, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    pfw = [lambda q=q, kv=kv: ops.attention(q, kv, heads=H, scale=dh ** -0.5) for q, kv in zip(pqs, pkvs)]
+    rec("perceiver_attn_fwd", _time_graph(pfw), pb, pf, K)
+    pos = [f() for f in pfw]
+    pgs = [torch.randn_like(o) for o in pos]
+    rec("perceiver_attn_bwd", _time_graph([lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
+                                            for o, q, kv, g in zip(pos, pqs, pkvs, pgs)]), 2.5 * pb, 2.5 * pf, K)
+    del pqs, pkvs, pos, pgs, pfw
+    # ---- K5 gate + residual + LN ------------------------------------------------------------------
+    rows = B * T
+    gb = 4 * rows * D * es
+    K = _k(gb, cap=16)
+    xs = [torch.randn(rows, D, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    brs = [torch.randn(rows, D, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    gate = torch.full((1,), 0.5, device=dev, dtype=dtype, requires_grad=True)
+    gam = torch.ones(D, device=dev, dtype=dtype, requires_grad=True)
+    bet = torch.zeros(D, device=dev, dtype=dtype, requires_grad=True)
+    gfw = [lambda x=x, b=b: ops.gate_residual_ln(b, x, gate, gam, bet) for x, b in zip(xs, brs)]
+    rec("gate_residual_ln_fwd", _time_graph(gfw), gb, 0.0, K)
+    outs = [f() for f in gfw]
+    g1s = [torch.randn(rows, D, device=dev, dtype=dtype) for _ in range(K)]
+    rec("gate_residual_ln_bwd", _time_graph([lambda o=o, x=x, b=b, g=g: torch.autograd.grad(
+        o, (b, x, gate, gam, bet), (g, g), retain_graph=True) for o, x, b, g in zip(outs, xs, brs, g1s)]),
+        6 * rows * D * es, 0.0, K)
+    del xs, brs, outs, g1s, gfw
+    # ---- K6 focal CE -----------------------------------------------------------------------------
+    nv = n_valid_rows if n_valid_rows else max(1, B * (Ti + 2))
+    z = [torch.randn(B, T, V, device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]
+    y = torch.full((B * T,), -100, device=dev, dtype=torch.int64)
+    idx = torch.randperm(B * T - B, device=dev)[:nv] + 1
+    y[idx] = torch.randint(0, V, (nv,), device=dev)
+    y = y.view(B, T)
+    y[:, 0] = -100
+    nv_eff = int((y[:, 1:] != -100).sum())
+    w = torch.ones(B, device=dev)
+    ffw = [lambda zz=zz: ops.focal_ce(zz, y, w) for zz in z]
+    rec("focal_ce_fwd", _time_graph(ffw), nv_eff * V * es, 0.0, 2)
+    ls = [f() for f in ffw]
+    rec("focal_ce_bwd", _time_graph([lambda l=l, zz=zz: torch.autograd.grad(l, zz, retain_graph=True)
+                                     for l, zz in zip(ls, z)]), nv_eff * V * es + B * T * V * es, 0.0, 2)
+    out["focal_ce_fwd"]["n_valid_rows"] = nv_eff
+    del z, ls, ffw
+    torch.cuda.empty_cache()
+    return out
