@@ -190,8 +190,14 @@ class BucketedAllReduce:
                 cur_n += 1
                 end = off + ((numel + 7) // 8) * 8
                 hook = self._make_hook(bidx)
-                self.handles.append(p.register_post_accumulate_grad_hook(hook))
-                p._unimp_grad_ready = self._make_direct_hook(hook, p)
+                if getattr(p, "_unimp_direct", False):
+                    # direct-accumulation parameters report from their own backward
+                    # (ops._grad_ready).  They must NOT also carry an autograd hook: the engine
+                    # still runs AccumulateGrad (and its post hooks) for an undefined gradient,
+                    # which would count the parameter twice and fire the bucket early.
+                    p._unimp_grad_ready = hook
+                else:
+                    self.handles.append(p.register_post_accumulate_grad_hook(hook))
                 if (end - cur_start) * esz >= bucket_bytes:
                     self.buckets.append((g["flat_g"][cur_start:end], cur_n))
                     cur_start = None
@@ -199,18 +205,12 @@ class BucketedAllReduce:
                 self.buckets.append((g["flat_g"][cur_start:g["flat_g"].numel()], cur_n))
         self.pending = [n for _, n in self.buckets]
 
-    def _make_direct_hook(self, hook, p):
-        # direct-accumulation parameters never run AccumulateGrad: their backward calls this
-        # after EVERY write; only the last micro-batch's write counts
-        def ready(_p):
-            hook(_p)
-        return ready
-
     def _make_hook(self, bidx):
         def hook(_p):
             if not self.armed:
                 return
             self.pending[bidx] -= 1
+            assert self.pending[bidx] >= 0, "a parameter reported its gradient twice in one step"
             if self.pending[bidx] == 0:
                 self.works.append(dist.all_reduce(self.buckets[bidx][0], op=dist.ReduceOp.SUM,
                                                   group=self.group, async_op=True))
