@@ -330,3 +330,56 @@ def test_fused_neox_layer_matches_hf_layer(dtype, tol, parallel):
     yb.backward(g)
     assert rel_err(yb, ya) < tol
     assert rel_err(xb.grad, xa.grad) < tol
+
+
+# ------------------------------------------------------------------ full-size property checks
+
+def test_xattn_full_size_tc_equals_simt_and_blocks_are_independent():
+    """BASELINE configs[2] shape (B=3, T=1024, Ti=8): the tcgen05 path equals the fp32-exact CUDA-core
+    path, and (size-independent property) changing image j's keys only changes rows that reference j."""
+    B, T, Ti, H, dh, n = 3, 1024, 8, 8, 64, 64
+    torch.manual_seed(0)
+    q = torch.randn(B, T, H * dh, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    kv = torch.randn(B, Ti * n, 2 * H * dh, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    tt = _mk_tt(B, T, Ti, seed=3).to(DEV)
+    go = torch.randn(B, T, H * dh, device=DEV, dtype=torch.bfloat16)
+    a = ops().masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=0.125)
+    ga = torch.autograd.grad(a, (q, kv), go)
+    b = ops().masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=0.125, force_simt=True)
+    gb = torch.autograd.grad(b, (q, kv), go)
+    assert rel_err(a, b) < 1e-2 and rel_err(ga[0], gb[0]) < 2e-2 and rel_err(ga[1], gb[1]) < 2e-2
+    kv2 = kv.detach().clone()
+    kv2[:, 3 * n:4 * n] += 1.0  # perturb image 3 only
+    c = ops().masked_cross_attention(q.detach(), kv2, tt, heads=H, n_latents=n, scale=0.125)
+    changed = (c != a.detach()).any(-1)
+    assert torch.equal(changed & (tt != 4), torch.zeros_like(changed))  # only rows with text_time == 4 moved
+    assert changed[tt == 4].all()
+    # rows before the first <image> are exactly zero and carry no query gradient
+    assert a.detach()[tt == 0].abs().max() == 0 and ga[0][tt == 0].abs().max() == 0
+
+
+def test_focal_ce_full_size_equals_oracle_on_the_valid_rows():
+    """BASELINE configs[4] shape (B=3, T=1024, V=74053, ~257 valid labels/sample): the loss only
+    depends on the valid rows, so the oracle is evaluated on those rows alone (a (771, V) problem)."""
+    B, T, V = 3, 1024, 74053
+    torch.manual_seed(1)
+    z = (2 * torch.randn(B, T, V, device=DEV)).to(torch.bfloat16).requires_grad_(True)
+    y = torch.full((B, T), -100, device=DEV, dtype=torch.int64)
+    y[:, T - 258:T - 1] = torch.randint(73029, 74053, (B, 257), device=DEV)  # img_* ids
+    w = torch.tensor([1.0, 2.0, 1.0], device=DEV)
+    loss = ops().focal_ce(z, y, w, gamma=2.0)
+    loss.backward()
+    rows_b, rows_t = torch.nonzero(y[:, 1:] != -100, as_tuple=True)
+    zv = z.detach()[rows_b, rows_t].double().cpu()           # logits at t score labels at t+1
+    yv = y[rows_b, rows_t + 1].cpu()
+    wv = w[rows_b].double().cpu()
+    lp = torch.log_softmax(zv, -1)
+    ce = -lp[torch.arange(len(yv)), yv]
+    pt = torch.exp(-ce)
+    want = (wv * ce * (1 - pt) ** 2).sum() / len(yv)
+    assert abs(float(loss) - float(want)) / float(want) < 1e-3
+    g = z.grad
+    assert g[:, -1].abs().max() == 0 and g[:, : T - 259].abs().max() == 0   # untouched rows: exact zeros
+    assert abs(float(g.float().sum())) < 1e-2                                  # each row of (p - y) sums to 0
+    # determinism: the same bits again
+    assert torch.equal(loss.detach(), ops().focal_ce(z.detach(), y, w, gamma=2.0))

@@ -202,3 +202,21 @@ def test_direct_grad_accumulation_equals_autograd_accumulation(dtype):
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     for n in flats[0]:
         assert rel_err(flats[0][n], flats[1][n]) < tol, n
+
+
+def test_beam_search_generate_runs_and_matches_greedy_prefix_semantics():
+    """eval_rec.py-style call (num_beams > 1): vision_x is repeat_interleaved, cached media /
+    cached x-attn K/V serve B*beams rows; beams=1 result is among the beams' hypotheses space
+    (sanity: shapes, prompt preserved, deterministic)."""
+    cfg, oracle, model, batch = _setup(torch.float32, ragged=False, seed=5)
+    ids = batch["input_ids"][:2]
+    L = int(batch["attention_masks"][:2].sum(1).min()) - 2
+    ids = ids[:, :L].cuda()
+    vis = batch["patch_images"][:2].unsqueeze(2).cuda()
+    model.eval()
+    kw = dict(attention_mask=torch.ones_like(ids), max_new_tokens=5, eos_token_id=-1,
+              pad_token_id=cfg.tokens.pad, do_sample=False, early_stopping=True)
+    a = model.generate(vision_x=vis, lang_x=ids, num_beams=3, num_return_sequences=1, **kw)
+    b = model.generate(vision_x=vis, lang_x=ids, num_beams=3, num_return_sequences=1, **kw)
+    assert a.shape == (2, L + 5) and torch.equal(a[:, :L], ids) and torch.equal(a, b)
+    assert not model.lang_encoder.is_conditioned() and not model.lang_encoder._use_cached_vision_x
