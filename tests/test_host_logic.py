@@ -126,3 +126,29 @@ def test_bucketed_allreduce_world2_equals_single_process_mean(accum):
             (net(x).pow(2).mean() / accum / world).backward()
     want = torch.cat([grp["flat_g"] for grp in opt.groups])
     assert torch.allclose(res[0][1], want, atol=1e-7, rtol=1e-5)
+
+
+def test_get_checkpoint_keeps_trainables_with_upstream_key_names_and_reloads():
+    """reference train_utils.py:258-265 + mmrec.py:513-514 (`load_state_dict(..., strict=False)`)."""
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import get_checkpoint
+
+    cfg = tiny_config()
+    m = build_flamingo(cfg, dtype=torch.float32, device="cpu", gate=0.3, seed=1)
+    sd = get_checkpoint(m, drop_frozen_aliases=True)
+    keys = set(sd)
+    assert "perceiver.latents" in keys and "perceiver.layers.0.0.to_kv.weight" in keys
+    assert "lang_encoder.gated_cross_attn_layers.0.attn.to_q.weight" in keys
+    assert "lang_encoder.gated_cross_attn_layers.1.ff_gate" in keys
+    assert "lang_encoder.gpt_neox.embed_in.weight" in keys                   # trainable input embeddings
+    assert not any(k.startswith("vision_encoder.") for k in keys)             # frozen tower dropped
+    assert "lang_encoder.embed_out.weight" not in keys                        # frozen output head dropped
+    assert not any("decoder_layer.attention" in k or k.startswith("lang_encoder.old_decoder_blocks") for k in keys)
+    # the reference's own behaviour keeps the aliased frozen LM blocks
+    assert any(k.startswith("lang_encoder.old_decoder_blocks") for k in get_checkpoint(m))
+    m2 = build_flamingo(cfg, dtype=torch.float32, device="cpu", gate=None, seed=2)
+    missing, unexpected = m2.load_state_dict(sd, strict=False)
+    assert not unexpected
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), m2.named_parameters()):
+        if p1.requires_grad:
+            assert torch.equal(p1, p2), n1

@@ -86,7 +86,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     mbar_init(&bar_q, 1); mbar_init(&bar_k, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1);
     mbar_init(&bar_p[0], 1); mbar_init(&bar_p[1], 1); mbar_init(&bar_o, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+    // the Q tile does not need TMEM: start its load before the allocation / first barrier
+    mbar_arrive_expect_tx(&bar_q, Q_BYTES);
+    tma_load_4d(sQ, &tq, &bar_q, 0, h, row0, b);
+    tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
     s_jlo = 1 << 30; s_jhi = -1;
   }
   if (warp == 4) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -95,11 +98,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-
-  if (issuer) {
-    mbar_arrive_expect_tx(&bar_q, Q_BYTES);
-    tma_load_4d(sQ, &tq, &bar_q, 0, h, row0, b);
-  }
 
   const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);   // S = Q K^T : A, B K-major
   const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);   // O = P V   : A K-major, B (V) MN-major
@@ -416,11 +414,15 @@ __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, MASKED ? 2 : 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                    const BwdArgs a) {
-  constexpr uint32_t S_COL = 0, DP_COL = 64, DQ_COL = 128, DKV_COL = 192, TMEM_COLS = 512;
+  // MASKED: dQ is written fresh per pair, after S has been consumed into registers, so it reuses
+  // S's columns: 256 TMEM columns per CTA => two CTAs per SM.  UNMASKED: dQ accumulates across key
+  // blocks and needs its own columns (320 -> 512).
+  constexpr uint32_t S_COL = 0, DP_COL = 64, DQ_COL = MASKED ? 0 : 128, DKV_COL = MASKED ? 128 : 192,
+                     TMEM_COLS = MASKED ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sdO = smem;                 // [128 q][64]   \  contiguous: B operand [dO | Q], N = 128
@@ -453,14 +455,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const uint32_t idesc_dkv = make_idesc(128, 128, 1, 1);  // [P|dS]^T [dO|Q] (both MN-major)
   const float l2e = 1.4426950408889634f;
 
-  const int n_qt = (a.Lq + TQ - 1) / TQ;
   const int n_kb = (a.Lk + KB - 1) / KB;
-  const int n_pairs = MASKED ? n_qt : n_kb;
   uint32_t ph_qdo = 0, ph_kv = 0, ph_s = 0, ph_g = 0;
   bool kv_loaded = false, qdo_loaded = false, acc_started = false;
   uint32_t r[32];
+  int p_lo = 0, p_hi = MASKED ? -1 : n_kb - 1;
+  if (MASKED) {
+    // One pass over this sample's text_time: which query rows reference image block blockIdx.x?
+    // (rows that reference nothing get dq = 0 here, from the block-0 CTAs)
+    __shared__ int s_lo, s_hi;
+    if (tid == 0) { s_lo = 1 << 30; s_hi = -1; }
+    __syncthreads();
+    const int kb0 = (int)blockIdx.x;
+    int lo = 1 << 30, hi = -1;
+    for (int row = tid; row < a.Lq; row += FWD_THREADS) {
+      const int t = a.tt[(int64_t)b * a.Lq + row];
+      if (t > a.Ti || t == kb0 + 1) { lo = min(lo, row); hi = max(hi, row); }
+      if (t <= 0 && kb0 == 0) {
+        __nv_bfloat16* dst = a.dq + (int64_t)b * a.dq_bs + (int64_t)row * a.dq_rs + h * DH;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (hi >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    p_lo = s_lo / TQ;
+    p_hi = s_hi >= 0 ? s_hi / TQ : -1;
+  }
 
-  for (int pidx = 0; pidx < n_pairs; ++pidx) {
+  for (int pidx = p_lo; pidx <= p_hi; ++pidx) {
     const int qt = MASKED ? pidx : 0;
     const int kb = MASKED ? (int)blockIdx.x : pidx;
     const int row = qt * TQ + tid;
@@ -471,14 +494,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       if (valid) ttr = a.tt[(int64_t)b * a.Lq + row];
       uniform = ttr > a.Ti;
       mine = valid && (uniform || ttr == kb + 1);
-      const bool zero_row = valid && ttr <= 0 && kb == 0;  // rows nobody attends: dq = 0, by block 0
-      const int any_mine = __syncthreads_or(mine ? 1 : 0);
-      if (zero_row) {
-        __nv_bfloat16* dst = a.dq + (int64_t)b * a.dq_bs + (int64_t)row * a.dq_rs + h * DH;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0, 0, 0, 0);
-      }
-      if (!any_mine) continue;  // CTA-uniform
+      if (!__syncthreads_or(mine ? 1 : 0)) continue;  // CTA-uniform (non-monotonic text_time only)
     }
     // ---- loads + S / dP ---------------------------------------------------------------
     if (issuer) {
