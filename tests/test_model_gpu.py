@@ -16,7 +16,7 @@ from unimp_b200.synth import make_batch
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: dict(logits=1e-4, loss=1e-4, grad=2e-3),
-       torch.bfloat16: dict(logits=2e-2, loss=1e-2, grad=8e-2)}
+       torch.bfloat16: dict(logits=2e-2, loss=1e-3, grad=8e-2)}  # BASELINE.json north_star tolerances
 
 
 def _setup(dtype, ragged=True, seed=1234):

@@ -124,13 +124,15 @@ def _neox_fusable(layer, x, kw) -> bool:
     return att.rotary_ndims % 2 == 0 and (att.rotary_ndims // 2) % npv == 0 and att.head_size % npv == 0
 
 
-def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None):
+def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None):
     """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
     our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
     qkv projection (`unimp_rotary_qkv_*`), q/k/v reach SDPA as strided views.  GEMMs stay on
     cuBLAS and the causal attention core on cuDNN SDPA (K4: not in the north star).  Same
     parameters, same arithmetic; ~11 launches instead of ~30 per layer.
-    `h1`: input_layernorm(x) if the caller already produced it in a fused epilogue."""
+    `h1`: input_layernorm(x) if the caller already produced it in a fused epilogue.
+    `next_ln`: the LayerNorm that reads this layer's output first (next layer's x-attn norm or
+    input_layernorm); if given, returns (y, next_ln(y)) from the same launch as the last residual."""
     F = torch.nn.functional
     att = layer.attention
     B, T, D = x.shape
@@ -151,10 +153,13 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None):
         h2 = ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps)
         m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
                      mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
-        return ops.gate_residual(m, ops.gate_residual(o, x, None), None)
-    x1, h2 = ops.gate_residual_ln(o, x, None, ln2.weight, ln2.bias, ln2.eps)
-    m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
-                 mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+        x1 = ops.gate_residual(o, x, None)
+    else:
+        x1, h2 = ops.gate_residual_ln(o, x, None, ln2.weight, ln2.bias, ln2.eps)
+        m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+                     mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+    if next_ln is not None:
+        return ops.gate_residual_ln(m, x1, None, next_ln.weight, next_ln.bias, next_ln.eps)
     return ops.gate_residual(m, x1, None)
 
 
@@ -167,6 +172,14 @@ class FlamingoLayer(nn.Module):
         self.media_locations = None
         self.text_time = None
         self.use_cached_media = False
+        self._next_holder = [None]   # next FlamingoLayer (a list: not a registered submodule)
+        self._pre = None             # (x, first_ln(x)) handed over by the previous layer
+
+    def first_ln(self):
+        """The LayerNorm that reads this layer's input first."""
+        if self.gated_cross_attn_layer is not None:
+            return self.gated_cross_attn_layer.attn.norm
+        return getattr(self.decoder_layer, "input_layernorm", None)
 
     def is_conditioned(self) -> bool:
         return self.vis_x is not None and self.media_locations is not None
@@ -185,7 +198,11 @@ class FlamingoLayer(nn.Module):
 
     def forward(self, lang_x, attention_mask=None, **decoder_layer_kwargs):
         fuse = _neox_fusable(self.decoder_layer, lang_x, decoder_layer_kwargs)
-        h1 = None
+        pre, self._pre = self._pre, None
+        x_ln = pre[1] if (pre is not None and pre[0] is lang_x) else None  # first_ln(lang_x), fused upstream
+        h1 = None if self.gated_cross_attn_layer is not None else x_ln
+        nxt = self._next_holder[0]
+        next_ln = nxt.first_ln() if (fuse and nxt is not None) else None
         if self.gated_cross_attn_layer is not None:
             if self.vis_x is None:
                 raise ValueError("vis_x must be conditioned before forward pass")
@@ -197,11 +214,16 @@ class FlamingoLayer(nn.Module):
             out = self.gated_cross_attn_layer(
                 lang_x, self.vis_x, media_locations=self.media_locations,
                 use_cached_media=self.use_cached_media, text_time=tt,
-                next_ln=self.decoder_layer.input_layernorm if fuse else None)
+                next_ln=self.decoder_layer.input_layernorm if fuse else None, x_ln=x_ln)
             lang_x, h1 = out if fuse else (out, None)
         if fuse:
-            return fused_neox_layer(self.decoder_layer, lang_x, attention_mask,
-                                    decoder_layer_kwargs["position_embeddings"], h1)
+            out = fused_neox_layer(self.decoder_layer, lang_x, attention_mask,
+                                   decoder_layer_kwargs["position_embeddings"], h1, next_ln)
+            if next_ln is not None:
+                y, y_ln = out
+                nxt._pre = (y, y_ln)   # consumed (and cleared) by the next layer's forward
+                return y
+            return out
         return self.decoder_layer(lang_x, attention_mask=attention_mask, **decoder_layer_kwargs)
 
 
@@ -231,10 +253,11 @@ class FlamingoLMMixin(nn.Module):
         self._use_cached_vision_x = False
 
     def init_flamingo_layers(self, gradient_checkpointing=False):
-        self._set_decoder_layers(nn.ModuleList([
-            FlamingoLayer(g, d, gradient_checkpointing)
-            for g, d in zip(self.gated_cross_attn_layers, self.old_decoder_blocks)
-        ]))
+        layers = [FlamingoLayer(g, d, gradient_checkpointing)
+                  for g, d in zip(self.gated_cross_attn_layers, self.old_decoder_blocks)]
+        for a, b in zip(layers[:-1], layers[1:]):
+            a._next_holder[0] = b
+        self._set_decoder_layers(nn.ModuleList(layers))
 
     def forward(self, input_ids=None, attention_mask=None, labels=None, **kwargs):
         if not self.initialized_flamingo:

@@ -124,9 +124,11 @@ class MaskedCrossAttention(nn.Module):
         B, Ti, n, Dv = media.shape
         return ops.linear_acc(media.reshape(B, Ti * n, Dv), self.to_kv.weight)
 
-    def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None):
+    def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None,
+                x_ln=None):
         """x (B,T,D); media (B,Ti,n,Dv); `text_time` int32 (B,T) may be passed precomputed
-        (FlamingoLMMixin does, once per forward); otherwise derived from media_locations."""
+        (FlamingoLMMixin does, once per forward); otherwise derived from media_locations.
+        `x_ln`: self.norm(x) if the producer of x already emitted it from a fused epilogue."""
         B, T, D = x.shape
         _, Ti, n = media.shape[:3]
         if text_time is None:
@@ -138,7 +140,8 @@ class MaskedCrossAttention(nn.Module):
                     f"media_location.shape is {media_locations.shape} but x.shape is {x.shape}")
             text_time = ops.text_time(media_locations.to(torch.int64), 1,
                                       use_cached=use_cached_media, T_out=T)
-        x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        if x_ln is None:
+            x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         q = ops.linear_acc(x_ln, self.to_q.weight)
         if use_cached_media and not torch.is_grad_enabled():
             if self._kv_cache is None or self._kv_cache.shape[0] != B:
@@ -168,12 +171,12 @@ class GatedCrossAttentionBlock(nn.Module):
         self.ff_gate = nn.Parameter(torch.tensor([0.0]))
 
     def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None,
-                next_ln=None):
+                next_ln=None, x_ln=None):
         """`next_ln`: the LayerNorm module that consumes the block's output next (the decoder
         layer's input_layernorm); if given, its output is produced by the same K5 launch as the
         last gated residual and the call returns (x, next_ln(x))."""
         a = self.attn(x, media, media_locations=media_locations,
-                      use_cached_media=use_cached_media, text_time=text_time)
+                      use_cached_media=use_cached_media, text_time=text_time, x_ln=x_ln)
         # x = a*tanh(attn_gate) + x, fused with ff's LayerNorm                     (K5)
         x, h = ops.gate_residual_ln(a, x, self.attn_gate, self.ff[0].weight, self.ff[0].bias,
                                     self.ff[0].eps)
