@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU micro-batch (default: workload's)")
     ap.add_argument("--accum", type=int, default=2, help="gradient accumulation (reference: 2)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--no-fuse-accum", action="store_true",
+                    help="run the accumulation window as sequential micro-batches (reference style)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -273,6 +275,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    import copy
     import torch.distributed as dist
     from unimp_b200 import _lib
     from unimp_b200.factory import build_flamingo
@@ -310,14 +313,22 @@ def main():
     if use_graph:
         # whole optimizer step captured once (DESIGN.md "launch overhead"); replays read the
         # step's inputs from static device buffers that are refilled before every replay
-        graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma)
+        graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma,
+                                   fuse_accum=not args.no_fuse_accum)
     config["launch"] = "cuda-graph replay of the whole step" if use_graph else "eager"
+    config["accum_window"] = (
+        f"{args.accum} micro-batches of {wl.B} run as ONE forward/backward over {args.accum * wl.B} samples "
+        "(identical arithmetic: per-sample ops, per-micro-batch loss normalisation kept; "
+        "tests/test_model_gpu.py::test_fused_accumulation_window_equals_sequential_micro_batches)"
+        if (not args.no_fuse_accum and args.accum > 1) else "sequential micro-batches")
+
+    fuse = not args.no_fuse_accum and args.accum > 1
 
     def run_step(mbs):
         if graphed is not None:
             return graphed(mbs)
         return train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
-                          micro_batches=mbs)
+                          micro_batches=mbs, fuse_accum=fuse)
 
     def step_resident(i):
         # inputs already resident in HBM (the graphed path copies them device->device into its
@@ -374,7 +385,7 @@ def main():
         cnt = LaunchCounter()
         cnt.install()
         train_step(model, None, tk, opt, reducer, gamma=wl.gamma, accum_steps=args.accum,
-                   micro_batches=[dev[a % n_batches] for a in range(args.accum)])
+                   micro_batches=[dev[a % n_batches] for a in range(args.accum)], fuse_accum=fuse)
         torch.cuda.synchronize()
         cnt.uninstall()
         per_step = cnt.kernels()
@@ -385,7 +396,10 @@ def main():
                                   endofchunk_token_id=tk.endofchunk, media_token_id=tk.media,
                                   pad_token_id=tk.pad)
             n_valid = int((lab[:, 1:] != -100).sum())
-            kernels = kbench.run(cfg, wl, peaks, n_valid_rows=n_valid)
+            wl_k = copy.copy(wl)   # the shapes the timed region actually launches
+            if fuse:
+                wl_k.B, n_valid = wl.B * args.accum, n_valid * args.accum
+            kernels = kbench.run(cfg, wl_k, peaks, n_valid_rows=n_valid)
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):

@@ -220,3 +220,34 @@ def test_beam_search_generate_runs_and_matches_greedy_prefix_semantics():
     b = model.generate(vision_x=vis, lang_x=ids, num_beams=3, num_return_sequences=1, **kw)
     assert a.shape == (2, L + 5) and torch.equal(a[:, :L], ids) and torch.equal(a, b)
     assert not model.lang_encoder.is_conditioned() and not model.lang_encoder._use_cached_vision_x
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_accumulation_window_equals_sequential_micro_batches(dtype):
+    """One forward/backward over the concatenated accumulation window == the reference's sequential
+    micro-batches (per-micro-batch loss normalisation kept): same loss, same accumulated gradients."""
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import FlatAdamW, get_grouped_params, unimp_loss, unimp_loss_fused
+
+    cfg = tiny_config()
+    mbs = [{k: v.cuda() for k, v in make_batch(cfg, WORKLOADS["C1-tiny"], seed=i, ragged=(i == 0)).items()}
+           for i in range(2)]
+    res = []
+    for fused in (False, True):
+        model = build_flamingo(cfg, dtype=dtype, device="cuda", gate=0.5, seed=0)
+        opt = FlatAdamW(get_grouped_params(model, 0.1), lr=1e-3)
+        opt.zero_grad()
+        if fused:
+            loss, _ = unimp_loss_fused(model, mbs, cfg.tokens)
+            loss.backward()
+        else:
+            loss = 0.0
+            for mb in mbs:
+                l, _, _ = unimp_loss(model, mb, cfg.tokens)
+                (l / 2).backward()
+                loss = loss + l.detach() / 2
+        res.append((float(loss), {n: p.grad.detach().float().clone() for g in opt.groups for (n, p, _, _) in g["spans"]}))
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert abs(res[0][0] - res[1][0]) < tol * abs(res[0][0])
+    for n in res[0][1]:
+        assert rel_err(res[1][1][n], res[0][1][n]) < tol, n

@@ -269,14 +269,53 @@ def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True):
     return loss, out[0], out["logits"]
 
 
+def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True):
+    """An accumulation window of `len(mbs)` micro-batches in ONE forward/backward.
+
+    The reference accumulates gradients over `gradient_accumulation_steps` micro-batches
+    (`accelerator.accumulate`, UniMP/mmrec.py:175) because a 4B model with ZeRO-2 state does not
+    leave room for more on its GPUs; on 180 GB there is room, and the arithmetic is the same:
+    every op on the path is independent per sample (attention, LayerNorm, GEMM rows), and the
+    loss keeps the reference's PER-MICRO-BATCH normalisation — sum_k L_k / accum with
+    L_k = sum(w * CE * focal) / n_valid_k over micro-batch k's own rows — so the accumulated
+    gradient is identical; only the launches are shared (2x the rows per GEMM / kernel).
+    Requires equal T across the window (a real loader pads to the window max)."""
+    accum = len(mbs)
+    cat = {k: torch.cat([mb[k] for mb in mbs], 0) for k in mbs[0]}
+    images = cat["patch_images"].unsqueeze(2)
+    input_ids, attention_mask, weights = cat["input_ids"], cat["attention_masks"], cat["weights"]
+    labels = ops.mask_labels(input_ids, answer_token_id=tokens.answer,
+                             endofchunk_token_id=tokens.endofchunk, media_token_id=tokens.media,
+                             pad_token_id=tokens.pad)
+    out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=None)
+    logits = out["logits"]
+    B = mbs[0]["input_ids"].shape[0]
+    loss = None
+    for k in range(accum):
+        sl = slice(k * B, (k + 1) * B)
+        lk = ops.focal_ce(logits[sl], labels[sl], weights[sl], gamma=gamma, use_focal=use_reweight)
+        loss = lk if loss is None else loss + lk
+    return loss / accum, logits
+
+
 def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce | None = None, *,
-               gamma=2.0, use_reweight=True, lr_scale=1.0, accum_steps=1, micro_batches=None):
+               gamma=2.0, use_reweight=True, lr_scale=1.0, accum_steps=1, micro_batches=None,
+               fuse_accum=False):
     """fwd + focal loss + bwd + (overlapped) all-reduce + clip + AdamW. Returns the loss
     tensor of the last micro-batch (device scalar; caller decides when to read it)."""
     mbs = micro_batches if micro_batches is not None else [batch]
     assert len(mbs) == accum_steps
     opt.zero_grad()
     loss = None
+    if fuse_accum and len(mbs) > 1:
+        if reducer is not None:
+            reducer.armed = True
+        loss, _ = unimp_loss_fused(model, mbs, tokens, gamma=gamma, use_reweight=use_reweight)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step(lr_scale=lr_scale, grad_scale=reducer.grad_scale if reducer is not None else 1.0)
+        return loss
     for i, mb in enumerate(mbs):
         if reducer is not None:
             reducer.armed = i == len(mbs) - 1
@@ -298,7 +337,8 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, tokens, opt: FlatAdamW, reducer, example_mbs, *, gamma=2.0,
-                 use_reweight=True, warmup_iters=3, capture_error_mode=None):
+                 use_reweight=True, warmup_iters=3, capture_error_mode=None, fuse_accum=False):
+        self.fuse_accum = fuse_accum and len(example_mbs) > 1
         # NOTE: with NCCL in the graph, run the whole process on a NON-default stream
         # (`torch.cuda.set_stream(torch.cuda.Stream())` before building the model): gradient
         # accumulators remember the stream they were created on, and the legacy default stream
@@ -326,6 +366,16 @@ class GraphedTrainStep:
     def _body(self):
         self.opt.zero_grad()
         loss = None
+        if self.fuse_accum:
+            if self.reducer is not None:
+                self.reducer.armed = True
+            loss, _ = unimp_loss_fused(self.model, self.static, self.tokens, gamma=self.gamma,
+                                       use_reweight=self.use_reweight)
+            loss.backward()
+            if self.reducer is not None:
+                self.reducer.finish()
+            self.opt.step_kernels(self.grad_scale)
+            return loss.detach()
         for i, mb in enumerate(self.static):
             if self.reducer is not None:
                 self.reducer.armed = i == self.accum - 1
