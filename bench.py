@@ -400,10 +400,14 @@ def main():
             if fuse:
                 wl_k.B, n_valid = wl.B * args.accum, n_valid * args.accum
             kernels = kbench.run(cfg, wl_k, peaks, n_valid_rows=n_valid)
+            # DRAM traffic per launch of the same kernel at the same shape, from the committed
+            # ncu --set full capture (profiles/r1_ncu_full_kernels.csv); null if the shape differs
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("xattn_fwd")
+                tj = json.load(open(tpath))
+                if tj.get("shape") == {"B": wl_k.B, "T": wl_k.T, "Ti": wl_k.Ti}:
+                    traffic = tj["bytes_per_launch"].get("xattn_fwd")
             kx = kernels["xattn_fwd"]
             # the kernel the metric names; at this workload (2.4 MB, 100 MFLOP per launch) it is
             # latency-bound: AI = 42 FLOP/B is left of the ridge (~210), so the bound is HBM
