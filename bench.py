@@ -313,8 +313,15 @@ def main():
     if use_graph:
         # whole optimizer step captured once (DESIGN.md "launch overhead"); replays read the
         # step's inputs from static device buffers that are refilled before every replay
-        graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma,
-                                   fuse_accum=not args.no_fuse_accum)
+        try:
+            graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma,
+                                       fuse_accum=not args.no_fuse_accum)
+        except Exception as ex:  # noqa: BLE001  (never fail the bench on a capture problem: say so)
+            if world > 1:
+                raise
+            graphed, use_graph = None, False
+            config["graph_capture_error"] = repr(ex)[:300]
+            torch.cuda.synchronize()
     config["launch"] = "cuda-graph replay of the whole step" if use_graph else "eager"
     config["accum_window"] = (
         f"{args.accum} micro-batches of {wl.B} run as ONE forward/backward over {args.accum * wl.B} samples "
