@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--model", default="4b", choices=["4b", "tiny"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU micro-batch (default: workload's)")
     ap.add_argument("--accum", type=int, default=2, help="gradient accumulation (reference: 2)")
+    ap.add_argument("--dp", default="zero1", choices=["zero1", "allreduce"],
+                    help="N>1: sharded optimizer (reduce-scatter/all-gather) or plain all-reduce")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-fuse-accum", action="store_true",
                     help="run the accumulation window as sequential micro-batches (reference style)")
@@ -280,8 +282,8 @@ def main():
     from unimp_b200 import _lib
     from unimp_b200.factory import build_flamingo
     from unimp_b200.synth import make_batch
-    from unimp_b200.train import (BucketedAllReduce, FlatAdamW, GraphedTrainStep, get_grouped_params,
-                                  train_step)
+    from unimp_b200.train import (BucketedAllReduce, FlatAdamW, GraphedTrainStep, ShardedDataParallel,
+                                  get_grouped_params, train_step)
 
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -296,8 +298,15 @@ def main():
 
     model = build_flamingo(cfg, dtype=torch.bfloat16, device="cuda", seed=0, gate=0.5)
     model.train()
-    opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4)
-    reducer = BucketedAllReduce(opt) if world > 1 else None
+    sharded = world > 1 and args.dp == "zero1"
+    opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4, shard_world=world if sharded else 1,
+                    allocate_states=not sharded)
+    reducer = None
+    if world > 1:
+        reducer = ShardedDataParallel(opt) if sharded else BucketedAllReduce(opt)
+        config["parallelism"] = f"dp{world}, " + (
+            "sharded optimizer: bucketed reduce-scatter overlapped with backward, AdamW on 1/N, all-gather"
+            if sharded else "bucketed all-reduce overlapped with backward")
     tk = cfg.tokens
 
     n_batches = args.accum * 4

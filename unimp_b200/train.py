@@ -80,7 +80,10 @@ class FlatAdamW:
     """
 
     def __init__(self, groups, *, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0,
-                 direct_grads=True):
+                 direct_grads=True, shard_world=1, allocate_states=True):
+        """`shard_world` > 1 pads every parameter span to a multiple of 8*shard_world elements so
+        that any run of whole spans splits evenly into `shard_world` 16-byte-aligned shards
+        (ShardedDataParallel); `allocate_states=False` leaves master/m/v to the sharded owner."""
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
         self.step_count = 0
         self.groups = []
@@ -96,7 +99,8 @@ class FlatAdamW:
             n_direct = sum(1 for np in named if is_direct(*np))
             p0 = named[0][1]
             dev, dt = p0.device, p0.dtype
-            sizes = [((p.numel() + 7) // 8) * 8 for _, p in named]  # keep 16-byte alignment
+            al = 8 * max(1, shard_world)  # keep 16-byte alignment (per shard)
+            sizes = [((p.numel() + al - 1) // al) * al for _, p in named]
             total = sum(sizes)
             flat_p = torch.zeros(total, dtype=dt, device=dev)
             flat_g = torch.zeros(total, dtype=dt, device=dev)
@@ -118,9 +122,10 @@ class FlatAdamW:
                 tail_start = 0
             self.groups.append({
                 "weight_decay": g["weight_decay"], "flat_p": flat_p, "flat_g": flat_g,
-                "master": flat_p.float(), "m": torch.zeros(total, dtype=torch.float32, device=dev),
-                "v": torch.zeros(total, dtype=torch.float32, device=dev), "spans": spans,
-                "n_direct": n_direct, "tail": flat_g[tail_start:],
+                "master": flat_p.float() if allocate_states else None,
+                "m": torch.zeros(total, dtype=torch.float32, device=dev) if allocate_states else None,
+                "v": torch.zeros(total, dtype=torch.float32, device=dev) if allocate_states else None,
+                "spans": spans, "sizes": sizes, "n_direct": n_direct, "tail": flat_g[tail_start:],
             })
         dev = self.groups[0]["flat_p"].device
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -146,6 +151,7 @@ class FlatAdamW:
             for (_, p, _, _) in g["spans"][:g["n_direct"]]:
                 if p._unimp_fresh:
                     p.grad.zero_()
+                    p._unimp_fresh = False
 
     def grad_norm(self) -> torch.Tensor:
         return self.gnorm_sq.sqrt()
@@ -176,6 +182,21 @@ class FlatAdamW:
         """clip_grad_norm_(max_grad_norm) over ALL groups, then AdamW."""
         self.prepare_step(lr_scale)
         self.step_kernels(grad_scale)
+
+    def step_with(self, reducer, *, lr_scale=None):
+        """finish the reducer's collectives, then the (possibly sharded) optimizer kernels.
+        lr_scale=None: the caller already ran prepare_step (graph replay)."""
+        if lr_scale is not None:
+            self.prepare_step(lr_scale)
+        if reducer is None:
+            self.step_kernels(1.0)
+            return
+        self._zero_unwritten()   # before the last collectives are issued
+        reducer.finish()
+        if reducer.sharded and reducer.world > 1:
+            reducer.sharded_step()
+        else:
+            self.step_kernels(reducer.grad_scale)
 
 
 class BucketedAllReduce:
@@ -208,7 +229,7 @@ class BucketedAllReduce:
                     cur_start, cur_n = off, 0
                 bidx = len(self.buckets)
                 cur_n += 1
-                end = off + ((numel + 7) // 8) * 8
+                end = off + g["sizes"][g["spans"].index((name, p, off, numel))]
                 hook = self._make_hook(bidx)
                 if getattr(p, "_unimp_direct", False):
                     # direct-accumulation parameters report from their own backward
@@ -232,9 +253,14 @@ class BucketedAllReduce:
             self.pending[bidx] -= 1
             assert self.pending[bidx] >= 0, "a parameter reported its gradient twice in one step"
             if self.pending[bidx] == 0:
-                self.works.append(dist.all_reduce(self.buckets[bidx][0], op=dist.ReduceOp.SUM,
-                                                  group=self.group, async_op=True))
+                self.works.append(self._launch(bidx))
         return hook
+
+    sharded = False
+
+    def _launch(self, bidx):
+        return dist.all_reduce(self.buckets[bidx][0], op=dist.ReduceOp.SUM, group=self.group,
+                               async_op=True)
 
     def finish(self):
         """Wait for every bucket (stream-level wait for NCCL; no host sync) and re-arm."""
@@ -242,8 +268,7 @@ class BucketedAllReduce:
             return
         for b, left in enumerate(self.pending):
             if left != 0 and self.armed:  # a parameter got no gradient this step: reduce anyway
-                self.works.append(dist.all_reduce(self.buckets[b][0], op=dist.ReduceOp.SUM,
-                                                  group=self.group, async_op=True))
+                self.works.append(self._launch(b))
         for w in self.works:
             w.wait()
         self.works = []
@@ -252,6 +277,73 @@ class BucketedAllReduce:
     @property
     def grad_scale(self) -> float:
         return 1.0 / self.world
+
+
+class ShardedDataParallel(BucketedAllReduce):
+    """Data parallelism with a SHARDED optimizer — the B200-native counterpart of the reference's
+    DeepSpeed ZeRO-2 (`UniMP/accelerate_configs/accelerate_config_zero2.yaml:1-21`), weights still
+    replicated (they fit 180 GB many times over).
+
+    Per bucket of the flat gradient buffer: reduce-scatter (SUM) as soon as its last gradient lands
+    (same hooks and overlap as BucketedAllReduce, half the wire volume of an all-reduce at that
+    point); every rank then runs the fused clip+AdamW kernel on ITS 1/world shard only (fp32
+    master / m / v exist only for the shard: optimizer memory and the 28 B/param HBM pass both
+    shrink by `world`), writes the bf16 working copy of the shard in place, and an all-gather
+    rebuilds the full bf16 parameter bucket.  The clip norm is the all-reduced sum of the shards'
+    squared norms.  Results equal BucketedAllReduce + FlatAdamW (tests/dp_check.py)."""
+
+    sharded = True
+
+    def __init__(self, opt: FlatAdamW, *, bucket_bytes: int = 112 << 20, group=None):
+        super().__init__(opt, bucket_bytes=bucket_bytes, group=group)
+        self.opt = opt
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.shards = []
+        if self.world == 1:
+            return
+        # buckets were cut on the gradient buffers; find each bucket's group / offset
+        for (gview, _n) in self.buckets:
+            grp = next(g for g in opt.groups
+                       if g["flat_g"].data_ptr() <= gview.data_ptr() < g["flat_g"].data_ptr() + g["flat_g"].numel() * g["flat_g"].element_size())
+            start = (gview.data_ptr() - grp["flat_g"].data_ptr()) // gview.element_size()
+            L = gview.numel()
+            assert L % (8 * self.world) == 0, "build FlatAdamW with shard_world=world"
+            S = L // self.world
+            lo = start + self.rank * S
+            p_shard = grp["flat_p"][lo:lo + S]
+            self.shards.append({
+                "g_full": gview, "g_shard": grp["flat_g"][lo:lo + S],
+                "p_full": grp["flat_p"][start:start + L], "p_shard": p_shard,
+                "master": p_shard.float(), "m": torch.zeros(S, dtype=torch.float32, device=p_shard.device),
+                "v": torch.zeros(S, dtype=torch.float32, device=p_shard.device),
+                "weight_decay": grp["weight_decay"],
+            })
+
+    def _launch(self, bidx):
+        sh = self.shards[bidx]
+        # in place: the output is this rank's slice of the input (NCCL in-place reduce-scatter)
+        return dist.reduce_scatter_tensor(sh["g_shard"], sh["g_full"], op=dist.ReduceOp.SUM,
+                                          group=self.group, async_op=True)
+
+    @torch.no_grad()
+    def sharded_step(self):
+        """Device side of the optimizer step (capturable).  Call after finish()."""
+        opt = self.opt
+        opt.gnorm_sq.zero_()
+        for sh in self.shards:
+            ops.sumsq_(sh["g_shard"], opt.gnorm_sq)
+        dist.all_reduce(opt.gnorm_sq, op=dist.ReduceOp.SUM, group=self.group)
+        works = []
+        for sh in self.shards:
+            ops.adamw_step_(sh["master"], sh["p_shard"], sh["g_shard"], sh["m"], sh["v"],
+                            hyper=opt.hyper, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps,
+                            weight_decay=sh["weight_decay"],
+                            gnorm_sq=opt.gnorm_sq if opt.max_grad_norm > 0 else None,
+                            max_norm=opt.max_grad_norm, grad_scale=self.grad_scale)
+            works.append(dist.all_gather_into_tensor(sh["p_full"], sh["p_shard"], group=self.group,
+                                                     async_op=True))
+        for w in works:
+            w.wait()
 
 
 def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True):
@@ -312,18 +404,14 @@ def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce 
             reducer.armed = True
         loss, _ = unimp_loss_fused(model, mbs, tokens, gamma=gamma, use_reweight=use_reweight)
         loss.backward()
-        if reducer is not None:
-            reducer.finish()
-        opt.step(lr_scale=lr_scale, grad_scale=reducer.grad_scale if reducer is not None else 1.0)
+        opt.step_with(reducer, lr_scale=lr_scale)
         return loss
     for i, mb in enumerate(mbs):
         if reducer is not None:
             reducer.armed = i == len(mbs) - 1
         loss, _, _ = unimp_loss(model, mb, tokens, gamma=gamma, use_reweight=use_reweight)
         (loss / accum_steps if accum_steps > 1 else loss).backward()
-    if reducer is not None:
-        reducer.finish()
-    opt.step(lr_scale=lr_scale, grad_scale=reducer.grad_scale if reducer is not None else 1.0)
+    opt.step_with(reducer, lr_scale=lr_scale)
     return loss
 
 
@@ -372,9 +460,7 @@ class GraphedTrainStep:
             loss, _ = unimp_loss_fused(self.model, self.static, self.tokens, gamma=self.gamma,
                                        use_reweight=self.use_reweight)
             loss.backward()
-            if self.reducer is not None:
-                self.reducer.finish()
-            self.opt.step_kernels(self.grad_scale)
+            self.opt.step_with(self.reducer)
             return loss.detach()
         for i, mb in enumerate(self.static):
             if self.reducer is not None:
@@ -382,9 +468,7 @@ class GraphedTrainStep:
             loss, _, _ = unimp_loss(self.model, mb, self.tokens, gamma=self.gamma,
                                     use_reweight=self.use_reweight)
             (loss / self.accum if self.accum > 1 else loss).backward()
-        if self.reducer is not None:
-            self.reducer.finish()
-        self.opt.step_kernels(self.grad_scale)
+        self.opt.step_with(self.reducer)
         return loss.detach()
 
     def __call__(self, mbs, lr_scale: float = 1.0):
