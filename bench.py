@@ -303,9 +303,12 @@ def main():
                     allocate_states=not sharded)
     reducer = None
     if world > 1:
-        reducer = ShardedDataParallel(opt) if sharded else BucketedAllReduce(opt)
+        reducer = (ShardedDataParallel(opt, deferred_gather_module=model.perceiver,
+                                       gather_start_module=model.vision_encoder) if sharded
+                   else BucketedAllReduce(opt))
         config["parallelism"] = f"dp{world}, " + (
-            "sharded optimizer: bucketed reduce-scatter overlapped with backward, AdamW on 1/N, all-gather"
+            "sharded optimizer: bucketed reduce-scatter overlapped with backward, AdamW on 1/N, "
+            "parameter all-gather overlapped with the next step's ViT forward"
             if sharded else "bucketed all-reduce overlapped with backward")
     tk = cfg.tokens
 

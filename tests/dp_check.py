@@ -69,12 +69,17 @@ def main():
         err = float((got - want).norm() / want.norm())
         assert err < 1e-5, f"graph rep {rep}: rel err {err}"
     # ---- sharded optimizer (reduce-scatter -> AdamW on 1/world -> all-gather) == all-reduce + full AdamW
-    def run(mode, graph):
+    def run(mode, graph, deferred=False):
         m = build_flamingo(cfg, dtype=dtype, device="cuda", gate=0.5, seed=0)
         sharded = mode == "zero1"
         o = FlatAdamW(get_grouped_params(m, 0.1), lr=1e-3, shard_world=world if sharded else 1,
                       allocate_states=not sharded)
-        r = (ShardedDataParallel if sharded else BucketedAllReduce)(o, bucket_bytes=256 << 10)
+        if sharded:
+            r = ShardedDataParallel(o, bucket_bytes=256 << 10,
+                                    deferred_gather_module=m.perceiver if deferred else None,
+                                    gather_start_module=m.vision_encoder if deferred else None)
+        else:
+            r = BucketedAllReduce(o, bucket_bytes=256 << 10)
         mbs = batches(rank)
         if graph:
             gs = GraphedTrainStep(m, cfg.tokens, o, r, mbs, warmup_iters=2, fuse_accum=True)  # steps 1, 2
@@ -82,18 +87,20 @@ def main():
         else:
             for _ in range(3):
                 train_step(m, None, cfg.tokens, o, r, accum_steps=2, micro_batches=mbs, fuse_accum=True)
+        if sharded:
+            r.sync_params()
         torch.cuda.synchronize()
         return torch.cat([g["flat_p"].float() for g in o.groups]), [n for g in o.groups for (n, _, _, _) in g["spans"]], o
 
     p_ar, _, o_ar = run("allreduce", False)
-    for graph in (False, True):
-        p_z, names, o_z = run("zero1", graph)
+    for graph, deferred in ((False, False), (True, False), (False, True), (True, True)):
+        p_z, names, o_z = run("zero1", graph, deferred)
         # layouts differ only by span padding: compare parameter by parameter
         for ga, gz in zip(o_ar.groups, o_z.groups):
             for (na, pa, _, _), (nz, pz, _, _) in zip(ga["spans"], gz["spans"]):
                 assert na == nz
                 err = float((pz.float() - pa.float()).norm() / pa.float().norm().clamp_min(1e-20))
-                assert err < 2e-6, f"zero1 (graph={graph}) vs allreduce: {na} rel err {err}"
+                assert err < 2e-6, f"zero1 (graph={graph}, deferred={deferred}) vs allreduce: {na} rel err {err}"
         # every rank holds the same full parameters after the all-gather
         chk = p_z.clone()
         dist.all_reduce(chk, op=dist.ReduceOp.MAX)

@@ -11,13 +11,15 @@ from unimp_b200 import openflamingo_4b_config
 from unimp_b200.config import WORKLOADS
 from unimp_b200.factory import build_flamingo
 from unimp_b200.synth import make_batch
-from unimp_b200.train import FlatAdamW, BucketedAllReduce, get_grouped_params, GraphedTrainStep
+from unimp_b200.train import FlatAdamW, BucketedAllReduce, ShardedDataParallel, get_grouped_params, GraphedTrainStep
 cfg = openflamingo_4b_config(); wl = copy.copy(WORKLOADS["C2-rec"])
 model = build_flamingo(cfg, dtype=torch.bfloat16, device="cuda", gate=0.5).train()
-opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4)
-red = BucketedAllReduce(opt, bucket_bytes=int(os.environ.get("BUCKET_MB", 112)) << 20)
+world = dist.get_world_size()
+opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4, shard_world=world, allocate_states=False)
+red = ShardedDataParallel(opt, deferred_gather_module=model.perceiver if os.environ.get("DEFER", "1") == "1" else None,
+                          gather_start_module=model.vision_encoder if os.environ.get("UNIMP_AG_AT_VIT") else None)
 mbs = [{k: v.cuda() for k, v in make_batch(cfg, wl, seed=rank * 10 + i).items()} for i in range(2)]
-g = GraphedTrainStep(model, cfg.tokens, opt, red, mbs)
+g = GraphedTrainStep(model, cfg.tokens, opt, red, mbs, fuse_accum=True)
 for _ in range(3):
     g(mbs)
 torch.cuda.synchronize(); dist.barrier()
@@ -30,7 +32,13 @@ if rank == 0:
     nccl = [(s, e) for s, e, n in ev if "nccl" in n.lower()]
     for s_, e_, n_ in ev:
         if "nccl" in n_.lower():
-            print(f"   {(s_-t0)/1e3:7.2f} ms {(e_-s_)/1e3:6.2f} ms {n_[:80]}")
+            ov = sum(max(0, min(e_, ce) - max(s_, cs)) for cs, ce, cn in ev if "nccl" not in cn.lower())
+            print(f"   {(s_-t0)/1e3:7.2f} ms {(e_-s_)/1e3:6.2f} ms ov {ov/1e3:5.2f}  {n_[:60]}")
+    print("first 40 events:")
+    for s_, e_, n_ in ev[:40]:
+        print(f"   @{(s_-t0)/1e3:7.3f} ms {(e_-s_)/1e3:6.3f} ms {n_[:70]}")
+    firstp = [(s_ - t0) / 1e3 for s_, e_, n_ in ev if "gate_residual_ln" in n_][:1]
+    print("first LN kernel at", firstp)
     print("pending after step:", red.pending, "armed", red.armed)
     comp = [(s, e) for s, e, n in ev if "nccl" not in n.lower()]
     print(f"buckets {len(red.buckets)} sizes MB {[round(b[0].numel()*2/2**20) for b in red.buckets]}")

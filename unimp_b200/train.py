@@ -294,9 +294,25 @@ class ShardedDataParallel(BucketedAllReduce):
 
     sharded = True
 
-    def __init__(self, opt: FlatAdamW, *, bucket_bytes: int = 112 << 20, group=None):
+    def __init__(self, opt: FlatAdamW, *, bucket_bytes: int = 112 << 20, group=None,
+                 deferred_gather_module=None, gather_start_module=None):
+        """`deferred_gather_module`: if given (the Flamingo model's `perceiver`), the parameter
+        all-gather of step k is not run at the end of step k but at the START of step k+1, on the
+        NCCL stream, underneath the frozen ViT forward (which reads no trainable parameter); a
+        forward-pre-hook on that module waits for it.  Between steps only a rank's own shards are
+        current: call `sync_params()` before evaluating / checkpointing."""
         super().__init__(opt, bucket_bytes=bucket_bytes, group=group)
         self.opt = opt
+        self.deferred = deferred_gather_module is not None and self.world > 1
+        self._ag_works = []
+        self._params_stale = False
+        self._start_at_module = gather_start_module is not None
+        if self.deferred:
+            deferred_gather_module.register_forward_pre_hook(lambda m, a: self.wait_params())
+            if gather_start_module is not None:
+                # fork the NCCL work from a point where the compute stream is already busy
+                gather_start_module.register_forward_pre_hook(
+                    lambda m, a: self.gather_params_async() if self._params_stale else None)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.shards = []
         if self.world == 1:
@@ -340,10 +356,36 @@ class ShardedDataParallel(BucketedAllReduce):
                             weight_decay=sh["weight_decay"],
                             gnorm_sq=opt.gnorm_sq if opt.max_grad_norm > 0 else None,
                             max_norm=opt.max_grad_norm, grad_scale=self.grad_scale)
-            works.append(dist.all_gather_into_tensor(sh["p_full"], sh["p_shard"], group=self.group,
-                                                     async_op=True))
+            if not self.deferred:
+                works.append(dist.all_gather_into_tensor(sh["p_full"], sh["p_shard"],
+                                                         group=self.group, async_op=True))
         for w in works:
             w.wait()
+        self._params_stale = self.deferred
+
+    def begin_step(self):
+        if self.deferred and not self._start_at_module:
+            self.gather_params_async()
+
+    def gather_params_async(self):
+        """Start of a step (deferred mode): rebuild the full bf16 parameters from the shards the
+        previous step updated; overlaps whatever runs until wait_params()."""
+        if not self.deferred or self._ag_works:
+            return
+        self._ag_works = [dist.all_gather_into_tensor(sh["p_full"], sh["p_shard"], group=self.group,
+                                                      async_op=True) for sh in self.shards]
+
+    def wait_params(self):
+        for w in self._ag_works:
+            w.wait()
+        self._ag_works = []
+        self._params_stale = False
+
+    def sync_params(self):
+        """Make every rank's full parameters current (after the last step / before eval)."""
+        if self.deferred:
+            self.gather_params_async()
+            self.wait_params()
 
 
 def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True):
@@ -397,6 +439,8 @@ def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce 
     tensor of the last micro-batch (device scalar; caller decides when to read it)."""
     mbs = micro_batches if micro_batches is not None else [batch]
     assert len(mbs) == accum_steps
+    if reducer is not None and reducer.sharded:
+        reducer.begin_step()
     opt.zero_grad()
     loss = None
     if fuse_accum and len(mbs) > 1:
@@ -452,6 +496,8 @@ class GraphedTrainStep:
             self.loss = self._body()
 
     def _body(self):
+        if self.reducer is not None and self.reducer.sharded:
+            self.reducer.begin_step()
         self.opt.zero_grad()
         loss = None
         if self.fuse_accum:
