@@ -311,6 +311,16 @@ int make_tmap_bhld(CUtensorMap* out, const void* base, int64_t batch_stride, int
                    int L, int H, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return UNIMP_E_DEVICE; }
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on THIS thread.  Autograd
+  // worker threads may not have one bound yet when a backward reaches us before any runtime call
+  // (seen as CUDA_ERROR_INVALID_CONTEXT under ncu), so bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if (B == 1) batch_stride = row_stride * (int64_t)L;  // a size-1 dim may carry any stride
   cuuint64_t dims[4] = {(cuuint64_t)DH, (cuuint64_t)H, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)DH * 2, (cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
