@@ -8,8 +8,10 @@
 //       all of S = Q K^T for the tile lives in TMEM (<= 384 fp32 columns), so softmax is a
 //       plain two-pass row softmax with no online rescaling of O.
 //
-// One CTA = one (128-row query tile, head, batch).  Thread t owns query row t = TMEM lane t.
-// Thread 0 additionally issues every TMA and MMA (tcgen05.mma is a single-thread instruction).
+// Forward: one CTA = one (128-row query tile, head, batch), 160 threads: warps 0-3 own one query
+// row each (thread t = TMEM lane t: softmax / epilogue), lane 0 of warp 4 issues every TMA and
+// every tcgen05.mma (a single-thread instruction) and warp 4 owns the TMEM allocation.
+// All mbarrier waits are bounded (trap, never hang).
 //
 // Roofline: fwd FLOPs = 4*dh*Lq*Lk_attended per (b,h); bytes = Q + O + K + V (+lse).
 #include "common.cuh"
