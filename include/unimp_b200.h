@@ -147,23 +147,27 @@ int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void*
  * logits (B,T,V) with row stride `ld` elements (ld >= V); labels (B,T) int64 with -100;
  * row (b,t), t < T-1, is scored against labels[b,t+1].  weights (B) fp32.
  * use_focal == 0 reproduces plain weighted CE (reference --use_reweight off).
+ * group_size: samples are normalised in groups of `group_size` consecutive samples (one group =
+ * one micro-batch of the reference's gradient-accumulation window, UniMP/mmrec.py:175,213);
+ * group_size == B is the reference's single-batch formula.  G = B / group_size.
  * Outputs: row_lse, row_pt (B*T) fp32 (undefined on ignored rows);
- *          acc[0] = sum_i w*CE*(1-pt)^gamma, acc[1] = n_valid (fp32);
- *          *loss = acc[0]/acc[1]  (NaN when n_valid == 0, as the reference does).
+ *          acc[2g] = sum_{i in g} w*CE*(1-pt)^gamma, acc[2g+1] = n_valid_g (fp32, 2*G floats);
+ *          *loss = mean_g(acc[2g]/acc[2g+1])  (NaN when a group has no valid label, as the
+ *          reference does).
  * The sum runs in a fixed order: the loss is bit-reproducible run to run.
  * workspace: unimp_focal_ce_workspace(B,T,V,dtype) bytes of caller scratch. */
 int64_t unimp_focal_ce_workspace(int B, int T, int V, int dtype);
 int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t* labels,
                        const float* weights, float gamma, int use_focal, float* row_lse,
                        float* row_pt, float* acc, float* loss, void* workspace, int B, int T,
-                       int V, int dtype, void* stream);
+                       int V, int group_size, int dtype, void* stream);
 /* d_logits (B,T,V) row stride ld_out, fully written: zero on ignored rows and at t = T-1.
  * g_loss: device scalar (fp32) upstream gradient of the loss. */
 int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t* labels,
                        const float* weights, float gamma, int use_focal, const float* row_lse,
                        const float* row_pt, const float* acc, const float* g_loss,
-                       void* d_logits, int64_t ld_out, int B, int T, int V, int dtype,
-                       void* stream);
+                       void* d_logits, int64_t ld_out, int B, int T, int V, int group_size,
+                       int dtype, void* stream);
 
 /* ---- a9 (f2): answer-span label masking on the GPU -----------------------------------
  * Replaces the Python double loop of reference UniMP/mmrec.py:143-168. */

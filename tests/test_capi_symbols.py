@@ -37,7 +37,7 @@ def test_error_string_and_argument_validation_without_gpu():
     rc = lib.unimp_text_time(None, 1, 1, 1, 0, 1, None, None)
     assert rc == -1
     assert b"NULL" in lib.unimp_last_error_string()
-    rc = lib.unimp_focal_ce_fwd(None, 0, None, None, 2.0, 1, None, None, None, None, None, 1, 2, 3, 1, None)
+    rc = lib.unimp_focal_ce_fwd(None, 0, None, None, 2.0, 1, None, None, None, None, None, 1, 2, 3, 1, 1, None)
     assert rc == -1
 
 

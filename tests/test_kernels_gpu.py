@@ -383,3 +383,25 @@ def test_focal_ce_full_size_equals_oracle_on_the_valid_rows():
     assert abs(float(g.float().sum())) < 1e-2                                  # each row of (p - y) sums to 0
     # determinism: the same bits again
     assert torch.equal(loss.detach(), ops().focal_ce(z.detach(), y, w, gamma=2.0))
+
+
+@pytest.mark.parametrize("dtype,tol_l,tol_g", [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1e-3, 2e-2)])
+def test_focal_ce_group_normalisation_equals_mean_of_per_group_losses(dtype, tol_l, tol_g):
+    """group_size: one launch over an accumulation window == mean over micro-batches of the
+    reference loss (each normalised by its own number of valid labels)."""
+    torch.manual_seed(5)
+    B, T, V, gs = 6, 20, 515, 3
+    z = (2 * torch.randn(B, T, V)).to(dtype)
+    y = torch.randint(0, V, (B, T))
+    y[:3, :12] = -100           # groups with different n_valid
+    y[3:, :4] = -100
+    w = torch.tensor([2.0, 1.0, 1.0, 1.0, 2.0, 1.0])
+    zr = z.double().requires_grad_(True)
+    ref = sum(focal_loss(zr[g * gs:(g + 1) * gs], y[g * gs:(g + 1) * gs], w[g * gs:(g + 1) * gs].double(), gamma=2.0)
+              for g in range(B // gs)) / (B // gs)
+    ref.backward()
+    zd = z.to(DEV).requires_grad_(True)
+    loss = ops().focal_ce(zd, y.to(DEV), w.to(DEV), gamma=2.0, group_size=gs)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol_l
+    assert rel_err(zd.grad, zr.grad) < tol_g

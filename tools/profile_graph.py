@@ -15,7 +15,7 @@ wl = copy.copy(WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C2-rec"])
 model = build_flamingo(cfg, dtype=torch.bfloat16, device="cuda", gate=0.5).train()
 opt = FlatAdamW(get_grouped_params(model, 0.1), lr=2e-4)
 mbs = [{k: v.cuda() for k, v in make_batch(cfg, wl, seed=i).items()} for i in range(2)]
-g = GraphedTrainStep(model, cfg.tokens, opt, None, mbs)
+g = GraphedTrainStep(model, cfg.tokens, opt, None, mbs, fuse_accum=os.environ.get('FUSE', '1') == '1')
 for _ in range(3):
     g(mbs)
 torch.cuda.synchronize()

@@ -105,10 +105,16 @@ focal_ce_finish_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* 
                        const float* __restrict__ weights, const float* __restrict__ partial,
                        int nchunks, float gamma, int use_focal, float* __restrict__ row_lse,
                        float* __restrict__ row_pt, float* __restrict__ acc, float* __restrict__ loss,
-                       int B, int T_) {
+                       int B, int T_, int group_size) {
+  // Samples are normalised in groups of `group_size` (one group = one micro-batch of the
+  // reference's accumulation window): loss = mean_g( sum_g(w*CE*focal) / n_valid_g ).
+  const int G = B / group_size;
+  float total = 0.f;
+  __shared__ float sh[32];
+  for (int g = 0; g < G; ++g) {
   float lsum = 0.f, nval = 0.f;
-  const int rows = B * T_;
-  for (int row = threadIdx.x; row < rows; row += blockDim.x) {
+  const int row_lo = g * group_size * T_, rows = (g + 1) * group_size * T_;
+  for (int row = row_lo + threadIdx.x; row < rows; row += blockDim.x) {
     const int t = row % T_;
     if (t == T_ - 1) continue;
     const int64_t y = labels[row + 1];
@@ -129,14 +135,15 @@ focal_ce_finish_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* 
     lsum += l;
     nval += 1.f;
   }
-  __shared__ float sh[32];
   lsum = block_sum(lsum, sh);
   nval = block_sum(nval, sh);
   if (threadIdx.x == 0) {
-    acc[0] = lsum;
-    acc[1] = nval;
-    *loss = lsum / nval;  // NaN when nothing is valid, as the reference (mmrec.py:213)
+    acc[2 * g] = lsum;
+    acc[2 * g + 1] = nval;
   }
+  total += lsum / nval;  // NaN when nothing is valid, as the reference (mmrec.py:213)
+  }
+  if (threadIdx.x == 0) *loss = total / G;
 }
 
 // grid (B*T, nchunks): writes every element of d_logits.
@@ -146,7 +153,7 @@ focal_ce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __r
                     const float* __restrict__ weights, float gamma, int use_focal,
                     const float* __restrict__ row_lse, const float* __restrict__ row_pt,
                     const float* __restrict__ acc, const float* __restrict__ g_loss,
-                    T* __restrict__ d_logits, int64_t ld_out, int T_, int V) {
+                    T* __restrict__ d_logits, int64_t ld_out, int T_, int V, int group_size, int G) {
   constexpr int N = Vec16<T>::N;
   const int row = blockIdx.x;
   const int t = row % T_;
@@ -168,7 +175,8 @@ focal_ce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __r
       const float ce = -logf(fmaxf(pt, 1e-38f));
       c = powf(omp, gamma) + gamma * powf(omp, gamma - 1.f) * pt * ce;
     }
-    coef = c * weights[row / T_] * (*g_loss) / acc[1];
+    const int b = row / T_;
+    coef = c * weights[b] * (*g_loss) / (acc[2 * (b / group_size) + 1] * G);
     vec_in = ((reinterpret_cast<uintptr_t>(rp) ^ reinterpret_cast<uintptr_t>(op)) & 15) == 0;
   }
 #pragma unroll
@@ -226,12 +234,15 @@ extern "C" int64_t unimp_focal_ce_workspace(int B, int T, int V, int dtype) {
 extern "C" int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t* labels,
                                   const float* weights, float gamma, int use_focal,
                                   float* row_lse, float* row_pt, float* acc, float* loss,
-                                  void* workspace, int B, int T, int V, int dtype, void* stream) {
+                                  void* workspace, int B, int T, int V, int group_size, int dtype,
+                                  void* stream) {
   UNIMP_CHECK_ARG(logits && labels && weights && row_lse && row_pt && acc && loss && workspace,
                   UNIMP_E_NULL, "focal_ce_fwd: NULL pointer");
   UNIMP_CHECK_ARG(B > 0 && T > 1 && V > 0 && ld >= V, UNIMP_E_SHAPE,
                   "focal_ce_fwd: bad shape B=%d T=%d V=%d ld=%lld", B, T, V, (long long)ld);
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_fwd: dtype");
+  UNIMP_CHECK_ARG(group_size > 0 && B % group_size == 0, UNIMP_E_SHAPE,
+                  "focal_ce_fwd: group_size=%d must divide B=%d", group_size, B);
   cudaStream_t st = (cudaStream_t)stream;
   const int nch = ce_nchunks(V, dtype);
   dim3 grid(B * T, nch);
@@ -242,14 +253,14 @@ extern "C" int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t*
     UNIMP_CHECK_LAUNCH();
     focal_ce_finish_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>(
         (const __nv_bfloat16*)logits, ld, labels, weights, partial, nch, gamma, use_focal,
-        row_lse, row_pt, acc, loss, B, T);
+        row_lse, row_pt, acc, loss, B, T, group_size);
   } else {
     focal_ce_partial_kernel<float><<<grid, CE_THREADS, 0, st>>>((const float*)logits, ld, labels,
                                                                   partial, T, V);
     UNIMP_CHECK_LAUNCH();
     focal_ce_finish_kernel<float><<<1, 1024, 0, st>>>((const float*)logits, ld, labels, weights,
                                                        partial, nch, gamma, use_focal, row_lse,
-                                                       row_pt, acc, loss, B, T);
+                                                       row_pt, acc, loss, B, T, group_size);
   }
   UNIMP_CHECK_LAUNCH();
   return 0;
@@ -259,22 +270,24 @@ extern "C" int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t*
                                   const float* weights, float gamma, int use_focal,
                                   const float* row_lse, const float* row_pt, const float* acc,
                                   const float* g_loss, void* d_logits, int64_t ld_out, int B, int T,
-                                  int V, int dtype, void* stream) {
+                                  int V, int group_size, int dtype, void* stream) {
   UNIMP_CHECK_ARG(logits && labels && weights && row_lse && row_pt && acc && g_loss && d_logits,
                   UNIMP_E_NULL, "focal_ce_bwd: NULL pointer");
   UNIMP_CHECK_ARG(B > 0 && T > 1 && V > 0 && ld >= V && ld_out >= V, UNIMP_E_SHAPE,
                   "focal_ce_bwd: bad shape");
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_bwd: dtype");
+  UNIMP_CHECK_ARG(group_size > 0 && B % group_size == 0, UNIMP_E_SHAPE,
+                  "focal_ce_bwd: group_size=%d must divide B=%d", group_size, B);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(B * T, ce_nchunks(V, dtype));
   if (dtype == UNIMP_BF16)
     focal_ce_bwd_kernel<__nv_bfloat16><<<grid, CE_THREADS, 0, st>>>(
         (const __nv_bfloat16*)logits, ld, labels, weights, gamma, use_focal, row_lse, row_pt, acc,
-        g_loss, (__nv_bfloat16*)d_logits, ld_out, T, V);
+        g_loss, (__nv_bfloat16*)d_logits, ld_out, T, V, group_size, B / group_size);
   else
     focal_ce_bwd_kernel<float><<<grid, CE_THREADS, 0, st>>>(
         (const float*)logits, ld, labels, weights, gamma, use_focal, row_lse, row_pt, acc, g_loss,
-        (float*)d_logits, ld_out, T, V);
+        (float*)d_logits, ld_out, T, V, group_size, B / group_size);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }

@@ -86,7 +86,7 @@ class PerceiverResampler(nn.Module):
     def forward(self, x):
         """x (b, T, F, v, D) -> (b, T, n, D)."""
         b, T, Fr, v, D = x.shape
-        x = x.reshape(b, T, Fr * v, D)
+        x = x.reshape(b, T, Fr * v, D).contiguous()  # once (the ViT output is a CLS-dropping slice)
         latents = self.latents.to(x.dtype).expand(b, T, -1, -1).contiguous()
         latents_ln = None
         n_layers = len(self.layers)

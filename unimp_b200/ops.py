@@ -260,10 +260,12 @@ def layer_norm(x, gamma, beta, eps: float = 1e-5):
 
 class _FocalCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, labels, weights, gamma, use_focal):
+    def forward(ctx, logits, labels, weights, gamma, use_focal, group_size):
         dt = _dt(logits)
         assert logits.dim() == 3 and labels.shape == logits.shape[:2]
         B, T, V = logits.shape
+        group_size = B if group_size is None else int(group_size)
+        assert B % group_size == 0
         if logits.stride(2) != 1 or logits.stride(0) != T * logits.stride(1):
             logits = logits.contiguous()
         ld = logits.stride(1)
@@ -273,35 +275,39 @@ class _FocalCE(torch.autograd.Function):
         lib = _lib.load()
         row_lse = torch.empty(B * T, dtype=torch.float32, device=dev)
         row_pt = torch.empty(B * T, dtype=torch.float32, device=dev)
-        acc = torch.empty(2, dtype=torch.float32, device=dev)
+        acc = torch.empty(2 * (B // group_size), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         ws = torch.empty(lib.unimp_focal_ce_workspace(B, T, V, dt), dtype=torch.uint8, device=dev)
         check(lib.unimp_focal_ce_fwd(logits.data_ptr(), ld, labels.data_ptr(), weights.data_ptr(),
                                      float(gamma), int(use_focal), row_lse.data_ptr(),
                                      row_pt.data_ptr(), acc.data_ptr(), loss.data_ptr(),
-                                     ws.data_ptr(), B, T, V, dt, _stream()), "unimp_focal_ce_fwd")
+                                     ws.data_ptr(), B, T, V, group_size, dt, _stream()),
+              "unimp_focal_ce_fwd")
         ctx.save_for_backward(logits, labels, weights, row_lse, row_pt, acc)
-        ctx.cfg = (float(gamma), int(use_focal), ld, dt)
+        ctx.cfg = (float(gamma), int(use_focal), ld, dt, group_size)
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
         logits, labels, weights, row_lse, row_pt, acc = ctx.saved_tensors
-        gamma, use_focal, ld, dt = ctx.cfg
+        gamma, use_focal, ld, dt, group_size = ctx.cfg
         B, T, V = logits.shape
         g = g_loss.to(torch.float32).contiguous()
         buf = torch.empty((B, T, ld), dtype=logits.dtype, device=logits.device)
         check(_lib.load().unimp_focal_ce_bwd(logits.data_ptr(), ld, labels.data_ptr(),
                                              weights.data_ptr(), gamma, use_focal,
                                              row_lse.data_ptr(), row_pt.data_ptr(), acc.data_ptr(),
-                                             g.data_ptr(), buf.data_ptr(), ld, B, T, V, dt,
-                                             _stream()), "unimp_focal_ce_bwd")
-        return (buf[..., :V] if ld != V else buf), None, None, None, None
+                                             g.data_ptr(), buf.data_ptr(), ld, B, T, V, group_size,
+                                             dt, _stream()), "unimp_focal_ce_bwd")
+        return (buf[..., :V] if ld != V else buf), None, None, None, None, None
 
 
-def focal_ce(logits, labels, weights, *, gamma: float = 2.0, use_focal: bool = True):
-    """K6: reference UniMP/mmrec.py:190-213 on (B,T,V) logits, (B,T) labels, (B,) weights."""
-    return _FocalCE.apply(logits, labels, weights, gamma, use_focal)
+def focal_ce(logits, labels, weights, *, gamma: float = 2.0, use_focal: bool = True,
+             group_size: int | None = None):
+    """K6: reference UniMP/mmrec.py:190-213 on (B,T,V) logits, (B,T) labels, (B,) weights.
+    `group_size`: normalise per group of that many consecutive samples and average the groups
+    (an accumulation window of micro-batches in one call); default: one group = the whole batch."""
+    return _FocalCE.apply(logits, labels, weights, gamma, use_focal, group_size)
 
 
 # --------------------------------------------------------------------------- LM / ViT fusions

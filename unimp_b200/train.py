@@ -424,12 +424,9 @@ def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True):
     out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=None)
     logits = out["logits"]
     B = mbs[0]["input_ids"].shape[0]
-    loss = None
-    for k in range(accum):
-        sl = slice(k * B, (k + 1) * B)
-        lk = ops.focal_ce(logits[sl], labels[sl], weights[sl], gamma=gamma, use_focal=use_reweight)
-        loss = lk if loss is None else loss + lk
-    return loss / accum, logits
+    # one launch over the whole window; the kernel normalises each micro-batch by its own n_valid
+    loss = ops.focal_ce(logits, labels, weights, gamma=gamma, use_focal=use_reweight, group_size=B)
+    return loss, logits
 
 
 def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce | None = None, *,
