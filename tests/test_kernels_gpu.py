@@ -405,3 +405,37 @@ def test_focal_ce_group_normalisation_equals_mean_of_per_group_losses(dtype, tol
     loss.backward()
     assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol_l
     assert rel_err(zd.grad, zr.grad) < tol_g
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_masked_cross_attention_other_latent_counts(dtype, tol):
+    """num_latents != 64 (not the upstream default) is served by the CUDA-core path."""
+    B, T, Ti, H, dh, n = 2, 40, 3, 8, 64, 32
+    torch.manual_seed(9)
+    q = torch.randn(B, T, H * dh).to(dtype).double()
+    kv = torch.randn(B, Ti * n, 2 * H * dh).to(dtype).double()
+    tt = _mk_tt(B, T, Ti, seed=1)
+    go = torch.randn(B, T, H * dh).to(dtype).double()
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    ref = _dense_attn_ref(qr, kvr, tt.long(), H, n, 0.125)
+    ref.backward(go)
+    qd, kvd = q.to(DEV, dtype).requires_grad_(True), kv.to(DEV, dtype).requires_grad_(True)
+    out = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=0.125)
+    out.backward(go.to(DEV, dtype))
+    assert rel_err(out, ref) < tol and rel_err(qd.grad, qr.grad) < tol and rel_err(kvd.grad, kvr.grad) < tol
+
+
+def test_layer_norm_wide_rows_and_bad_shapes():
+    x = torch.randn(9, 8192, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    g = torch.ones(8192, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    b = torch.zeros(8192, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    y = ops().layer_norm(x, g, b)
+    ref = torch.nn.functional.layer_norm(x.float(), (8192,), g.float(), b.float())
+    assert rel_err(y, ref) < 1e-2
+    y.sum().backward()
+    assert torch.isfinite(x.grad).all() and torch.isfinite(g.grad).all()
+    from unimp_b200._lib import UnimpError
+    with pytest.raises(UnimpError):
+        ops().layer_norm(torch.randn(4, 100, device=DEV, dtype=torch.bfloat16),
+                         torch.ones(100, device=DEV, dtype=torch.bfloat16),
+                         torch.zeros(100, device=DEV, dtype=torch.bfloat16))   # D % 8 != 0
