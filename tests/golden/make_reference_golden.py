@@ -1,0 +1,267 @@
+"""Generates tests/golden/ref_*.pt by RUNNING THE REFERENCE'S OWN CODE (in this container only).
+
+    python tests/golden/make_reference_golden.py          # needs /root/reference
+
+What is executed is the unmodified reference, imported from where it lies:
+
+* `UniMP/mmrec.py::train_one_epoch` (`:65-302`) — the real training-loop body: batch unpack
+  (`:135-141`), the answer-span label state machine (`:143-168`), the model call, the task-weighted
+  focal loss (`:190-213`) and `accelerator.backward`.  The module's missing third-party imports
+  (`open_flamingo`, `accelerate`, `wandb`, `webdataset`, ...) are replaced by empty
+  stub modules — none of them is touched by `train_one_epoch` — and the loop is driven with a
+  recording model (returns prescribed logits, records the labels it was handed), a recording
+  accelerator (`backward` keeps the loss and calls `loss.backward()`), and no-op optimizer /
+  scheduler.  What comes out — labels, loss, dloss/dlogits — IS the reference's arithmetic for the
+  in-tree half of the path.
+* `UniMP/pipeline/mm_utils/collate_rec.py::collate_fn` (`:38-74`) — the batch layout.
+* `UniMP/pipeline/train/train_utils.py::get_checkpoint` (`:258-265`).
+* `get_grouped_params` / `apply_decay` (`UniMP/mmrec.py:609-631`) — nested inside `main()`, so its
+  FunctionDef node is lifted out of the parsed source with `ast` and compiled as is.
+
+No reference source is copied into the repo; only the small input/output vectors are committed.
+The third-party half (open_flamingo v2.0.1) is absent from /root/reference and stays unpinned.
+"""
+import argparse
+import ast
+import contextlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/UniMP"
+
+# modules the reference imports at module top that this image does not have (or that drag in
+# datasets / webdataset); train_one_epoch / collate_fn / get_checkpoint use none of them
+STUB_PREFIXES = ("wandb", "open_flamingo", "accelerate", "webdataset", "braceexpand", "deepspeed",
+                 "pipeline.train.data", "pipeline.eval")
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {})
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.startswith(STUB_PREFIXES):
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _Stub(spec.name)
+
+    def exec_module(self, module):
+        module.__path__ = []
+
+
+def import_reference():
+    import transformers  # noqa: real package, imported BEFORE the stub finder so its own
+    import transformers.modeling_outputs  # noqa  optional-dependency probes see the real environment
+    sys.meta_path.insert(0, _StubFinder())
+    sys.path.insert(0, REF)
+    import mmrec  # noqa: the reference's training script, unmodified
+    from pipeline.mm_utils.collate_rec import collate_fn
+    from pipeline.train.train_utils import get_checkpoint
+    return mmrec, collate_fn, get_checkpoint
+
+
+# ------------------------------------------------------------------------------------------------
+class Tok:
+    """Callable like the HF tokenizer at `mmrec.py:84-88`: tok(text)["input_ids"][-1]."""
+
+    def __init__(self, ids, pad):
+        self.ids, self.pad_token_id = ids, pad
+
+    def __call__(self, text, add_special_tokens=False):
+        return {"input_ids": [self.ids[text]]}
+
+
+class RecordingModel(torch.nn.Module):
+    def __init__(self, logits):
+        super().__init__()
+        self.logits = torch.nn.Parameter(logits.clone())
+        self.seen = {}
+
+    def forward(self, vision_x=None, lang_x=None, attention_mask=None, labels=None):
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+        self.seen = {"vision_x_shape": tuple(vision_x.shape), "labels": labels.clone()}
+        return CausalLMOutputWithPast(loss=self.logits.sum() * 0.0, logits=self.logits)
+
+
+class RecordingAccelerator:
+    sync_gradients = True
+
+    def __init__(self):
+        self.loss = None
+
+    @contextlib.contextmanager
+    def accumulate(self, model):
+        yield
+
+    def backward(self, loss):
+        self.loss = loss.detach().clone()
+        loss.backward()
+
+    def clip_grad_norm_(self, params, max_norm):
+        return None
+
+
+class _Noop:
+    param_groups = [{"lr": 0.0}]
+
+    def step(self):
+        pass
+
+    def zero_grad(self):
+        pass
+
+
+def run_reference_step(mmrec, batch, logits, tok_ids, pad, *, gamma, use_reweight):
+    args = argparse.Namespace(num_epochs=1, precision="fp32", task="rec", gamma=gamma, rank=0,
+                              use_reweight=use_reweight, mask_lm_head=False,
+                              gradient_accumulation_steps=1, batch_size=batch["input_ids"].shape[0],
+                              world_size=1, report_to_wandb=False, logging_steps=10 ** 9)
+    model, acc = RecordingModel(logits), RecordingAccelerator()
+    loader = [{"net_input": {k: v.clone() for k, v in batch.items()}}]
+    mmrec.train_one_epoch(args, model, 0, loader, Tok(tok_ids, pad), _Noop(), _Noop(), 0, acc, None)
+    return {"labels": model.seen["labels"], "vision_x_shape": model.seen["vision_x_shape"],
+            "loss": acc.loss, "dlogits": model.logits.grad.clone()}
+
+
+def lifted_get_grouped_params(weight_decay):
+    """`get_grouped_params` is a closure inside `main()` (`mmrec.py:609-631`): lift its FunctionDef
+    out of the parsed module and compile it unchanged; `args` is the only free variable."""
+    src = open(os.path.join(REF, "mmrec.py")).read()
+    tree = ast.parse(src)
+    node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "get_grouped_params")
+    mod = ast.Module(body=[node], type_ignores=[])
+    ns = {"args": argparse.Namespace(weight_decay=weight_decay)}
+    exec(compile(mod, "mmrec.py::get_grouped_params", "exec"), ns)
+    return ns["get_grouped_params"], node.lineno, node.end_lineno
+
+
+def main():
+    torch.set_num_threads(1)
+    sys.path.insert(0, ROOT)
+    from unimp_b200 import tiny_config
+    from unimp_b200.config import WORKLOADS, Workload
+    from unimp_b200.synth import make_batch
+
+    mmrec, collate_fn, get_checkpoint = import_reference()
+    cfg = tiny_config()
+    tk = cfg.tokens
+    tok_ids = {"<image>": tk.media, "<|endofchunk|>": tk.endofchunk, "<answer>": tk.answer}
+    V = cfg.vocab
+    g = torch.Generator().manual_seed(4321)
+
+    # ---- train-step cases: labels + focal loss + its gradient ---------------------------------
+    cases = []
+    b1 = make_batch(cfg, WORKLOADS["C1-tiny"], seed=1234, ragged=True)
+    b2 = make_batch(cfg, Workload("golden-b3", B=3, Ti=2, T=48, row_weights=(2.0, 1.0)), seed=77)
+    # hand-written adversarial rows for the state machine (mmrec.py:146-156): <answer> twice in a
+    # row, <|endofchunk|> outside an answer, pad inside an answer, <image> inside an answer,
+    # an answer that never closes, <answer> at position 0
+    A, E, M, P = tk.answer, tk.endofchunk, tk.media, tk.pad
+    adv = torch.tensor([
+        [1, 5, A, A, 7, E, E, 9, A, 11, P, 12, E, M, 13, A],
+        [A, 3, 4, E, M, 5, A, 6, M, 7, 8, 9, 10, 11, 12, 13],
+        [1, E, 2, M, 3, 4, 5, 6, 7, 8, 9, A, 10, 2, P, P],
+    ], dtype=torch.int64)
+    b3 = {"input_ids": adv, "attention_masks": (adv != P).long(),
+          "patch_images": torch.zeros(3, 1, 3, 2, 2), "weights": torch.tensor([1.0, 2.0, 0.5])}
+    for name, batch, gamma, use in [("c1_ragged_g2", b1, 2.0, True), ("b3_g2", b2, 2.0, True),
+                                    ("b3_g0.5", b2, 0.5, True), ("b3_plain", b2, 2.0, False),
+                                    ("adversarial_g2", b3, 2.0, True)]:
+        B, T = batch["input_ids"].shape
+        # logits on a 1/8 grid in [-6, 6): exact in fp32 AND bf16, stored as int8 (small fixture)
+        logits_i8 = torch.randint(-48, 48, (B, T, V), generator=g, dtype=torch.int8)
+        logits = logits_i8.float() * 0.125
+        out = run_reference_step(mmrec, batch, logits, tok_ids, tk.pad, gamma=gamma, use_reweight=use)
+        assert out["vision_x_shape"][2] == 1            # unsqueeze(2): (B, Ti, 1, C, H, W)
+        cases.append({"name": name, "input_ids": batch["input_ids"], "weights": batch["weights"],
+                      "logits_i8": logits_i8, "logits_scale": 0.125, "gamma": gamma, "use_reweight": use,
+                      "labels": out["labels"], "loss": out["loss"],
+                      # dense gradient is zero off the valid rows: keep only those
+                      "dlogits_rows": out["dlogits"].flatten(0, 1).abs().sum(-1).nonzero().flatten(),
+                      "dlogits_vals": out["dlogits"].flatten(0, 1)[
+                          out["dlogits"].flatten(0, 1).abs().sum(-1).nonzero().flatten()],
+                      "vision_x_shape": out["vision_x_shape"]})
+        print(name, "loss", float(out["loss"]), "n_valid", int((out["labels"][:, 1:] != -100).sum()))
+    torch.save({"tokens": {"answer": A, "endofchunk": E, "media": M, "pad": P}, "cases": cases,
+                "source": "UniMP/mmrec.py::train_one_epoch executed unmodified"},
+               os.path.join(HERE, "ref_train_step.pt"))
+
+    # ---- collate_fn ------------------------------------------------------------------------------
+    lens = [9, 14, 5]
+    samples = [{"net_input": {"input_ids": torch.randint(1, 90, (n,), generator=g),
+                              "attention_masks": torch.ones(n, dtype=torch.int64),
+                              "weights": w,
+                              "patch_images": torch.randn(2, 3, 4, 4, generator=g)}}
+               for n, w in zip(lens, [2.0, 1.0, 1.0])]
+    ref_batch = collate_fn(samples, pad_idx=tk.pad, eos_idx=tk.eos)
+    torch.save({"samples": samples, "pad_idx": tk.pad, "eos_idx": tk.eos, "batch": ref_batch,
+                "source": "UniMP/pipeline/mm_utils/collate_rec.py::collate_fn executed unmodified"},
+               os.path.join(HERE, "ref_collate.pt"))
+
+    # ---- get_checkpoint + weight-decay groups on the real tiny module tree ------------------------
+    names = [
+        "perceiver.latents", "perceiver.layers.0.0.norm_media.weight", "perceiver.layers.0.0.to_q.weight",
+        "perceiver.layers.0.1.0.bias", "perceiver.norm.weight",
+        "lang_encoder.gated_cross_attn_layers.0.attn_gate", "lang_encoder.gated_cross_attn_layers.0.ff_gate",
+        "lang_encoder.gated_cross_attn_layers.0.attn.norm.weight",
+        "lang_encoder.gated_cross_attn_layers.0.attn.norm.bias",
+        "lang_encoder.gated_cross_attn_layers.0.attn.to_q.weight",
+        "lang_encoder.gated_cross_attn_layers.0.attn.to_kv.weight",
+        "lang_encoder.gated_cross_attn_layers.0.attn.to_out.weight",
+        "lang_encoder.gated_cross_attn_layers.0.ff.0.weight", "lang_encoder.gated_cross_attn_layers.0.ff.0.bias",
+        "lang_encoder.gated_cross_attn_layers.0.ff.1.weight", "lang_encoder.gated_cross_attn_layers.0.ff.3.weight",
+        "lang_encoder.gpt_neox.embed_in.weight", "lang_encoder.embed_out.weight",
+        "lang_encoder.gpt_neox.layers.0.gated_cross_attn_layer.attn.to_q.weight",
+        "lang_encoder.gpt_neox.layers.0.gated_cross_attn_layer.ff.0.weight",
+        "lang_encoder.gpt_neox.layers.0.decoder_layer.attention.dense.weight",
+        "vision_encoder.transformer.resblocks.0.ln_1.weight",
+    ]
+
+    class _Named(torch.nn.Module):
+        def __init__(self, names):
+            super().__init__()
+            self._n = names
+            self._p = [torch.nn.Parameter(torch.zeros(1)) for _ in names]
+
+        def named_parameters(self, *a, **k):
+            return iter(zip(self._n, self._p))
+
+    ggp, l0, l1 = lifted_get_grouped_params(0.1)
+    m = _Named(names)
+    groups = ggp(m)
+    wd_ids = {id(p) for p in groups[0]["params"]}
+    decay = {n: (id(p) in wd_ids) for n, p in zip(m._n, m._p)}
+    assert groups[0]["weight_decay"] == 0.1 and groups[1]["weight_decay"] == 0.0
+
+    class _Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.frozen = torch.nn.Linear(3, 3)
+            self.train_me = torch.nn.Linear(3, 2, bias=False)
+            self.alias = torch.nn.ModuleList([self.frozen])   # same tensors under a 2nd name
+            self.register_buffer("buf", torch.zeros(2))
+            for p in self.frozen.parameters():
+                p.requires_grad_(False)
+
+    ck = get_checkpoint(_Toy())
+    torch.save({"decay": decay, "grouped_params_lines": (l0, l1), "toy_checkpoint_keys": sorted(ck.keys()),
+                "source": "mmrec.py::get_grouped_params (ast-lifted) and train_utils.py::get_checkpoint, unmodified"},
+               os.path.join(HERE, "ref_host_rules.pt"))
+    print("decay", sum(decay.values()), "of", len(decay), "| toy checkpoint keys", sorted(ck.keys()))
+
+
+if __name__ == "__main__":
+    main()
