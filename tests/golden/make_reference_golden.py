@@ -18,6 +18,12 @@ What is executed is the unmodified reference, imported from where it lies:
 * `get_grouped_params` / `apply_decay` (`UniMP/mmrec.py:609-631`) — nested inside `main()`, so its
   FunctionDef node is lifted out of the parsed source with `ast` and compiled as is.
 
+* `UniMP/xformers_model/clip.py::CLIPVisionModel` (`:488-543`; attention `:88-141`) — the in-tree
+  ViT tower.  Its only missing dependency is `xformers.ops.memory_efficient_attention`, for which a
+  dense statement of that op's documented contract is injected (inputs `(B, M, H, K)`,
+  `softmax(q kT * scale) v`); embeddings, pre-LN, blocks, quick-GELU MLP and the
+  `last_hidden_state` convention are the reference's code.
+
 No reference source is copied into the repo; only the small input/output vectors are committed.
 The third-party half (open_flamingo v2.0.1) is absent from /root/reference and stays unpinned.
 """
@@ -148,6 +154,46 @@ def lifted_get_grouped_params(weight_decay):
     return ns["get_grouped_params"], node.lineno, node.end_lineno
 
 
+def reference_vit_golden(cfg, g):
+    """Runs the reference's in-tree CLIP vision tower on the C1 tiny shape."""
+    xf, xo = types.ModuleType("xformers"), types.ModuleType("xformers.ops")
+
+    def memory_efficient_attention(q, k, v, attn_bias=None, p=0.0, scale=None):
+        assert attn_bias is None and p == 0.0
+        scale = q.shape[-1] ** -0.5 if scale is None else scale
+        a = (torch.einsum("bmhk,bnhk->bhmn", q.double(), k.double()) * scale).softmax(-1)
+        return torch.einsum("bhmn,bnhk->bmhk", a, v.double()).to(q.dtype)
+
+    xo.memory_efficient_attention = memory_efficient_attention
+    xo.LowerTriangularMask = type("LowerTriangularMask", (), {})
+    xf.ops = xo
+    sys.modules["xformers"], sys.modules["xformers.ops"] = xf, xo
+    from transformers import CLIPVisionConfig
+    from xformers_model import clip as ref_clip  # the reference's file, unmodified
+
+    vc = CLIPVisionConfig(hidden_size=cfg.vis_width, num_hidden_layers=cfg.vis_layers,
+                          num_attention_heads=cfg.vis_heads, intermediate_size=cfg.vis_mlp,
+                          image_size=cfg.image_size, patch_size=cfg.patch_size, hidden_act="quick_gelu")
+    model = ref_clip.CLIPVisionModel(vc).eval()
+    # weights on a 1/256 grid (exact in fp32 and bf16), stored as int8; LN weights around 1
+    sd_i8 = {}
+    for k, v in model.state_dict().items():
+        if not v.is_floating_point():
+            continue
+        q = torch.randint(-64, 64, v.shape, generator=g, dtype=torch.int8)
+        sd_i8[k] = q
+        base = 1.0 if (k.endswith("norm.weight") or "layer_norm" in k and k.endswith(".weight")
+                       or k.endswith("layrnorm.weight")) else 0.0
+        v.copy_(base + q.float() / 256.0)
+    pixels_i8 = torch.randint(-96, 96, (3, 3, cfg.image_size, cfg.image_size), generator=g, dtype=torch.int8)
+    with torch.no_grad():
+        out = model(pixel_values=pixels_i8.float() / 32.0).last_hidden_state
+    return {"state_i8": sd_i8, "state_scale": 1.0 / 256.0, "pixels_i8": pixels_i8, "pixel_scale": 1.0 / 32.0,
+            "last_hidden_state": out,
+            "source": "UniMP/xformers_model/clip.py::CLIPVisionModel executed unmodified; "
+                      "xformers.ops.memory_efficient_attention replaced by its dense definition"}
+
+
 def main():
     torch.set_num_threads(1)
     sys.path.insert(0, ROOT)
@@ -198,6 +244,11 @@ def main():
     torch.save({"tokens": {"answer": A, "endofchunk": E, "media": M, "pad": P}, "cases": cases,
                 "source": "UniMP/mmrec.py::train_one_epoch executed unmodified"},
                os.path.join(HERE, "ref_train_step.pt"))
+
+    # ---- the in-tree ViT tower ---------------------------------------------------------------
+    vit = reference_vit_golden(cfg, g)
+    torch.save(vit, os.path.join(HERE, "ref_vit_tower.pt"))
+    print("vit tokens", tuple(vit["last_hidden_state"].shape), "rms", float(vit["last_hidden_state"].pow(2).mean().sqrt()))
 
     # ---- collate_fn ------------------------------------------------------------------------------
     lens = [9, 14, 5]

@@ -151,3 +151,47 @@ def test_cuda_focal_ce_equals_the_reference_run(name, dtype, tol_l, tol_g):
     zero_rows = torch.ones(z.grad.flatten(0, 1).shape[0], dtype=torch.bool)
     zero_rows[c["dlogits_rows"]] = False
     assert z.grad.flatten(0, 1)[zero_rows.to(DEV)].abs().max() == 0
+
+
+# ------------------------------------------------------------------------------- the in-tree ViT tower
+
+def _vit_fixture():
+    blob = torch.load(os.path.join(GOLDEN, "ref_vit_tower.pt"), weights_only=False)
+    ln = ("norm.weight", "norm1.weight", "norm2.weight")
+    sd = {k: (1.0 if k.endswith(ln) else 0.0) + q.float() * blob["state_scale"]
+          for k, q in blob["state_i8"].items()}
+    return sd, blob["pixels_i8"].float() * blob["pixel_scale"], blob["last_hidden_state"]
+
+
+def test_oracle_vision_tower_equals_the_reference_xformers_clip():
+    """The oracle's tower (HF CLIPVisionModel) against reference `UniMP/xformers_model/clip.py`."""
+    from transformers import CLIPVisionModel
+
+    from unimp_b200 import tiny_config
+    from util import hf_configs
+
+    torch.set_num_threads(1)
+    sd, pixels, want = _vit_fixture()
+    vis = CLIPVisionModel(hf_configs(tiny_config())[0]).eval()
+    missing, unexpected = vis.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    with torch.no_grad():
+        got = vis(pixel_values=pixels).last_hidden_state
+    assert rel_err(got, want) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_cuda_vision_tower_equals_the_reference_xformers_clip(dtype, tol):
+    """Our ViT (tcgen05 attention for bf16, fused residual+LN, quick-GELU kernels) against the
+    reference's in-tree tower; patch tokens = last_hidden_state[:, 1:] (no post-LN)."""
+    from unimp_b200 import tiny_config
+    from unimp_b200.vit import VisionTransformer, load_hf_clip_vision_weights
+
+    cfg = tiny_config()
+    sd, pixels, want = _vit_fixture()
+    vit = VisionTransformer(image_size=cfg.image_size, patch_size=cfg.patch_size, width=cfg.vis_width,
+                            layers=cfg.vis_layers, heads=cfg.vis_heads, mlp=cfg.vis_mlp).to(DEV, dtype)
+    load_hf_clip_vision_weights(vit, {k: v.to(DEV, dtype) for k, v in sd.items()})
+    _, tokens = vit(pixels.to(DEV, dtype))
+    assert rel_err(tokens.float(), want[:, 1:]) < tol
