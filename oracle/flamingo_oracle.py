@@ -1,6 +1,8 @@
 """Plain-PyTorch restatement of the open_flamingo v2.0.1 model arithmetic (oracle).
 
-TEST INFRASTRUCTURE — see oracle/__init__.py.  PARITY UNPINNED.
+TEST INFRASTRUCTURE — see oracle/__init__.py.  PARITY UNPINNED for the open_flamingo classes
+below (the package is absent); the vision tower this file wraps (HF `CLIPVisionModel`) IS pinned
+against the reference's in-tree `UniMP/xformers_model/clip.py` (tests/test_reference_golden.py).
 
 The reference imports these classes from the un-vendored ``open_flamingo`` package
 (reference ``UniMP/mmrec.py:20-22``; pinned ``requirements.txt:35``); the call sites

@@ -1,8 +1,9 @@
 """Restatement of UniMP's in-tree label masking and focal-loss head (oracle).
 
-TEST INFRASTRUCTURE — see oracle/__init__.py.  PARITY UNPINNED (the reference has no
-fixtures for it), but unlike the model half this arithmetic IS in the reference tree, so
-every function cites the lines it follows.
+TEST INFRASTRUCTURE — see oracle/__init__.py.  PINNED: this arithmetic IS in the reference
+tree, every function cites the lines it follows, and tests/test_reference_golden.py checks it
+(labels bit-exact, loss and dloss/dlogits to 1e-6) against vectors obtained by running the
+unmodified `UniMP/mmrec.py::train_one_epoch` (tests/golden/make_reference_golden.py).
 """
 from __future__ import annotations
 
