@@ -206,7 +206,10 @@ def cpu_oracle_samples_per_s(cfg, wl, *, batch, steps, warmup, accum=1):
 class LaunchCounter:
     """Counts the kernels launched through the C ABI during one eager step (the graph replays the
     same launches).  Kernels per C-ABI call are the launch lists of the .cu files."""
-    PER_CALL = {"unimp_focal_ce_fwd": 2, "unimp_gate_residual_ln_bwd": 2}
+    # kernels per call: focal CE forward = row pass + fixed-order finish; LN backward = row pass
+    # (+ the column/gate fold only when d_gate / d_gamma / d_beta are requested: args 10-12, g_ln = 1)
+    PER_CALL = {"unimp_focal_ce_fwd": lambda a: 2,
+                "unimp_gate_residual_ln_bwd": lambda a: 2 if (((a[11] or a[12]) and a[1]) or a[10]) else 1}
 
     def __init__(self):
         self.calls = {}
@@ -228,13 +231,15 @@ class LaunchCounter:
             setattr(self.lib, n, f)
 
     def _wrap(self, name, fn):
+        per = self.PER_CALL.get(name, lambda a: 1)
+
         def w(*a):
-            self.calls[name] = self.calls.get(name, 0) + 1
+            self.calls[name] = self.calls.get(name, 0) + per(a)
             return fn(*a)
         return w
 
     def kernels(self):
-        return {n: c * self.PER_CALL.get(n, 1) for n, c in self.calls.items()}
+        return dict(self.calls)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -133,6 +133,8 @@ int unimp_gate_residual_ln_fwd(const void* branch, const void* x, const void* ga
  * d_x = g_xout + LNbwd(g_ln);  d_branch = d_x * tanh(gate);
  * d_gate = sum(d_x * branch) * (1 - tanh^2)  ; d_gamma/d_beta = column sums (`dtype`,
  * written not accumulated; any of the three may be NULL).
+ * Ungated residual (branch != NULL, gate == NULL): d_branch == d_x, `branch` is not read and
+ * d_branch may be NULL (the caller hands d_x to both inputs); if given it receives a copy.
  * partial is caller scratch of unimp_gate_residual_ln_bwd_workspace() bytes. */
 int64_t unimp_gate_residual_ln_bwd_workspace(int64_t rows, int D);
 int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void* branch,
@@ -188,6 +190,13 @@ int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const i
                          int rot, int64_t cs_batch_stride, int dtype, void* stream);
 /* CLIP QuickGELU x*sigmoid(1.702x), in place (ViT MLP; forward only: the tower is frozen). */
 int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream);
+/* Exact (erf) GELU of the FeedForward blocks: open_flamingo helpers.FeedForward's nn.GELU()
+ * (GatedCrossAttentionBlock.ff, PerceiverResampler ff) and GPT-NeoX mlp.act.
+ * y = x * Phi(x);  dx = dy * (Phi(x) + x * phi(x)).  n elements, contiguous, n % (16/sizeof) == 0.
+ * y may alias x; dx may alias dy.  bf16: Phi from a 1.5e-7-accurate rational erfc (well below bf16
+ * resolution); fp32: erff. */
+int unimp_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
+int unimp_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream);
 
 /* ---- f1: fused AdamW over a flat parameter group --------------------------------------
  * Replaces torch.optim.AdamW.step for one param group (reference UniMP/mmrec.py:671) with

@@ -191,6 +191,29 @@ def test_gate_residual_ln(dtype, tol, rows, D, mode):
         assert rel_err(got, want) < tol, mode
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("rows,D", [(1536, 2560), (771, 1024), (3, 8192), (50, 128)])
+@pytest.mark.parametrize("gated", [False, True])
+def test_residual_ln_backward_with_frozen_affine(dtype, tol, rows, D, gated):
+    """The LM / ViT towers' variant: LayerNorm parameters frozen (no column sums); ungated residual
+    hands ONE buffer to both d_branch and d_x.  Row counts that do not divide the persistent grid."""
+    torch.manual_seed(rows)
+    f64 = torch.float64
+    branch, x = (torch.randn(rows, D).to(dtype) for _ in range(2))
+    gamma, beta = (1 + 0.1 * torch.randn(D)).to(dtype), (0.1 * torch.randn(D)).to(dtype)
+    g1, g2 = (torch.randn(rows, D).to(dtype) for _ in range(2))
+    gate = torch.tensor([0.7]).to(dtype)
+    b_, x_ = branch.to(f64).requires_grad_(True), x.to(f64).requires_grad_(True)
+    xo = b_ * (gate.to(f64).tanh() if gated else 1.0) + x_
+    ln = torch.nn.functional.layer_norm(xo, (D,), gamma.to(f64), beta.to(f64), 1e-5)
+    (xo * g1.to(f64) + ln * g2.to(f64)).sum().backward()
+    db, dx = branch.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    xo_d, ln_d = ops().gate_residual_ln(db, dx, gate.to(DEV) if gated else None, gamma.to(DEV), beta.to(DEV), 1e-5)
+    (xo_d * g1.to(DEV) + ln_d * g2.to(DEV)).sum().backward()
+    for got, want in [(xo_d, xo), (ln_d, ln), (db.grad, b_.grad), (dx.grad, x_.grad)]:
+        assert rel_err(got, want) < tol
+
+
 # ------------------------------------------------------------------ focal CE
 
 @pytest.mark.parametrize("dtype,tol_l,tol_g", [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1e-3, 2e-2)])
@@ -301,6 +324,29 @@ def test_quick_gelu(dtype, tol):
     want = x.double() * torch.sigmoid(1.702 * x.double())
     got = ops().quick_gelu_(x.to(DEV).clone())
     assert rel_err(got, want) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 4e-3)])
+@pytest.mark.parametrize("shape", [(3, 8), (1536, 10240), (7, 4096), (64 * 12 + 1, 264)])
+def test_gelu_fwd_bwd_matches_exact_erf_gelu(dtype, tol, shape):
+    """unimp_gelu_fwd/bwd against fp64 erf-GELU (nn.GELU() of upstream's FeedForward, GPT-NeoX
+    mlp.act); inputs span the tails (|x| up to ~12) where the rational erfc must stay accurate in
+    ABSOLUTE terms.  bf16 bar = one rounding (2^-8); fp32 bar 2e-6."""
+    torch.manual_seed(shape[0])
+    x = (torch.randn(*shape) * 3.0).to(dtype)
+    x.view(-1)[:8] = torch.tensor([-12.0, -6.0, -3.0, -0.0, 0.0, 3.0, 6.0, 12.0]).to(dtype)
+    g = torch.randn(*shape).to(dtype)
+    xr = x.double().requires_grad_(True)
+    yr = torch.nn.functional.gelu(xr)
+    yr.backward(g.double())
+    xd = x.to(DEV).requires_grad_(True)
+    yd = ops().gelu(xd)
+    yd.backward(g.to(DEV))
+    assert rel_err(yd, yr) < tol and rel_err(xd.grad, xr.grad) < tol
+    # elementwise absolute bound too (a Frobenius norm hides tail errors)
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -22
+    assert ((yd.double().cpu() - yr.detach()).abs() <= ulp * yr.detach().abs() + 1e-6).all()
+    assert ((xd.grad.double().cpu() - xr.grad).abs() <= ulp * xr.grad.abs() + 1e-6 * (1 + g.double().abs())).all()
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])

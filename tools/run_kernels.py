@@ -68,6 +68,16 @@ timeit("gate_residual_ln_fwd", lambda: ops.gate_residual_ln(br, x, gate, gam, be
 xo, ln = ops.gate_residual_ln(br, x, gate, gam, bet)
 g1, g2 = torch.randn_like(xo), torch.randn_like(ln)
 timeit("gate_residual_ln_bwd", lambda: torch.autograd.grad((xo, ln), (br, x, gate, gam, bet), (g1, g2), retain_graph=True), 6 * rows * D * 2)
+# the LM towers' variant: ungated residual, frozen LayerNorm
+xo2, ln2 = ops.gate_residual_ln(br, x, None, gam.detach(), bet.detach())
+timeit("residual_ln_bwd_frozen", lambda: torch.autograd.grad((xo2, ln2), (br, x), (g1, g2), retain_graph=True), 4 * rows * D * 2)
+# exact GELU of the FeedForward blocks
+h = torch.randn(rows, 4 * D, device=dev, dtype=bf, requires_grad=True)
+timeit("gelu_fwd", lambda: ops.gelu(h), 2 * rows * 4 * D * 2)
+hy = ops.gelu(h)
+hg = torch.randn_like(hy)
+timeit("gelu_bwd", lambda: torch.autograd.grad(hy, h, hg, retain_graph=True), 3 * rows * 4 * D * 2)
+del h, hy, hg
 # K6 (img_gen-like: many valid rows) and rec-like (few valid rows)
 for nm, Tl, nvalid in (("focal_ce_rec", T, 4), ("focal_ce_imggen", 1024, 257)):
     z = torch.randn(B, Tl, V, device=dev, dtype=bf, requires_grad=True)

@@ -19,57 +19,55 @@ static inline int ln_threads(int D, int n_per_vec) {
   return t;
 }
 
-template <typename T>
-__global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ x,
-                                            const T* __restrict__ gate,
-                                            const T* __restrict__ gamma, const T* __restrict__ beta,
-                                            T* __restrict__ x_out, T* __restrict__ ln_out,
-                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
-                                            int D, float eps) {
+// SMALL: <= 128 threads per row (D <= 4096 bf16) compiled for <= 56 registers: 96-thread CTAs
+// at D = 2560 then sit 12 per SM and all 1536 rows of the 6 x 256 window are resident at once.
+template <typename T, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 128 : 1024, SMALL ? 9 : 1) gate_residual_ln_fwd_kernel(
+    const T* __restrict__ branch, const T* __restrict__ x, const T* __restrict__ gate,
+    const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ x_out,
+    T* __restrict__ ln_out, float* __restrict__ mean_o, float* __restrict__ rstd_o, int D, float eps) {
   constexpr int N = Vec16<T>::N;
   const int64_t row = blockIdx.x;
   const int nvec = D / N;
   const T* xr = x + row * D;
   const T* br = branch ? branch + row * D : nullptr;
-  float v[LN_VPT][N];
   const float tg = br ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
+  // The row stays in registers in its STORAGE type (packed bf16: 4 registers per 8 elements) and
+  // is unpacked on demand by each pass; every load of the row is issued before the first use, so
+  // a CTA pays one DRAM round trip, and <= 64 registers keep all rows of a 1536 x 2560
+  // activation resident in a single wave.
+  Vec16<T> xv[LN_VPT], bv[LN_VPT];
+#pragma unroll
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+      xv[k].load(xr + j * N);
+      if (br) bv[k].load_stream(br + j * N);
+    }
+  }
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < LN_VPT; ++k) {
     const int j = threadIdx.x + k * blockDim.x;
     if (j < nvec) {
-      Vec16<T> a;
-      a.load(xr + j * N);
-      a.unpack(v[k]);
+      float v[N];
+      xv[k].unpack(v);
       if (br) {
-        Vec16<T> b;
         float bf[N];
-        b.load_stream(br + j * N);
-        b.unpack(bf);
+        bv[k].unpack(bf);
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[k][i] = fmaf(bf[i], tg, v[k][i]);
+        for (int i = 0; i < N; ++i) v[i] = fmaf(bf[i], tg, v[i]);
         // the residual stream is stored in T: LN must see the rounded value the next
         // consumer reads, so statistics are taken on the rounded x_out.
-        Vec16<T> o;
-        o.pack(v[k]);
-        o.store(x_out + row * D + j * N);
-        o.unpack(v[k]);
+        xv[k].pack(v);
+        xv[k].store(x_out + row * D + j * N);
+        xv[k].unpack(v);
       }
 #pragma unroll
-      for (int i = 0; i < N; ++i) s += v[k][i];
+      for (int i = 0; i < N; ++i) s += v[i];
     }
   }
   if (!gamma) return;
-  // issue the affine-parameter loads now so their latency hides under the two reductions
-  Vec16<T> gv[LN_VPT], bv[LN_VPT];
-#pragma unroll
-  for (int k = 0; k < LN_VPT; ++k) {
-    const int j = threadIdx.x + k * blockDim.x;
-    if (j < nvec) {
-      gv[k].load(gamma + j * N);
-      bv[k].load(beta + j * N);
-    }
-  }
   __shared__ float sh[32];
   const float mean = block_sum(s, sh) / D;
   float q = 0.f;
@@ -77,9 +75,11 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
   for (int k = 0; k < LN_VPT; ++k) {
     const int j = threadIdx.x + k * blockDim.x;
     if (j < nvec) {
+      float v[N];
+      xv[k].unpack(v);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const float d = v[k][i] - mean;
+        const float d = v[i] - mean;
         q += d * d;
       }
     }
@@ -90,15 +90,27 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
     mean_o[row] = mean;
     rstd_o[row] = rstd;
   }
+  // gamma / beta are shared by every row (L1/L2 hits); their loads are issued together, after
+  // the reductions, so they do not hold registers while the row is in flight
+  Vec16<T> gv[LN_VPT], ev[LN_VPT];
 #pragma unroll
   for (int k = 0; k < LN_VPT; ++k) {
     const int j = threadIdx.x + k * blockDim.x;
     if (j < nvec) {
-      float gf[N], bf[N], o[N];
-      gv[k].unpack(gf);
-      bv[k].unpack(bf);
+      gv[k].load(gamma + j * N);
+      ev[k].load(beta + j * N);
+    }
+  }
 #pragma unroll
-      for (int i = 0; i < N; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gf[i], bf[i]);
+  for (int k = 0; k < LN_VPT; ++k) {
+    const int j = threadIdx.x + k * blockDim.x;
+    if (j < nvec) {
+      float v[N], gf[N], bf[N], o[N];
+      xv[k].unpack(v);
+      gv[k].unpack(gf);
+      ev[k].unpack(bf);
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[i] = fmaf((v[i] - mean) * rstd, gf[i], bf[i]);
       Vec16<T> ov;
       ov.pack(o);
       ov.store(ln_out + row * D + j * N);
@@ -106,13 +118,18 @@ __global__ void gate_residual_ln_fwd_kernel(const T* __restrict__ branch, const 
   }
 }
 
-// R row-groups of TG threads per CTA, each group walking its own rows, so that (nearly) every row
-// of a 768-row activation is in flight at once; column partials (d_gamma, d_beta) live in
-// registers per thread, are folded across the R groups through shared memory in a fixed order,
-// and leave the CTA as one partial row: partial[G][2*D + 1] (last = d_gate).
-constexpr int LN_BWD_MAX_R = 12;       // row-groups per CTA: R = clamp(192 / TG, 1, 12): small CTAs,
-                                       // so 2-3 of them fit the register file of an SM
-static inline int ln_bwd_r(int TG) { int r = 192 / TG; return r < 1 ? 1 : (r > LN_BWD_MAX_R ? LN_BWD_MAX_R : r); }
+// Backward.  R row-groups of TG threads per CTA, each group walking its own rows of a persistent
+// grid; a thread owns VPT 16-byte vectors of the row (VPT = 2 for D <= 8192 bf16: TG = 160 at
+// D = 2560, every lane busy).  Per row ALL operand loads (g_ln, x_out, g_xout, branch) are issued
+// before the first use, so a row costs one DRAM round trip (the previous version loaded g_xout /
+// branch only after the row reduction: two dependent round trips per row); gamma sits in
+// registers for the whole kernel.  Column partials (d_gamma, d_beta) live in registers per thread,
+// are folded across the R groups through shared memory in a fixed order (deterministic), and
+// leave the CTA as one partial row: partial[G][2*D + 1] (last = d_gate).
+// Ungated residual (gate == NULL): d_branch == d_x, so `branch` is not read and d_branch is only
+// written if the caller asks for it (ops.py hands d_x to both inputs): 4 passes instead of 6.
+constexpr int LN_BWD_MAX_R = 12;       // named barriers 1..12
+constexpr int LN_BWD_MAX_THREADS = 640;
 
 __device__ __forceinline__ float group_sum(float v, float* sh, int rg, int tg_threads, int t) {
   const int lane = t & 31, w = t >> 5, nw = tg_threads >> 5;
@@ -124,70 +141,82 @@ __device__ __forceinline__ float group_sum(float v, float* sh, int rg, int tg_th
   return warp_sum(r);
 }
 
-// COLS = false: the LayerNorm's affine parameters are frozen (the LM / ViT towers): no column
-// partials are kept, which frees 64 registers per thread and the final fold.
-// two sums with one pair of barriers
+// two sums with one pair of barriers (sh: 64 floats per group, up to 32 warps per group)
 __device__ __forceinline__ void group_sum2(float& a, float& b, float* sh, int rg, int tg_threads, int t) {
   const int lane = t & 31, w = t >> 5, nw = tg_threads >> 5;
   a = warp_sum(a);
   b = warp_sum(b);
   asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
-  if (lane == 0) { sh[w] = a; sh[16 + w] = b; }
+  if (lane == 0) { sh[w] = a; sh[32 + w] = b; }
   asm volatile("bar.sync %0, %1;" ::"r"(rg + 1), "r"(tg_threads) : "memory");
-  float ra = (lane < nw) ? sh[lane] : 0.f, rb = (lane < nw) ? sh[16 + lane] : 0.f;
+  float ra = (lane < nw) ? sh[lane] : 0.f, rb = (lane < nw) ? sh[32 + lane] : 0.f;
   a = warp_sum(ra);
   b = warp_sum(rb);
 }
 
-template <typename T, bool COLS>
-__global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ g_ln,
-                                            const T* __restrict__ branch, const T* __restrict__ x_out,
-                                            const T* __restrict__ gate,
-                                            const T* __restrict__ gamma,
-                                            const float* __restrict__ mean_i,
-                                            const float* __restrict__ rstd_i, T* __restrict__ d_x,
-                                            T* __restrict__ d_branch, float* __restrict__ partial,
-                                            int64_t rows, int D, int TG, int R) {
+// COLS = false: the LayerNorm's affine parameters are frozen (the LM / ViT towers): no column
+// partials are kept.
+template <typename T, bool COLS, int VPT>
+__global__ void __launch_bounds__(LN_BWD_MAX_THREADS)
+gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ g_ln,
+                            const T* __restrict__ branch, const T* __restrict__ x_out,
+                            const T* __restrict__ gate, const T* __restrict__ gamma,
+                            const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
+                            T* __restrict__ d_x, T* __restrict__ d_branch, float* __restrict__ partial,
+                            int64_t rows, int D, int TG, int R) {
   constexpr int N = Vec16<T>::N;
-  extern __shared__ float sdyn[];          // [2*D] column sums, then LN_BWD_R*32 scratch, then R
+  extern __shared__ float sdyn[];          // [2*D] column sums, then MAX_R*64 scratch, then MAX_R
   const int nvec = D / N;
   const int rg = threadIdx.x / TG, t = threadIdx.x - rg * TG;
-  float* sh = sdyn + 2 * D + rg * 32;
-  float* sgate = sdyn + 2 * D + LN_BWD_MAX_R * 32;
+  float* sh = sdyn + 2 * D + rg * 64;
+  float* sgate = sdyn + 2 * D + LN_BWD_MAX_R * 64;
   const bool has_ln = g_ln != nullptr && gamma != nullptr;
+  const bool gated = branch != nullptr && gate != nullptr;   // only then is `branch` needed
   const float tg = branch ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
-  float dg[COLS ? LN_VPT : 1][N], db[COLS ? LN_VPT : 1][N];
+  float dg[COLS ? VPT : 1][N], db[COLS ? VPT : 1][N];
   float dgate = 0.f;
   if (COLS) {
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k)
+    for (int k = 0; k < VPT; ++k)
 #pragma unroll
       for (int i = 0; i < N; ++i) dg[k][i] = db[k][i] = 0.f;
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sdyn[i] = 0.f;
   }
+  Vec16<T> gm_raw[VPT];
+  if (has_ln) {
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = t + k * TG;
+      if (j < nvec) gm_raw[k].load(gamma + j * N);
+    }
+  }
 
   for (int64_t row = (int64_t)blockIdx.x * R + rg; row < rows; row += (int64_t)gridDim.x * R) {
-    Vec16<T> gl_raw[LN_VPT], xo_raw[LN_VPT];
+    Vec16<T> gl_raw[VPT], xo_raw[VPT], gx_raw[VPT], br_raw[VPT];
     float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
+    const int64_t base = row * D;
+    // ---- every load of the row, up front -------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int j = t + k * TG;
+      if (j < nvec) {
+        if (has_ln) {
+          gl_raw[k].load_stream(g_ln + base + j * N);
+          xo_raw[k].load_stream(x_out + base + j * N);
+        }
+        if (g_xout) gx_raw[k].load_stream(g_xout + base + j * N);
+        if (gated) br_raw[k].load_stream(branch + base + j * N);
+      }
+    }
     if (has_ln) {
       mean = mean_i[row];
       rstd = rstd_i[row];
 #pragma unroll
-      for (int k = 0; k < LN_VPT; ++k) {
+      for (int k = 0; k < VPT; ++k) {
         const int j = t + k * TG;
         if (j < nvec) {
-          gl_raw[k].load_stream(g_ln + row * D + j * N);
-          xo_raw[k].load_stream(x_out + row * D + j * N);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < LN_VPT; ++k) {
-        const int j = t + k * TG;
-        if (j < nvec) {
-          Vec16<T> gmv;
           float gl[N], xo[N], gm[N];
-          gmv.load(gamma + j * N);
-          gmv.unpack(gm);
+          gm_raw[k].unpack(gm);
           gl_raw[k].unpack(gl);
           xo_raw[k].unpack(xo);
 #pragma unroll
@@ -207,23 +236,19 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
       s2 /= D;
     }
 #pragma unroll
-    for (int k = 0; k < LN_VPT; ++k) {
+    for (int k = 0; k < VPT; ++k) {
       const int j = t + k * TG;
       if (j < nvec) {
         float dx[N];
         if (g_xout) {
-          Vec16<T> a;
-          a.load_stream(g_xout + row * D + j * N);
-          a.unpack(dx);
+          gx_raw[k].unpack(dx);
         } else {
 #pragma unroll
           for (int i = 0; i < N; ++i) dx[i] = 0.f;
         }
         if (has_ln) {
-          Vec16<T> gmv;
           float gl[N], xo[N], gm[N];
-          gmv.load(gamma + j * N);
-          gmv.unpack(gm);
+          gm_raw[k].unpack(gm);
           gl_raw[k].unpack(gl);
           xo_raw[k].unpack(xo);
 #pragma unroll
@@ -234,12 +259,10 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
         }
         Vec16<T> o;
         o.pack(dx);
-        o.store(d_x + row * D + j * N);
-        if (branch) {
-          Vec16<T> b;
+        o.store(d_x + base + j * N);
+        if (gated) {
           float bf[N], dbr[N];
-          b.load_stream(branch + row * D + j * N);
-          b.unpack(bf);
+          br_raw[k].unpack(bf);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             dgate += dx[i] * bf[i];
@@ -247,7 +270,9 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
           }
           Vec16<T> ob;
           ob.pack(dbr);
-          ob.store(d_branch + row * D + j * N);
+          ob.store(d_branch + base + j * N);
+        } else if (d_branch) {
+          o.store(d_branch + base + j * N);   // ungated residual: d_branch == d_x
         }
       }
     }
@@ -259,7 +284,7 @@ __global__ void gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const 
   for (int g = 0; COLS && g < R; ++g) {
     if (rg == g && has_ln) {
 #pragma unroll
-      for (int k = 0; k < LN_VPT; ++k) {
+      for (int k = 0; k < VPT; ++k) {
         const int j = t + k * TG;
         if (j < nvec) {
 #pragma unroll
@@ -310,11 +335,82 @@ __global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ par
   }
 }
 
-static inline int ln_bwd_grid(int64_t rows, int R, bool cols) {
+// Launch geometry of the backward: VPT, threads per row group, row groups per CTA, grid.
+struct LnBwdGeom {
+  int vpt, TG, R, G, smem;
+};
+
+template <typename K>
+static int ln_bwd_ctas_per_sm(K kernel, int threads, int smem) {
+  int n = 0;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  return n;
+}
+
+template <typename T, bool COLS>
+static LnBwdGeom ln_bwd_geom(int64_t rows, int D) {
+  constexpr int N = 16 / (int)sizeof(T);
+  const int nvec = D / N;
+  LnBwdGeom g;
+  int tg2 = (((nvec + 1) / 2 + 31) / 32) * 32;
+  if (tg2 <= 512) {
+    g.vpt = 2;
+    g.TG = tg2;
+  } else {                       // wide rows (D > 8192 bf16): correctness path, spills
+    g.vpt = 4;
+    g.TG = (((nvec + 3) / 4 + 31) / 32) * 32;   // <= 512: the entry point bounds D
+  }
+  // column partials cost one partial row per CTA: few, fat CTAs (one per SM).  Without them,
+  // 320-thread CTAs (two or three per SM) keep more rows in flight.
+  const int target = COLS ? LN_BWD_MAX_THREADS : 320;
+  int R = target / g.TG;
+  R = R < 1 ? 1 : (R > LN_BWD_MAX_R ? LN_BWD_MAX_R : R);
+  g.R = R;
+  const int threads = g.TG * R;
+  g.smem = (2 * D + LN_BWD_MAX_R * 64 + LN_BWD_MAX_R) * (int)sizeof(float);
+  // resident CTAs per SM: asked of the runtime once per (kernel, threads, smem)
+  constexpr int NC = 16;
+  static int cached_key[NC], cached_val[NC], n_cached = 0;
+  const int key = (g.vpt << 28) ^ (threads << 17) ^ g.smem;
+  int per_sm = 0;
+  for (int i = 0; i < n_cached; ++i)
+    if (cached_key[i] == key) per_sm = cached_val[i];
+  if (!per_sm) {
+    per_sm = g.vpt == 2
+        ? ln_bwd_ctas_per_sm(gate_residual_ln_bwd_kernel<T, COLS, 2>, threads, g.smem)
+        : ln_bwd_ctas_per_sm(gate_residual_ln_bwd_kernel<T, COLS, 4>, threads, g.smem);
+    if (n_cached < NC) {
+      cached_key[n_cached] = key;
+      cached_val[n_cached] = per_sm;
+      ++n_cached;
+    }
+  }
+  int64_t gmax = (int64_t)per_sm * UNIMP_NUM_SMS;
+  if (gmax > 3 * UNIMP_NUM_SMS) gmax = 3 * UNIMP_NUM_SMS;   // workspace holds 3*SMs partial rows
+  // balanced passes: every CTA walks the same number of rows (no ragged last wave)
   const int64_t need = (rows + R - 1) / R;
-  // 192-thread CTAs: ~150 registers with column partials (2 CTAs/SM), ~96 without (3 CTAs/SM)
-  const int64_t g = cols ? 2 * UNIMP_NUM_SMS : 3 * UNIMP_NUM_SMS;
-  return (int)(need < g ? need : g);
+  const int64_t passes = (need + gmax - 1) / gmax;
+  g.G = (int)((need + passes - 1) / passes);
+  return g;
+}
+
+template <typename T, bool COLS>
+static void ln_bwd_launch(const LnBwdGeom& g, cudaStream_t st, const void* g_xout, const void* g_ln,
+                          const void* branch, const void* x_out, const void* gate, const void* gamma,
+                          const float* mean, const float* rstd, void* d_x, void* d_branch,
+                          void* partial, int64_t rows, int D) {
+  if (g.vpt == 2)
+    gate_residual_ln_bwd_kernel<T, COLS, 2><<<g.G, g.TG * g.R, g.smem, st>>>(
+        (const T*)g_xout, (const T*)g_ln, (const T*)branch, (const T*)x_out, (const T*)gate,
+        (const T*)gamma, mean, rstd, (T*)d_x, (T*)d_branch, (float*)partial, rows, D, g.TG, g.R);
+  else
+    gate_residual_ln_bwd_kernel<T, COLS, 4><<<g.G, g.TG * g.R, g.smem, st>>>(
+        (const T*)g_xout, (const T*)g_ln, (const T*)branch, (const T*)x_out, (const T*)gate,
+        (const T*)gamma, mean, rstd, (T*)d_x, (T*)d_branch, (float*)partial, rows, D, g.TG, g.R);
 }
 
 }  // namespace unimp
@@ -341,17 +437,18 @@ extern "C" int unimp_gate_residual_ln_fwd(const void* branch, const void* x, con
   if (rows == 0) return 0;
   const int threads = ln_threads(D, npv);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == UNIMP_BF16)
-    gate_residual_ln_fwd_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, st>>>(
-        (const __nv_bfloat16*)branch, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate,
-        (const __nv_bfloat16*)gamma,
-        (const __nv_bfloat16*)beta, (__nv_bfloat16*)x_out, (__nv_bfloat16*)ln_out, mean, rstd, D,
-        eps);
-  else
-    gate_residual_ln_fwd_kernel<float><<<(unsigned)rows, threads, 0, st>>>(
-        (const float*)branch, (const float*)x, (const float*)gate, (const float*)gamma,
-        (const float*)beta,
-        (float*)x_out, (float*)ln_out, mean, rstd, D, eps);
+#define UNIMP_LN_FWD_LAUNCH(TT, SM)                                                                   \
+  gate_residual_ln_fwd_kernel<TT, SM><<<(unsigned)rows, threads, 0, st>>>(                             \
+      (const TT*)branch, (const TT*)x, (const TT*)gate, (const TT*)gamma, (const TT*)beta, (TT*)x_out, \
+      (TT*)ln_out, mean, rstd, D, eps)
+  if (dtype == UNIMP_BF16) {
+    if (threads <= 128) UNIMP_LN_FWD_LAUNCH(__nv_bfloat16, true);
+    else UNIMP_LN_FWD_LAUNCH(__nv_bfloat16, false);
+  } else {
+    if (threads <= 128) UNIMP_LN_FWD_LAUNCH(float, true);
+    else UNIMP_LN_FWD_LAUNCH(float, false);
+  }
+#undef UNIMP_LN_FWD_LAUNCH
   UNIMP_CHECK_LAUNCH();
   return 0;
 }
@@ -371,49 +468,42 @@ extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, 
   UNIMP_CHECK_ARG(g_xout || g_ln, UNIMP_E_NULL, "gate_residual_ln_bwd: no incoming gradient");
   UNIMP_CHECK_ARG(!g_ln || (gamma && x_out && mean && rstd), UNIMP_E_NULL,
                   "gate_residual_ln_bwd: g_ln given without gamma/x_out/mean/rstd");
-  UNIMP_CHECK_ARG(!branch || d_branch, UNIMP_E_NULL,
-                  "gate_residual_ln_bwd: branch given without d_branch");
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE,
                   "gate_residual_ln_bwd: dtype");
   const int npv = dtype == UNIMP_BF16 ? 8 : 4;
-  UNIMP_CHECK_ARG(rows > 0 && D > 0 && D % npv == 0 && D / npv <= 1024 * LN_VPT, UNIMP_E_SHAPE,
-                  "gate_residual_ln_bwd: bad rows/D");
+  UNIMP_CHECK_ARG(rows > 0 && D > 0 && D % npv == 0 && D / npv <= 2048, UNIMP_E_SHAPE,
+                  "gate_residual_ln_bwd: bad rows/D (D=%d must be a multiple of %d and <= %d)", D, npv,
+                  2048 * npv);
   UNIMP_CHECK_ARG(aligned16(g_xout) && aligned16(g_ln) && aligned16(branch) && aligned16(x_out) &&
                       aligned16(gamma) && aligned16(d_x) && aligned16(d_branch),
                   UNIMP_E_ALIGN, "gate_residual_ln_bwd: pointers must be 16-byte aligned");
-  const int TG = ln_threads(D, npv);
-  const int R = ln_bwd_r(TG);
-  UNIMP_CHECK_ARG(TG * R <= 384, UNIMP_E_SHAPE,
-                  "gate_residual_ln_bwd: D=%d too large for the register budget", D);
-  const int threads = TG * R;
-  const int smem = (2 * D + LN_BWD_MAX_R * 32 + LN_BWD_MAX_R) * (int)sizeof(float);
+  UNIMP_CHECK_ARG(!(branch && gate) || d_branch, UNIMP_E_NULL,
+                  "gate_residual_ln_bwd: gated branch given without d_branch");
   cudaStream_t st = (cudaStream_t)stream;
   const bool cols = (d_gamma || d_beta) && g_ln;
-  const int G = ln_bwd_grid(rows, R, cols);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<__nv_bfloat16, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gate_residual_ln_bwd_kernel<float, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-#define UNIMP_LN_BWD_LAUNCH(TT, CC)                                                                  \
-  gate_residual_ln_bwd_kernel<TT, CC><<<G, threads, smem, st>>>(                                      \
-      (const TT*)g_xout, (const TT*)g_ln, (const TT*)branch, (const TT*)x_out, (const TT*)gate,       \
-      (const TT*)gamma, mean, rstd, (TT*)d_x, (TT*)d_branch, (float*)partial, rows, D, TG, R)
+  LnBwdGeom g;
   if (dtype == UNIMP_BF16) {
-    if (cols) UNIMP_LN_BWD_LAUNCH(__nv_bfloat16, true);
-    else UNIMP_LN_BWD_LAUNCH(__nv_bfloat16, false);
+    if (cols) {
+      g = ln_bwd_geom<__nv_bfloat16, true>(rows, D);
+      ln_bwd_launch<__nv_bfloat16, true>(g, st, g_xout, g_ln, branch, x_out, gate, gamma, mean, rstd, d_x,
+                                         d_branch, partial, rows, D);
+    } else {
+      g = ln_bwd_geom<__nv_bfloat16, false>(rows, D);
+      ln_bwd_launch<__nv_bfloat16, false>(g, st, g_xout, g_ln, branch, x_out, gate, gamma, mean, rstd, d_x,
+                                          d_branch, partial, rows, D);
+    }
   } else {
-    if (cols) UNIMP_LN_BWD_LAUNCH(float, true);
-    else UNIMP_LN_BWD_LAUNCH(float, false);
+    if (cols) {
+      g = ln_bwd_geom<float, true>(rows, D);
+      ln_bwd_launch<float, true>(g, st, g_xout, g_ln, branch, x_out, gate, gamma, mean, rstd, d_x,
+                                 d_branch, partial, rows, D);
+    } else {
+      g = ln_bwd_geom<float, false>(rows, D);
+      ln_bwd_launch<float, false>(g, st, g_xout, g_ln, branch, x_out, gate, gamma, mean, rstd, d_x,
+                                  d_branch, partial, rows, D);
+    }
   }
-#undef UNIMP_LN_BWD_LAUNCH
+  const int G = g.G;
   UNIMP_CHECK_LAUNCH();
   if (!cols && !d_gate) return 0;
   const int W = 2 * D + 1;

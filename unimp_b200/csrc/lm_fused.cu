@@ -4,6 +4,11 @@
 //       chunk / cat / rotate_half temporaries (HF apply_rotary_pos_emb: ~10 launches -> 1);
 //       backward un-rotates dq/dk and packs dq|dk|dv into d_qkv in one pass.
 //   unimp_quick_gelu : x * sigmoid(1.702 x), in place (CLIP ViT MLP, forward only).
+//   unimp_gelu_fwd/bwd : exact (erf) GELU of the FeedForward blocks (GatedCrossAttentionBlock.ff,
+//       PerceiverResampler ff, GPT-NeoX mlp.act).  HBM-bound by design: 4 vectors in flight per
+//       thread; in bf16 the normal CDF comes from a 1.5e-7-accurate rational erfc (2 MUFU + ~12
+//       FP32 ops per element instead of erff's ~25, which is what keeps the stock kernel
+//       issue-bound at half the HBM rate); fp32 (the 1e-4 parity mode) uses erff itself.
 #include "common.cuh"
 
 namespace unimp {
@@ -118,6 +123,92 @@ __global__ void quick_gelu_kernel(T* __restrict__ x, int64_t nvec) {
   }
 }
 
+// Phi(x) (standard normal CDF) and phi(x) (its density).
+template <bool FAST>
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float E = __expf(-0.5f * x * x);
+  pdf = 0.3989422804014327f * E;
+  if (FAST) {
+    // erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt2
+    // (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7): shares exp(-x^2/2) with the density.
+    const float z = fabsf(x) * 0.7071067811865476f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float half_erfc = 0.5f * p * t * E;          // 0.5 erfc(|z|) = Phi(-|x|)
+    cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
+  } else {
+    cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
+  }
+}
+
+constexpr int GELU_U = 4;   // 16-byte vectors in flight per thread and operand
+
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                       int64_t nvec) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < nvec; j0 += stride * GELU_U) {
+    Vec16<T> v[GELU_U];
+#pragma unroll
+    for (int u = 0; u < GELU_U; ++u)
+      if (j0 + u * stride < nvec) v[u].load_stream(x + (j0 + u * stride) * N);
+#pragma unroll
+    for (int u = 0; u < GELU_U; ++u) {
+      if (j0 + u * stride < nvec) {
+        float f[N];
+        v[u].unpack(f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          float c, d;
+          normal_cdf_pdf<FAST>(f[i], c, d);
+          f[i] *= c;
+        }
+        v[u].pack(f);
+        v[u].store(y + (j0 + u * stride) * N);
+      }
+    }
+  }
+}
+
+// dx = dy * (Phi(x) + x phi(x))
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                       T* __restrict__ dx, int64_t nvec) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < nvec; j0 += stride * GELU_U) {
+    Vec16<T> v[GELU_U], g[GELU_U];
+#pragma unroll
+    for (int u = 0; u < GELU_U; ++u) {
+      if (j0 + u * stride < nvec) {
+        v[u].load_stream(x + (j0 + u * stride) * N);
+        g[u].load_stream(dy + (j0 + u * stride) * N);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GELU_U; ++u) {
+      if (j0 + u * stride < nvec) {
+        float f[N], gf[N];
+        v[u].unpack(f);
+        g[u].unpack(gf);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          float c, d;
+          normal_cdf_pdf<FAST>(f[i], c, d);
+          gf[i] *= fmaf(f[i], d, c);
+        }
+        g[u].pack(gf);
+        g[u].store(dx + (j0 + u * stride) * N);
+      }
+    }
+  }
+}
+
 }  // namespace unimp
 
 using namespace unimp;
@@ -196,6 +287,52 @@ extern "C" int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream) {
     quick_gelu_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n / npv);
   else
     quick_gelu_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, n / npv);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+static int gelu_check(const char* who, const void* a, const void* b, const void* c, int64_t n, int dtype) {
+  UNIMP_CHECK_ARG(a && b && c, UNIMP_E_NULL, "%s: NULL pointer", who);
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "%s: dtype", who);
+  const int npv = dtype == UNIMP_BF16 ? 8 : 4;
+  UNIMP_CHECK_ARG(n >= 0 && n % npv == 0 && aligned16(a) && aligned16(b) && aligned16(c), UNIMP_E_ALIGN,
+                  "%s: n %% %d != 0 or unaligned pointer", who, npv);
+  return 0;
+}
+
+static unsigned gelu_blocks(int64_t nvec) {
+  // one pass of GELU_U vectors per thread when it fits; never more than 8 CTAs per SM
+  int64_t blocks = (nvec + 256 * GELU_U - 1) / (256 * GELU_U);
+  if (blocks > 8 * UNIMP_NUM_SMS) blocks = 8 * UNIMP_NUM_SMS;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+extern "C" int unimp_gelu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
+  int rc = gelu_check("gelu_fwd", x, y, y, n, dtype);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  const int64_t nvec = n / (dtype == UNIMP_BF16 ? 8 : 4);
+  if (dtype == UNIMP_BF16)
+    gelu_fwd_kernel<__nv_bfloat16, true><<<gelu_blocks(nvec), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec);
+  else
+    gelu_fwd_kernel<float, false><<<gelu_blocks(nvec), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (float*)y, nvec);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int unimp_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream) {
+  int rc = gelu_check("gelu_bwd", x, dy, dx, n, dtype);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  const int64_t nvec = n / (dtype == UNIMP_BF16 ? 8 : 4);
+  if (dtype == UNIMP_BF16)
+    gelu_bwd_kernel<__nv_bfloat16, true><<<gelu_blocks(nvec), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec);
+  else
+    gelu_bwd_kernel<float, false><<<gelu_blocks(nvec), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (const float*)dy, (float*)dx, nvec);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }

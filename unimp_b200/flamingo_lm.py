@@ -124,6 +124,15 @@ def _neox_fusable(layer, x, kw) -> bool:
     return att.rotary_ndims % 2 == 0 and (att.rotary_ndims // 2) % npv == 0 and att.head_size % npv == 0
 
 
+def _is_exact_gelu(act) -> bool:
+    """GPT-NeoX `hidden_act="gelu"` (RedPajama-INCITE): HF GELUActivation / nn.GELU, erf form."""
+    from transformers.activations import GELUActivation
+
+    if isinstance(act, GELUActivation):
+        return act.act is torch.nn.functional.gelu
+    return isinstance(act, torch.nn.GELU) and act.approximate == "none"
+
+
 def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None):
     """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
     our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
@@ -149,14 +158,15 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
                                        scale=att.scaling)
     o = F.linear(a.transpose(1, 2).reshape(B, T, D), att.dense.weight, att.dense.bias)
     mlp = layer.mlp
+    act = ops.gelu if _is_exact_gelu(mlp.act) else mlp.act
     if layer.use_parallel_residual:
         h2 = ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps)
-        m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+        m = F.linear(act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
                      mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
         x1 = ops.gate_residual(o, x, None)
     else:
         x1, h2 = ops.gate_residual_ln(o, x, None, ln2.weight, ln2.bias, ln2.eps)
-        m = F.linear(mlp.act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+        m = F.linear(act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
                      mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
     if next_ln is not None:
         return ops.gate_residual_ln(m, x1, None, next_ln.weight, next_ln.bias, next_ln.eps)

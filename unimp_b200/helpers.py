@@ -33,7 +33,7 @@ def FeedForward(dim: int, mult: int = 4) -> nn.Sequential:
 def _ff_tail(ff: nn.Sequential, ln_out: torch.Tensor) -> torch.Tensor:
     """Linear -> GELU -> Linear of a FeedForward whose LayerNorm was already applied (fused)."""
     h = ops.linear_acc(ln_out, ff[1].weight)
-    h = F.gelu(h)
+    h = ops.gelu(h)
     return ops.linear_acc(h, ff[3].weight)
 
 

@@ -119,7 +119,30 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     rec("gate_residual_ln_bwd", _time_graph([lambda o=o, x=x, b=b, g=g: torch.autograd.grad(
         o, (b, x, gate, gam, bet), (g, g), retain_graph=True) for o, x, b, g in zip(outs, xs, brs, g1s)]),
         6 * rows * D * es, 0.0, K)
-    del xs, brs, outs, g1s, gfw
+    del outs, gfw
+    # the LM towers' variant: ungated residual + frozen LayerNorm (no column sums, d_branch == d_x)
+    gam_f, bet_f = gam.detach(), bet.detach()
+    outs = [ops.gate_residual_ln(b, x, None, gam_f, bet_f) for x, b in zip(xs, brs)]
+    rec("residual_ln_bwd_frozen", _time_graph([lambda o=o, x=x, b=b, g=g: torch.autograd.grad(
+        o, (b, x), (g, g), retain_graph=True) for o, x, b, g in zip(outs, xs, brs, g1s)]),
+        4 * rows * D * es, 0.0, K)
+    del xs, brs, outs, g1s
+    # ---- exact GELU of the FeedForward blocks (rows x 4D) ---------------------------------------
+    F4 = cfg.ff_mult * D
+    K = _k(2 * rows * F4 * es, cap=8)
+    hs = [torch.randn(rows, F4, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    rec("gelu_fwd", _time_graph([lambda h=h: ops.gelu(h) for h in hs]), 2 * rows * F4 * es, 0.0, K)
+    ys = [ops.gelu(h) for h in hs]
+    gys = [torch.randn(rows, F4, device=dev, dtype=dtype) for _ in range(K)]
+    rec("gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
+                                 for y, h, g in zip(ys, hs, gys)]), 3 * rows * F4 * es, 0.0, K)
+    # the stock kernels at the same shape, for the record (not on the product path)
+    rec("torch_gelu_fwd", _time_graph([lambda h=h: torch.nn.functional.gelu(h) for h in hs]),
+        2 * rows * F4 * es, 0.0, K)
+    ts = [torch.nn.functional.gelu(h) for h in hs]
+    rec("torch_gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
+                                       for y, h, g in zip(ts, hs, gys)]), 3 * rows * F4 * es, 0.0, K)
+    del hs, ys, ts, gys
     # ---- K6 focal CE -----------------------------------------------------------------------------
     nv = n_valid_rows if n_valid_rows else max(1, B * (Ti + 2))
     z = [torch.randn(B, T, V, device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]

@@ -221,7 +221,10 @@ class _GateResidualLN(torch.autograd.Function):
             g_ln = g_ln.contiguous()
         lib = _lib.load()
         d_x = torch.empty_like(xo)
-        d_branch = torch.empty_like(xo) if has_b else None
+        # ungated residual (gate None): d_branch == d_x, the kernel neither reads `branch` nor
+        # writes a second copy; the same tensor is handed to both inputs
+        gated = has_b and gate is not None
+        d_branch = torch.empty_like(xo) if gated else None
         need_gate = has_b and gate is not None and ctx.needs_input_grad[2]
         need_affine = has_ln and g_ln is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         d_gate = torch.empty_like(gate) if need_gate else None
@@ -238,7 +241,7 @@ class _GateResidualLN(torch.autograd.Function):
         if has_ln and d_gamma is None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
             d_gamma = torch.zeros_like(gamma)
             d_beta = torch.zeros_like(gamma)
-        return d_branch, d_x, d_gate, d_gamma, d_beta, None
+        return (d_branch if gated else (d_x if has_b else None)), d_x, d_gate, d_gamma, d_beta, None
 
 
 def gate_residual_ln(branch, x, gate, gamma, beta, eps: float = 1e-5):
@@ -364,6 +367,32 @@ def quick_gelu_(x):
     assert x.is_contiguous()
     check(_lib.load().unimp_quick_gelu(x.data_ptr(), x.numel(), _dt(x), _stream()), "unimp_quick_gelu")
     return x
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(_lib.load().unimp_gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _dt(x), _stream()),
+              "unimp_gelu_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        check(_lib.load().unimp_gelu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(),
+                                         _dt(x), _stream()), "unimp_gelu_bwd")
+        return dx
+
+
+def gelu(x):
+    """Exact (erf) GELU, `nn.GELU()` of upstream's FeedForward and GPT-NeoX `mlp.act`
+    (`unimp_gelu_fwd/bwd`; numel must be a multiple of 8 (bf16) / 4 (fp32))."""
+    return _Gelu.apply(x)
 
 
 # --------------------------------------------------------------------------- direct grad accumulation
