@@ -13,98 +13,131 @@
 
 namespace unimp {
 
-// out[b,t,h,{q,k,v},:] = rotary(qkv) (v and the non-rotary tail copied); thread = one 16-byte
-// vector.  cos/sin: (cb, T, rot) with the two halves duplicated (HF layout).
-template <typename T>
-__global__ void rotary_qkv_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out,
-                                      const T* __restrict__ cs, const T* __restrict__ sn, int64_t total,
-                                      int Tn, int H, int dh, int rot, int64_t cs_bstride) {
-  constexpr int N = Vec16<T>::N;
-  const int half = rot / 2, vpd = dh / N;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int v = (int)(idx % vpd);
-  const int which = (int)((idx / vpd) % 3);
-  const int64_t bth = idx / (3 * vpd);
-  const int64_t bt = bth / H;
-  const int t = (int)(bt % Tn);
-  const int64_t b = bt / Tn;
-  const int d0 = v * N;
-  const T* src = qkv + bth * 3 * dh + which * dh;
-  T* dst = out + bth * 3 * dh + which * dh + d0;
-  Vec16<T> x;
-  x.load(src + d0);
-  if (which == 2 || d0 >= rot) {
-    x.store(dst);
-    return;
-  }
-  // q*cos + rotate_half(q)*sin: first half: x1 c - x2 s ; second half: x2 c + x1 s
-  const bool first = d0 < half;
-  Vec16<T> xo, c, s_;
-  xo.load(src + (first ? d0 + half : d0 - half));
-  c.load(cs + b * cs_bstride + (int64_t)t * rot + d0);
-  s_.load(sn + b * cs_bstride + (int64_t)t * rot + d0);
-  float xf[N], xof[N], cf[N], sf[N], o[N];
-  x.unpack(xf); xo.unpack(xof); c.unpack(cf); s_.unpack(sf);
-#pragma unroll
-  for (int i = 0; i < N; ++i) o[i] = first ? xf[i] * cf[i] - xof[i] * sf[i] : xf[i] * cf[i] + xof[i] * sf[i];
-  Vec16<T> ov;
-  ov.pack(o);
-  ov.store(dst);
+// Work decomposition shared by the two rotary kernels.  One CTA per (b, t) row of the packed
+// (B, T, H, 3, dh) projection; a work item is (head, {q,k,v}, slot): slot p < hv owns the vector
+// pair (p, p + hv) of the two rotary halves (hv = rot/2 / N) — the rotation reads x1 and x2 once
+// and writes both outputs, instead of every output vector re-reading its partner — and slots
+// p >= hv copy one vector of the non-rotary tail.  32-bit index math only (the previous
+// one-vector-per-thread version spent its time in six 64-bit divisions per thread).
+struct RotaryGeom {
+  int hv, P, items;   // vectors per rotary half, slots per (head, part), items per row
+};
+
+__device__ __forceinline__ void rotary_item(int it, const RotaryGeom& g, int& h, int& which, int& p) {
+  const unsigned hw = (unsigned)it / (unsigned)g.P;
+  p = it - (int)hw * g.P;
+  h = (int)(hw / 3u);
+  which = (int)(hw - 3u * (unsigned)h);
 }
 
-// d_qkv[b,t,h,{q,k,v},:] from dq/dk/dv (B,H,T,dh) strided views; thread = one 16-byte vector.
+// out[b,t,h,{q,k,v},:] = rotary(qkv) (v and the non-rotary tail copied).
+// cos/sin: (cb, T, rot), HF layout (the two halves need not be duplicates: both are read).
 template <typename T>
-__global__ void rotary_qkv_bwd_kernel(const T* __restrict__ dq, const T* __restrict__ dk,
-                                      const T* __restrict__ dv, int64_t q_sb, int64_t q_sh, int64_t q_st,
-                                      int64_t k_sb, int64_t k_sh, int64_t k_st, int64_t v_sb, int64_t v_sh,
-                                      int64_t v_st, const T* __restrict__ cs, const T* __restrict__ sn,
-                                      T* __restrict__ d_qkv, int64_t total, int Tn, int H, int dh, int rot,
-                                      int64_t cs_bstride) {
+__global__ void __launch_bounds__(256) rotary_qkv_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out,
+                                                             const T* __restrict__ cs, const T* __restrict__ sn,
+                                                             int Tn, int H, int dh, int rot, int64_t cs_bstride,
+                                                             RotaryGeom g) {
   constexpr int N = Vec16<T>::N;
-  const int half = rot / 2, vpd = dh / N;  // vectors per head-dim
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int v = (int)(idx % vpd);
-  const int which = (int)((idx / vpd) % 3);
-  const int64_t bth = idx / (3 * vpd);
-  const int h = (int)(bth % H);
-  const int64_t bt = bth / H;
-  const int t = (int)(bt % Tn);
-  const int64_t b = bt / Tn;
-  const T* src = which == 0 ? dq + b * q_sb + h * q_sh + (int64_t)t * q_st
-               : which == 1 ? dk + b * k_sb + h * k_sh + (int64_t)t * k_st
-                            : dv + b * v_sb + h * v_sh + (int64_t)t * v_st;
-  T* dst = d_qkv + bth * 3 * dh + which * dh + v * N;
-  const int d0 = v * N;
-  Vec16<T> g;
-  g.load(src + d0);
-  if (which == 2 || d0 >= rot) {
-    g.store(dst);
-    return;
-  }
-  // out1 = x1 c1 - x2 s1 ; out2 = x2 c2 + x1 s2   =>   dx1 = g1 c1 + g2 s2 ; dx2 = -g1 s1 + g2 c2
-  const bool first = d0 < half;
-  Vec16<T> go, c, s;
-  go.load(src + (first ? d0 + half : d0 - half));
+  const int64_t row = blockIdx.x;
+  const int t = (int)(row % Tn);
+  const int64_t b = row / Tn;
+  const int half = rot / 2;
   const T* cp = cs + b * cs_bstride + (int64_t)t * rot;
   const T* sp = sn + b * cs_bstride + (int64_t)t * rot;
-  float gf[N], gof[N], cf[N], sf[N], o[N];
-  g.unpack(gf); go.unpack(gof);
-  if (first) {
-    c.load(cp + d0); s.load(sp + d0 + half);
-    c.unpack(cf); s.unpack(sf);
+  const T* srow = qkv + row * H * 3 * dh;
+  T* drow = out + row * H * 3 * dh;
+  for (int it = threadIdx.x; it < g.items; it += blockDim.x) {
+    int h, which, p;
+    rotary_item(it, g, h, which, p);
+    const int off = (h * 3 + which) * dh;
+    if (p >= g.hv) {                               // non-rotary tail: one vector
+      const int d = rot + (p - g.hv) * N;
+      Vec16<T> x;
+      x.load_stream(srow + off + d);
+      x.store(drow + off + d);
+      continue;
+    }
+    const int d0 = p * N;
+    Vec16<T> x1, x2;
+    x1.load_stream(srow + off + d0);
+    x2.load_stream(srow + off + d0 + half);
+    if (which == 2) {
+      x1.store(drow + off + d0);
+      x2.store(drow + off + d0 + half);
+      continue;
+    }
+    // q*cos + rotate_half(q)*sin: first half: x1 c1 - x2 s1 ; second half: x2 c2 + x1 s2
+    Vec16<T> c1, s1, c2, s2;
+    c1.load(cp + d0); s1.load(sp + d0);
+    c2.load(cp + d0 + half); s2.load(sp + d0 + half);
+    float a[N], bb[N], c1f[N], s1f[N], c2f[N], s2f[N], o1[N], o2[N];
+    x1.unpack(a); x2.unpack(bb); c1.unpack(c1f); s1.unpack(s1f); c2.unpack(c2f); s2.unpack(s2f);
 #pragma unroll
-    for (int i = 0; i < N; ++i) o[i] = gf[i] * cf[i] + gof[i] * sf[i];
-  } else {
-    c.load(cp + d0); s.load(sp + d0 - half);
-    c.unpack(cf); s.unpack(sf);
-#pragma unroll
-    for (int i = 0; i < N; ++i) o[i] = gf[i] * cf[i] - gof[i] * sf[i];
+    for (int i = 0; i < N; ++i) {
+      o1[i] = a[i] * c1f[i] - bb[i] * s1f[i];
+      o2[i] = bb[i] * c2f[i] + a[i] * s2f[i];
+    }
+    x1.pack(o1); x2.pack(o2);
+    x1.store(drow + off + d0);
+    x2.store(drow + off + d0 + half);
   }
-  Vec16<T> ov;
-  ov.pack(o);
-  ov.store(dst);
+}
+
+// d_qkv[b,t,h,{q,k,v},:] from dq/dk/dv (B,H,T,dh) strided views: un-rotates dq/dk and packs
+// dq|dk|dv in one pass.
+template <typename T>
+__global__ void __launch_bounds__(256) rotary_qkv_bwd_kernel(
+    const T* __restrict__ dq, const T* __restrict__ dk, const T* __restrict__ dv, int64_t q_sb, int64_t q_sh,
+    int64_t q_st, int64_t k_sb, int64_t k_sh, int64_t k_st, int64_t v_sb, int64_t v_sh, int64_t v_st,
+    const T* __restrict__ cs, const T* __restrict__ sn, T* __restrict__ d_qkv, int Tn, int H, int dh, int rot,
+    int64_t cs_bstride, RotaryGeom g) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t row = blockIdx.x;
+  const int t = (int)(row % Tn);
+  const int64_t b = row / Tn;
+  const int half = rot / 2;
+  const T* cp = cs + b * cs_bstride + (int64_t)t * rot;
+  const T* sp = sn + b * cs_bstride + (int64_t)t * rot;
+  const T* qb = dq + b * q_sb + (int64_t)t * q_st;
+  const T* kb = dk + b * k_sb + (int64_t)t * k_st;
+  const T* vb = dv + b * v_sb + (int64_t)t * v_st;
+  T* drow = d_qkv + row * H * 3 * dh;
+  for (int it = threadIdx.x; it < g.items; it += blockDim.x) {
+    int h, which, p;
+    rotary_item(it, g, h, which, p);
+    const T* src = which == 0 ? qb + h * q_sh : which == 1 ? kb + h * k_sh : vb + h * v_sh;
+    T* dst = drow + (h * 3 + which) * dh;
+    if (p >= g.hv) {
+      const int d = rot + (p - g.hv) * N;
+      Vec16<T> x;
+      x.load_stream(src + d);
+      x.store(dst + d);
+      continue;
+    }
+    const int d0 = p * N;
+    Vec16<T> g1, g2;
+    g1.load_stream(src + d0);
+    g2.load_stream(src + d0 + half);
+    if (which == 2) {
+      g1.store(dst + d0);
+      g2.store(dst + d0 + half);
+      continue;
+    }
+    // out1 = x1 c1 - x2 s1 ; out2 = x2 c2 + x1 s2   =>   dx1 = g1 c1 + g2 s2 ; dx2 = g2 c2 - g1 s1
+    Vec16<T> c1, s1, c2, s2;
+    c1.load(cp + d0); s1.load(sp + d0);
+    c2.load(cp + d0 + half); s2.load(sp + d0 + half);
+    float a[N], bb[N], c1f[N], s1f[N], c2f[N], s2f[N], o1[N], o2[N];
+    g1.unpack(a); g2.unpack(bb); c1.unpack(c1f); s1.unpack(s1f); c2.unpack(c2f); s2.unpack(s2f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      o1[i] = a[i] * c1f[i] + bb[i] * s2f[i];
+      o2[i] = bb[i] * c2f[i] - a[i] * s1f[i];
+    }
+    g1.pack(o1); g2.pack(o2);
+    g1.store(dst + d0);
+    g2.store(dst + d0 + half);
+  }
 }
 
 template <typename T>
@@ -213,6 +246,24 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ x, 
 
 using namespace unimp;
 
+static RotaryGeom rotary_geom(int H, int dh, int rot, int dtype) {
+  const int n = dtype == UNIMP_BF16 ? 8 : 4;
+  RotaryGeom g;
+  g.hv = (rot / 2) / n;
+  g.P = g.hv + (dh - rot) / n;
+  g.items = H * 3 * g.P;
+  return g;
+}
+
+static int rotary_threads(const RotaryGeom& g) {
+  // whole passes over the row's items: 480 items (4B: 32 heads x 3 x 5 slots) -> 160 threads x 3
+  int best = 256;
+  for (int th = 256; th >= 96; th -= 32)
+    if (g.items % th == 0) { best = th; break; }
+  if (g.items < best) best = ((g.items + 31) / 32) * 32;
+  return best;
+}
+
 static int rotary_check(const char* who, int B, int T, int H, int dh, int rot, int dtype) {
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "%s: dtype", who);
   const int n = dtype == UNIMP_BF16 ? 8 : 4;
@@ -231,17 +282,17 @@ extern "C" int unimp_rotary_qkv_fwd(const void* qkv, void* out, const void* cos,
   if (rc) return rc;
   UNIMP_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(cos) && aligned16(sin), UNIMP_E_ALIGN,
                   "rotary_qkv_fwd: pointers must be 16-byte aligned");
-  const int n = dtype == UNIMP_BF16 ? 8 : 4;
-  const int64_t total = (int64_t)B * T * H * 3 * (dh / n);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const RotaryGeom g = rotary_geom(H, dh, rot, dtype);
+  const unsigned rows = (unsigned)((int64_t)B * T);
+  const int threads = rotary_threads(g);
   if (dtype == UNIMP_BF16)
-    rotary_qkv_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    rotary_qkv_fwd_kernel<__nv_bfloat16><<<rows, threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, (const __nv_bfloat16*)cos,
-        (const __nv_bfloat16*)sin, total, T, H, dh, rot, cs_batch_stride);
+        (const __nv_bfloat16*)sin, T, H, dh, rot, cs_batch_stride, g);
   else
-    rotary_qkv_fwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)qkv, (float*)out, (const float*)cos, (const float*)sin, total, T, H, dh, rot,
-        cs_batch_stride);
+    rotary_qkv_fwd_kernel<float><<<rows, threads, 0, (cudaStream_t)stream>>>(
+        (const float*)qkv, (float*)out, (const float*)cos, (const float*)sin, T, H, dh, rot,
+        cs_batch_stride, g);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }
@@ -259,18 +310,19 @@ extern "C" int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* 
   UNIMP_CHECK_ARG(aligned16(dq) && aligned16(dk) && aligned16(dv) && aligned16(d_qkv) && aligned16(cos) &&
                       aligned16(sin),
                   UNIMP_E_ALIGN, "rotary_qkv_bwd: pointers must be 16-byte aligned");
-  const int64_t total = (int64_t)B * T * H * 3 * (dh / n);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const RotaryGeom g = rotary_geom(H, dh, rot, dtype);
+  const unsigned rows = (unsigned)((int64_t)B * T);
+  const int threads = rotary_threads(g);
   const int64_t* s = strides9;  // HOST array: {q_sb,q_sh,q_st, k_sb,k_sh,k_st, v_sb,v_sh,v_st} in elements
   if (dtype == UNIMP_BF16)
-    rotary_qkv_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    rotary_qkv_bwd_kernel<__nv_bfloat16><<<rows, threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dq, (const __nv_bfloat16*)dk, (const __nv_bfloat16*)dv, s[0], s[1], s[2], s[3],
         s[4], s[5], s[6], s[7], s[8], (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin,
-        (__nv_bfloat16*)d_qkv, total, T, H, dh, rot, cs_batch_stride);
+        (__nv_bfloat16*)d_qkv, T, H, dh, rot, cs_batch_stride, g);
   else
-    rotary_qkv_bwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    rotary_qkv_bwd_kernel<float><<<rows, threads, 0, (cudaStream_t)stream>>>(
         (const float*)dq, (const float*)dk, (const float*)dv, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7],
-        s[8], (const float*)cos, (const float*)sin, (float*)d_qkv, total, T, H, dh, rot, cs_batch_stride);
+        s[8], (const float*)cos, (const float*)sin, (float*)d_qkv, T, H, dh, rot, cs_batch_stride, g);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }

@@ -133,6 +133,21 @@ def _is_exact_gelu(act) -> bool:
     return isinstance(act, torch.nn.GELU) and act.approximate == "none"
 
 
+_MASK_CACHE = [None, None, None]   # (bool mask object, dtype, additive mask)
+
+
+def _additive_mask(mask, dtype):
+    """SDPA turns a boolean attn_mask into an additive one on EVERY call (one `where` launch per
+    decoder layer).  HF hands the same mask tensor to all layers of a forward: convert it once.
+    The cache holds a reference to the mask it was built from (identity, not address, is the key)."""
+    if mask is None or mask.dtype != torch.bool:
+        return mask
+    if _MASK_CACHE[0] is not mask or _MASK_CACHE[1] != dtype:
+        add = torch.zeros(mask.shape, dtype=dtype, device=mask.device).masked_fill_(~mask, float("-inf"))
+        _MASK_CACHE[0], _MASK_CACHE[1], _MASK_CACHE[2] = mask, dtype, add
+    return _MASK_CACHE[2]
+
+
 def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None):
     """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
     our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
@@ -153,6 +168,7 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     cos, sin = position_embeddings
     q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
                              rotary_dim=rot)
+    attention_mask = _additive_mask(attention_mask, x.dtype)
     a = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0,
                                        is_causal=attention_mask is None and T > 1,
                                        scale=att.scaling)
