@@ -1,5 +1,5 @@
 """Cold-cache timings of the K5 (gate+residual+LN) and rotary / GELU kernels alone (dev tool).
-Same method as unimp_b200/kbench.py; geometry knobs come from the environment."""
+Same method as unimp_b200/kbench.py."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,6 +7,8 @@ from unimp_b200 import ops
 from unimp_b200.kbench import _time_graph, _k
 
 dev, dt = "cuda", torch.bfloat16
+# backward launches captured in a graph must not touch the legacy stream: run everything on a side stream
+torch.cuda.set_stream(torch.cuda.Stream())
 rows, D = int(os.environ.get("ROWS", 1536)), int(os.environ.get("D", 2560))
 es = 2
 res = {}

@@ -6,8 +6,6 @@
 // (algorithmic bytes 4*rows*D*sizeof(T)).  Backward is one pass too (read g_xout, g_ln,
 // branch, x_out; write d_x, d_branch) with per-CTA column partials for d_gamma/d_beta/d_gate
 // reduced by a second small kernel in fixed order (deterministic).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace unimp {
@@ -368,9 +366,7 @@ static LnBwdGeom ln_bwd_geom(int64_t rows, int D) {
   }
   // column partials cost one partial row per CTA: few, fat CTAs (one per SM).  Without them,
   // 320-thread CTAs (two or three per SM) keep more rows in flight.
-  static const int t_cols = getenv("UNIMP_LN_BWD_COLS_THREADS") ? atoi(getenv("UNIMP_LN_BWD_COLS_THREADS")) : LN_BWD_MAX_THREADS;
-  static const int t_nocols = getenv("UNIMP_LN_BWD_THREADS") ? atoi(getenv("UNIMP_LN_BWD_THREADS")) : 320;
-  const int target = COLS ? t_cols : t_nocols;
+  const int target = COLS ? LN_BWD_MAX_THREADS : 320;
   int R = target / g.TG;
   R = R < 1 ? 1 : (R > LN_BWD_MAX_R ? LN_BWD_MAX_R : R);
   g.R = R;

@@ -156,26 +156,41 @@ __global__ void quick_gelu_kernel(T* __restrict__ x, int64_t nvec) {
   }
 }
 
-// Phi(x) (standard normal CDF) and phi(x) (its density).
+// Phi(-|x|) (the small tail of the standard normal CDF) and E = exp(-x^2/2).
+//   FAST: erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt2
+//   (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7); it shares exp(-x^2/2) with the density, the
+//   1/2 and the 1/sqrt2 are folded into the constants: ~15 instructions per element with 2 MUFU.
 template <bool FAST>
-__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float E = __expf(-0.5f * x * x);
-  pdf = 0.3989422804014327f * E;
+__device__ __forceinline__ float normal_tail(float x, float& E) {
+  const float ax = fabsf(x);
+  E = __expf(-0.5f * x * x);
   if (FAST) {
-    // erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt2
-    // (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7): shares exp(-x^2/2) with the density.
-    const float z = fabsf(x) * 0.7071067811865476f;
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float half_erfc = 0.5f * p * t * E;          // 0.5 erfc(|z|) = Phi(-|x|)
-    cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
-  } else {
-    cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.7071067811865476f, ax, 1.f)));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    return p * t * E;                                   // 0.5 erfc(|x|/sqrt2)
   }
+  return 0.5f * erfcf(ax * 0.7071067811865476f);
+}
+
+// gelu(x) = x Phi(x) = max(x, 0) - |x| Phi(-|x|)
+template <bool FAST>
+__device__ __forceinline__ float gelu_value(float x) {
+  float E;
+  const float h = normal_tail<FAST>(x, E);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
+
+// d gelu / dx = Phi(x) + x phi(x)
+template <bool FAST>
+__device__ __forceinline__ float gelu_slope(float x) {
+  float E;
+  const float h = normal_tail<FAST>(x, E);
+  const float cdf = x >= 0.f ? 1.f - h : h;
+  return fmaf(x * 0.3989422804014327f, E, cdf);
 }
 
 constexpr int GELU_U = 4;   // 16-byte vectors in flight per thread and operand
@@ -196,11 +211,7 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ x, 
         float f[N];
         v[u].unpack(f);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          float c, d;
-          normal_cdf_pdf<FAST>(f[i], c, d);
-          f[i] *= c;
-        }
+        for (int i = 0; i < N; ++i) f[i] = gelu_value<FAST>(f[i]);
         v[u].pack(f);
         v[u].store(y + (j0 + u * stride) * N);
       }
@@ -230,11 +241,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ x, 
         v[u].unpack(f);
         g[u].unpack(gf);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          float c, d;
-          normal_cdf_pdf<FAST>(f[i], c, d);
-          gf[i] *= fmaf(f[i], d, c);
-        }
+        for (int i = 0; i < N; ++i) gf[i] *= gelu_slope<FAST>(f[i]);
         g[u].pack(gf);
         g[u].store(dx + (j0 + u * stride) * N);
       }
