@@ -47,6 +47,25 @@ helpers.MaskedCrossAttention.forward = no_cache_forward
 run()
 t_plain, out_b = run()
 helpers.MaskedCrossAttention.forward = orig
+# the CUDA-graph decoder (unimp_b200/decode.py): same decoding rules, one graph replay per token
+from unimp_b200.decode import GraphedDecoder
+dec = GraphedDecoder(model)
+def run_graphed(n):
+    torch.cuda.synchronize(); t0 = time.time()
+    out = dec.generate(vis, ids, torch.ones_like(ids), num_beams=beams, max_new_tokens=n, eos_token_id=-1,
+                       pad_token_id=cfg.tokens.pad, early_stopping=False)
+    torch.cuda.synchronize()
+    return time.time() - t0, out
+try:
+    run_graphed(new)
+    t_graph, out_c = run_graphed(new)
+    t_long, _ = run_graphed(3 * new)
+    per_tok = (t_long - t_graph) / (2 * new)
+    print(f"cuda-graph decoder         : {t_graph*1e3:8.1f} ms  ({new/t_graph:6.1f} tokens/s incl. prefill + capture; "
+          f"steady state {per_tok*1e3:.2f} ms/token = {1/per_tok:.1f} tokens/s)"
+          f"  same tokens as HF path: {out_c.shape == out_a.shape and torch.equal(out_c, out_a)}")
+except Exception:
+    import traceback; traceback.print_exc()
 print(f"prompt {L} tokens, Ti={wl.Ti}, beams {beams}, {new} new tokens")
 print(f"cached K/V + decode kernel : {t_cached*1e3:8.1f} ms  ({new/t_cached:6.1f} tokens/s)")
 print(f"recompute to_kv every step : {t_plain*1e3:8.1f} ms  ({new/t_plain:6.1f} tokens/s)")

@@ -148,7 +148,7 @@ def _additive_mask(mask, dtype):
     return _MASK_CACHE[2]
 
 
-def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None):
+def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None, kv_step=None):
     """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
     our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
     qkv projection (`unimp_rotary_qkv_*`), q/k/v reach SDPA as strided views.  GEMMs stay on
@@ -156,7 +156,10 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     parameters, same arithmetic; ~11 launches instead of ~30 per layer.
     `h1`: input_layernorm(x) if the caller already produced it in a fused epilogue.
     `next_ln`: the LayerNorm that reads this layer's output first (next layer's x-attn norm or
-    input_layernorm); if given, returns (y, next_ln(y)) from the same launch as the last residual."""
+    input_layernorm); if given, returns (y, next_ln(y)) from the same launch as the last residual.
+    `kv_step` = (k_cache, v_cache, cursor): single-token decode against static (B,H,T_max,dh)
+    caches — the new key/value are written at the device-side `cursor` (capturable in a CUDA
+    graph) and attention runs over the whole cache under the additive `attention_mask`."""
     F = torch.nn.functional
     att = layer.attention
     B, T, D = x.shape
@@ -169,8 +172,13 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
                              rotary_dim=rot)
     attention_mask = _additive_mask(attention_mask, x.dtype)
+    if kv_step is not None:
+        k_cache, v_cache, cursor = kv_step
+        k_cache.index_copy_(2, cursor, k)
+        v_cache.index_copy_(2, cursor, v)
+        k, v = k_cache, v_cache
     a = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0,
-                                       is_causal=attention_mask is None and T > 1,
+                                       is_causal=attention_mask is None and T > 1 and kv_step is None,
                                        scale=att.scaling)
     o = F.linear(a.transpose(1, 2).reshape(B, T, D), att.dense.weight, att.dense.bias)
     mlp = layer.mlp
