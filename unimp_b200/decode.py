@@ -266,7 +266,8 @@ class GraphedDecoder:
         eos = model.eoc_token_id if eos_token_id is None else eos_token_id
         B, T0 = lang_x.shape
         nb = num_beams
-        Bf, Tmax = B * nb, T0 + max_new_tokens
+        Bf = B * nb
+        Tmax = (T0 + max_new_tokens + 15) // 16 * 16     # cache length; the tail past the cursor stays masked
         dev = lang_x.device
         ids = lang_x.repeat_interleave(nb, dim=0)
         mask = torch.ones_like(ids) if attention_mask is None else attention_mask.repeat_interleave(nb, dim=0)
