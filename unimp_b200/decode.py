@@ -202,6 +202,9 @@ class GraphedDecoder:
     deterministic decoding (num_beams >= 1, do_sample=False, no logits processors).  Needs the
     GPT-NeoX language model (the 4B-instruct configuration) on a CUDA device."""
 
+    # additive-mask value for key slots that are not visible (padding, slots past the cursor)
+    MASK_FILL = float("-inf")
+
     def __init__(self, model, *, sync_every: int = 8):
         from transformers.models.gpt_neox.modeling_gpt_neox import GPTNeoXLayer
 
@@ -290,8 +293,8 @@ class GraphedDecoder:
         S.cur = torch.full((1,), T0, dtype=torch.int64, device=dev)      # K/V slot of the next token
         S.n_media = (ids == lm.media_token_id).sum(-1, keepdim=True).to(torch.int32)
         S.logits = torch.zeros((Bf, out.logits.shape[-1]), dtype=torch.float32, device=dev)
-        S.add_mask = torch.full((Bf, 1, 1, Tmax), float("-inf"), dtype=dtype, device=dev)
-        S.add_mask[:, 0, 0, :T0] = torch.zeros((), dtype=dtype, device=dev).expand(Bf, T0).masked_fill(mask == 0, float("-inf"))
+        S.add_mask = torch.full((Bf, 1, 1, Tmax), self.MASK_FILL, dtype=dtype, device=dev)
+        S.add_mask[:, 0, 0, :T0] = torch.zeros((), dtype=dtype, device=dev).expand(Bf, T0).masked_fill(mask == 0, self.MASK_FILL)
         S.k, S.v = [], []
         for i in range(len(self.layers)):
             k, v = cache.layers[i].keys, cache.layers[i].values          # (Bf,H,T0,dh)
@@ -338,6 +341,8 @@ class GraphedDecoder:
                 graph.replay()
                 n_steps += 1
             result = search.result(num_return_sequences)                 # (reads device state: syncs)
+            self.last_n_steps = n_steps
+            self.last_logits_finite = bool(torch.isfinite(S.logits).all())
         finally:
             del graph
             lm.clear_conditioned_layers()
