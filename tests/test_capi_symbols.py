@@ -49,3 +49,49 @@ def test_ops_refuse_cpu_tensors():
 
     with pytest.raises(_lib.UnimpError):
         ops.layer_norm(torch.zeros(2, 8), torch.ones(8), torch.zeros(8))
+
+
+def header_prototypes():
+    """name -> list of parameter type strings, parsed from the header's prototypes."""
+    src = open(os.path.join(ROOT, "include", "unimp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"\b(unimp_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = " ".join(m.group(2).split())
+        out[m.group(1)] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and pointer / integer / float class of every argument in unimp_b200/_lib.py agree with
+    include/unimp_b200.h (a drifted binding corrupts arguments silently)."""
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def klass(ctype_decl):
+        if "*" in ctype_decl:
+            return "ptr"
+        if re.search(r"\bunimp_view\b|\bUnimpView\b|\bView\b", ctype_decl):
+            return "view"
+        if re.search(r"\bfloat\b", ctype_decl):
+            return "f32"
+        if re.search(r"\bint64_t\b", ctype_decl):
+            return "i64"
+        if re.search(r"\bint\b", ctype_decl):
+            return "i32"
+        return "view"   # a by-value struct typedef
+
+    def cklass(t):
+        if t is _lib.View:
+            return "view"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int64))) and t not in (
+                ctypes.c_int, ctypes.c_int64, ctypes.c_float):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_int64: "i64", ctypes.c_float: "f32"}[t]
+
+    for name, params in protos.items():
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for i, (p, t) in enumerate(zip(params, argtypes)):
+            assert klass(p) == cklass(t), (name, i, p, t)

@@ -214,12 +214,11 @@ class GraphedDecoder:
         if not all(isinstance(l.decoder_layer, GPTNeoXLayer) for l in self.layers):
             raise TypeError("GraphedDecoder drives GPT-NeoX decoder layers")
         self.sync_every = max(1, int(sync_every))
-        self._session = None
+        self.last_n_steps, self.last_logits_finite = 0, True   # of the last generate() (diagnostics)
 
     # -------------------------------------------------------------------------------- one token
     def _token_step(self, S):
         """tokens (Bf,1) -> logits (Bf,V); writes K/V at S.cur.  Everything here is captured."""
-        from . import ops
         from .flamingo_lm import fused_neox_layer
 
         lm = self.lm
