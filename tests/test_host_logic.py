@@ -128,6 +128,99 @@ def test_bucketed_allreduce_world2_equals_single_process_mean(accum):
     assert torch.allclose(res[0][1], want, atol=1e-7, rtol=1e-5)
 
 
+def _cpu_optimizer_kernels():
+    """Test-side stand-ins for `unimp_sumsq` / `unimp_adamw_step` (the arithmetic of
+    unimp_b200/csrc/misc.cu::adamw_kernel, restated with torch) so that the COLLECTIVE plumbing of
+    the sharded optimizer can run under gloo on a GPU-less box.  The kernels themselves are tested
+    against torch.optim.AdamW on the GPU (tests/test_kernels_gpu.py::test_fused_adamw_matches_torch)."""
+    from unimp_b200 import ops
+
+    def sumsq_(grad, acc):
+        acc += grad.float().pow(2).sum()
+
+    def adamw_step_(master, param, grad, m, v, *, hyper, beta1, beta2, eps, weight_decay, gnorm_sq=None,
+                    max_norm=0.0, grad_scale=1.0):
+        lr, bc1, bc2_sqrt = (float(x) for x in hyper)
+        clip = grad_scale
+        if gnorm_sq is not None:
+            clip *= min(1.0, max_norm / (float(gnorm_sq.sqrt()) * grad_scale + 1e-6))
+        g = grad.float() * clip
+        master.mul_(1.0 - lr * weight_decay)
+        m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+        master.sub_((lr / bc1) * (m / (v.sqrt() / bc2_sqrt + eps)))
+        param.copy_(master)
+
+    ops.sumsq_, ops.adamw_step_ = sumsq_, adamw_step_
+
+
+def _toy_net_and_groups():
+    torch.manual_seed(0)  # identical weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.Tanh(), torch.nn.Linear(40, 8))
+    groups = [{"params": [(n, p) for n, p in net.named_parameters() if "weight" in n], "weight_decay": 0.1},
+              {"params": [(n, p) for n, p in net.named_parameters() if "bias" in n], "weight_decay": 0.0}]
+    return net, groups
+
+
+def _sharded_worker(rank, world, port, steps, deferred, q):
+    from unimp_b200.train import ShardedDataParallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _cpu_optimizer_kernels()
+    net, groups = _toy_net_and_groups()
+    opt = FlatAdamW(groups, lr=1e-2, shard_world=world, allocate_states=False)
+    red = ShardedDataParallel(opt, bucket_bytes=1024, deferred_gather_module=net[0] if deferred else None)
+    assert len(red.buckets) >= 3 and len(red.shards) == len(red.buckets)
+    for sh in red.shards:   # a rank owns exactly 1/world of every bucket, 16-byte aligned
+        assert sh["g_shard"].numel() * world == sh["g_full"].numel()
+        assert sh["g_shard"].data_ptr() % 16 == 0 and sh["master"].numel() == sh["g_shard"].numel()
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.randn(5, 24, generator=g) for _ in range(steps)]
+    for x in xs:
+        red.begin_step()
+        opt.zero_grad()
+        red.armed = True
+        net(x).pow(2).mean().backward()
+        opt.step_with(red, lr_scale=1.0)
+    red.sync_params()
+    flat = torch.cat([grp["flat_p"] for grp in opt.groups])
+    q.put((rank, flat.clone(), [x.clone() for x in xs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+def test_sharded_data_parallel_world2_equals_single_process_adamw(deferred):
+    """The default N>1 path (reduce-scatter, AdamW on the 1/N shard, all-gather — immediate or
+    deferred to the next step's forward) over gloo with world_size 2: after 3 steps every rank
+    holds the parameters a single process gets from AdamW on the rank-averaged gradients."""
+    world, steps = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, steps, deferred, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(res[0][1], res[1][1])            # replicas stay bit-identical
+    # single-process reference with the same stand-in kernels: mean of the per-rank losses
+    _cpu_optimizer_kernels()
+    net, groups = _toy_net_and_groups()
+    opt = FlatAdamW(groups, lr=1e-2, shard_world=world)
+    for s in range(steps):
+        opt.zero_grad()
+        for r in range(world):
+            (net(res[r][2][s]).pow(2).mean() / world).backward()
+        opt.step()
+    want = torch.cat([grp["flat_p"] for grp in opt.groups])
+    assert torch.allclose(res[0][1], want, atol=1e-6, rtol=1e-5)
+    assert (res[0][1] - want).abs().max() < 1e-5 and (want != 0).any()
+
+
 def test_get_checkpoint_keeps_trainables_with_upstream_key_names_and_reloads():
     """reference train_utils.py:258-265 + mmrec.py:513-514 (`load_state_dict(..., strict=False)`)."""
     from unimp_b200.factory import build_flamingo
