@@ -130,3 +130,18 @@ def test_graphed_decoder_ragged_prompts_and_bf16():
                                          early_stopping=True)
     assert out.shape[0] == 10 and torch.equal(out[:, :ids.shape[1]], ids.repeat_interleave(5, 0))
     assert int(out.min()) >= 0 and int(out.max()) < cfg.vocab
+
+
+def test_graphed_decoder_host_logic_on_cpu_with_test_doubles():
+    """Prefill, static K/V caches, key masks, rotary positions, beam re-ordering and step counting
+    of `GraphedDecoder`, run in a throw-away subprocess where tests/standins.py replaces the CUDA ops
+    by dense PyTorch doubles: token matrices equal `Flamingo.generate` on the same doubles."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "standins.py"), "decode"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DECODE CHECK ALL EQUAL" in r.stdout and "DIFFERENT" not in r.stdout
