@@ -245,3 +245,18 @@ def test_get_checkpoint_keeps_trainables_with_upstream_key_names_and_reloads():
     for (n1, p1), (n2, p2) in zip(m.named_parameters(), m2.named_parameters()):
         if p1.requires_grad:
             assert torch.equal(p1, p2), n1
+
+
+def test_additive_mask_cache_is_keyed_on_identity_dtype_and_version():
+    """`fused_neox_layer` converts HF's boolean attention mask once per forward; the cache must not
+    serve a stale conversion after an in-place edit or for another dtype."""
+    from unimp_b200.flamingo_lm import _additive_mask
+
+    m = torch.tensor([[True, False, True]])
+    a = _additive_mask(m, torch.float32)
+    assert _additive_mask(m, torch.float32) is a and a.tolist() == [[0.0, float("-inf"), 0.0]]
+    assert _additive_mask(m, torch.bfloat16).dtype == torch.bfloat16
+    m[0, 1] = True
+    assert _additive_mask(m, torch.float32).tolist() == [[0.0, 0.0, 0.0]]
+    assert _additive_mask(m.clone(), torch.float32) is not _additive_mask(m, torch.float32)
+    assert _additive_mask(None, torch.float32) is None and _additive_mask(a, torch.float32) is a   # non-bool: as is

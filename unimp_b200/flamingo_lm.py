@@ -133,7 +133,7 @@ def _is_exact_gelu(act) -> bool:
     return isinstance(act, torch.nn.GELU) and act.approximate == "none"
 
 
-_MASK_CACHE = [None, None, None]   # (bool mask object, dtype, additive mask)
+_MASK_CACHE = [None, None, None]   # (bool mask object, (dtype, version), additive mask)
 
 
 def _additive_mask(mask, dtype):
@@ -142,9 +142,10 @@ def _additive_mask(mask, dtype):
     The cache holds a reference to the mask it was built from (identity, not address, is the key)."""
     if mask is None or mask.dtype != torch.bool:
         return mask
-    if _MASK_CACHE[0] is not mask or _MASK_CACHE[1] != dtype:
+    key = (dtype, mask._version)       # an in-place edit of the same mask object invalidates the entry
+    if _MASK_CACHE[0] is not mask or _MASK_CACHE[1] != key:
         add = torch.zeros(mask.shape, dtype=dtype, device=mask.device).masked_fill_(~mask, float("-inf"))
-        _MASK_CACHE[0], _MASK_CACHE[1], _MASK_CACHE[2] = mask, dtype, add
+        _MASK_CACHE[0], _MASK_CACHE[1], _MASK_CACHE[2] = mask, key, add
     return _MASK_CACHE[2]
 
 
