@@ -145,3 +145,16 @@ def test_graphed_decoder_host_logic_on_cpu_with_test_doubles():
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DECODE CHECK ALL EQUAL" in r.stdout and "DIFFERENT" not in r.stdout
+
+
+def test_graphed_decoder_rejects_what_it_does_not_implement():
+    """Sampling / n-gram blocking / other HF generate options must fail loudly, not be ignored."""
+    from unimp_b200.decode import GraphedDecoder
+
+    dec = GraphedDecoder.__new__(GraphedDecoder)       # argument validation needs no model
+    x = torch.zeros(1, 4, dtype=torch.int64)
+    for kw in (dict(do_sample=True), dict(no_repeat_ngram_size=3), dict(temperature=0.7), dict(top_k=5)):
+        with pytest.raises(NotImplementedError):
+            dec.generate(None, x, None, **kw)
+    with pytest.raises(ValueError):
+        dec.generate(None, x, None, num_beams=2, num_return_sequences=3)

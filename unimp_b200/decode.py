@@ -260,9 +260,20 @@ class GraphedDecoder:
     @torch.no_grad()
     def generate(self, vision_x, lang_x, attention_mask=None, *, num_beams: int = 1, max_new_tokens: int = 20,
                  eos_token_id=None, pad_token_id=None, num_return_sequences: int = 1, early_stopping=False,
-                 length_penalty: float = 1.0):
+                 length_penalty: float = 1.0, do_sample: bool = False, no_repeat_ngram_size: int = 0,
+                 **unsupported):
+        """Arguments as `Flamingo.generate` / HF `generate` (reference call:
+        `UniMP/pipeline/eval/eval_exp.py:101-114`).  Deterministic decoding only: sampling, n-gram
+        blocking and other logits processors raise — use `Flamingo.generate` for those."""
         from types import SimpleNamespace
 
+        if do_sample or no_repeat_ngram_size or unsupported:
+            raise NotImplementedError(
+                "GraphedDecoder implements greedy / beam search without logits processors; got "
+                f"do_sample={do_sample}, no_repeat_ngram_size={no_repeat_ngram_size}, "
+                f"{sorted(unsupported)} — use Flamingo.generate for these")
+        if num_return_sequences > num_beams:
+            raise ValueError("num_return_sequences has to be smaller or equal to num_beams")
         model, lm = self.model, self.lm
         assert lang_x.is_cuda, "GraphedDecoder needs a CUDA device (there is no CPU path)"
         eos = model.eoc_token_id if eos_token_id is None else eos_token_id
