@@ -55,6 +55,23 @@ def test_search_rules_equal_transformers_generate(nb, nrs, early, lp, vocab, see
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("B,T0,new,nb", [(1, 3, 1, 2), (1, 9, 20, 5), (3, 4, 6, 3), (3, 5, 2, 1), (4, 2, 15, 2)])
+def test_search_rules_other_batch_sizes_prompt_lengths_and_budgets(B, T0, new, nb):
+    """Batch of one, three-row batches (rows finish at different steps), a single new token, long budgets."""
+    torch.set_num_threads(1)
+    m = _tiny_lm(29, 7)
+    g = torch.Generator().manual_seed(B * 100 + T0)
+    prompt = torch.randint(3, 29, (B, T0), generator=g)
+    kw = dict(max_new_tokens=new, eos_token_id=1, pad_token_id=2, do_sample=False)
+    if nb > 1:
+        kw.update(num_beams=nb, num_return_sequences=nb, early_stopping=True)
+    with torch.no_grad():
+        want = m.generate(prompt, attention_mask=torch.ones_like(prompt), **kw)
+    got = generate_with(lambda rows: m(input_ids=rows).logits[:, -1, :], prompt, num_beams=nb, max_new_tokens=new,
+                        eos_token_id=1, pad_token_id=2, num_return_sequences=nb, early_stopping=True)
+    assert got.shape == want.shape and torch.equal(got, want)
+
+
 def test_eos_is_actually_exercised():
     """Guard for the test above: with these tiny models some hypotheses do end in EOS and some runs
     stop before max_new_tokens (otherwise the finished-pool rules would go untested)."""
