@@ -95,3 +95,54 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert len(params) == len(argtypes), (name, params, argtypes)
         for i, (p, t) in enumerate(zip(params, argtypes)):
             assert klass(p) == cklass(t), (name, i, p, t)
+
+
+def _entry_points():
+    skip = {"unimp_version", "unimp_last_error_string", "unimp_device_ok"}
+    return sorted(n for n in _lib.SIGNATURES if n not in skip and not n.endswith("_workspace"))
+
+
+def _null_args(name):
+    vals = []
+    for t in _lib.SIGNATURES[name][1]:
+        if t is _lib.View:
+            vals.append(_lib.View(None, 0, 0))
+        elif t in (ctypes.c_int, ctypes.c_int64):
+            vals.append(1)
+        elif t is ctypes.c_float:
+            vals.append(1.0)
+        else:
+            vals.append(None)
+    return vals
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", _entry_points())
+def test_every_entry_point_rejects_null_pointers_before_launching(name):
+    """C-ABI error convention: invalid arguments return a negative code and leave a
+    message in unimp_last_error_string(); nothing is launched (this runs on a GPU-less box)."""
+    lib = _lib.load()
+    rc = getattr(lib, name)(*_null_args(name))
+    assert rc < 0, (name, rc)
+    msg = lib.unimp_last_error_string().decode()
+    assert name.replace("unimp__", "").replace("unimp_", "") in msg and "NULL" in msg, msg
+
+
+def test_shape_dtype_and_alignment_are_validated_before_launching():
+    lib = _lib.load()
+    P = 4096   # a non-NULL, 16-byte aligned "pointer": validation must fail before it is ever read
+    # K5 forward: D must be a multiple of the vector width; dtype must be known; pointers aligned
+    f = lib.unimp_gate_residual_ln_fwd
+    assert f(None, P, None, P, P, None, P, P, P, 4, 100, 1e-5, 1, None) < 0 and b"multiple" in lib.unimp_last_error_string()
+    assert f(None, P, None, P, P, None, P, P, P, 4, 128, 1e-5, 7, None) < 0 and b"dtype" in lib.unimp_last_error_string()
+    assert f(None, P + 8, None, P, P, None, P, P, P, 4, 128, 1e-5, 1, None) < 0 and b"aligned" in lib.unimp_last_error_string()
+    # K5 backward: a gated branch needs somewhere to put d_branch
+    b = lib.unimp_gate_residual_ln_bwd
+    assert b(P, P, P, P, P, P, P, P, P, None, None, None, None, P, 4, 128, 1, None) < 0
+    assert b"d_branch" in lib.unimp_last_error_string()
+    # GELU: element count must be whole vectors
+    assert lib.unimp_gelu_fwd(P, P, 12, 1, None) < 0 and lib.unimp_gelu_bwd(P, P, P, 12, 1, None) < 0
+    # rotary: rot/2 must be whole vectors
+    assert lib.unimp_rotary_qkv_fwd(P, P + 4096, P, P, 1, 1, 2, 64, 24, 0, 1, None) < 0
