@@ -146,3 +146,17 @@ def test_shape_dtype_and_alignment_are_validated_before_launching():
     assert lib.unimp_gelu_fwd(P, P, 12, 1, None) < 0 and lib.unimp_gelu_bwd(P, P, P, 12, 1, None) < 0
     # rotary: rot/2 must be whole vectors
     assert lib.unimp_rotary_qkv_fwd(P, P + 4096, P, P, 1, 1, 2, 64, 24, 0, 1, None) < 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built .so every op raises (the product never routes around it)."""
+    import torch
+
+    from unimp_b200 import ops
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libunimp_b200.so"))
+    with pytest.raises(_lib.UnimpError, match="no CPU fallback"):
+        _lib.load()
+    with pytest.raises(_lib.UnimpError):
+        ops.gelu(torch.zeros(8))
