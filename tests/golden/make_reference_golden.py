@@ -24,6 +24,13 @@ What is executed is the unmodified reference, imported from where it lies:
   `softmax(q kT * scale) v`); embeddings, pre-LN, blocks, quick-GELU MLP and the
   `last_hidden_state` convention are the reference's code.
 
+* `UniMP/pipeline/mm_utils/rec_dataset.py::RecDataset.process_train_{rec,rate_exp,img_gen}_pair`
+  (`:372-456`, `:1100-1156`, `:719-777`) with `extract_meta` / `extract_meta_gen` (`:301-337`) — the
+  prompt templates — called unbound on a stand-in `self` (fake item metadata, tiny JPEGs, a
+  word-level tokenizer that splits the added tokens out the way HF does), then the reference's
+  `collate_fn` and the label masking of `train_one_epoch`: the token GRAMMAR of real batches, which
+  `unimp_b200/synth.py` must reproduce.
+
 No reference source is copied into the repo; only the small input/output vectors are committed.
 The third-party half (open_flamingo v2.0.1) is absent from /root/reference and stays unpinned.
 """
@@ -194,6 +201,86 @@ def reference_vit_golden(cfg, g):
                       "xformers.ops.memory_efficient_attention replaced by its dense definition"}
 
 
+class WordTokenizer:
+    """Stand-in for the HF tokenizer the reference builds (`mmrec.py:538-595`): added tokens
+    (`<image>`, `<answer>`, `<|endofchunk|>`, `item_N`, `img_N`, `rate_N`) are matched first, the rest
+    is split on whitespace / punctuation and hashed into the plain-text id range."""
+
+    def __init__(self, tk):
+        import re
+        self.tk = tk
+        self.rx = re.compile(r"<image>|<answer>|<\|endofchunk\|>|item_\d+|img_\d+|rate_\d+|[A-Za-z0-9]+|[^\sA-Za-z0-9]")
+
+    def ids(self, text):
+        tk, out = self.tk, []
+        for w in self.rx.findall(text):
+            if w == "<image>":
+                out.append(tk.media)
+            elif w == "<answer>":
+                out.append(tk.answer)
+            elif w == "<|endofchunk|>":
+                out.append(tk.endofchunk)
+            elif w.startswith("item_"):
+                out.append(tk.first_item + int(w[5:]) % tk.n_items)
+            elif w.startswith("img_"):
+                out.append(tk.first_img + int(w[4:]) % tk.n_img)
+            elif w.startswith("rate_"):
+                out.append(tk.first_item + tk.n_items - 1 - int(w[5:]) % 6)   # some added-token id
+            else:
+                out.append(1 + sum(ord(c) * (i + 7) for i, c in enumerate(w)) % (tk.n_plain - 1))
+        return out
+
+    def __call__(self, text, return_tensors="pt", add_special_tokens=False, truncation=False):
+        ids = torch.tensor([self.ids(text)], dtype=torch.int64)
+        return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+
+
+def reference_dataset_batches(mmrec, collate_fn, cfg, tok_ids):
+    """Real batch structure: RecDataset sample builders -> collate_fn -> train_one_epoch labels."""
+    import tempfile
+    import types as _t
+
+    import numpy as np
+    from PIL import Image
+    from pipeline.mm_utils.rec_dataset import RecDataset
+    from torchvision import transforms
+
+    tk = cfg.tokens
+    np.random.seed(7)
+    tmp = tempfile.mkdtemp(prefix="unimp_golden_")
+    items = list(range(1, 13))
+    for it in items:
+        Image.fromarray((np.random.rand(10, 10, 3) * 255).astype("uint8")).save(os.path.join(tmp, f"{it}.jpg"))
+    meta = {str(it): {"category": f"Cat{it % 3} sub", "brand": "" if it % 4 == 0 else f"Brand{it}",
+                      "title": f"Title of item {it} with words", "price": "" if it % 5 == 0 else f"{it}.99",
+                      "retrieval": [items[(it + 3) % len(items)]], "keywords": f"kw{it} red shoes"}
+            for it in items}
+    ds = _t.SimpleNamespace(
+        seqs=[[(it, f"great item {it} really", 1 + it % 5) for it in items[s:s + 6]] for s in range(0, 6)],
+        history_len=2, img_folder=tmp, subset="all", use_semantic=False, meta_data=meta,
+        img_id2semantic={str(it): [it, it + 1, it + 2, it + 3] for it in items},
+        patch_resize_transform=transforms.Compose([transforms.Resize((8, 8)), transforms.ToTensor()]),
+        tokenizer=WordTokenizer(tk),
+        bos_item=torch.LongTensor([tk.bos]), eos_item=torch.LongTensor([tk.eos]),
+        bos_mask=torch.LongTensor([1]), eos_mask=torch.LongTensor([1]))
+    ds.extract_meta = lambda i: RecDataset.extract_meta(ds, i)
+    ds.extract_meta_gen = lambda i: RecDataset.extract_meta_gen(ds, i)
+    out = {}
+    for task, fn in (("rec", RecDataset.process_train_rec_pair), ("rate_exp", RecDataset.process_train_rate_exp_pair),
+                     ("img_gen", RecDataset.process_train_img_gen_pair)):
+        samples = [fn(ds, i) for i in range(3)]
+        batch = collate_fn(samples, pad_idx=tk.pad, eos_idx=tk.eos)["net_input"]
+        B, T = batch["input_ids"].shape
+        step = run_reference_step(mmrec, batch, torch.zeros(B, T, cfg.vocab), tok_ids, tk.pad, gamma=2.0,
+                                  use_reweight=True)
+        out[task] = {"input_ids": batch["input_ids"], "attention_masks": batch["attention_masks"],
+                     "weights": batch["weights"], "n_images": batch["patch_images"].shape[1],
+                     "labels": step["labels"]}
+        print("dataset", task, tuple(batch["input_ids"].shape), "images", batch["patch_images"].shape[1],
+              "weights", batch["weights"].tolist(), "valid labels", int((step["labels"] != -100).sum()))
+    return out
+
+
 def main():
     torch.set_num_threads(1)
     sys.path.insert(0, ROOT)
@@ -249,6 +336,16 @@ def main():
     vit = reference_vit_golden(cfg, g)
     torch.save(vit, os.path.join(HERE, "ref_vit_tower.pt"))
     print("vit tokens", tuple(vit["last_hidden_state"].shape), "rms", float(vit["last_hidden_state"].pow(2).mean().sqrt()))
+
+    # ---- real batch structure from the dataset code -------------------------------------------
+    ds = reference_dataset_batches(mmrec, collate_fn, cfg, tok_ids)
+    torch.save({"tokens": {"answer": A, "endofchunk": E, "media": M, "pad": P, "bos": tk.bos, "eos": tk.eos,
+                           "first_item": tk.first_item, "n_items": tk.n_items, "first_img": tk.first_img,
+                           "n_img": tk.n_img, "n_plain": tk.n_plain},
+                "tasks": ds,
+                "source": "RecDataset.process_train_{rec,rate_exp,img_gen}_pair + collate_fn + train_one_epoch "
+                          "label masking, executed unmodified on stand-in data"},
+               os.path.join(HERE, "ref_dataset_batches.pt"))
 
     # ---- collate_fn ------------------------------------------------------------------------------
     lens = [9, 14, 5]

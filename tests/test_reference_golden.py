@@ -195,3 +195,105 @@ def test_cuda_vision_tower_equals_the_reference_xformers_clip(dtype, tol):
     load_hf_clip_vision_weights(vit, {k: v.to(DEV, dtype) for k, v in sd.items()})
     _, tokens = vit(pixels.to(DEV, dtype))
     assert rel_err(tokens.float(), want[:, 1:]) < tol
+
+
+# ------------------------------------------------------------------------------- real batch structure
+
+def _dataset_fixture():
+    return torch.load(os.path.join(GOLDEN, "ref_dataset_batches.pt"), weights_only=False)
+
+
+def _classes(row, tok):
+    """One letter per token: B bos/eos (same id in the GPT-NeoX vocabulary), M <image>, A <answer>,
+    C <|endofchunk|>, P pad, i item / rating id, g image-token id, t plain text."""
+    out = []
+    for v in row.tolist():
+        if v == tok["media"]:
+            out.append("M")
+        elif v == tok["answer"]:
+            out.append("A")
+        elif v == tok["endofchunk"]:
+            out.append("C")
+        elif v == tok["pad"]:
+            out.append("P")
+        elif v == tok["bos"]:
+            out.append("B")
+        elif tok["first_item"] <= v < tok["first_item"] + tok["n_items"]:
+            out.append("i")
+        elif tok["first_img"] <= v < tok["first_img"] + tok["n_img"]:
+            out.append("g")
+        else:
+            out.append("t")
+    return "".join(out)
+
+
+REC_GRAMMAR = r"B(Mt+AiC)+t+AiBP*"        # rec_dataset.py:414,424,444-445 + collate right padding
+
+
+@pytest.mark.parametrize("task", ["rec", "rate_exp", "img_gen"])
+def test_oracle_labels_on_batches_built_by_the_reference_dataset_code(task):
+    """Batches assembled by the reference's RecDataset sample builders + collate_fn; labels from the
+    reference's train loop.  The oracle's state machine must agree bit for bit, and what survives
+    the masking is exactly the answer spans plus the trailing EOS."""
+    from oracle.loss_oracle import mask_labels
+
+    blob = _dataset_fixture()
+    tok, d = blob["tokens"], blob["tasks"][task]
+    labels = mask_labels(d["input_ids"], answer_token_id=tok["answer"], endofchunk_token_id=tok["endofchunk"],
+                         media_token_id=tok["media"], pad_token_id=tok["pad"])
+    assert torch.equal(labels, d["labels"])
+    assert d["weights"].tolist() == ([2.0] * 3 if task == "rec" else [1.0] * 3)   # rec_dataset.py:452 vs others
+    for row, lab in zip(d["input_ids"], d["labels"]):
+        cls = _classes(row, tok)
+        kept = "".join(c for c, l in zip(cls, lab.tolist()) if l != -100)
+        if task == "rec":
+            import re
+            assert re.fullmatch(REC_GRAMMAR, cls), cls
+            assert kept == "i" * cls.count("A") + "B"          # one item per <answer>, then EOS
+        elif task == "img_gen":
+            # one retrieved image, one answer: the image-token ids ("img_N," - the reference joins them
+            # with commas, rec_dataset.py:750-752) and the trailing EOS are what is scored
+            assert cls.count("M") == 1 and cls.count("A") == 1
+            assert kept == cls[cls.index("A") + 1:].rstrip("P") and kept.count("g") == 4 and kept.endswith("B")
+        else:
+            assert kept.endswith("B") and kept.count("i") == cls.count("A")   # rate id + explanation words
+
+
+@pytest.mark.parametrize("name", ["C1-tiny", "C2-rec"])
+def test_synthetic_batches_follow_the_grammar_of_the_reference_dataset(name):
+    """unimp_b200/synth.py (what bench.py and the parity tests feed the model) produces rows of the
+    same token grammar as the reference's rec sample builder, with the same label survivors."""
+    import re
+
+    from oracle.loss_oracle import mask_labels
+    from unimp_b200 import openflamingo_4b_config, tiny_config
+    from unimp_b200.config import WORKLOADS
+    from unimp_b200.synth import make_batch
+
+    cfg = tiny_config() if name == "C1-tiny" else openflamingo_4b_config()
+    tk = cfg.tokens
+    tok = {"answer": tk.answer, "endofchunk": tk.endofchunk, "media": tk.media, "pad": tk.pad, "bos": tk.bos,
+           "first_item": tk.first_item, "n_items": tk.n_items, "first_img": tk.first_img, "n_img": tk.n_img}
+    wl = WORKLOADS[name]
+    b = make_batch(cfg, wl, seed=5)
+    labels = mask_labels(b["input_ids"], answer_token_id=tk.answer, endofchunk_token_id=tk.endofchunk,
+                         media_token_id=tk.media, pad_token_id=tk.pad)
+    for row, lab in zip(b["input_ids"], labels):
+        cls = _classes(row, tok)
+        assert re.fullmatch(REC_GRAMMAR, cls), cls
+        assert cls.count("M") == wl.Ti
+        kept = "".join(c for c, l in zip(cls, lab.tolist()) if l != -100)
+        assert kept == "i" * cls.count("A") + "B"
+    assert b["weights"].tolist() == [2.0] * wl.B                  # the rec task weight
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["rec", "rate_exp", "img_gen"])
+def test_cuda_mask_labels_on_batches_built_by_the_reference_dataset_code(task):
+    from unimp_b200 import ops
+
+    blob = _dataset_fixture()
+    tok, d = blob["tokens"], blob["tasks"][task]
+    got = ops.mask_labels(d["input_ids"].to(DEV), answer_token_id=tok["answer"], endofchunk_token_id=tok["endofchunk"],
+                          media_token_id=tok["media"], pad_token_id=tok["pad"])
+    assert torch.equal(got.cpu(), d["labels"])
