@@ -8,6 +8,9 @@ weights), so this reproduces only the *layout* the reference's collate produces:
 BOS/EOS (`:444-445`), and `collate_fn` right-pads ids with pad_token_id / masks with 0 and
 stacks images (`UniMP/pipeline/mm_utils/collate_rec.py:51-55,70-72`).  Output keys follow
 `collate_rec.py:59-72`: input_ids, attention_masks, patch_images, weights.
+`tests/test_reference_golden.py` checks the rows against the token grammar of batches built by the
+reference's own `RecDataset.process_train_rec_pair` + `collate_fn` (fixture
+`tests/golden/ref_dataset_batches.pt`).
 """
 from __future__ import annotations
 
