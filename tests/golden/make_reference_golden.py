@@ -31,6 +31,10 @@ What is executed is the unmodified reference, imported from where it lies:
   `collate_fn` and the label masking of `train_one_epoch`: the token GRAMMAR of real batches, which
   `unimp_b200/synth.py` must reproduce.
 
+* the vocabulary growth of `main()` (`UniMP/mmrec.py:538-581`: `<answer>`, `rate_*`, `s_*`, `item_*`,
+  `img_*,` appended to the tokenizer in that order) — the statements are lifted out of `main()` by
+  line range with `ast` and executed against a recording tokenizer.
+
 No reference source is copied into the repo; only the small input/output vectors are committed.
 The third-party half (open_flamingo v2.0.1) is absent from /root/reference and stays unpinned.
 """
@@ -199,6 +203,30 @@ def reference_vit_golden(cfg, g):
             "last_hidden_state": out,
             "source": "UniMP/xformers_model/clip.py::CLIPVisionModel executed unmodified; "
                       "xformers.ops.memory_efficient_attention replaced by its dense definition"}
+
+
+def lifted_vocab_growth(subset="all", use_semantic=False):
+    """Executes the `tokenizer.add_special_tokens / add_tokens` block of `main()` unmodified and
+    returns the tokens in the order the reference appends them."""
+    src = open(os.path.join(REF, "mmrec.py")).read()
+    tree = ast.parse(src)
+    main_fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "main")
+    seg = lambda n: ast.get_source_segment(src, n) or ""
+    first = next(i for i, n in enumerate(main_fn.body) if "tokenizer.add_special_tokens" in seg(n))
+    last = next(i for i, n in enumerate(main_fn.body) if "resize_token_embeddings" in seg(n))
+    block = main_fn.body[first:last]
+    added = []
+
+    class Rec:
+        def add_special_tokens(self, d):
+            added.extend(d["additional_special_tokens"])
+
+        def add_tokens(self, toks):
+            added.extend(toks)
+
+    ns = {"tokenizer": Rec(), "args": argparse.Namespace(subset=subset, use_semantic=use_semantic)}
+    exec(compile(ast.Module(body=block, type_ignores=[]), "mmrec.py::main[vocab growth]", "exec"), ns)
+    return added, block[0].lineno, block[-1].end_lineno
 
 
 class WordTokenizer:
@@ -404,8 +432,22 @@ def main():
             for p in self.frozen.parameters():
                 p.requires_grad_(False)
 
+    import hashlib
+    vocab_added, v0, v1 = lifted_vocab_growth("all", False)
+    groups, cur = [], None
+    for i, t in enumerate(vocab_added):           # runs of tokens sharing a prefix
+        pre = t.rstrip(",0123456789")
+        if cur is None or cur[0] != pre:
+            cur = [pre, i, 0, t, t]
+            groups.append(cur)
+        cur[2] += 1
+        cur[4] = t
+    vocab = {"lines": (v0, v1), "n_added": len(vocab_added), "groups": [tuple(g) for g in groups],
+             "sha256": hashlib.sha256("\n".join(vocab_added).encode()).hexdigest()}
+    print("vocab growth lines", v0, v1, "added", len(vocab_added), [(g[0], g[2]) for g in groups])
+
     ck = get_checkpoint(_Toy())
-    torch.save({"decay": decay, "grouped_params_lines": (l0, l1), "toy_checkpoint_keys": sorted(ck.keys()),
+    torch.save({"decay": decay, "vocab_growth": vocab, "grouped_params_lines": (l0, l1), "toy_checkpoint_keys": sorted(ck.keys()),
                 "source": "mmrec.py::get_grouped_params (ast-lifted) and train_utils.py::get_checkpoint, unmodified"},
                os.path.join(HERE, "ref_host_rules.pt"))
     print("decay", sum(decay.values()), "of", len(decay), "| toy checkpoint keys", sorted(ck.keys()))

@@ -23,6 +23,33 @@ def test_vocab_layout_matches_reference_token_growth():
     assert t.first_item - t.answer - 1 == 10 and t.first_img == t.first_item + 22738
 
 
+def test_vocab_layout_equals_the_reference_vocab_growth_run():
+    """`tests/golden/ref_host_rules.pt::vocab_growth` = the tokens `main()` appends to the tokenizer,
+    obtained by executing `UniMP/mmrec.py:538-581` unmodified against a recording tokenizer.  Ids
+    are positional (upstream's factory adds <|endofchunk|>, <image>, <PAD> first), so the order of
+    that list IS the id layout `openflamingo_4b_config()` must encode."""
+    import hashlib
+    import os
+
+    from util import GOLDEN
+
+    v = torch.load(os.path.join(GOLDEN, "ref_host_rules.pt"), weights_only=False)["vocab_growth"]
+    cfg = openflamingo_4b_config()
+    t = cfg.tokens
+    base = 50277                                  # RedPajama-INCITE tokenizer length (SURVEY.md s9)
+    assert (t.endofchunk, t.media, t.pad) == (base, base + 1, base + 2)
+    first_added = base + 3
+    starts = {g[0]: (first_added + g[1], g[2]) for g in v["groups"]}
+    assert starts["<answer>"] == (t.answer, 1)
+    assert starts["item_"] == (t.first_item, t.n_items)
+    assert starts["img_"] == (t.first_img, t.n_img)
+    assert first_added + v["n_added"] == cfg.vocab == 74053
+    # the exact token strings, in order (what a real tokenizer would be given)
+    want = (["<answer>"] + [f"rate_{i}" for i in range(1, 6)] + [f"s_{i}" for i in range(5)]
+            + [f"item_{i}" for i in range(t.n_items)] + [f"img_{i}," for i in range(t.n_img)])
+    assert hashlib.sha256("\n".join(want).encode()).hexdigest() == v["sha256"]
+
+
 @pytest.mark.parametrize("name", ["C1-tiny", "C2-rec", "C5-imggen"])
 def test_synthetic_batch_has_the_reference_prompt_structure(name):
     cfg = tiny_config() if name == "C1-tiny" else openflamingo_4b_config()
