@@ -23,8 +23,7 @@ src = os.path.join(ROOT, "unimp_b200", "csrc", "wip", "gate_ln_bwd_pipelined.cu"
 so = os.path.join(ROOT, "build", "libunimp_wip.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math",
-                       "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-o", so, src,
-                       os.path.join(ROOT, "unimp_b200", "csrc", "capi.cu"), "-lcudart"])
+                       "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-o", so, src, "-lcudart"])
 wip = C.CDLL(so)
 f = wip.unimp__gate_residual_ln_bwd_pipelined_main
 f.restype = C.c_int
