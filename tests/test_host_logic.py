@@ -287,3 +287,87 @@ def test_additive_mask_cache_is_keyed_on_identity_dtype_and_version():
     assert _additive_mask(m, torch.float32).tolist() == [[0.0, 0.0, 0.0]]
     assert _additive_mask(m.clone(), torch.float32) is not _additive_mask(m, torch.float32)
     assert _additive_mask(None, torch.float32) is None and _additive_mask(a, torch.float32) is a   # non-bool: as is
+
+
+def test_resize_token_embeddings_on_the_product_model():
+    """reference `UniMP/mmrec.py:595`: `lang_encoder.resize_token_embeddings(len(tokenizer))` after
+    the vocabulary grew.  The product's padded output head must survive it: old rows kept, both
+    embeddings at the new size, still an nn.Linear, re-wrapped for the new (odd) width, frozen /
+    trainable flags kept, state-dict shape exactly (V, D)."""
+    import copy
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.flamingo_lm import PaddedOutputHead
+
+    cfg = copy.copy(tiny_config())
+    cfg.vocab = 515                                    # odd, like the reference's 74 053
+    m = build_flamingo(cfg, dtype=torch.float32, device="cpu", seed=3)
+    lm = m.lang_encoder
+    assert isinstance(lm.embed_out, PaddedOutputHead) and isinstance(lm.embed_out, torch.nn.Linear)
+    w_out, w_in = lm.embed_out.weight.detach().clone(), lm.get_input_embeddings().weight.detach().clone()
+    lm.resize_token_embeddings(523)
+    head = lm.get_output_embeddings()
+    assert isinstance(head, PaddedOutputHead) and head.out_features == 523
+    assert tuple(head.weight.shape) == (523, cfg.lm_hidden)
+    assert tuple(lm.get_input_embeddings().weight.shape) == (523, cfg.lm_hidden)
+    assert torch.equal(head.weight[:515], w_out) and torch.equal(lm.get_input_embeddings().weight[:515], w_in)
+    assert not head.weight.requires_grad and lm.get_input_embeddings().weight.requires_grad
+    sd = m.state_dict()
+    assert tuple(sd["lang_encoder.embed_out.weight"].shape) == (523, cfg.lm_hidden)
+    lm.resize_token_embeddings(520)                    # multiple of 8: a plain Linear is enough
+    assert type(lm.get_output_embeddings()) is torch.nn.Linear
+    assert torch.equal(lm.get_output_embeddings().weight[:515], w_out)
+
+
+def test_adamw_hyper_staging_ring_never_overwrites_an_in_flight_buffer():
+    """one reused pinned buffer + non_blocking copy let step k run with step k+n's lr
+    and bias corrections.  Every prepare_step must stage through a different buffer than the
+    previous HYPER_RING-1 calls."""
+    net = torch.nn.Linear(8, 8)
+    opt = FlatAdamW([{"params": list(net.named_parameters()), "weight_decay": 0.0}], lr=1e-3)
+    seen = []
+    for s in range(1, 2 * opt.HYPER_RING + 1):
+        opt.prepare_step(lr_scale=s)
+        slot = opt.step_count % opt.HYPER_RING
+        seen.append(slot)
+        assert opt._hyper_ring[slot][0].item() == pytest.approx(1e-3 * s)
+        assert opt.hyper[0].item() == pytest.approx(1e-3 * s)
+        assert opt.hyper[1].item() == pytest.approx(1 - 0.9 ** s, rel=1e-6)
+    for i in range(opt.HYPER_RING, len(seen)):
+        assert len(set(seen[i - opt.HYPER_RING + 1:i + 1])) == opt.HYPER_RING   # no reuse inside the window
+
+
+def test_cached_media_kv_is_rebuilt_for_new_media_and_after_an_optimizer_step():
+    """the decode-time to_kv(media) cache was keyed on batch size only."""
+    from unimp_b200 import helpers, ops
+
+    attn = helpers.MaskedCrossAttention(dim=32, dim_visual=16)
+    calls = []
+    attn.project_media = lambda media: calls.append(media) or torch.zeros(1)
+    a, b = torch.randn(2, 2, 64, 16), torch.randn(2, 2, 64, 16)
+    attn.cached_media_kv(a); attn.cached_media_kv(a)
+    assert len(calls) == 1
+    attn.cached_media_kv(b)                            # same batch size, new images
+    assert len(calls) == 2
+    ops.bump_weights_epoch()                           # an optimizer step (raw-pointer update)
+    attn.cached_media_kv(b)
+    assert len(calls) == 3
+    b.add_(1.0)                                        # media edited in place
+    attn.cached_media_kv(b)
+    assert len(calls) == 4
+
+
+def test_direct_grad_parameter_fails_loudly_when_autograd_delivers_its_gradient():
+    """a direct-accumulation parameter reached through plain autograd used to lose its
+    gradient silently."""
+    class Blk(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q = torch.nn.Linear(4, 4, bias=False)
+    net = Blk()
+    opt = FlatAdamW([{"params": list(net.named_parameters()), "weight_decay": 0.0}], lr=1e-3)
+    assert not opt._guards                             # CPU tensors are never "direct"
+    net.to_q.weight._unimp_direct = True               # emulate the CUDA registration
+    opt.groups[0]["n_direct"] = 1
+    opt._install_direct_guards()
+    with pytest.raises(RuntimeError, match="direct gradient accumulation"):
+        net.to_q(torch.randn(2, 4)).sum().backward()

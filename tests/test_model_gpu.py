@@ -150,12 +150,17 @@ def test_graphed_train_step_matches_eager():
 
     model, opt = fresh()
     eager = [float(train_step(model, None, cfg.tokens, opt, None, accum_steps=2, micro_batches=mbs))
-             for _ in range(6)]
+             for _ in range(4)]
     model, opt = fresh()
-    g = GraphedTrainStep(model, cfg.tokens, opt, None, mbs, warmup_iters=3)  # steps 1-3 run eagerly
-    got = [float(g(mbs)) for _ in range(3)]                                  # steps 4, 5, 6
-    assert opt.step_count == 6
-    for a, b in zip(got, eager[3:]):
+    before = [t.clone() for t in opt.state_tensors()]
+    g = GraphedTrainStep(model, cfg.tokens, opt, None, mbs, warmup_iters=3)
+    # building the graph consumes NO optimizer step: state and step counter untouched
+    assert opt.step_count == 0
+    for a, b in zip(before, opt.state_tensors()):
+        assert torch.equal(a, b)
+    got = [float(g(mbs)) for _ in range(4)]                                  # steps 1..4
+    assert opt.step_count == 4
+    for a, b in zip(got, eager):
         assert abs(a - b) < 2e-3 * abs(b)
 
 

@@ -317,7 +317,7 @@ class GraphedDecoder:
         for layer in self.layers:                                        # to_kv(media): once per block
             blk = layer.gated_cross_attn_layer
             if blk is not None:
-                blk.attn._kv_cache = blk.attn.project_media(layer.vis_x)
+                blk.attn.cached_media_kv(layer.vis_x)
         first_logits = out.logits[:, -1, :].float()
         del out
 

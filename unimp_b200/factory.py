@@ -15,7 +15,7 @@ from transformers import GPTNeoXConfig, GPTNeoXForCausalLM
 
 from .config import FlamingoConfig, openflamingo_4b_config, tiny_config
 from .flamingo import Flamingo
-from .flamingo_lm import FlamingoLMMixin, PaddedOutputHead, extend_instance
+from .flamingo_lm import FlamingoLMMixin, extend_instance, wrap_output_head
 from .vit import VisionTransformer
 
 _LM_ARCH = {
@@ -55,8 +55,7 @@ def build_flamingo(cfg: FlamingoConfig, *, dtype=torch.bfloat16, device="cuda", 
     model.perceiver.requires_grad_(True)
     model.lang_encoder.gated_cross_attn_layers.requires_grad_(True)
     model.lang_encoder.get_input_embeddings().requires_grad_(True)
-    if model.lang_encoder.embed_out.out_features % 8:
-        model.lang_encoder.embed_out = PaddedOutputHead(model.lang_encoder.embed_out)
+    wrap_output_head(model.lang_encoder)
     if gate is not None:
         with torch.no_grad():
             for blk in model.lang_encoder.gated_cross_attn_layers:

@@ -73,15 +73,18 @@ class _PaddedHeadFn(torch.autograd.Function):
         return (gp.reshape(-1, Vp) @ w_pad).reshape(*lead, w_pad.shape[1]), None, None
 
 
-class PaddedOutputHead(nn.Module):
-    """Drop-in for the frozen, bias-free `embed_out` Linear (state-dict key `weight`, shape (V, D)
-    unchanged); see _PaddedHeadFn."""
+class PaddedOutputHead(nn.Linear):
+    """Drop-in for the frozen, bias-free `embed_out` Linear: still an `nn.Linear` (state-dict key
+    `weight`, shape (V, D), `in_features` / `out_features` unchanged), so everything that inspects
+    the head — HF `resize_token_embeddings` (reference `UniMP/mmrec.py:595`), `tie_weights`,
+    checkpoint code — keeps working; see _PaddedHeadFn for what forward does differently."""
 
     def __init__(self, linear: nn.Linear, multiple: int = 128):
-        super().__init__()
         assert linear.bias is None
-        self.weight = linear.weight
+        nn.Module.__init__(self)
         self.in_features, self.out_features = linear.in_features, linear.out_features
+        self.weight = linear.weight
+        self.register_parameter("bias", None)
         self.multiple = multiple
         self._wp = None
 
@@ -97,10 +100,30 @@ class PaddedOutputHead(nn.Module):
             self._wp = wp
         return wp
 
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        # the parameter may be a view of the padded buffer: serialise exactly (V, D), own storage
+        w = self.weight if keep_vars else self.weight.detach().clone()
+        destination[prefix + "weight"] = w
+
     def forward(self, h):
         if self.weight.requires_grad or not h.is_cuda:
             return torch.nn.functional.linear(h, self.weight)
         return _PaddedHeadFn.apply(h, self._padded(), self.out_features)
+
+    def gathered(self, h_rows):
+        """logits of a (N, D) row selection, padded stride, [:V] view (head+loss fusion)."""
+        return _PaddedHeadFn.apply(h_rows, self._padded(), self.out_features)
+
+
+def wrap_output_head(lm):
+    """(Re-)wrap `lm.embed_out` when its width needs padding for the aligned cuBLAS path."""
+    head = lm.get_output_embeddings()
+    if isinstance(head, PaddedOutputHead):
+        return head
+    if (isinstance(head, nn.Linear) and head.bias is None and not head.weight.requires_grad
+            and head.out_features % 8):
+        lm.set_output_embeddings(PaddedOutputHead(head))
+    return lm.get_output_embeddings()
 
 
 def _neox_fusable(layer, x, kw) -> bool:
@@ -221,8 +244,8 @@ class FlamingoLayer(nn.Module):
 
     def condition_vis_x(self, vis_x):
         self.vis_x = vis_x
-        if vis_x is None and self.gated_cross_attn_layer is not None:
-            self.gated_cross_attn_layer.attn._kv_cache = None
+        if self.gated_cross_attn_layer is not None:
+            self.gated_cross_attn_layer.attn._kv_cache = None   # new media (or none): never stale
 
     def condition_media_locations(self, media_locations, text_time=None):
         self.media_locations = media_locations
@@ -332,6 +355,25 @@ class FlamingoLMMixin(nn.Module):
         return CausalLMOutputWithPast(loss=loss, logits=logits,
                                       past_key_values=out.past_key_values,
                                       hidden_states=out.hidden_states, attentions=out.attentions)
+
+    def resize_token_embeddings(self, new_num_tokens=None, *args, **kwargs):
+        """reference `UniMP/mmrec.py:595` (`lang_encoder.resize_token_embeddings(len(tokenizer))`
+        after the vocabulary grew): unwrap the padded head to a plain nn.Linear of exactly (V, D),
+        let HF resize both embeddings, re-wrap for the new width."""
+        head = self.get_output_embeddings()
+        if isinstance(head, PaddedOutputHead):
+            plain = nn.Linear(head.in_features, head.out_features, bias=False,
+                              device=head.weight.device, dtype=head.weight.dtype)
+            with torch.no_grad():
+                plain.weight.copy_(head.weight)
+            plain.weight.requires_grad_(head.weight.requires_grad)
+            self.set_output_embeddings(plain)
+        out = super().resize_token_embeddings(new_num_tokens, *args, **kwargs)
+        new_head = self.get_output_embeddings()
+        if isinstance(head, PaddedOutputHead) and new_head is not None:
+            new_head.weight.requires_grad_(head.weight.requires_grad)
+        wrap_output_head(self)
+        return out
 
     def is_conditioned(self) -> bool:
         return all(l.is_conditioned() for l in self._get_decoder_layers())

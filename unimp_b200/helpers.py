@@ -124,6 +124,14 @@ class MaskedCrossAttention(nn.Module):
         B, Ti, n, Dv = media.shape
         return ops.linear_acc(media.reshape(B, Ti * n, Dv), self.to_kv.weight)
 
+    def cached_media_kv(self, media):
+        """to_kv(media), computed once per (media tensor, weight version) — decode-time cache."""
+        key = (id(media), media._version, self.to_kv.weight._version, self.to_kv.weight.data_ptr(),
+               ops.weights_epoch())   # FlatAdamW updates weights through raw pointers: no _version bump
+        if self._kv_cache is None or self._kv_cache[0] != key:
+            self._kv_cache = (key, self.project_media(media), media)  # `media` kept alive: id stays unique
+        return self._kv_cache[1]
+
     def forward(self, x, media, media_locations=None, use_cached_media=False, text_time=None,
                 x_ln=None):
         """x (B,T,D); media (B,Ti,n,Dv); `text_time` int32 (B,T) may be passed precomputed
@@ -144,9 +152,10 @@ class MaskedCrossAttention(nn.Module):
             x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         q = ops.linear_acc(x_ln, self.to_q.weight)
         if use_cached_media and not torch.is_grad_enabled():
-            if self._kv_cache is None or self._kv_cache.shape[0] != B:
-                self._kv_cache = self.project_media(media)
-            kv = self._kv_cache
+            # keyed on the media tensor (identity + version) and on the projection weights'
+            # version: new images of the same batch size, or an optimizer step between two
+            # cached forwards, rebuild the cache (upstream recomputes to_kv(media) every call)
+            kv = self.cached_media_kv(media)
             if T == 1:
                 out = ops.xattn_decode(q, kv, text_time[:, 0].contiguous(), heads=self.heads,
                                        n_latents=n, scale=self.scale)

@@ -467,6 +467,19 @@ def embedding_acc(ids, w):
 
 # --------------------------------------------------------------------------- optimizer pieces
 
+_WEIGHTS_EPOCH = [0]
+
+
+def weights_epoch() -> int:
+    """Counts optimizer steps taken through raw-pointer kernels (they do not bump a tensor's
+    `_version`); caches derived from trainable weights key on it."""
+    return _WEIGHTS_EPOCH[0]
+
+
+def bump_weights_epoch():
+    _WEIGHTS_EPOCH[0] += 1
+
+
 def sumsq_(grad: torch.Tensor, acc: torch.Tensor):
     """acc[0] += sum(grad^2)."""
     check(_lib.load().unimp_sumsq(grad.data_ptr(), grad.numel(), acc.data_ptr(), _dt(grad),

@@ -132,9 +132,40 @@ class FlatAdamW:
         # step-dependent scalars (lr, bias corrections) live in device memory so that a captured
         # CUDA graph of the whole step stays valid from step to step
         self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(3, dtype=torch.float32)
+        # The host runs ahead of the GPU (graph replays, no sync): the H2D copy of step k's scalars
+        # may not have executed when step k+n is prepared.  A ring of pinned staging buffers, each
+        # guarded by an event recorded after its copy, keeps every in-flight copy's source intact.
+        self._hyper_ring = [torch.zeros(3, dtype=torch.float32) for _ in range(self.HYPER_RING)]
+        self._hyper_events = [None] * self.HYPER_RING
         if dev.type == "cuda":
-            self._hyper_host = self._hyper_host.pin_memory()
+            self._hyper_ring = [h.pin_memory() for h in self._hyper_ring]
+        self._guards = []
+        if direct_grads:
+            self._install_direct_guards()
+
+    HYPER_RING = 8
+
+    def _install_direct_guards(self):
+        """A direct-accumulation parameter must get its gradient from ops.linear_acc /
+        ops.embedding_acc (which return None to autograd).  If a DEFINED gradient reaches it
+        through ordinary autograd (someone called `module(x)` / `F.linear` on it), AccumulateGrad
+        would add onto last step's stale buffer and the step would silently drop it: fail loudly."""
+        for g in self.groups:
+            for (name, p, _, _) in g["spans"][:g["n_direct"]]:
+                def guard(grad, name=name):
+                    raise RuntimeError(
+                        f"parameter {name} is registered for direct gradient accumulation "
+                        "(FlatAdamW(direct_grads=True)) but received a gradient through autograd: "
+                        "route its forward through unimp_b200.ops.linear_acc / embedding_acc, or "
+                        "build the optimizer with direct_grads=False")
+                self._guards.append(p.register_hook(guard))
+
+    def state_tensors(self):
+        """Every tensor an optimizer step mutates (for snapshot / restore)."""
+        out = []
+        for g in self.groups:
+            out += [t for t in (g["flat_p"], g["master"], g["m"], g["v"]) if t is not None]
+        return out
 
     def zero_grad(self):
         """Non-direct gradients are memset; direct ones are only flagged: their first backward
@@ -160,9 +191,19 @@ class FlatAdamW:
         """Host side of a step: advance the step count and upload (lr, bias corrections).
         Call BEFORE replaying a captured step (step() calls it itself)."""
         self.step_count += 1
+        ops.bump_weights_epoch()
         h = ops.adamw_hyper(self.lr * lr_scale, self.betas[0], self.betas[1], self.step_count)
-        self._hyper_host.copy_(torch.tensor(h))
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        slot = self.step_count % self.HYPER_RING
+        ev = self._hyper_events[slot]
+        if ev is not None:
+            ev.synchronize()       # the copy that last used this staging buffer has executed
+        host = self._hyper_ring[slot]
+        host[0], host[1], host[2] = h
+        self.hyper.copy_(host, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = ev or torch.cuda.Event()
+            ev.record()
+            self._hyper_events[slot] = ev
 
     @torch.no_grad()
     def step_kernels(self, grad_scale: float = 1.0):
@@ -335,6 +376,9 @@ class ShardedDataParallel(BucketedAllReduce):
                 "weight_decay": grp["weight_decay"],
             })
 
+    def state_tensors(self):
+        return [t for sh in self.shards for t in (sh["master"], sh["m"], sh["v"])]
+
     def _launch(self, bidx):
         sh = self.shards[bidx]
         # in place: the output is this rank's slice of the input (NCCL in-place reduce-scatter)
@@ -479,14 +523,31 @@ class GraphedTrainStep:
         self.static = [{k: v.clone() for k, v in mb.items()} for mb in example_mbs]
         self.accum = len(self.static)
         self.grad_scale = reducer.grad_scale if reducer is not None else 1.0
+        # Warm-up (allocator pools, cuBLAS workspaces, NCCL channels) runs REAL steps; they must not
+        # count: every tensor a step mutates is snapshotted and restored and the step counter is
+        # rewound, so the first replay is optimizer step 1 at the schedule's step-0 learning rate
+        # (reference: lr_scheduler runs from step 0, UniMP/mmrec.py:688-693).  lr_scale = 0 as well,
+        # so that the replicas cannot drift even between snapshot and restore.
+        state = list(opt.state_tensors())
+        if reducer is not None and hasattr(reducer, "state_tensors"):
+            state += reducer.state_tensors()
+        step0 = opt.step_count
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            snap = [t.clone() for t in state]
             for _ in range(warmup_iters):
-                self.opt.prepare_step()
+                self.opt.prepare_step(0.0)
                 self._body()
+            # (deferred all-gather mode: the reducer is left "params stale" on purpose, so that the
+            # capture below records the gather at the ViT entry; the restore makes every rank's
+            # full parameter buffer current regardless)
+            for t, s0 in zip(state, snap):
+                t.copy_(s0)
+            del snap
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        opt.step_count = step0
         self.graph = torch.cuda.CUDAGraph()
         # capture records the launches without running them: no step is consumed here
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
