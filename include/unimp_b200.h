@@ -171,6 +171,24 @@ int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t* labels,
                        void* d_logits, int64_t ld_out, int B, int T, int V, int group_size,
                        int dtype, void* stream);
 
+/* Head + loss fusion: the same loss over PRE-GATHERED logits rows.  Only rows
+ * (b,t) whose shifted label labels[b,t+1] != -100 matter to reference UniMP/mmrec.py:190-213
+ * (24 of 1536 at configs[1]); the host gathers those hidden rows before the output head, so
+ * logits is (R,V) with row stride ld.  targets[r] = the row's own label (-100 = unused padding
+ * slot of a fixed-capacity gather), row_weights[r] = weights[b] of the row's sample,
+ * row_groups[r] in [0,G) = its normalisation group (may be NULL when G == 1).
+ * Same outputs as unimp_focal_ce_fwd; workspace: unimp_focal_ce_workspace(R, 1, V, dtype).
+ * d_logits (R,V) row stride ld_out, fully written (zero rows for padding slots). */
+int unimp_focal_ce_rows_fwd(const void* logits, int64_t ld, const int64_t* targets,
+                            const float* row_weights, const int32_t* row_groups, float gamma,
+                            int use_focal, float* row_lse, float* row_pt, float* acc, float* loss,
+                            void* workspace, int R, int G, int V, int dtype, void* stream);
+int unimp_focal_ce_rows_bwd(const void* logits, int64_t ld, const int64_t* targets,
+                            const float* row_weights, const int32_t* row_groups, float gamma,
+                            int use_focal, const float* row_lse, const float* row_pt,
+                            const float* acc, const float* g_loss, void* d_logits, int64_t ld_out,
+                            int R, int G, int V, int dtype, void* stream);
+
 /* ---- a9 (f2): answer-span label masking on the GPU -----------------------------------
  * Replaces the Python double loop of reference UniMP/mmrec.py:143-168. */
 int unimp_mask_labels(const int64_t* input_ids, int64_t answer_id, int64_t endofchunk_id,

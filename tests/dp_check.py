@@ -82,8 +82,10 @@ def main():
             r = BucketedAllReduce(o, bucket_bytes=256 << 10)
         mbs = batches(rank)
         if graph:
-            gs = GraphedTrainStep(m, cfg.tokens, o, r, mbs, warmup_iters=2, fuse_accum=True)  # steps 1, 2
-            gs(mbs)                                                                             # step 3
+            gs = GraphedTrainStep(m, cfg.tokens, o, r, mbs, warmup_iters=2, fuse_accum=True)  # consumes no step
+            assert o.step_count == 0
+            for _ in range(3):
+                gs(mbs)                                                                         # steps 1-3
         else:
             for _ in range(3):
                 train_step(m, None, cfg.tokens, o, r, accum_steps=2, micro_batches=mbs, fuse_accum=True)

@@ -256,3 +256,63 @@ def test_fused_accumulation_window_equals_sequential_micro_batches(dtype):
     assert abs(res[0][0] - res[1][0]) < tol * abs(res[0][0])
     for n in res[0][1]:
         assert rel_err(res[1][1][n], res[0][1][n]) < tol, n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("capacity", [True, 64])
+def test_head_loss_fusion_on_label_rows_equals_the_dense_path(dtype, capacity):
+    """gathering the rows with a valid shifted label BEFORE embed_out (exact gather or
+    a fixed-capacity, graph-safe one) gives the same focal loss, the same logged HF mean CE, the
+    same logits on those rows and the same gradients as the dense (B,T,V) path of
+    reference UniMP/mmrec.py:177-213."""
+    from unimp_b200 import ops
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import FlatAdamW, get_grouped_params, unimp_loss, unimp_loss_fused
+
+    cfg = tiny_config()
+    mbs = [{k: v.cuda() for k, v in make_batch(cfg, WORKLOADS["C1-tiny"], seed=i, ragged=(i == 0)).items()}
+           for i in range(2)]
+    res = {}
+    for mode in ("dense", "rows"):
+        model = build_flamingo(cfg, dtype=dtype, device="cuda", gate=0.5, seed=0)
+        opt = FlatAdamW(get_grouped_params(model, 0.1), lr=1e-3)
+        opt.zero_grad()
+        kw = {} if mode == "dense" else {"label_rows": capacity}
+        l1, hf1, lg1 = unimp_loss(model, mbs[0], cfg.tokens, **kw)            # single micro-batch
+        l1.backward()
+        g1 = {n: p.grad.detach().float().clone() for g in opt.groups for (n, p, _, _) in g["spans"]}
+        opt.zero_grad()
+        l2, lg2 = unimp_loss_fused(model, mbs, cfg.tokens, **kw)               # accumulation window
+        l2.backward()
+        g2 = {n: p.grad.detach().float().clone() for g in opt.groups for (n, p, _, _) in g["spans"]}
+        res[mode] = (float(l1), float(hf1), lg1.detach().float(), g1, float(l2), lg2.detach().float(), g2)
+    d, r = res["dense"], res["rows"]
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert abs(d[0] - r[0]) < tol * abs(d[0]) and abs(d[1] - r[1]) < tol * abs(d[1])
+    assert abs(d[4] - r[4]) < tol * abs(d[4])
+    labels = ops.mask_labels(mbs[0]["input_ids"], answer_token_id=cfg.tokens.answer,
+                             endofchunk_token_id=cfg.tokens.endofchunk, media_token_id=cfg.tokens.media,
+                             pad_token_id=cfg.tokens.pad)
+    idx, tgt, _ = ops.gather_label_rows(labels)
+    V = d[2].shape[-1]
+    want_rows = d[2].reshape(-1, V)[idx.cpu()]
+    assert rel_err(r[2][:idx.numel()], want_rows) < (1e-6 if dtype == torch.float32 else 1e-2)
+    if capacity is not True:
+        assert r[2].shape[0] == capacity
+    for n in d[3]:
+        assert rel_err(r[3][n], d[3][n]) < tol, n
+        assert rel_err(r[6][n], d[6][n]) < tol, n
+
+
+def test_head_loss_fusion_overflow_of_the_static_capacity_is_loud():
+    """A fixed-capacity gather that cannot hold every valid row must not return a plausible loss."""
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import unimp_loss
+
+    cfg = tiny_config()
+    model = build_flamingo(cfg, dtype=torch.float32, device="cuda", gate=0.5)
+    gb = {k: v.cuda() for k, v in make_batch(cfg, WORKLOADS["C1-tiny"], seed=0).items()}
+    loss, _, _ = unimp_loss(model, gb, cfg.tokens, label_rows=2)
+    assert torch.isnan(loss)
+    loss, _, _ = unimp_loss(model, gb, cfg.tokens, label_rows=512)
+    assert torch.isfinite(loss)

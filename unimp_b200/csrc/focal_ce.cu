@@ -50,16 +50,45 @@ __device__ __forceinline__ void load_slot(const T* row, int V, const RowSlots<T>
   }
 }
 
-// grid (B*T, nchunks). partial[(row*nchunks + c)*2 + {0,1}] = (max, sum exp(x-max)).
+// Two row addressings share every kernel below:
+//   dense  (T_ > 0): logits (B,T,V); row (b,t) is scored against labels[b,t+1]; weight weights[b];
+//                    normalisation group b / group_size.
+//   rows   (T_ == 0): logits (R,V) are pre-gathered rows (head + loss fusion: only rows with a
+//                    valid label ever reach the head GEMM); labels[r] is the row's own target
+//                    (-100 = padding slot), weights[r] its sample's weight, groups[r] its group.
+struct RowMeta {
+  int64_t y;
+  float w;
+  int g;
+};
+__device__ __forceinline__ int64_t row_target(const int64_t* __restrict__ labels, int row, int T_) {
+  if (T_ > 0) return (row % T_ == T_ - 1) ? -100 : labels[row + 1];
+  return labels[row];
+}
+__device__ __forceinline__ RowMeta row_meta(const int64_t* __restrict__ labels,
+                                            const float* __restrict__ weights,
+                                            const int32_t* __restrict__ groups, int row, int T_,
+                                            int group_size) {
+  RowMeta m;
+  m.y = row_target(labels, row, T_);
+  if (T_ > 0) {
+    m.w = weights[row / T_];
+    m.g = (row / T_) / group_size;
+  } else {
+    m.w = weights[row];
+    m.g = groups ? groups[row] : 0;
+  }
+  return m;
+}
+
+// grid (rows, nchunks). partial[(row*nchunks + c)*2 + {0,1}] = (max, sum exp(x-max)).
 template <typename T>
 __global__ void __launch_bounds__(CE_THREADS)
 focal_ce_partial_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
                         float* __restrict__ partial, int T_, int V) {
   constexpr int N = Vec16<T>::N;
-  const int row = blockIdx.x;  // b*T + t
-  const int t = row % T_;
-  if (t == T_ - 1) return;
-  if (labels[row + 1] == -100) return;  // shifted label of (b,t) is labels[b,t+1]
+  const int row = blockIdx.x;  // b*T + t (dense) or gathered row index
+  if (row_target(labels, row, T_) == -100) return;
   const T* rp = logits + (int64_t)row * ld;
   RowSlots<T> rs(rp, V);
   const int slots_per_cta = CE_THREADS * CE_SLOTS_PER_THREAD;
@@ -102,23 +131,24 @@ focal_ce_partial_kernel(const T* __restrict__ logits, int64_t ld, const int64_t*
 template <typename T>
 __global__ void __launch_bounds__(1024)
 focal_ce_finish_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
-                       const float* __restrict__ weights, const float* __restrict__ partial,
+                       const float* __restrict__ weights, const int32_t* __restrict__ groups,
+                       const float* __restrict__ partial,
                        int nchunks, float gamma, int use_focal, float* __restrict__ row_lse,
                        float* __restrict__ row_pt, float* __restrict__ acc, float* __restrict__ loss,
-                       int B, int T_, int group_size) {
+                       int n_rows, int G, int T_, int group_size) {
   // Samples are normalised in groups of `group_size` (one group = one micro-batch of the
   // reference's accumulation window): loss = mean_g( sum_g(w*CE*focal) / n_valid_g ).
-  const int G = B / group_size;
   float total = 0.f;
   __shared__ float sh[32];
   for (int g = 0; g < G; ++g) {
   float lsum = 0.f, nval = 0.f;
-  const int row_lo = g * group_size * T_, rows = (g + 1) * group_size * T_;
+  // dense: group g owns a contiguous row range; rows mode: filter by the row's group id
+  const int row_lo = T_ > 0 ? g * group_size * T_ : 0;
+  const int rows = T_ > 0 ? (g + 1) * group_size * T_ : n_rows;
   for (int row = row_lo + threadIdx.x; row < rows; row += blockDim.x) {
-    const int t = row % T_;
-    if (t == T_ - 1) continue;
-    const int64_t y = labels[row + 1];
-    if (y == -100) continue;
+    const RowMeta rm = row_meta(labels, weights, groups, row, T_, group_size);
+    const int64_t y = rm.y;
+    if (y == -100 || rm.g != g) continue;
     const float* p = partial + (int64_t)row * nchunks * 2;
     float m = -INFINITY;
     for (int c = 0; c < nchunks; ++c) m = fmaxf(m, p[2 * c]);
@@ -130,7 +160,7 @@ focal_ce_finish_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* 
     const float pt = expf(xy - lse);
     row_lse[row] = lse;
     row_pt[row] = pt;
-    float l = weights[row / T_] * ce;
+    float l = rm.w * ce;
     if (use_focal) l *= powf(fmaxf(1.f - pt, 0.f), gamma);
     lsum += l;
     nval += 1.f;
@@ -150,19 +180,19 @@ focal_ce_finish_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* 
 template <typename T>
 __global__ void __launch_bounds__(CE_THREADS)
 focal_ce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
-                    const float* __restrict__ weights, float gamma, int use_focal,
+                    const float* __restrict__ weights, const int32_t* __restrict__ groups,
+                    float gamma, int use_focal,
                     const float* __restrict__ row_lse, const float* __restrict__ row_pt,
                     const float* __restrict__ acc, const float* __restrict__ g_loss,
                     T* __restrict__ d_logits, int64_t ld_out, int T_, int V, int group_size, int G) {
   constexpr int N = Vec16<T>::N;
   const int row = blockIdx.x;
-  const int t = row % T_;
   T* op = d_logits + (int64_t)row * ld_out;
   RowSlots<T> os(op, V);
   const int slots_per_cta = CE_THREADS * CE_SLOTS_PER_THREAD;
   const int s0 = blockIdx.y * slots_per_cta;
-  int64_t y = -100;
-  if (t != T_ - 1) y = labels[row + 1];
+  const RowMeta rm = row_meta(labels, weights, groups, row, T_, group_size);
+  const int64_t y = rm.y;
   float coef = 0.f, lse = 0.f;
   const T* rp = logits + (int64_t)row * ld;
   bool vec_in = false;
@@ -175,8 +205,7 @@ focal_ce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __r
       const float ce = -logf(fmaxf(pt, 1e-38f));
       c = powf(omp, gamma) + gamma * powf(omp, gamma - 1.f) * pt * ce;
     }
-    const int b = row / T_;
-    coef = c * weights[b] * (*g_loss) / (acc[2 * (b / group_size) + 1] * G);
+    coef = c * rm.w * (*g_loss) / (acc[2 * rm.g + 1] * G);
     vec_in = ((reinterpret_cast<uintptr_t>(rp) ^ reinterpret_cast<uintptr_t>(op)) & 15) == 0;
   }
 #pragma unroll
@@ -231,6 +260,53 @@ extern "C" int64_t unimp_focal_ce_workspace(int B, int T, int V, int dtype) {
   return (int64_t)B * T * ce_nchunks(V, dtype) * 2 * sizeof(float);
 }
 
+
+static int focal_fwd_launch(const void* logits, int64_t ld, const int64_t* labels,
+                            const float* weights, const int32_t* groups, float gamma, int use_focal,
+                            float* row_lse, float* row_pt, float* acc, float* loss, void* workspace,
+                            int n_rows, int G, int T, int V, int group_size, int dtype,
+                            cudaStream_t st) {
+  const int nch = ce_nchunks(V, dtype);
+  dim3 grid(n_rows, nch);
+  float* partial = (float*)workspace;
+  if (dtype == UNIMP_BF16) {
+    focal_ce_partial_kernel<__nv_bfloat16><<<grid, CE_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)logits, ld, labels, partial, T, V);
+    UNIMP_CHECK_LAUNCH();
+    focal_ce_finish_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>(
+        (const __nv_bfloat16*)logits, ld, labels, weights, groups, partial, nch, gamma, use_focal,
+        row_lse, row_pt, acc, loss, n_rows, G, T, group_size);
+  } else {
+    focal_ce_partial_kernel<float><<<grid, CE_THREADS, 0, st>>>((const float*)logits, ld, labels,
+                                                                  partial, T, V);
+    UNIMP_CHECK_LAUNCH();
+    focal_ce_finish_kernel<float><<<1, 1024, 0, st>>>((const float*)logits, ld, labels, weights,
+                                                       groups, partial, nch, gamma, use_focal,
+                                                       row_lse, row_pt, acc, loss, n_rows, G, T,
+                                                       group_size);
+  }
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+static int focal_bwd_launch(const void* logits, int64_t ld, const int64_t* labels,
+                            const float* weights, const int32_t* groups, float gamma, int use_focal,
+                            const float* row_lse, const float* row_pt, const float* acc,
+                            const float* g_loss, void* d_logits, int64_t ld_out, int n_rows, int G,
+                            int T, int V, int group_size, int dtype, cudaStream_t st) {
+  dim3 grid(n_rows, ce_nchunks(V, dtype));
+  if (dtype == UNIMP_BF16)
+    focal_ce_bwd_kernel<__nv_bfloat16><<<grid, CE_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)logits, ld, labels, weights, groups, gamma, use_focal, row_lse, row_pt,
+        acc, g_loss, (__nv_bfloat16*)d_logits, ld_out, T, V, group_size, G);
+  else
+    focal_ce_bwd_kernel<float><<<grid, CE_THREADS, 0, st>>>(
+        (const float*)logits, ld, labels, weights, groups, gamma, use_focal, row_lse, row_pt, acc,
+        g_loss, (float*)d_logits, ld_out, T, V, group_size, G);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t* labels,
                                   const float* weights, float gamma, int use_focal,
                                   float* row_lse, float* row_pt, float* acc, float* loss,
@@ -243,27 +319,9 @@ extern "C" int unimp_focal_ce_fwd(const void* logits, int64_t ld, const int64_t*
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_fwd: dtype");
   UNIMP_CHECK_ARG(group_size > 0 && B % group_size == 0, UNIMP_E_SHAPE,
                   "focal_ce_fwd: group_size=%d must divide B=%d", group_size, B);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int nch = ce_nchunks(V, dtype);
-  dim3 grid(B * T, nch);
-  float* partial = (float*)workspace;
-  if (dtype == UNIMP_BF16) {
-    focal_ce_partial_kernel<__nv_bfloat16><<<grid, CE_THREADS, 0, st>>>(
-        (const __nv_bfloat16*)logits, ld, labels, partial, T, V);
-    UNIMP_CHECK_LAUNCH();
-    focal_ce_finish_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>(
-        (const __nv_bfloat16*)logits, ld, labels, weights, partial, nch, gamma, use_focal,
-        row_lse, row_pt, acc, loss, B, T, group_size);
-  } else {
-    focal_ce_partial_kernel<float><<<grid, CE_THREADS, 0, st>>>((const float*)logits, ld, labels,
-                                                                  partial, T, V);
-    UNIMP_CHECK_LAUNCH();
-    focal_ce_finish_kernel<float><<<1, 1024, 0, st>>>((const float*)logits, ld, labels, weights,
-                                                       partial, nch, gamma, use_focal, row_lse,
-                                                       row_pt, acc, loss, B, T, group_size);
-  }
-  UNIMP_CHECK_LAUNCH();
-  return 0;
+  return focal_fwd_launch(logits, ld, labels, weights, nullptr, gamma, use_focal, row_lse, row_pt, acc,
+                          loss, workspace, B * T, B / group_size, T, V, group_size, dtype,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t* labels,
@@ -278,16 +336,37 @@ extern "C" int unimp_focal_ce_bwd(const void* logits, int64_t ld, const int64_t*
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_bwd: dtype");
   UNIMP_CHECK_ARG(group_size > 0 && B % group_size == 0, UNIMP_E_SHAPE,
                   "focal_ce_bwd: group_size=%d must divide B=%d", group_size, B);
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(B * T, ce_nchunks(V, dtype));
-  if (dtype == UNIMP_BF16)
-    focal_ce_bwd_kernel<__nv_bfloat16><<<grid, CE_THREADS, 0, st>>>(
-        (const __nv_bfloat16*)logits, ld, labels, weights, gamma, use_focal, row_lse, row_pt, acc,
-        g_loss, (__nv_bfloat16*)d_logits, ld_out, T, V, group_size, B / group_size);
-  else
-    focal_ce_bwd_kernel<float><<<grid, CE_THREADS, 0, st>>>(
-        (const float*)logits, ld, labels, weights, gamma, use_focal, row_lse, row_pt, acc, g_loss,
-        (float*)d_logits, ld_out, T, V, group_size, B / group_size);
-  UNIMP_CHECK_LAUNCH();
-  return 0;
+  return focal_bwd_launch(logits, ld, labels, weights, nullptr, gamma, use_focal, row_lse, row_pt, acc,
+                          g_loss, d_logits, ld_out, B * T, B / group_size, T, V, group_size, dtype,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int unimp_focal_ce_rows_fwd(const void* logits, int64_t ld, const int64_t* targets,
+                                       const float* row_weights, const int32_t* row_groups,
+                                       float gamma, int use_focal, float* row_lse, float* row_pt,
+                                       float* acc, float* loss, void* workspace, int R, int G, int V,
+                                       int dtype, void* stream) {
+  UNIMP_CHECK_ARG(logits && targets && row_weights && row_lse && row_pt && acc && loss && workspace,
+                  UNIMP_E_NULL, "focal_ce_rows_fwd: NULL pointer");
+  UNIMP_CHECK_ARG(R > 0 && G > 0 && V > 0 && ld >= V && (G == 1 || row_groups), UNIMP_E_SHAPE,
+                  "focal_ce_rows_fwd: bad shape R=%d G=%d V=%d ld=%lld", R, G, V, (long long)ld);
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_rows_fwd: dtype");
+  return focal_fwd_launch(logits, ld, targets, row_weights, row_groups, gamma, use_focal, row_lse,
+                          row_pt, acc, loss, workspace, R, G, 0, V, 1, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int unimp_focal_ce_rows_bwd(const void* logits, int64_t ld, const int64_t* targets,
+                                       const float* row_weights, const int32_t* row_groups,
+                                       float gamma, int use_focal, const float* row_lse,
+                                       const float* row_pt, const float* acc, const float* g_loss,
+                                       void* d_logits, int64_t ld_out, int R, int G, int V, int dtype,
+                                       void* stream) {
+  UNIMP_CHECK_ARG(logits && targets && row_weights && row_lse && row_pt && acc && g_loss && d_logits,
+                  UNIMP_E_NULL, "focal_ce_rows_bwd: NULL pointer");
+  UNIMP_CHECK_ARG(R > 0 && G > 0 && V > 0 && ld >= V && ld_out >= V && (G == 1 || row_groups),
+                  UNIMP_E_SHAPE, "focal_ce_rows_bwd: bad shape");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "focal_ce_rows_bwd: dtype");
+  return focal_bwd_launch(logits, ld, targets, row_weights, row_groups, gamma, use_focal, row_lse,
+                          row_pt, acc, g_loss, d_logits, ld_out, R, G, 0, V, 1, dtype,
+                          (cudaStream_t)stream);
 }

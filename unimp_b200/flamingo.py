@@ -35,7 +35,9 @@ class Flamingo(nn.Module):
         self._use_cached_vision_x = False
 
     def forward(self, vision_x, lang_x, attention_mask=None, labels=None,
-                clear_conditioned_layers=True, past_key_values=None, use_cache=False):
+                clear_conditioned_layers=True, past_key_values=None, use_cache=False,
+                label_rows=None):
+        """`label_rows` is product-only (default: upstream behaviour): see FlamingoLMMixin.forward."""
         assert (
             self.lang_encoder.initialized_flamingo
         ), "Flamingo layers are not initialized. Please call `init_flamingo` first."
@@ -50,8 +52,9 @@ class Flamingo(nn.Module):
         else:
             self._encode_vision_x(vision_x=vision_x)
             self._condition_media_locations(input_ids=lang_x)
+        extra = {} if label_rows is None else {"label_rows": label_rows}
         output = self.lang_encoder(input_ids=lang_x, attention_mask=attention_mask, labels=labels,
-                                   past_key_values=past_key_values, use_cache=use_cache)
+                                   past_key_values=past_key_values, use_cache=use_cache, **extra)
         if clear_conditioned_layers:
             self.lang_encoder.clear_conditioned_layers()
         return output

@@ -11,12 +11,25 @@ from the one-pass focal-CE kernel rather than HF's fp32 upcast + CrossEntropyLos
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+from typing import Optional
+
 import torch
 import torch.nn as nn
 from transformers.modeling_outputs import CausalLMOutputWithPast
 
 from . import ops
 from .helpers import GatedCrossAttentionBlock
+
+
+@dataclass
+class LabelRowsOutput(CausalLMOutputWithPast):
+    """`forward(..., label_rows=...)`: `logits` holds ONLY the rows the loss reads — (R, V), row r
+    = position `row_index[r]` of the flattened (B*T) sequence, scored against `row_targets[r]`
+    (-100 = unused slot of a fixed-capacity gather).  `loss` (= out[0]) is the HF mean CE."""
+    row_index: Optional[torch.LongTensor] = None
+    row_targets: Optional[torch.LongTensor] = None
+    overflow: Optional[torch.Tensor] = None
 
 
 def getattr_recursive(obj, att):
@@ -317,7 +330,13 @@ class FlamingoLMMixin(nn.Module):
             a._next_holder[0] = b
         self._set_decoder_layers(nn.ModuleList(layers))
 
-    def forward(self, input_ids=None, attention_mask=None, labels=None, **kwargs):
+    def forward(self, input_ids=None, attention_mask=None, labels=None, label_rows=None, **kwargs):
+        """`label_rows` (product-only, default off = upstream behaviour): head + loss fusion for
+        training.  The reference's loss (UniMP/mmrec.py:190-213) and HF's logged
+        mean CE read only rows whose shifted label is not -100 (24 of 1536 at configs[1]); with
+        `label_rows=True` (exact, one host sync) or an int capacity (static shapes, graph-safe)
+        those hidden rows are gathered BEFORE `embed_out`, so the head GEMM, the logits and
+        d_logits are (R, V) instead of (B, T, V).  Returns a LabelRowsOutput."""
         if not self.initialized_flamingo:
             raise ValueError("Flamingo layers are not initialized. Call `init_flamingo` first.")
         media_locations = input_ids == self.media_token_id
@@ -346,6 +365,8 @@ class FlamingoLMMixin(nn.Module):
         else:
             kwargs["input_ids"] = input_ids
         kwargs["attention_mask"] = attention_mask
+        if label_rows is not None and label_rows is not False:
+            return self._forward_label_rows(labels, label_rows, kwargs)
         out = super().forward(**kwargs)  # HF forward without labels: no fp32 logits copy
         if labels is None:
             return out
@@ -355,6 +376,25 @@ class FlamingoLMMixin(nn.Module):
         return CausalLMOutputWithPast(loss=loss, logits=logits,
                                       past_key_values=out.past_key_values,
                                       hidden_states=out.hidden_states, attentions=out.attentions)
+
+    def _forward_label_rows(self, labels, label_rows, kwargs):
+        if labels is None:
+            raise ValueError("label_rows needs labels (it gathers the rows the loss reads)")
+        kwargs.pop("logits_to_keep", None)
+        base = self.base_model(**kwargs)                       # decoder stack + final LayerNorm
+        hidden = base.last_hidden_state                        # (B, T, D)
+        B, T, D = hidden.shape
+        cap = None if label_rows is True else int(label_rows)
+        idx, targets, overflow = ops.gather_label_rows(labels.to(hidden.device), cap)
+        rows = hidden.reshape(B * T, D).index_select(0, idx)   # backward: scatter-add of R rows
+        head = self.get_output_embeddings()
+        logits = head.gathered(rows) if isinstance(head, PaddedOutputHead) and not head.weight.requires_grad \
+            and rows.is_cuda else head(rows)
+        ones = torch.ones(idx.shape[0], dtype=torch.float32, device=logits.device)
+        loss = ops.focal_ce_rows(logits, targets, ones, None, n_groups=1, gamma=0.0, use_focal=False)
+        return LabelRowsOutput(loss=loss, logits=logits, past_key_values=base.past_key_values,
+                               hidden_states=base.hidden_states, attentions=base.attentions,
+                               row_index=idx, row_targets=targets, overflow=overflow)
 
     def resize_token_embeddings(self, new_num_tokens=None, *args, **kwargs):
         """reference `UniMP/mmrec.py:595` (`lang_encoder.resize_token_embeddings(len(tokenizer))`

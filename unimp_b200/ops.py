@@ -313,6 +313,83 @@ def focal_ce(logits, labels, weights, *, gamma: float = 2.0, use_focal: bool = T
     return _FocalCE.apply(logits, labels, weights, gamma, use_focal, group_size)
 
 
+class _FocalCERows(torch.autograd.Function):
+    """Same loss over pre-gathered logits rows (head + loss fusion)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, row_w, row_g, G, gamma, use_focal):
+        dt = _dt(logits)
+        assert logits.dim() == 2 and logits.stride(1) == 1
+        R, V = logits.shape
+        ld = logits.stride(0)
+        dev = logits.device
+        targets = targets.to(device=dev, dtype=torch.int64).contiguous()
+        row_w = row_w.to(device=dev, dtype=torch.float32).contiguous()
+        if row_g is not None:
+            row_g = row_g.to(device=dev, dtype=torch.int32).contiguous()
+        assert targets.shape == (R,) and row_w.shape == (R,)
+        lib = _lib.load()
+        row_lse = torch.empty(R, dtype=torch.float32, device=dev)
+        row_pt = torch.empty(R, dtype=torch.float32, device=dev)
+        acc = torch.empty(2 * G, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.unimp_focal_ce_workspace(R, 1, V, dt), dtype=torch.uint8, device=dev)
+        check(lib.unimp_focal_ce_rows_fwd(logits.data_ptr(), ld, targets.data_ptr(), row_w.data_ptr(),
+                                          _ptr(row_g), float(gamma), int(use_focal),
+                                          row_lse.data_ptr(), row_pt.data_ptr(), acc.data_ptr(),
+                                          loss.data_ptr(), ws.data_ptr(), R, int(G), V, dt, _stream()),
+              "unimp_focal_ce_rows_fwd")
+        ctx.save_for_backward(logits, targets, row_w, row_g, row_lse, row_pt, acc)
+        ctx.cfg = (float(gamma), int(use_focal), ld, dt, int(G))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        logits, targets, row_w, row_g, row_lse, row_pt, acc = ctx.saved_tensors
+        gamma, use_focal, ld, dt, G = ctx.cfg
+        R, V = logits.shape
+        g = g_loss.to(torch.float32).contiguous()
+        buf = torch.empty((R, ld), dtype=logits.dtype, device=logits.device)
+        check(_lib.load().unimp_focal_ce_rows_bwd(logits.data_ptr(), ld, targets.data_ptr(),
+                                                  row_w.data_ptr(), _ptr(row_g), gamma, use_focal,
+                                                  row_lse.data_ptr(), row_pt.data_ptr(),
+                                                  acc.data_ptr(), g.data_ptr(), buf.data_ptr(), ld,
+                                                  R, G, V, dt, _stream()), "unimp_focal_ce_rows_bwd")
+        return (buf[:, :V] if ld != V else buf), None, None, None, None, None, None
+
+
+def focal_ce_rows(logits_rows, targets, row_weights, row_groups=None, *, n_groups: int = 1,
+                  gamma: float = 2.0, use_focal: bool = True):
+    """K6 on pre-gathered rows: logits (R,V), targets (R,) (-100 = unused slot), row_weights (R,),
+    row_groups (R,) int32 in [0, n_groups).  loss = mean_g( sum_g(w*CE*focal) / n_valid_g )."""
+    return _FocalCERows.apply(logits_rows, targets, row_weights, row_groups, n_groups, gamma, use_focal)
+
+
+def gather_label_rows(labels, capacity=None):
+    """Which (b,t) rows does the loss read?  Those whose SHIFTED label labels[b,t+1] != -100
+    (reference UniMP/mmrec.py:194-195).  Returns (row_index (R,), targets (R,), overflow flag):
+    `capacity=None`: exact R (one host sync); otherwise R = capacity, static shapes (CUDA-graph
+    safe), unused slots have target -100 and point at row 0; `overflow` (0-dim bool tensor) is
+    True if more rows were valid than `capacity` — the caller must make that loud."""
+    B, T = labels.shape
+    tgt = torch.full_like(labels, -100)
+    tgt[:, :-1] = labels[:, 1:]
+    tgt = tgt.reshape(-1)
+    valid = tgt != -100
+    if capacity is None:
+        idx = valid.nonzero().squeeze(1)
+        return idx, tgt[idx], None
+    R = int(capacity)
+    pos = valid.cumsum(0) - 1
+    slot = torch.where(valid & (pos < R), pos, torch.full_like(pos, R))
+    buf = torch.full((R + 1,), B * T, dtype=torch.int64, device=labels.device)
+    buf.scatter_(0, slot, torch.arange(B * T, device=labels.device))
+    idx = buf[:R]
+    pad = idx >= B * T
+    idx = idx.masked_fill(pad, 0)
+    return idx, tgt[idx].masked_fill(pad, -100), valid.sum() > R
+
+
 # --------------------------------------------------------------------------- LM / ViT fusions
 
 class _RotaryQKV(torch.autograd.Function):

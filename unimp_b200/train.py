@@ -432,9 +432,25 @@ class ShardedDataParallel(BucketedAllReduce):
             self.wait_params()
 
 
-def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True):
+def _rows_loss(out, weights, T, micro_batch, n_groups, gamma, use_reweight):
+    """Focal loss of reference `UniMP/mmrec.py:190-213` over a LabelRowsOutput: row r belongs to
+    sample row_index[r] // T, whose task weight and micro-batch (normalisation group) it takes."""
+    sample = out.row_index // T
+    row_w = weights.to(torch.float32)[sample]
+    row_g = (sample // micro_batch).to(torch.int32) if n_groups > 1 else None
+    loss = ops.focal_ce_rows(out["logits"], out.row_targets, row_w, row_g, n_groups=n_groups,
+                             gamma=gamma, use_focal=use_reweight)
+    if out.overflow is not None:
+        # more valid rows than the static capacity: the loss would silently miss rows -> NaN it
+        loss = loss + torch.where(out.overflow, float("nan"), 0.0).to(loss.dtype)
+    return loss
+
+
+def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True, label_rows=None):
     """One forward + loss exactly as the reference's loop body (`UniMP/mmrec.py:135-213`).
-    batch: collate_rec.py:59-72 keys.  Returns (focal loss, logged HF mean CE, logits)."""
+    batch: collate_rec.py:59-72 keys.  Returns (focal loss, logged HF mean CE, logits).
+    `label_rows` (True or a static row capacity): head + loss fusion — logits are then the (R, V)
+    rows the loss reads (FlamingoLMMixin.forward); default None keeps the dense (B, T, V) logits."""
     images = batch["patch_images"].unsqueeze(2)                      # mmrec.py:135-137
     input_ids = batch["input_ids"]
     attention_mask = batch["attention_masks"]
@@ -442,12 +458,17 @@ def unimp_loss(model, batch, tokens, *, gamma=2.0, use_reweight=True):
     labels = ops.mask_labels(input_ids, answer_token_id=tokens.answer,          # mmrec.py:143-168
                              endofchunk_token_id=tokens.endofchunk,
                              media_token_id=tokens.media, pad_token_id=tokens.pad)
+    if label_rows is not None:
+        out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=labels,
+                    label_rows=label_rows)
+        B, T = input_ids.shape
+        return _rows_loss(out, weights, T, B, 1, gamma, use_reweight), out[0], out["logits"]
     out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=labels)
     loss = ops.focal_ce(out["logits"], labels, weights, gamma=gamma, use_focal=use_reweight)
     return loss, out[0], out["logits"]
 
 
-def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True):
+def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True, label_rows=None):
     """An accumulation window of `len(mbs)` micro-batches in ONE forward/backward.
 
     The reference accumulates gradients over `gradient_accumulation_steps` micro-batches
@@ -465,9 +486,15 @@ def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True):
     labels = ops.mask_labels(input_ids, answer_token_id=tokens.answer,
                              endofchunk_token_id=tokens.endofchunk, media_token_id=tokens.media,
                              pad_token_id=tokens.pad)
+    B = mbs[0]["input_ids"].shape[0]
+    if label_rows is not None:
+        out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=labels,
+                    label_rows=label_rows)
+        loss = _rows_loss(out, weights, input_ids.shape[1], B, accum, gamma, use_reweight)
+        unimp_loss_fused.last_hf_loss = out[0]     # the value mmrec.py:182 logs
+        return loss, out["logits"]
     out = model(vision_x=images, lang_x=input_ids, attention_mask=attention_mask, labels=None)
     logits = out["logits"]
-    B = mbs[0]["input_ids"].shape[0]
     # one launch over the whole window; the kernel normalises each micro-batch by its own n_valid
     loss = ops.focal_ce(logits, labels, weights, gamma=gamma, use_focal=use_reweight, group_size=B)
     return loss, logits
@@ -475,7 +502,7 @@ def unimp_loss_fused(model, mbs, tokens, *, gamma=2.0, use_reweight=True):
 
 def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce | None = None, *,
                gamma=2.0, use_reweight=True, lr_scale=1.0, accum_steps=1, micro_batches=None,
-               fuse_accum=False):
+               fuse_accum=False, label_rows=None):
     """fwd + focal loss + bwd + (overlapped) all-reduce + clip + AdamW. Returns the loss
     tensor of the last micro-batch (device scalar; caller decides when to read it)."""
     mbs = micro_batches if micro_batches is not None else [batch]
@@ -487,14 +514,16 @@ def train_step(model, batch, tokens, opt: FlatAdamW, reducer: BucketedAllReduce 
     if fuse_accum and len(mbs) > 1:
         if reducer is not None:
             reducer.armed = True
-        loss, _ = unimp_loss_fused(model, mbs, tokens, gamma=gamma, use_reweight=use_reweight)
+        loss, _ = unimp_loss_fused(model, mbs, tokens, gamma=gamma, use_reweight=use_reweight,
+                                   label_rows=label_rows)
         loss.backward()
         opt.step_with(reducer, lr_scale=lr_scale)
         return loss
     for i, mb in enumerate(mbs):
         if reducer is not None:
             reducer.armed = i == len(mbs) - 1
-        loss, _, _ = unimp_loss(model, mb, tokens, gamma=gamma, use_reweight=use_reweight)
+        loss, _, _ = unimp_loss(model, mb, tokens, gamma=gamma, use_reweight=use_reweight,
+                                label_rows=label_rows)
         (loss / accum_steps if accum_steps > 1 else loss).backward()
     opt.step_with(reducer, lr_scale=lr_scale)
     return loss
@@ -510,7 +539,13 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, tokens, opt: FlatAdamW, reducer, example_mbs, *, gamma=2.0,
-                 use_reweight=True, warmup_iters=3, capture_error_mode=None, fuse_accum=False):
+                 use_reweight=True, warmup_iters=3, capture_error_mode=None, fuse_accum=False,
+                 label_rows=None):
+        """`label_rows`: static capacity (int) of the head + loss fusion's row gather — an upper
+        bound on the number of valid labels per forward (per window when `fuse_accum`); None keeps
+        dense logits.  `True` is not allowed here (its exact gather needs a host sync)."""
+        assert label_rows is None or (label_rows is not True and int(label_rows) > 0)
+        self.label_rows = label_rows
         self.fuse_accum = fuse_accum and len(example_mbs) > 1
         # NOTE: with NCCL in the graph, run the whole process on a NON-default stream
         # (`torch.cuda.set_stream(torch.cuda.Stream())` before building the model): gradient
@@ -562,7 +597,7 @@ class GraphedTrainStep:
             if self.reducer is not None:
                 self.reducer.armed = True
             loss, _ = unimp_loss_fused(self.model, self.static, self.tokens, gamma=self.gamma,
-                                       use_reweight=self.use_reweight)
+                                       use_reweight=self.use_reweight, label_rows=self.label_rows)
             loss.backward()
             self.opt.step_with(self.reducer)
             return loss.detach()
@@ -570,7 +605,7 @@ class GraphedTrainStep:
             if self.reducer is not None:
                 self.reducer.armed = i == self.accum - 1
             loss, _, _ = unimp_loss(self.model, mb, self.tokens, gamma=self.gamma,
-                                    use_reweight=self.use_reweight)
+                                    use_reweight=self.use_reweight, label_rows=self.label_rows)
             (loss / self.accum if self.accum > 1 else loss).backward()
         self.opt.step_with(self.reducer)
         return loss.detach()
