@@ -19,6 +19,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "train samples/s" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
     assert d["config"]["workload"].startswith("C1-tiny")
+    # the CPU arm's config says what ONE of its steps covers (it used to copy the GPU arm's)
+    assert d["config"]["step_sample"] == {"per_step_batch": 1, "accum": 1, "of": {"per_gpu_batch": 2, "accum": 2}}
+    assert "CPU arm: each step = 1 sample x accum 1" in d["config"]["workload"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

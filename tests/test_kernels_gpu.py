@@ -3,7 +3,7 @@ same seeded inputs.  Tolerances: fp32 rel 1e-4; bf16 rel 2e-2 (BASELINE.json nor
 import pytest
 import torch
 
-from util import max_rel, rel_err
+from util import assert_close, max_rel, rel_err
 
 from oracle.flamingo_oracle import MaskedCrossAttention as OracleMCA
 from oracle.loss_oracle import focal_loss, mask_labels as oracle_mask_labels
@@ -98,9 +98,9 @@ def test_masked_cross_attention_fwd_bwd(dtype, tol, B, T, Ti, overflow, simt):
     out = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=dh ** -0.5,
                                        force_simt=simt)
     out.backward(go.to(DEV, dtype))
-    assert rel_err(out, ref) < tol
-    assert rel_err(qd.grad, qr.grad) < tol
-    assert rel_err(kvd.grad, kvr.grad) < tol
+    assert_close(out, ref, tol, "o")
+    assert_close(qd.grad, qr.grad, tol, "dq")
+    assert_close(kvd.grad, kvr.grad, tol, "dkv")
     zero_rows = (tt == 0)
     assert out.detach().cpu()[zero_rows].abs().max() == 0 if zero_rows.any() else True
 
@@ -121,9 +121,34 @@ def test_unmasked_attention_fwd_bwd(dtype, tol, Bt, Lq, Lk, H, simt):
     ref.backward(go)
     d = qkv.to(DEV, dtype).requires_grad_(True)
     out = ops().attention(d[:, :Lq, :inner], d[:, :Lk, inner:], heads=H, scale=0.125, force_simt=simt)
+    assert_close(out, ref, tol, "o")
+    if dtype == torch.bfloat16 and not simt and Lq > 128:
+        # the tensor-core unmasked backward serves the Perceiver (Lq <= 128); the ViT tower is
+        # frozen.  No silent detour through the CUDA cores: the call must fail, and say why.
+        from unimp_b200._lib import UnimpError
+        with pytest.raises(UnimpError, match="Lq <= 128"):
+            out.backward(go.to(DEV, dtype))
+        return
     out.backward(go.to(DEV, dtype))
-    assert rel_err(out, ref) < tol
-    assert rel_err(d.grad, r.grad) < tol
+    assert_close(d.grad, r.grad, tol, "dqkv")
+
+
+def test_bf16_attention_never_falls_back_to_cuda_cores_silently():
+    """north_star: 'no multi-backend dispatch'.  bf16 shapes outside the tcgen05 kernels' coverage are
+    errors that name the constraint; the CUDA-core kernels run only for fp32 or via the explicit hook."""
+    from unimp_b200._lib import UnimpError
+    H, dh = 8, 64
+    q = torch.randn(2, 64, H * dh, device=DEV, dtype=torch.bfloat16)
+    tt = torch.ones(2, 64, device=DEV, dtype=torch.int32)
+    kv32 = torch.randn(2, 2 * 32, 2 * H * dh, device=DEV, dtype=torch.bfloat16)     # n_latents = 32
+    with pytest.raises(UnimpError, match="n_latents == 64"):
+        ops().masked_cross_attention(q, kv32, tt, heads=H, n_latents=32, scale=0.125)
+    kv_long = torch.randn(2, 512, 2 * H * dh, device=DEV, dtype=torch.bfloat16)     # Lk > 384
+    with pytest.raises(UnimpError, match="Lk <= 384"):
+        ops().attention(q, kv_long, heads=H, scale=0.125)
+    # the same calls are served in fp32 (parity mode) and through the explicit CUDA-core hook
+    ops().masked_cross_attention(q.float(), kv32.float(), tt, heads=H, n_latents=32, scale=0.125)
+    ops().attention(q, kv_long, heads=H, scale=0.125, force_simt=True)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
@@ -187,8 +212,8 @@ def test_gate_residual_ln(dtype, tol, rows, D, mode):
         ln_d = o.layer_norm(dx, dga, dbe, 1e-5)
         (ln_d * g2.to(DEV, dtype)).sum().backward()
         pairs = [(ln_d, ln), (dx.grad, x_.grad), (dga.grad, ga_.grad), (dbe.grad, be_.grad)]
-    for got, want in pairs:
-        assert rel_err(got, want) < tol, mode
+    for i, (got, want) in enumerate(pairs):
+        assert_close(got, want, tol, f"{mode}[{i}]")
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
@@ -210,8 +235,8 @@ def test_residual_ln_backward_with_frozen_affine(dtype, tol, rows, D, gated):
     db, dx = branch.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
     xo_d, ln_d = ops().gate_residual_ln(db, dx, gate.to(DEV) if gated else None, gamma.to(DEV), beta.to(DEV), 1e-5)
     (xo_d * g1.to(DEV) + ln_d * g2.to(DEV)).sum().backward()
-    for got, want in [(xo_d, xo), (ln_d, ln), (db.grad, b_.grad), (dx.grad, x_.grad)]:
-        assert rel_err(got, want) < tol
+    for i, (got, want) in enumerate([(xo_d, xo), (ln_d, ln), (db.grad, b_.grad), (dx.grad, x_.grad)]):
+        assert_close(got, want, tol, f"frozen-affine[{i}]")
 
 
 # ------------------------------------------------------------------ focal CE
@@ -237,6 +262,9 @@ def test_focal_ce_fwd_bwd(dtype, tol_l, tol_g, B, T, V, gamma, use):
     loss.backward()
     assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol_l
     assert rel_err(zd.grad, zr.grad) < tol_g
+    # element-wise: d_logits is sparse (one spike per valid row), so bound against the largest
+    # reference element instead of the RMS
+    assert float((zd.grad.double().cpu() - zr.grad).abs().max()) < 2 * tol_g * float(zr.grad.abs().max())
     # rows that carry no label get an exactly-zero gradient, and so does the last step
     assert zd.grad[:, -1].abs().max() == 0
     if B > 1:
@@ -380,9 +408,11 @@ def test_fused_neox_layer_matches_hf_layer(dtype, tol, parallel):
 
 # ------------------------------------------------------------------ full-size property checks
 
-def test_xattn_full_size_tc_equals_simt_and_blocks_are_independent():
-    """BASELINE configs[2] shape (B=3, T=1024, Ti=8): the tcgen05 path equals the fp32-exact CUDA-core
-    path, and (size-independent property) changing image j's keys only changes rows that reference j."""
+def test_xattn_full_size_tc_equals_fp64_dense_oracle_and_blocks_are_independent():
+    """BASELINE configs[2] shape (B=3, T=1024, Ti=8): the tcgen05 path against the fp64 dense
+    restatement of upstream's masked attention (the oracle arithmetic, evaluated on the GPU so it
+    finishes in seconds), and against the CUDA-core path; plus the size-independent property that
+    changing image j's keys only changes rows that reference j."""
     B, T, Ti, H, dh, n = 3, 1024, 8, 8, 64, 64
     torch.manual_seed(0)
     q = torch.randn(B, T, H * dh, device=DEV, dtype=torch.bfloat16, requires_grad=True)
@@ -394,6 +424,13 @@ def test_xattn_full_size_tc_equals_simt_and_blocks_are_independent():
     b = ops().masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=0.125, force_simt=True)
     gb = torch.autograd.grad(b, (q, kv), go)
     assert rel_err(a, b) < 1e-2 and rel_err(ga[0], gb[0]) < 2e-2 and rel_err(ga[1], gb[1]) < 2e-2
+    q64 = q.detach().double().requires_grad_(True)
+    kv64 = kv.detach().double().requires_grad_(True)
+    want = _dense_attn_ref(q64, kv64, tt.long(), H, n, 0.125)
+    gw = torch.autograd.grad(want, (q64, kv64), go.double())
+    assert_close(a, want, 2e-2, "o (C3 shape)")
+    assert_close(ga[0], gw[0], 2e-2, "dq (C3 shape)")
+    assert_close(ga[1], gw[1], 2e-2, "dkv (C3 shape)")
     kv2 = kv.detach().clone()
     kv2[:, 3 * n:4 * n] += 1.0  # perturb image 3 only
     c = ops().masked_cross_attention(q.detach(), kv2, tt, heads=H, n_latents=n, scale=0.125)
@@ -485,3 +522,37 @@ def test_layer_norm_wide_rows_and_bad_shapes():
         ops().layer_norm(torch.randn(4, 100, device=DEV, dtype=torch.bfloat16),
                          torch.ones(100, device=DEV, dtype=torch.bfloat16),
                          torch.zeros(100, device=DEV, dtype=torch.bfloat16))   # D % 8 != 0
+
+
+@pytest.mark.parametrize("dtype,tol_l,tol_g", [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1e-3, 2e-2)])
+def test_focal_ce_rows_equals_the_dense_kernel_and_the_reference_loss(dtype, tol_l, tol_g):
+    """Head + loss fusion: the loss over pre-gathered rows (padded stride, unused slots, two
+    normalisation groups) == reference UniMP/mmrec.py:190-213 evaluated per micro-batch."""
+    torch.manual_seed(11)
+    B, T, V, gs = 4, 24, 74053 if dtype == torch.bfloat16 else 1003, 2
+    z = (2 * torch.randn(B, T, V)).to(dtype)
+    y = torch.full((B, T), -100)
+    y[0, 5:9] = torch.randint(0, V, (4,)); y[1, 20:24] = torch.randint(0, V, (4,))
+    y[2, 1:3] = torch.randint(0, V, (2,)); y[3, 10] = V - 1
+    w = torch.tensor([2.0, 1.0, 1.0, 2.0])
+    zr = z.double().requires_grad_(True)
+    ref = sum(focal_loss(zr[g * gs:(g + 1) * gs], y[g * gs:(g + 1) * gs], w[g * gs:(g + 1) * gs].double(), gamma=2.0)
+              for g in range(B // gs)) / (B // gs)
+    ref.backward()
+    idx, tgt, ovf = ops().gather_label_rows(y.to(DEV), 16)          # capacity 16 > 11 valid rows
+    assert not bool(ovf) and int((tgt != -100).sum()) == 11
+    Vp = (V + 127) // 128 * 128
+    rows = torch.zeros(16, Vp, device=DEV, dtype=dtype)
+    rows[:, :V] = z.to(DEV).reshape(B * T, V)[idx]
+    zrows = rows[:, :V].detach().requires_grad_(True)
+    sample = idx // T
+    loss = ops().focal_ce_rows(zrows, tgt, w.to(DEV)[sample], (sample // gs).to(torch.int32), n_groups=B // gs,
+                               gamma=2.0)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol_l
+    want_rows = zr.grad.reshape(B * T, V)[idx.cpu()]
+    want_rows[tgt.cpu() == -100] = 0
+    assert rel_err(zrows.grad, want_rows) < tol_g
+    assert zrows.grad[tgt == -100].abs().max() == 0                  # unused slots: exact zeros
+    dense = ops().focal_ce(z.to(DEV), y.to(DEV), w.to(DEV), gamma=2.0, group_size=gs)
+    assert abs(float(loss) - float(dense)) < 1e-5 * abs(float(dense))

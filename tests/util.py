@@ -64,6 +64,22 @@ def rel_err(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def worst_elem(a, b):
+    """Largest single-element error, in units of the reference tensor's RMS.  A Frobenius-relative
+    bound lets one wrong row of a 1536-row tensor through; this does not (a wrong row scores ~1)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    rms = float(b.pow(2).mean().sqrt().clamp_min(1e-30))
+    return float((a - b).abs().max()) / rms
+
+
+def assert_close(a, b, tol, what="", elem_factor=5.0):
+    """Frobenius-relative error < tol AND every element within elem_factor * tol of the reference's
+    RMS (bf16: tol 2e-2 -> 0.1 RMS; fp32: tol 1e-4 -> 5e-4 RMS)."""
+    fro, worst = rel_err(a, b), worst_elem(a, b)
+    assert fro < tol, f"{what}: Frobenius-relative error {fro:.3e} >= {tol:.1e}"
+    assert worst < elem_factor * tol, f"{what}: worst element off by {worst:.3e} RMS >= {elem_factor * tol:.1e}"
+
+
 def max_rel(a, b, floor=1e-6):
     a, b = a.double().cpu(), b.double().cpu()
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())

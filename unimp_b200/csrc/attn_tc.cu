@@ -343,15 +343,16 @@ static bool view_ok(const void* p, int64_t bs, int64_t rs) {
   return aligned16(p) && (bs % 8 == 0) && (rs % 8 == 0);
 }
 
-bool attn_fwd_tc_supported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o,
-                           const int32_t* tt, int Lq, int Lk, int n, int dh) {
+// nullptr if the tensor-core path covers the call, else the constraint it violates.
+const char* attn_fwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o,
+                                    const int32_t* tt, int Lq, int Lk, int n, int dh) {
   (void)Lq;
-  if (dh != DH) return false;
+  if (dh != DH) return "dim_head must be 64";
   if (!view_ok(q.ptr, q.batch_stride, q.row_stride) || !view_ok(k.ptr, k.batch_stride, k.row_stride) ||
       !view_ok(v.ptr, v.batch_stride, v.row_stride) || !view_ok(o.ptr, o.batch_stride, o.row_stride))
-    return false;
-  if (tt) return n == KB;
-  return Lk <= MAX_BLOCKS_UNMASKED * KB;
+    return "q/k/v/o views must be 16-byte aligned with row and batch strides that are multiples of 8 elements";
+  if (tt) return n == KB ? nullptr : "masked cross-attention needs n_latents == 64 (one key block per image)";
+  return Lk <= MAX_BLOCKS_UNMASKED * KB ? nullptr : "unmasked attention needs Lk <= 384 (all of S in TMEM)";
 }
 
 template <bool MASKED>
@@ -674,18 +675,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-bool attn_bwd_tc_supported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t d_o,
-                           unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, const int32_t* tt,
-                           int Lq, int Lk, int n, int dh) {
+const char* attn_bwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t d_o,
+                                    unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv,
+                                    const int32_t* tt, int Lq, int Lk, int n, int dh) {
   (void)Lk;
-  if (dh != DH) return false;
+  if (dh != DH) return "dim_head must be 64";
   if (!view_ok(q.ptr, q.batch_stride, q.row_stride) || !view_ok(k.ptr, k.batch_stride, k.row_stride) ||
       !view_ok(v.ptr, v.batch_stride, v.row_stride) || !view_ok(d_o.ptr, d_o.batch_stride, d_o.row_stride) ||
       !view_ok(dq.ptr, dq.batch_stride, dq.row_stride) || !view_ok(dk.ptr, dk.batch_stride, dk.row_stride) ||
       !view_ok(dv.ptr, dv.batch_stride, dv.row_stride))
-    return false;
-  if (tt) return n == KB;
-  return Lq <= TQ;
+    return "views must be 16-byte aligned with row and batch strides that are multiples of 8 elements";
+  if (tt) return n == KB ? nullptr : "masked cross-attention needs n_latents == 64 (one key block per image)";
+  return Lq <= TQ ? nullptr
+                  : "unmasked backward needs Lq <= 128 (Perceiver latents; the ViT tower is frozen, forward only)";
 }
 
 template <bool MASKED>

@@ -30,15 +30,15 @@ int launch_xattn_decode(unimp_view_t, unimp_view_t, unimp_view_t, const int32_t*
 int launch_attn_fwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
                        unimp_mview_t o, float* lse, int B, int Lq, int Lk, int H, int n, int Ti,
                        float scale, cudaStream_t st);
-bool attn_fwd_tc_supported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o,
-                           const int32_t* tt, int Lq, int Lk, int n, int dh);
+const char* attn_fwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o,
+                                    const int32_t* tt, int Lq, int Lk, int n, int dh);
 int launch_attn_bwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
                        unimp_view_t o, unimp_view_t d_o, const float* lse, void* workspace,
                        unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, int B, int Lq, int Lk,
                        int H, int n, int Ti, float scale, cudaStream_t st);
-bool attn_bwd_tc_supported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t d_o,
-                           unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, const int32_t* tt,
-                           int Lq, int Lk, int n, int dh);
+const char* attn_bwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t d_o,
+                                    unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv,
+                                    const int32_t* tt, int Lq, int Lk, int n, int dh);
 
 static int check_attn_common(const char* who, unimp_view_t q, unimp_view_t k, unimp_view_t v,
                              const void* o, int B, int Lq, int Lk, int H, int dh, int dtype) {
@@ -78,8 +78,15 @@ extern "C" int64_t unimp_attn_bwd_workspace(int Bt, int Lq, int Lk, int H, int d
 static int attn_fwd_dispatch(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
                              unimp_mview_t o, float* lse, int B, int Lq, int Lk, int H, int n, int Ti,
                              int dh, float scale, int dtype, int force_simt, cudaStream_t st) {
-  if (dtype == UNIMP_BF16 && !force_simt && attn_fwd_tc_supported(q, k, v, o, tt, Lq, Lk, n, dh))
+  // bf16 is the tensor-core path, full stop: a shape it does not cover is an ERROR, never a silent
+  // detour through the CUDA cores.  The SIMT kernels serve fp32 (the 1e-4 parity mode) and the
+  // explicit unimp__attn_*_simt test hooks only.
+  if (dtype == UNIMP_BF16 && !force_simt) {
+    const char* why = attn_fwd_tc_unsupported(q, k, v, o, tt, Lq, Lk, n, dh);
+    UNIMP_CHECK_ARG(!why, UNIMP_E_SHAPE, "attention forward (bf16, tcgen05): %s [Lq=%d Lk=%d n=%d dh=%d]",
+                    why, Lq, Lk, n, dh);
     return launch_attn_fwd_tc(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
+  }
   if (dtype == UNIMP_BF16)
     return launch_attn_fwd_simt<__nv_bfloat16>(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
   return launch_attn_fwd_simt<float>(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
@@ -90,10 +97,13 @@ static int attn_bwd_dispatch(unimp_view_t q, unimp_view_t k, unimp_view_t v, con
                              unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv, int B, int Lq,
                              int Lk, int H, int n, int Ti, int dh, float scale, int dtype,
                              int force_simt, cudaStream_t st) {
-  if (dtype == UNIMP_BF16 && !force_simt &&
-      attn_bwd_tc_supported(q, k, v, d_o, dq, dk, dv, tt, Lq, Lk, n, dh))
+  if (dtype == UNIMP_BF16 && !force_simt) {
+    const char* why = attn_bwd_tc_unsupported(q, k, v, d_o, dq, dk, dv, tt, Lq, Lk, n, dh);
+    UNIMP_CHECK_ARG(!why, UNIMP_E_SHAPE, "attention backward (bf16, tcgen05): %s [Lq=%d Lk=%d n=%d dh=%d]",
+                    why, Lq, Lk, n, dh);
     return launch_attn_bwd_tc(q, k, v, tt, o, d_o, lse, ws, dq, dk, dv, B, Lq, Lk, H, n, Ti, scale,
                               st);
+  }
   if (dtype == UNIMP_BF16)
     return launch_attn_bwd_simt<__nv_bfloat16>(q, k, v, tt, o, d_o, lse, ws, dq, dk, dv, B, Lq, Lk, H,
                                                n, Ti, scale, st);

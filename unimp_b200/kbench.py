@@ -43,8 +43,61 @@ def _k(bytes_per_set, cap=48):
     return max(2, min(cap, (int(1.3 * L2_BYTES) + bytes_per_set - 1) // bytes_per_set))
 
 
-def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
-    """Returns {kernel: {avg_us, alg_bytes, flops, GB/s, TFLOP/s, frac_hbm, frac_tensor, sets}}."""
+def _eager_xattn(q, kv, tt, H, n, scale):
+    """The reference's MaskedCrossAttention core as upstream executes it (dense, materialised
+    (B,h,T,Ti*n) similarity + mask) — the eager-GPU column for K1."""
+    B, T, inner = q.shape
+    Lk = kv.shape[1]
+    dh = inner // H
+    k, v = kv.chunk(2, dim=-1)
+    qh = q.view(B, T, H, dh).transpose(1, 2) * scale
+    kh = k.reshape(B, Lk, H, dh).transpose(1, 2)
+    vh = v.reshape(B, Lk, H, dh).transpose(1, 2)
+    sim = torch.einsum("bhid,bhjd->bhij", qh, kh)
+    media_time = (torch.arange(Lk // n, device=q.device) + 1).repeat_interleave(n)
+    mask = tt[:, None, :, None] == media_time[None, None, None, :]
+    sim = sim.masked_fill(~mask, -torch.finfo(sim.dtype).max)
+    sim = sim - sim.amax(dim=-1, keepdim=True).detach()
+    attn = sim.softmax(dim=-1)
+    attn = attn.masked_fill((tt == 0)[:, None, :, None], 0.0)
+    out = torch.einsum("bhij,bhjd->bhid", attn, vh)
+    return out.transpose(1, 2).reshape(B, T, inner)
+
+
+def _eager_attn(q, kv, H, scale):
+    """PerceiverAttention core as upstream executes it (einsum / amax / softmax / einsum)."""
+    B, Lq, inner = q.shape
+    Lk = kv.shape[1]
+    dh = inner // H
+    k, v = kv.chunk(2, dim=-1)
+    qh = q.view(B, Lq, H, dh).transpose(1, 2) * scale
+    kh = k.reshape(B, Lk, H, dh).transpose(1, 2)
+    vh = v.reshape(B, Lk, H, dh).transpose(1, 2)
+    sim = torch.einsum("bhid,bhjd->bhij", qh, kh)
+    sim = sim - sim.amax(dim=-1, keepdim=True).detach()
+    out = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), vh)
+    return out.transpose(1, 2).reshape(B, Lq, inner)
+
+
+def _eager_focal(logits, labels, weights, gamma):
+    """reference UniMP/mmrec.py:190-213, line for line, on the GPU."""
+    n1, n2 = labels.shape[0], labels.shape[1] - 1
+    shift_logits = logits[:, :-1, :].contiguous()
+    lab = labels[:, 1:].contiguous().view(-1)
+    shift_logits = shift_logits.view(-1, shift_logits.size(-1))
+    lm_loss = torch.nn.functional.cross_entropy(shift_logits, lab, reduction="none").view(n1, n2)
+    loss = (weights[:, None] * lm_loss).view(-1)
+    p = torch.nn.functional.softmax(shift_logits, dim=-1)
+    pt = p[torch.arange(len(shift_logits), device=p.device), lab]
+    loss = loss * (1 - pt) ** gamma
+    return loss.sum() / (lab != -100).sum()
+
+
+def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
+    """Returns {kernel: {avg_us, alg_bytes, flops, GB/s, TFLOP/s, frac_hbm, frac_tensor, sets}}.
+    `eager`: also time what the reference would run on this GPU for the same op (plain PyTorch,
+    same dtype, same shapes, same cold-cache method) as `eager_<kernel>` rows, and add
+    `speedup_vs_eager` to our row."""
     dev = "cuda"
     es = 2 if dtype == torch.bfloat16 else 4
     B, T, Ti, n, H, dh, D, V = wl.B, wl.T, wl.Ti, cfg.n_latents, cfg.xattn_heads, cfg.xattn_dim_head, cfg.lm_hidden, cfg.vocab
@@ -79,6 +132,13 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     bwd = [lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
            for o, q, kv, g in zip(os_, qs, kvs, gos)]
     rec("xattn_bwd", _time_graph(bwd), 2.5 * xb, 2.5 * xf, K)
+    if eager:
+        efw = [lambda q=q, kv=kv: _eager_xattn(q, kv, tt, H, n, dh ** -0.5) for q, kv in zip(qs, kvs)]
+        rec("eager_xattn_fwd", _time_graph(efw), xb, xf, K)
+        eos = [f() for f in efw]
+        rec("eager_xattn_bwd", _time_graph([lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
+                                            for o, q, kv, g in zip(eos, qs, kvs, gos)]), 2.5 * xb, 2.5 * xf, K)
+        del efw, eos
     del qs, kvs, gos, os_, fwd, bwd
     # ---- K3 ViT self-attention ----------------------------------------------------------------
     N, L, Hv = B * Ti, cfg.n_patches + 1, cfg.vis_heads
@@ -88,6 +148,11 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     qkvs = [torch.randn(N, L, 3 * Hv * 64, device=dev, dtype=dtype) for _ in range(K)]
     rec("vit_attn_fwd", _time_graph([lambda x=x: ops.attention(x[..., :Hv * 64], x[..., Hv * 64:], heads=Hv, scale=0.125)
                                      for x in qkvs]), vb, vf, K)
+    if eager:
+        def sdpa(x):
+            q_, k_, v_ = (t.view(N, L, Hv, 64).transpose(1, 2) for t in x.chunk(3, dim=-1))
+            return torch.nn.functional.scaled_dot_product_attention(q_, k_, v_, scale=0.125)
+        rec("eager_vit_attn_fwd_sdpa", _time_graph([lambda x=x: sdpa(x) for x in qkvs]), vb, vf, K)
     del qkvs
     # ---- K2 perceiver attention -----------------------------------------------------------------
     Lk = cfg.n_patches + n
@@ -102,6 +167,13 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     pgs = [torch.randn_like(o) for o in pos]
     rec("perceiver_attn_bwd", _time_graph([lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
                                             for o, q, kv, g in zip(pos, pqs, pkvs, pgs)]), 2.5 * pb, 2.5 * pf, K)
+    if eager:
+        epf = [lambda q=q, kv=kv: _eager_attn(q, kv, H, dh ** -0.5) for q, kv in zip(pqs, pkvs)]
+        rec("eager_perceiver_attn_fwd", _time_graph(epf), pb, pf, K)
+        epo = [f() for f in epf]
+        rec("eager_perceiver_attn_bwd", _time_graph([lambda o=o, q=q, kv=kv, g=g: torch.autograd.grad(o, (q, kv), g, retain_graph=True)
+                                                      for o, q, kv, g in zip(epo, pqs, pkvs, pgs)]), 2.5 * pb, 2.5 * pf, K)
+        del epf, epo
     del pqs, pkvs, pos, pgs, pfw
     # ---- K5 gate + residual + LN ------------------------------------------------------------------
     rows = B * T
@@ -119,6 +191,17 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     rec("gate_residual_ln_bwd", _time_graph([lambda o=o, x=x, b=b, g=g: torch.autograd.grad(
         o, (b, x, gate, gam, bet), (g, g), retain_graph=True) for o, x, b, g in zip(outs, xs, brs, g1s)]),
         6 * rows * D * es, 0.0, K)
+    if eager:
+        def eg(b, x):
+            xo = b * gate.tanh() + x
+            return xo, torch.nn.functional.layer_norm(xo, (D,), gam, bet)
+        egf = [lambda x=x, b=b: eg(b, x) for x, b in zip(xs, brs)]
+        rec("eager_gate_residual_ln_fwd", _time_graph(egf), gb, 0.0, K)
+        eouts = [f() for f in egf]
+        rec("eager_gate_residual_ln_bwd", _time_graph([lambda o=o, x=x, b=b, g=g: torch.autograd.grad(
+            o, (b, x, gate, gam, bet), (g, g), retain_graph=True) for o, x, b, g in zip(eouts, xs, brs, g1s)]),
+            6 * rows * D * es, 0.0, K)
+        del egf, eouts
     del outs, gfw
     # the LM towers' variant: ungated residual + frozen LayerNorm (no column sums, d_branch == d_x)
     gam_f, bet_f = gam.detach(), bet.detach()
@@ -137,10 +220,10 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     rec("gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
                                  for y, h, g in zip(ys, hs, gys)]), 3 * rows * F4 * es, 0.0, K)
     # the stock kernels at the same shape, for the record (not on the product path)
-    rec("torch_gelu_fwd", _time_graph([lambda h=h: torch.nn.functional.gelu(h) for h in hs]),
+    rec("eager_gelu_fwd", _time_graph([lambda h=h: torch.nn.functional.gelu(h) for h in hs]),
         2 * rows * F4 * es, 0.0, K)
     ts = [torch.nn.functional.gelu(h) for h in hs]
-    rec("torch_gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
+    rec("eager_gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
                                        for y, h, g in zip(ts, hs, gys)]), 3 * rows * F4 * es, 0.0, K)
     del hs, ys, ts, gys
     # ---- K6 focal CE -----------------------------------------------------------------------------
@@ -159,6 +242,64 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None):
     rec("focal_ce_bwd", _time_graph([lambda l=l, zz=zz: torch.autograd.grad(l, zz, retain_graph=True)
                                      for l, zz in zip(ls, z)]), nv_eff * V * es + B * T * V * es, 0.0, 2)
     out["focal_ce_fwd"]["n_valid_rows"] = nv_eff
+    if eager:
+        w2 = torch.full((B,), 2.0, device=dev)
+        efw = [lambda zz=zz: _eager_focal(zz, y, w2, 2.0) for zz in z]
+        rec("eager_focal_ce_fwd", _time_graph(efw), nv_eff * V * es, 0.0, 2)
+        els = [f() for f in efw]
+        rec("eager_focal_ce_bwd", _time_graph([lambda l=l, zz=zz: torch.autograd.grad(l, zz, retain_graph=True)
+                                               for l, zz in zip(els, z)]), nv_eff * V * es + B * T * V * es, 0.0, 2)
+        del efw, els
     del z, ls, ffw
+    # ---- head + loss fusion: the same loss over the gathered valid rows only ---------------------
+    Rcap = max(64, (nv_eff + 63) // 64 * 64)
+    Vp = (V + 127) // 128 * 128
+    K = _k(Rcap * Vp * es, cap=24)
+    zr = [torch.randn(Rcap, Vp, device=dev, dtype=dtype)[:, :V].requires_grad_(True) for _ in range(K)]
+    tg = torch.full((Rcap,), -100, device=dev, dtype=torch.int64)
+    tg[:nv_eff] = torch.randint(0, V, (nv_eff,), device=dev)
+    rw = torch.ones(Rcap, device=dev)
+    rfw = [lambda zz=zz: ops.focal_ce_rows(zz, tg, rw, None) for zz in zr]
+    rec("focal_ce_rows_fwd", _time_graph(rfw), nv_eff * V * es, 0.0, K)
+    rls = [f() for f in rfw]
+    rec("focal_ce_rows_bwd", _time_graph([lambda l=l, zz=zz: torch.autograd.grad(l, zz, retain_graph=True)
+                                          for l, zz in zip(rls, zr)]), nv_eff * V * es + Rcap * V * es, 0.0, K)
+    del zr, rls, rfw
+    # ---- rotary on the packed qkv projection (GPT-NeoX, 32 heads x 80, rotary_pct 1.0) -----------
+    Hl, dl = cfg.lm_heads, cfg.lm_hidden // cfg.lm_heads
+    rot = int(dl * cfg.rotary_pct)
+    if rot % 16 == 0 and dl % 8 == 0:
+        rb = 2 * B * T * 3 * Hl * dl * es
+        K = _k(rb, cap=16)
+        qkvs = [torch.randn(B, T, 3 * Hl * dl, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+        cos = torch.randn(1, T, rot, device=dev, dtype=dtype)
+        sin = torch.randn(1, T, rot, device=dev, dtype=dtype)
+        rf = [lambda x=x: ops.rotary_qkv(x, cos, sin, heads=Hl, head_dim=dl, rotary_dim=rot) for x in qkvs]
+        rec("rotary_qkv_fwd", _time_graph(rf), rb, 0.0, K)
+        ro = [f() for f in rf]
+        gq = [tuple(torch.randn_like(t) for t in o) for o in ro]
+        rec("rotary_qkv_bwd", _time_graph([lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True)
+                                           for o, x, g in zip(ro, qkvs, gq)]), rb, 0.0, K)
+        del qkvs, ro, gq, rf
+    # ---- clip + AdamW over a 64 M-parameter slice (28 B/param; the step runs it over 1.15 B) -----
+    npar = 64 << 20
+    pw = torch.randn(npar, device=dev, dtype=dtype)
+    pg = torch.randn(npar, device=dev, dtype=dtype)
+    ma, m1, m2 = pw.float(), torch.zeros(npar, device=dev), torch.zeros(npar, device=dev)
+    hyper = torch.tensor(ops.adamw_hyper(2e-4, 0.9, 0.999, 10), device=dev, dtype=torch.float32)
+    gn = torch.ones(1, device=dev)
+    rec("adamw_clip_step", _time_graph([lambda: ops.adamw_step_(ma, pw, pg, m1, m2, hyper=hyper, beta1=0.9,
+                                                                 beta2=0.999, eps=1e-8, weight_decay=0.1,
+                                                                 gnorm_sq=gn, max_norm=1.0)] * 3),
+        npar * (2 * es + 6 * 4), 0.0, 3)
+    rec("grad_sumsq", _time_graph([lambda: ops.sumsq_(pg, gn)] * 3), npar * es, 0.0, 3)
+    del pw, pg, ma, m1, m2
+    if eager:
+        for name in list(out):
+            e = out.get("eager_" + name)
+            if e is not None:
+                out[name]["speedup_vs_eager"] = e["avg_us"] / out[name]["avg_us"]
+        if "eager_vit_attn_fwd_sdpa" in out:
+            out["vit_attn_fwd"]["speedup_vs_eager"] = out["eager_vit_attn_fwd_sdpa"]["avg_us"] / out["vit_attn_fwd"]["avg_us"]
     torch.cuda.empty_cache()
     return out
