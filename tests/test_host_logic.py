@@ -371,3 +371,8 @@ def test_direct_grad_parameter_fails_loudly_when_autograd_delivers_its_gradient(
     opt._install_direct_guards()
     with pytest.raises(RuntimeError, match="direct gradient accumulation"):
         net.to_q(torch.randn(2, 4)).sum().backward()
+    # the sanctioned route (backward returns None for the weight) must NOT trip the guard
+    from unimp_b200 import ops
+    net.to_q.weight._unimp_fresh = True
+    ops.linear_acc(torch.randn(2, 4, requires_grad=True), net.to_q.weight).sum().backward()
+    assert net.to_q.weight._unimp_fresh is False

@@ -492,7 +492,9 @@ def test_focal_ce_group_normalisation_equals_mean_of_per_group_losses(dtype, tol
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
 def test_masked_cross_attention_other_latent_counts(dtype, tol):
-    """num_latents != 64 (not the upstream default) is served by the CUDA-core path."""
+    """num_latents != 64 (not the upstream default) is served by the CUDA-core kernels: always in
+    fp32, and in bf16 only when asked for explicitly (force_simt) — the bf16 entry point itself
+    refuses (test_bf16_attention_never_falls_back_to_cuda_cores_silently)."""
     B, T, Ti, H, dh, n = 2, 40, 3, 8, 64, 32
     torch.manual_seed(9)
     q = torch.randn(B, T, H * dh).to(dtype).double()
@@ -503,7 +505,8 @@ def test_masked_cross_attention_other_latent_counts(dtype, tol):
     ref = _dense_attn_ref(qr, kvr, tt.long(), H, n, 0.125)
     ref.backward(go)
     qd, kvd = q.to(DEV, dtype).requires_grad_(True), kv.to(DEV, dtype).requires_grad_(True)
-    out = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=0.125)
+    out = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=0.125,
+                                       force_simt=dtype == torch.bfloat16)
     out.backward(go.to(DEV, dtype))
     assert rel_err(out, ref) < tol and rel_err(qd.grad, qr.grad) < tol and rel_err(kvd.grad, kvr.grad) < tol
 

@@ -153,6 +153,8 @@ class FlatAdamW:
         for g in self.groups:
             for (name, p, _, _) in g["spans"][:g["n_direct"]]:
                 def guard(grad, name=name):
+                    if grad is None:      # the engine runs hooks for an UNDEFINED gradient too
+                        return None
                     raise RuntimeError(
                         f"parameter {name} is registered for direct gradient accumulation "
                         "(FlatAdamW(direct_grads=True)) but received a gradient through autograd: "
