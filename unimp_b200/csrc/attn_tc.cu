@@ -14,6 +14,8 @@
 // All mbarrier waits are bounded (trap, never hang).
 //
 // Roofline: fwd FLOPs = 4*dh*Lq*Lk_attended per (b,h); bytes = Q + O + K + V (+lse).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -290,6 +292,219 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1 forward, round 2: masked media-located cross-attention, latency-oriented.
+//   * 3 CTAs per SM (128 TMEM columns, 65 KB shared memory, <= 136 registers): every (tile, head,
+//     sample) of configs[2] (384 CTAs) is resident in ONE wave, so the per-tile chains
+//     TMA -> S -> softmax -> PV -> store overlap each other instead of queueing.
+//   * the control warp derives the tile's image-block range from text_time itself and issues the
+//     K/V loads of the first two blocks BEFORE the TMEM allocation and the CTA-wide sync: the HBM
+//     round trip is in flight while the rest of the prologue runs.
+//   * no __syncthreads in the main loop: S-ready / P-ready are mbarriers (tcgen05.commit on one
+//     side, one arrive per worker warp on the other); S(j+1) is issued right behind PV(j), so a
+//     two-block tile pays one extra softmax, not one extra load round trip.
+//   * the row softmax reads S from TMEM twice (max, then exp) instead of holding 64 values in
+//     registers: that is what gets the kernel under the 3-CTA register budget.
+// ---------------------------------------------------------------------------------------------
+constexpr int XF_STAGES = 2;
+
+__global__ void __launch_bounds__(FWD_THREADS, 3)
+xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                    const __grid_constant__ CUtensorMap tv, const FwdArgs a) {
+  constexpr uint32_t S_COL = 0, O_COL = KB, TMEM_COLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;                    // XF_STAGES x 8 KB
+  uint8_t* sV = sK + XF_STAGES * KV_BYTES;       // XF_STAGES x 8 KB
+  uint8_t* sP = sV + XF_STAGES * KV_BYTES;       // 16 KB
+  __shared__ uint64_t bar_q, bar_kv[XF_STAGES], bar_s, bar_p, bar_pv, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_j[2];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = tid < TQ;
+  const int row0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(&bar_q, 1); mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1);
+      mbar_init(&bar_o, 1);
+#pragma unroll
+      for (int i = 0; i < XF_STAGES; ++i) mbar_init(&bar_kv[i], 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(&bar_q, Q_BYTES);
+      tma_load_4d(sQ, &tq, &bar_q, 0, h, row0, b);
+    }
+    // which image blocks do the tile's 128 rows reference?  (4 rows per lane)
+    int lo = 1 << 30, hi = -1;
+#pragma unroll
+    for (int i = 0; i < TQ / 32; ++i) {
+      const int r = row0 + lane + 32 * i;
+      if (r < a.Lq) {
+        const int t = a.tt[(int64_t)b * a.Lq + r];
+        if (t > a.Ti) { lo = 0; hi = a.Ti - 1; }
+        else if (t >= 1) { lo = min(lo, t - 1); hi = max(hi, t - 1); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      s_j[0] = lo; s_j[1] = hi;
+      const int nb = hi >= lo ? hi - lo + 1 : 0;
+      for (int it = 0; it < nb && it < XF_STAGES; ++it) {
+        mbar_arrive_expect_tx(&bar_kv[it], 2 * KV_BYTES);
+        tma_load_4d(sK + it * KV_BYTES, &tk, &bar_kv[it], 0, h, (lo + it) * a.n, b);
+        tma_load_4d(sV + it * KV_BYTES, &tv, &bar_kv[it], 0, h, (lo + it) * a.n, b);
+      }
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_slot, TMEM_COLS);
+  }
+  // this thread's row while the loads fly
+  const int row = row0 + tid;
+  const bool valid = worker && row < a.Lq;
+  int ttr = 0;
+  if (valid) ttr = a.tt[(int64_t)b * a.Lq + row];
+  const bool uniform = ttr > a.Ti;
+  const int blk = (ttr >= 1 && !uniform) ? ttr - 1 : -1;
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int jlo = s_j[0], jhi = s_j[1];
+  const int nblk = jhi >= jlo ? jhi - jlo + 1 : 0;
+
+  const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
+  const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);
+
+  if (tid == TQ) {
+    // ---- issuer: one thread issues every MMA and the (rare) K/V refills ----------------------
+    mbar_wait(&bar_q, 0);
+    if (nblk > 0) {
+      mbar_wait(&bar_kv[0], 0);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k4 = 0; k4 < DH / 16; ++k4)
+        umma_ss(tmem + S_COL, make_smem_desc(smem_u32(sQ) + k4 * 32, 16, 1024),
+                make_smem_desc(smem_u32(sK) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      umma_commit(&bar_s);
+    }
+    for (int it = 0; it < nblk; ++it) {
+      const int st = it % XF_STAGES;
+      mbar_wait(&bar_p, it & 1);                 // P_it is in shared memory, S_it has been read
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k4 = 0; k4 < KB / 16; ++k4)
+        umma_ss(tmem + O_COL, make_smem_desc(smem_u32(sP) + k4 * 32, 16, 1024),
+                make_smem_desc(smem_u32(sV + st * KV_BYTES) + k4 * 2048, 1024, 1024), idesc_o,
+                (it > 0 || k4 > 0));
+      umma_commit(&bar_pv);                      // PV_it done: sP and K/V stage `st` are free
+      if (it + 1 == nblk) umma_commit(&bar_o);
+      if (it + 1 < nblk) {
+        const int sn = (it + 1) % XF_STAGES;
+        mbar_wait(&bar_kv[sn], ((it + 1) / XF_STAGES) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < DH / 16; ++k4)
+          umma_ss(tmem + S_COL, make_smem_desc(smem_u32(sQ) + k4 * 32, 16, 1024),
+                  make_smem_desc(smem_u32(sK + sn * KV_BYTES) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+        umma_commit(&bar_s);                     // (also implies PV_it: MMAs complete in order)
+      }
+      if (it + XF_STAGES < nblk) {
+        mbar_wait(&bar_pv, it & 1);
+        mbar_arrive_expect_tx(&bar_kv[st], 2 * KV_BYTES);
+        tma_load_4d(sK + st * KV_BYTES, &tk, &bar_kv[st], 0, h, (jlo + it + XF_STAGES) * a.n, b);
+        tma_load_4d(sV + st * KV_BYTES, &tv, &bar_kv[st], 0, h, (jlo + it + XF_STAGES) * a.n, b);
+      }
+    }
+  }
+
+  float sum = 0.f, m_row = 0.f;
+  uint32_t r[32];
+  if (worker) {
+    for (int it = 0; it < nblk; ++it) {
+      const int j = jlo + it;
+      mbar_wait(&bar_s, it & 1);
+      tcgen05_fence_after();
+      const bool mine = uniform || blk == j;
+      const bool warp_any = __any_sync(0xffffffffu, mine);
+      float m = -INFINITY;
+      if (warp_any) {   // warp-uniform: tcgen05.ld is a warp-collective
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(lane_addr + S_COL + half * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));
+        }
+      }
+      if (uniform) m = 0.f;
+      const float ms = m * a.scale_log2;
+      float psum = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (warp_any) {
+          tmem_ld32(lane_addr + S_COL + half * 32, r);
+          tmem_ld_wait();
+        }
+        float p[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float v = 0.f;
+          if (mine) v = uniform ? 1.f : exp2f(__uint_as_float(r[c]) * a.scale_log2 - ms);
+          p[c] = v;
+          psum += v;
+        }
+        store_p_half(sP, tid, half, p);
+      }
+      if (mine) { sum += psum; m_row = m; }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p);
+    }
+    // ---- epilogue: O / sum -> global -----------------------------------------------------
+    const float lse_val = sum > 0.f ? m_row * a.scale + logf(sum) : -INFINITY;
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (nblk > 0) {
+      mbar_wait(&bar_o, 0);
+      tcgen05_fence_after();
+    }
+    __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (nblk > 0) {
+        tmem_ld32(lane_addr + O_COL + half * 32, r);
+        tmem_ld_wait();
+      }
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (nblk > 0 && inv > 0.f) {
+            v.x = pack_bf16(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
+          }
+          *reinterpret_cast<uint4*>(orow + half * 32 + c * 8) = v;
+        }
+      }
+    }
+    if (valid) a.lse[((int64_t)b * a.H + h) * a.Lq + row] = lse_val;
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 // ---- host ---------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -383,9 +598,42 @@ static int launch_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int3
   return 0;
 }
 
+static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
+                            unimp_mview_t o, float* lse, int B, int Lq, int Lk, int H, int n, int Ti,
+                            float scale, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bhld(&tq, q.ptr, q.batch_stride, q.row_stride, B, Lq, H, TQ))) return rc;
+  if ((rc = make_tmap_bhld(&tk, k.ptr, k.batch_stride, k.row_stride, B, Lk, H, KB))) return rc;
+  if ((rc = make_tmap_bhld(&tv, v.ptr, v.batch_stride, v.row_stride, B, Lk, H, KB))) return rc;
+  const int smem = 1024 + Q_BYTES + 2 * XF_STAGES * KV_BYTES + P_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("xattn_fwd_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr = true;
+  }
+  FwdArgs a;
+  a.o = (__nv_bfloat16*)o.ptr; a.o_bs = o.batch_stride; a.o_rs = o.row_stride;
+  a.lse = lse; a.tt = tt; a.Lq = Lq; a.Lk = Lk; a.H = H; a.n = n; a.Ti = Ti;
+  a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + TQ - 1) / TQ, H, B);
+  xattn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tk, tv, a);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+// UNIMP_XATTN_FWD_V1=1 selects the round-1 kernel (A/B measurements only).
+static bool use_v1_fwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UNIMP_XATTN_FWD_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int launch_attn_fwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt, unimp_mview_t o,
                        float* lse, int B, int Lq, int Lk, int H, int n, int Ti, float scale,
                        cudaStream_t st) {
+  if (tt && !use_v1_fwd()) return launch_xattn_fwd(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
   if (tt) return launch_fwd<true>(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
   return launch_fwd<false>(q, k, v, nullptr, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
 }

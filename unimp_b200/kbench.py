@@ -93,15 +93,11 @@ def _eager_focal(logits, labels, weights, gamma):
     return loss.sum() / (lab != -100).sum()
 
 
-def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
+def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True, only=None):
     """Returns {kernel: {avg_us, alg_bytes, flops, GB/s, TFLOP/s, frac_hbm, frac_tensor, sets}}.
     `eager`: also time what the reference would run on this GPU for the same op (plain PyTorch,
     same dtype, same shapes, same cold-cache method) as `eager_<kernel>` rows, and add
     `speedup_vs_eager` to our row."""
-    dev = "cuda"
-    es = 2 if dtype == torch.bfloat16 else 4
-    B, T, Ti, n, H, dh, D, V = wl.B, wl.T, wl.Ti, cfg.n_latents, cfg.xattn_heads, cfg.xattn_dim_head, cfg.lm_hidden, cfg.vocab
-    inner = H * dh
     out = {}
 
     def rec(name, us, byts, fl, sets):
@@ -112,7 +108,40 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
             d["frac_of_bf16_peak"] = d["TFLOP/s"] / peaks["bf16_tflops"]
         out[name] = d
 
+    def want(section):
+        return only is None or section in only
+
     torch.manual_seed(0)
+    if want("xattn"):
+        _run_xattn(cfg, wl, dtype, eager, rec)
+    if want("vit") or want("perceiver"):
+        _run_vit_perceiver(cfg, wl, dtype, eager, rec)
+    if want("k5") or want("gelu"):
+        _run_k5_gelu(cfg, wl, dtype, eager, rec)
+    if want("focal"):
+        _run_focal(cfg, wl, dtype, eager, rec, out, n_valid_rows)
+    if want("misc"):
+        _run_misc(cfg, wl, dtype, rec)
+    if eager:
+        for name in list(out):
+            e = out.get("eager_" + name)
+            if e is not None:
+                out[name]["speedup_vs_eager"] = e["avg_us"] / out[name]["avg_us"]
+        if "eager_vit_attn_fwd_sdpa" in out:
+            out["vit_attn_fwd"]["speedup_vs_eager"] = out["eager_vit_attn_fwd_sdpa"]["avg_us"] / out["vit_attn_fwd"]["avg_us"]
+    torch.cuda.empty_cache()
+    return out
+
+
+def _dims(cfg, wl, dtype):
+    es = 2 if dtype == torch.bfloat16 else 4
+    return ("cuda", es, wl.B, wl.T, wl.Ti, cfg.n_latents, cfg.xattn_heads, cfg.xattn_dim_head, cfg.lm_hidden,
+            cfg.vocab)
+
+
+def _run_xattn(cfg, wl, dtype, eager, rec):
+    dev, es, B, T, Ti, n, H, dh, D, V = _dims(cfg, wl, dtype)
+    inner = H * dh
     # ---- K1 masked x-attn ------------------------------------------------------------------
     xb = es * (2 * B * T * inner + 2 * B * Ti * n * inner) + 4 * B * T * H
     xf = 4.0 * H * dh * n * B * T
@@ -140,6 +169,11 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
                                             for o, q, kv, g in zip(eos, qs, kvs, gos)]), 2.5 * xb, 2.5 * xf, K)
         del efw, eos
     del qs, kvs, gos, os_, fwd, bwd
+
+
+def _run_vit_perceiver(cfg, wl, dtype, eager, rec):
+    dev, es, B, T, Ti, n, H, dh, D, V = _dims(cfg, wl, dtype)
+    inner = H * dh
     # ---- K3 ViT self-attention ----------------------------------------------------------------
     N, L, Hv = B * Ti, cfg.n_patches + 1, cfg.vis_heads
     vb = es * 4 * N * L * Hv * 64 + 4 * N * L * Hv
@@ -175,6 +209,10 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
                                                       for o, q, kv, g in zip(epo, pqs, pkvs, pgs)]), 2.5 * pb, 2.5 * pf, K)
         del epf, epo
     del pqs, pkvs, pos, pgs, pfw
+
+
+def _run_k5_gelu(cfg, wl, dtype, eager, rec):
+    dev, es, B, T, Ti, n, H, dh, D, V = _dims(cfg, wl, dtype)
     # ---- K5 gate + residual + LN ------------------------------------------------------------------
     rows = B * T
     gb = 4 * rows * D * es
@@ -226,6 +264,10 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
     rec("eager_gelu_bwd", _time_graph([lambda y=y, h=h, g=g: torch.autograd.grad(y, h, g, retain_graph=True)
                                        for y, h, g in zip(ts, hs, gys)]), 3 * rows * F4 * es, 0.0, K)
     del hs, ys, ts, gys
+
+
+def _run_focal(cfg, wl, dtype, eager, rec, out, n_valid_rows):
+    dev, es, B, T, Ti, n, H, dh, D, V = _dims(cfg, wl, dtype)
     # ---- K6 focal CE -----------------------------------------------------------------------------
     nv = n_valid_rows if n_valid_rows else max(1, B * (Ti + 2))
     z = [torch.randn(B, T, V, device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]
@@ -265,6 +307,10 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
     rec("focal_ce_rows_bwd", _time_graph([lambda l=l, zz=zz: torch.autograd.grad(l, zz, retain_graph=True)
                                           for l, zz in zip(rls, zr)]), nv_eff * V * es + Rcap * V * es, 0.0, K)
     del zr, rls, rfw
+
+
+def _run_misc(cfg, wl, dtype, rec):
+    dev, es, B, T, Ti, n, H, dh, D, V = _dims(cfg, wl, dtype)
     # ---- rotary on the packed qkv projection (GPT-NeoX, 32 heads x 80, rotary_pct 1.0) -----------
     Hl, dl = cfg.lm_heads, cfg.lm_hidden // cfg.lm_heads
     rot = int(dl * cfg.rotary_pct)
@@ -294,12 +340,3 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True):
         npar * (2 * es + 6 * 4), 0.0, 3)
     rec("grad_sumsq", _time_graph([lambda: ops.sumsq_(pg, gn)] * 3), npar * es, 0.0, 3)
     del pw, pg, ma, m1, m2
-    if eager:
-        for name in list(out):
-            e = out.get("eager_" + name)
-            if e is not None:
-                out[name]["speedup_vs_eager"] = e["avg_us"] / out[name]["avg_us"]
-        if "eager_vit_attn_fwd_sdpa" in out:
-            out["vit_attn_fwd"]["speedup_vs_eager"] = out["eager_vit_attn_fwd_sdpa"]["avg_us"] / out["vit_attn_fwd"]["avg_us"]
-    torch.cuda.empty_cache()
-    return out
