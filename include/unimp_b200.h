@@ -109,6 +109,22 @@ int unimp_attn_bwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_view_t 
                    unimp_mview_t dk, unimp_mview_t dv, int Bt, int Lq, int Lk, int H, int dh,
                    float scale, int dtype, void* stream);
 
+/* ---- a7 fused: MaskedCrossAttention (after its LayerNorm) as ONE kernel ------------------
+ * Replaces, in upstream `MaskedCrossAttention.forward` (helpers.py; call site reference
+ * UniMP/mmrec.py:177-181): q = to_q(x_ln); the masked attention core above; to_out(out).
+ *   x_ln (B,T,D) contiguous = self.norm(x);  w_q (H*dh, D) = to_q.weight;  k,v (B,Ti*n,H,dh)
+ *   views of to_kv(media);  w_out (D, H*dh) = to_out.weight;  text_time (B,T) int32.
+ * Outputs: y (B,T,D) contiguous = to_out(attention);  q, o (B,T,H*dh) contiguous and lse (B,H,T):
+ * the projected queries / attention output / log-sum-exp, saved for unimp_xattn_bwd.
+ * One 8-CTA thread-block cluster per 128-row tile (one head per CTA, x_ln tile TMA-multicast);
+ * needs H == 8, dh == 64, n == 64, D % 128 == 0, D <= 2560, bf16.
+ * unimp_xattn_block_supported returns 1 if the shape is covered, else 0. */
+int unimp_xattn_block_supported(int T, int Ti, int n, int H, int dh, int D, int dtype);
+int unimp_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, unimp_view_t v,
+                          const int32_t* text_time, const void* w_out, void* q, void* o, float* lse,
+                          void* y, int B, int T, int Ti, int n, int H, int dh, int D, float scale,
+                          int dtype, void* stream);
+
 /* ---- a12: decode step against cached cross-attention K/V ------------------------------
  * One new token per sequence attends the LAST image's n cached keys.  Upstream
  * recomputes to_kv(media) every step; the cache is new here.

@@ -559,3 +559,66 @@ def test_focal_ce_rows_equals_the_dense_kernel_and_the_reference_loss(dtype, tol
     assert zrows.grad[tgt == -100].abs().max() == 0                  # unused slots: exact zeros
     dense = ops().focal_ce(z.to(DEV), y.to(DEV), w.to(DEV), gamma=2.0, group_size=gs)
     assert abs(float(loss) - float(dense)) < 1e-5 * abs(float(dense))
+
+
+# ------------------------------------------------------------------ K1-fused (one cluster kernel)
+
+def _xblock_case(B, T, Ti, D, overflow, seed):
+    H, dh, n = 8, 64, 64
+    g = torch.Generator().manual_seed(seed)
+    bf = torch.bfloat16
+    x = torch.randn(B, T, D, generator=g).to(bf)
+    wq = (torch.randn(H * dh, D, generator=g) * D ** -0.5).to(bf)
+    wout = (torch.randn(D, H * dh, generator=g) * (H * dh) ** -0.5).to(bf)
+    kv = torch.randn(B, Ti * n, 2 * H * dh, generator=g).to(bf)
+    tt = _mk_tt(B, T, Ti, seed=seed, overflow=overflow)
+    go = torch.randn(B, T, D, generator=g).to(bf)
+    return x, wq, wout, kv, tt, go
+
+
+@pytest.mark.parametrize("B,T,Ti,D,overflow", [(2, 32, 2, 128, False), (3, 256, 2, 2560, False),
+                                               (1, 513, 8, 512, False), (2, 100, 5, 1024, True),
+                                               (2, 1024, 8, 2560, False)])
+def test_xattn_block_fused_kernel_equals_fp64_reference(B, T, Ti, D, overflow):
+    """K1-fused: to_q -> masked media-located attention -> to_out in one 8-CTA-cluster kernel
+    (x_ln tile TMA-multicast, O tiles exchanged through L2) against the fp64 dense restatement of
+    upstream MaskedCrossAttention, forward and backward, ragged tiles (T % 128),
+    tiles spanning several images, text_time == 0 and > Ti rows."""
+    H, dh, n = 8, 64, 64
+    x, wq, wout, kv, tt, go = _xblock_case(B, T, Ti, D, overflow, seed=B * T + D)
+    leaves = [t.double().requires_grad_(True) for t in (x, wq, kv, wout)]
+    x64, wq64, kv64, wout64 = leaves
+    q64 = x64 @ wq64.t()
+    a64 = _dense_attn_ref(q64, kv64, tt.long(), H, n, dh ** -0.5)
+    y64 = a64 @ wout64.t()
+    y64.backward(go.double())
+    dl = [t.to(DEV).requires_grad_(True) for t in (x, wq, kv, wout)]
+    xd, wqd, kvd, woutd = dl
+    y = ops().xattn_block(xd, wqd, kvd, tt.to(DEV), woutd, heads=H, n_latents=n, scale=dh ** -0.5)
+    y.backward(go.to(DEV))
+    assert_close(y, y64, 2e-2, "y")
+    assert_close(xd.grad, x64.grad, 2e-2, "d x_ln")
+    assert_close(wqd.grad, wq64.grad, 2e-2, "d to_q.weight")
+    assert_close(kvd.grad, kv64.grad, 2e-2, "d kv")
+    assert_close(woutd.grad, wout64.grad, 2e-2, "d to_out.weight")
+    # and it agrees with the three-launch form on the same inputs (same rounding points: q, P, o in bf16)
+    with torch.no_grad():
+        qd = torch.nn.functional.linear(xd, wqd)
+        o3 = ops().masked_cross_attention(qd, kvd, tt.to(DEV), heads=H, n_latents=n, scale=dh ** -0.5)
+        y3 = torch.nn.functional.linear(o3, woutd)
+    assert_close(y, y3, 1e-2, "fused vs unfused")
+    rows0 = (tt == 0)
+    if rows0.any():
+        assert y.detach().cpu()[rows0].abs().max() == 0       # text before the first <image>: exact zeros
+
+
+def test_xattn_block_rejects_shapes_it_does_not_cover():
+    from unimp_b200._lib import UnimpError
+    x = torch.randn(1, 64, 192, device=DEV, dtype=torch.bfloat16)          # D % 128 != 0
+    wq = torch.randn(512, 192, device=DEV, dtype=torch.bfloat16)
+    wout = torch.randn(192, 512, device=DEV, dtype=torch.bfloat16)
+    kv = torch.randn(1, 128, 1024, device=DEV, dtype=torch.bfloat16)
+    tt = torch.ones(1, 64, device=DEV, dtype=torch.int32)
+    assert not ops().xattn_block_supported(x, kv, heads=8, n_latents=64)
+    with pytest.raises(UnimpError, match="multiple of 128"):
+        ops().xattn_block(x, wq, kv, tt, wout, heads=8, n_latents=64, scale=0.125)

@@ -37,6 +37,9 @@ SIGNATURES = {
     "unimp_attn_fwd": (_i, [View, View, View, View, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "unimp_attn_bwd": (_i, [View, View, View, View, View, _p, _p, View, View, View,
                             _i, _i, _i, _i, _i, _f, _i, _p]),
+    "unimp_xattn_block_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "unimp_xattn_block_fwd": (_i, [_p, _p, View, View, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i,
+                                   _f, _i, _p]),
     "unimp_xattn_decode": (_i, [View, View, View, _p, View, _i, _i, _i, _i, _i, _f, _i, _p]),
     "unimp_gate_residual_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "unimp_gate_residual_ln_bwd_workspace": (_i64, [_i64, _i]),

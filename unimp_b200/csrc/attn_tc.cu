@@ -554,6 +554,34 @@ int make_tmap_bhld(CUtensorMap* out, const void* base, int64_t batch_stride, int
   return 0;
 }
 
+// Generic bf16 tiled map, SWIZZLE_128B (box inner extent = 64 elements = 128 bytes), zero fill out
+// of range.  dims / box: innermost first; strides_bytes: rank-1 entries (dims 1..rank-1).
+int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return UNIMP_E_DEVICE; }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, bx,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=%llu,%llu", (int)r, base, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    return UNIMP_E_SHAPE;
+  }
+  return 0;
+}
+
 static bool view_ok(const void* p, int64_t bs, int64_t rs) {
   return aligned16(p) && (bs % 8 == 0) && (rs % 8 == 0);
 }

@@ -40,6 +40,12 @@ const char* attn_bwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t
                                     unimp_mview_t dq, unimp_mview_t dk, unimp_mview_t dv,
                                     const int32_t* tt, int Lq, int Lk, int n, int dh);
 
+// xattn_block.cu (one cluster kernel: to_q GEMM -> masked attention -> to_out GEMM)
+const char* xattn_block_unsupported(int T, int Ti, int n, int H, int dh, int D, int dtype);
+int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, unimp_view_t v,
+                           const int32_t* tt, const void* w_out, void* q, void* o, float* lse, void* y,
+                           int B, int T, int Ti, int n, int D, float scale, cudaStream_t st);
+
 static int check_attn_common(const char* who, unimp_view_t q, unimp_view_t k, unimp_view_t v,
                              const void* o, int B, int Lq, int Lk, int H, int dh, int dtype) {
   UNIMP_CHECK_ARG(q.ptr && k.ptr && v.ptr && o, UNIMP_E_NULL, "%s: NULL pointer", who);
@@ -155,6 +161,28 @@ extern "C" int unimp_attn_bwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, un
                   "attn_bwd: NULL pointer");
   return attn_bwd_dispatch(q, k, v, nullptr, o, d_o, lse, workspace, dq, dk, dv, Bt, Lq, Lk, H, Lk, 1,
                            dh, scale, dtype, 0, (cudaStream_t)stream);
+}
+
+extern "C" int unimp_xattn_block_supported(int T, int Ti, int n, int H, int dh, int D, int dtype) {
+  return xattn_block_unsupported(T, Ti, n, H, dh, D, dtype) == nullptr ? 1 : 0;
+}
+
+extern "C" int unimp_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, unimp_view_t v,
+                                     const int32_t* text_time, const void* w_out, void* q, void* o,
+                                     float* lse, void* y, int B, int T, int Ti, int n, int H, int dh,
+                                     int D, float scale, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(x_ln && w_q && k.ptr && v.ptr && text_time && w_out && q && o && lse && y, UNIMP_E_NULL,
+                  "xattn_block_fwd: NULL pointer");
+  UNIMP_CHECK_ARG(B > 0 && T > 0 && Ti > 0, UNIMP_E_SHAPE, "xattn_block_fwd: bad shape B=%d T=%d Ti=%d", B, T,
+                  Ti);
+  const char* why = xattn_block_unsupported(T, Ti, n, H, dh, D, dtype);
+  UNIMP_CHECK_ARG(!why, UNIMP_E_SHAPE, "xattn_block_fwd: %s [H=%d dh=%d n=%d D=%d]", why, H, dh, n, D);
+  UNIMP_CHECK_ARG(aligned16(x_ln) && aligned16(w_q) && aligned16(w_out) && aligned16(q) && aligned16(o) &&
+                      aligned16(y) && aligned16(k.ptr) && aligned16(v.ptr) && k.row_stride % 8 == 0 &&
+                      v.row_stride % 8 == 0 && k.batch_stride % 8 == 0 && v.batch_stride % 8 == 0,
+                  UNIMP_E_ALIGN, "xattn_block_fwd: pointers must be 16-byte aligned, strides multiples of 8");
+  return launch_xattn_block_fwd(x_ln, w_q, k, v, text_time, w_out, q, o, lse, y, B, T, Ti, n, D, scale,
+                                (cudaStream_t)stream);
 }
 
 // Test hooks: same contracts, CUDA-core implementation forced (tt may be NULL = unmasked).

@@ -256,5 +256,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
 // and batch strides; box = 64 x 1 x box_rows x 1, SWIZZLE_128B, out-of-range rows read as zero.
 int make_tmap_bhld(CUtensorMap* out, const void* base, int64_t batch_stride, int64_t row_stride,
                    int B, int L, int H, int box_rows);
+// Generic bf16 tiled map (rank <= 5), SWIZZLE_128B, zero fill; dims / box innermost first,
+// strides_bytes for dims 1..rank-1.
+int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace unimp

@@ -9,6 +9,8 @@ stay on cuBLAS (`F.linear`).  No autocast: activations live in the parameters' d
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -118,6 +120,9 @@ class MaskedCrossAttention(nn.Module):
         self.to_out = nn.Linear(inner, dim, bias=False)
         self.only_attend_immediate_media = True
         self._kv_cache = None  # decode-time cache of to_kv(media) (new)
+        # K1-fused (one cluster kernel for to_q -> attention -> to_out) where the shape allows
+        # (bf16, 8 x 64 heads, 64 latents, D <= 2560); UNIMP_XATTN_FUSED=0 keeps the three-launch form
+        self.fused = os.environ.get("UNIMP_XATTN_FUSED", "1") != "0"
 
     def project_media(self, media):
         """to_kv over (B, Ti*n, Dv) -> packed (B, Ti*n, 2*inner)."""
@@ -150,6 +155,19 @@ class MaskedCrossAttention(nn.Module):
                                       use_cached=use_cached_media, T_out=T)
         if x_ln is None:
             x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        cached = use_cached_media and not torch.is_grad_enabled()
+        if self.fused and not (cached and T == 1):
+            kv = self.cached_media_kv(media) if cached else self.project_media(media)
+            if not cached:
+                self._kv_cache = None
+            if ops.xattn_block_supported(x_ln, kv, heads=self.heads, n_latents=n):
+                # to_q -> masked attention -> to_out in ONE cluster kernel (K1-fused)
+                return ops.xattn_block(x_ln, self.to_q.weight, kv, text_time, self.to_out.weight,
+                                       heads=self.heads, n_latents=n, scale=self.scale)
+            q = ops.linear_acc(x_ln, self.to_q.weight)
+            out = ops.masked_cross_attention(q, kv, text_time, heads=self.heads, n_latents=n,
+                                             scale=self.scale)
+            return ops.linear_acc(out, self.to_out.weight)
         q = ops.linear_acc(x_ln, self.to_q.weight)
         if use_cached_media and not torch.is_grad_enabled():
             # keyed on the media tensor (identity + version) and on the projection weights'

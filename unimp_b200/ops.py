@@ -154,6 +154,96 @@ def attention(q, kv, *, heads: int, scale: float, force_simt: bool = False):
     return _Attention.apply(q, kv, None, heads, kv.shape[1], 1, float(scale), force_simt)
 
 
+def _weight_grad(w, g2, x2):
+    """dW = g2^T x2 for a bias-free Linear weight: straight into the optimizer's flat gradient
+    buffer when the parameter is registered for direct accumulation (returns None), else returned
+    to autograd."""
+    if getattr(w, "_unimp_direct", False) and w.grad is not None:
+        if w._unimp_fresh:
+            torch.mm(g2.t(), x2, out=w.grad)
+            w._unimp_fresh = False
+        else:
+            w.grad.addmm_(g2.t(), x2)
+        _grad_ready(w)
+        return None
+    return g2.t() @ x2
+
+
+class _XattnBlock(torch.autograd.Function):
+    """y = to_out( masked_attention( to_q(x_ln), to_kv(media) ) ) in ONE kernel
+    (`unimp_xattn_block_fwd`); backward = the unfused pieces (dense projections on cuBLAS,
+    `unimp_xattn_bwd` for the core) on the q / o / lse the forward saved."""
+
+    @staticmethod
+    def forward(ctx, x_ln, w_q, kv, tt, w_out, heads, n, scale):
+        dt = _dt(x_ln)
+        x_ln = x_ln.contiguous()
+        kv = _inner_contig(kv)
+        B, T, D = x_ln.shape
+        inner = w_q.shape[0]
+        dh = inner // heads
+        Lk = kv.shape[1]
+        Ti = Lk // n
+        assert w_q.shape == (inner, D) and w_out.shape == (D, inner) and kv.shape == (B, Lk, 2 * inner)
+        assert w_q.is_contiguous() and w_out.is_contiguous() and w_q.dtype == x_ln.dtype == kv.dtype
+        assert tt.dtype == torch.int32 and tt.shape == (B, T) and tt.is_contiguous()
+        k, v = kv[..., :inner], kv[..., inner:]
+        q = torch.empty((B, T, inner), dtype=x_ln.dtype, device=x_ln.device)
+        o = torch.empty_like(q)
+        lse = torch.empty((B, heads, T), dtype=torch.float32, device=x_ln.device)
+        y = torch.empty((B, T, D), dtype=x_ln.dtype, device=x_ln.device)
+        check(_lib.load().unimp_xattn_block_fwd(x_ln.data_ptr(), w_q.data_ptr(), _view3(k), _view3(v),
+                                                tt.data_ptr(), w_out.data_ptr(), q.data_ptr(),
+                                                o.data_ptr(), lse.data_ptr(), y.data_ptr(), B, T, Ti, n,
+                                                heads, dh, D, float(scale), dt, _stream()),
+              "unimp_xattn_block_fwd")
+        ctx.save_for_backward(x_ln, w_q, kv, tt, w_out, q, o, lse)
+        ctx.cfg = (heads, n, Ti, float(scale), dt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_ln, w_q, kv, tt, w_out, q, o, lse = ctx.saved_tensors
+        heads, n, Ti, scale, dt = ctx.cfg
+        B, T, D = x_ln.shape
+        inner = q.shape[2]
+        dh = inner // heads
+        Lk = kv.shape[1]
+        dy = dy.contiguous()
+        dy2 = dy.reshape(B * T, D)
+        d_o = (dy2 @ w_out).view(B, T, inner)                      # y = o @ w_out^T
+        d_wout = _weight_grad(w_out, dy2, o.reshape(B * T, inner)) if ctx.needs_input_grad[4] else None
+        k, v = kv[..., :inner], kv[..., inner:]
+        dq = torch.empty_like(q)
+        dkv = torch.empty((B, Lk, 2 * inner), dtype=kv.dtype, device=kv.device)
+        dk, dv = dkv[..., :inner], dkv[..., inner:]
+        lib = _lib.load()
+        ws = torch.empty(lib.unimp_attn_bwd_workspace(B, T, Lk, heads, dh), dtype=torch.uint8, device=q.device)
+        check(lib.unimp_xattn_bwd(_view3(q), _view3(k), _view3(v), tt.data_ptr(), _view3(o), _view3(d_o),
+                                  lse.data_ptr(), ws.data_ptr(), _view3(dq), _view3(dk), _view3(dv), B, T,
+                                  Ti, n, heads, dh, scale, dt, _stream()), "unimp_xattn_bwd (fused block)")
+        dq2 = dq.reshape(B * T, inner)
+        d_x = (dq2 @ w_q).view(B, T, D) if ctx.needs_input_grad[0] else None     # q = x_ln @ w_q^T
+        d_wq = _weight_grad(w_q, dq2, x_ln.reshape(B * T, D)) if ctx.needs_input_grad[1] else None
+        return d_x, d_wq, (dkv if ctx.needs_input_grad[2] else None), None, d_wout, None, None, None
+
+
+def xattn_block_supported(x_ln, kv, *, heads: int, n_latents: int) -> bool:
+    if not x_ln.is_cuda or x_ln.dtype != torch.bfloat16:
+        return False
+    B, T, D = x_ln.shape
+    inner = kv.shape[2] // 2
+    return bool(_lib.load().unimp_xattn_block_supported(T, kv.shape[1] // n_latents, n_latents, heads,
+                                                        inner // heads, D, BF16))
+
+
+def xattn_block(x_ln, w_q, kv, text_time_i32, w_out, *, heads: int, n_latents: int, scale: float):
+    """K1-fused: to_q -> masked media-located attention -> to_out as one cluster kernel.
+    x_ln (B,T,D) = norm(x); w_q = to_q.weight (H*64, D); kv = to_kv(media) packed (B,Ti*n,2*H*64);
+    w_out = to_out.weight (D, H*64).  Returns to_out(attention) (B,T,D)."""
+    return _XattnBlock.apply(x_ln, w_q, kv, text_time_i32, w_out, heads, n_latents, float(scale))
+
+
 def xattn_decode(q, kv, n_media_i32, *, heads: int, n_latents: int, scale: float):
     """a12: single-token decode against cached packed K/V. q (B,1,H*64)."""
     dt = _dt(q)
