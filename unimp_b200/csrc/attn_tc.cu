@@ -639,6 +639,9 @@ static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, cons
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("xattn_fwd_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    // 3 CTAs x 65 KB per SM: ask for the largest shared-memory carve-out, or the driver sizes it for one
+    cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   FwdArgs a;

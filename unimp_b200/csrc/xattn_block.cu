@@ -7,10 +7,11 @@
 //
 // One thread-block CLUSTER of 8 CTAs per 128-row query tile, one head per CTA:
 //   phase 1  Q_h (128x64, TMEM) = x_ln tile (128 x D) . Wq_h^T, K = D in 64-wide chunks through a
-//            3-stage ring.  The x_ln chunk is the same for all 8 heads: every CTA loads 1/8 of it
-//            (16 rows) and TMA-MULTICASTS it into all 8 CTAs' rings (L2 reads of x_ln / 8); a ring
-//            slot is released by tcgen05.commit multicast to all 8 CTAs' "empty" barriers, because
-//            any of them may overwrite it next.
+//            6-stage ring (144 KB in flight per SM: the loads are L2-latency x bandwidth bound).
+//            The x_ln chunk is the same for all 8 heads: CTA (k mod 8) loads chunk k ONCE and
+//            TMA-MULTICASTS it into all 8 CTAs' rings (L2 reads of x_ln / 8); a ring slot is
+//            released by tcgen05.commit multicast to all 8 CTAs' "empty" barriers, because any of
+//            them may be the one that overwrites it next.
 //   phase 2  the attention core of attn_tc.cu (S = Q K^T, mask from text_time in registers, row
 //            softmax on the 128 TMEM-lane-owning threads, O = P V); Q goes TMEM -> bf16 ->
 //            swizzled shared memory (A operand) and to global (saved for backward).
@@ -33,16 +34,15 @@ using namespace tc;
 namespace xb {
 constexpr int TQ = 128, KB = 64, DH = 64, H = 8, INNER = H * DH;
 constexpr int THREADS = 192;
-constexpr int S1 = 3;                                  // phase-1 ring depth
+constexpr int S1 = 6;                                  // phase-1 ring depth (3 stages + 3 in the idle Wout ring)
 constexpr uint32_t A_BYTES = TQ * 64 * 2;              // 16 KB: x_ln chunk (128 rows x 64)
-constexpr uint32_t A_SLICE = A_BYTES / H;              // 2 KB: the 16 rows one CTA multicasts
 constexpr uint32_t B_BYTES = 64 * 64 * 2;              // 8 KB: Wq_h chunk
 constexpr uint32_t STAGE1 = A_BYTES + B_BYTES;         // 24 KB
 constexpr uint32_t Q_BYTES = TQ * DH * 2, P_BYTES = TQ * KB * 2, KV_BYTES = KB * DH * 2;
 constexpr int NS_MAX = 320;                            // output columns per CTA (D / 8), D <= 2560
 constexpr uint32_t W_STAGE = NS_MAX * 128;             // 40 KB: Wout rows [c*NS, +NS) x 64 K-columns
 constexpr uint32_t OFF_RING1 = 0;
-constexpr uint32_t OFF_Q = OFF_RING1 + S1 * STAGE1;    //  73728
+constexpr uint32_t OFF_Q = OFF_RING1 + 3 * STAGE1;     //  73728
 constexpr uint32_t OFF_P = OFF_Q + Q_BYTES;            //  90112
 constexpr uint32_t OFF_K = OFF_P + P_BYTES;            // 106496
 constexpr uint32_t OFF_V = OFF_K + 2 * KV_BYTES;       // 122880
@@ -50,6 +50,11 @@ constexpr uint32_t OFF_W = OFF_V + 2 * KV_BYTES;       // 139264
 constexpr uint32_t OFF_O = 0;                          // phase 3: 8 x 16 KB over the dead ring / Q / P / K / V
 constexpr uint32_t SMEM_BYTES = OFF_W + 2 * W_STAGE;   // 221184
 static_assert(OFF_O + H * Q_BYTES <= OFF_W, "the O tiles must not reach the Wout ring");
+static_assert(3 * STAGE1 <= 2 * W_STAGE, "ring stages 3-5 live in the Wout ring while it is idle");
+// phase-1 ring stage i: 0-2 at the front, 3-5 in the Wout ring (not needed before phase 2)
+__device__ __forceinline__ uint32_t stage1_off(int i) {
+  return i < 3 ? OFF_RING1 + (uint32_t)i * STAGE1 : OFF_W + (uint32_t)(i - 3) * STAGE1;
+}
 constexpr uint32_t Q_COL = 0, S_COL = 64, O_COL = 128, Y_COL = 0, TMEM_COLS = 512;
 constexpr uint16_t ALL = 0xFF;
 
@@ -104,7 +109,6 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   using namespace xb;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring1 = smem + OFF_RING1;
   uint8_t* sQ = smem + OFF_Q;
   uint8_t* sP = smem + OFF_P;
   uint8_t* sK = smem + OFF_K;
@@ -155,17 +159,12 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     if (lane == 0) {
       s_j[0] = lo; s_j[1] = hi;
       // loads that touch only THIS CTA's barriers may start before the cluster is in step:
-      // K/V of the first two blocks and the first two Wout chunks
+      // K/V of the first two image blocks
       const int nb = hi >= lo ? hi - lo + 1 : 0;
       for (int it = 0; it < nb && it < 2; ++it) {
         mbar_arrive_expect_tx(&bar_kv[it], 2 * KV_BYTES);
         tma_load_4d(sK + it * KV_BYTES, &tk, &bar_kv[it], 0, h, (lo + it) * a.n, b);
         tma_load_4d(sV + it * KV_BYTES, &tv, &bar_kv[it], 0, h, (lo + it) * a.n, b);
-      }
-      for (int kk = 0; kk < 2; ++kk) {
-        mbar_arrive_expect_tx(&full_w[kk], (uint32_t)NS * 128u);
-        for (int half = 0; half < a.nsplit; ++half)
-          tma_load_2d(sW + kk * W_STAGE + half * NSH * 128, &twout, &full_w[kk], kk * 64, h * NS + half * NSH);
       }
     }
     __syncwarp();
@@ -199,9 +198,17 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
         const int s = k % S1;
         if (k >= S1) mbar_wait_tag(&empty1[s], ((k / S1) - 1) & 1, T_EMPTY1 + s);
         mbar_arrive_expect_tx(&full1[s], STAGE1);
-        uint8_t* st = ring1 + s * STAGE1;
-        tma_load_3d_mc(st + h * A_SLICE, &tx, &full1[s], k * 64, t0 + 16 * h, b, ALL);
+        uint8_t* st = smem + stage1_off(s);
+        if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
         tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
+      }
+      // the Wout ring doubles as ring stages 3-5: its first two chunks are fetched once every
+      // phase-1 MMA of this CTA has completed (they arrive while phase 2 runs)
+      mbar_wait_tag(&bar_qacc, 0, T_QACC);
+      for (int kk = 0; kk < 2; ++kk) {
+        mbar_arrive_expect_tx(&full_w[kk], (uint32_t)NS * 128u);
+        for (int half = 0; half < a.nsplit; ++half)
+          tma_load_2d(sW + kk * W_STAGE + half * NSH * 128, &twout, &full_w[kk], kk * 64, h * NS + half * NSH);
       }
       for (int it = 0; it + 2 < nblk; ++it) {     // K/V refills (tiles that span > 2 images)
         mbar_wait_tag(&bar_pv, it & 1, T_PV);
@@ -218,7 +225,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
         const int s = k % S1;
         mbar_wait_tag(&full1[s], (k / S1) & 1, T_FULL1 + s);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(ring1 + s * STAGE1), sb = sa + A_BYTES;
+        const uint32_t sa = smem_u32(smem + stage1_off(s)), sb = sa + A_BYTES;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
           umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
@@ -422,7 +429,7 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
   {
     const uint64_t dims[3] = {(uint64_t)D, (uint64_t)T, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
-    const uint32_t box[3] = {64, 16, 1};
+    const uint32_t box[3] = {64, (uint32_t)TQ, 1};
     if ((rc = make_tmap_tiled(&tx, x_ln, 3, dims, strides, box))) return rc;
   }
   {
