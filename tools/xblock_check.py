@@ -81,12 +81,54 @@ def bench(B, T, Ti, D, tag):
           flush=True)
 
 
+def timeline(B, T, Ti, D):
+    """Per-CTA phase timestamps of one launch (unimp__xattn_block_debug test hook)."""
+    import ctypes
+    lib = _lib.load()
+    inner = H * dh
+    x = torch.randn(B, T, D, device=dev, dtype=bf)
+    wq = (torch.randn(inner, D, device=dev) * D ** -0.5).to(bf)
+    wo = (torch.randn(D, inner, device=dev) * inner ** -0.5).to(bf)
+    kv = torch.randn(B, Ti * n, 2 * inner, device=dev, dtype=bf)
+    tt = mk_tt(B, T, Ti)
+    n_cta = 8 * ((T + 127) // 128) * B
+    buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
+    f = lib.unimp__xattn_block_debug
+    f.argtypes = [ctypes.c_void_p]
+    f.restype = None
+    with torch.no_grad():
+        for _ in range(3):
+            ops.xattn_block(x, wq, kv, tt, wo, heads=H, n_latents=n, scale=0.125)
+        torch.cuda.synchronize()
+        f(buf.data_ptr())
+        ops.xattn_block(x, wq, kv, tt, wo, heads=H, n_latents=n, scale=0.125)
+        torch.cuda.synchronize()
+        f(None)
+    t = buf.view(n_cta, 16).cpu().double()
+    t0 = t[:, 0].min()
+    names = ["start", "csync1", "ph1 done", "attn done", "o stored", "csync2", "O tiles in", "to_out done",
+             "y stored", "end", "1st chunk", "half K"]
+    print(f"XB timeline B={B} T={T} Ti={Ti} D={D} ({n_cta} CTAs); ns since the first CTA's start: median [min, max]")
+    for i, nm in enumerate(names):
+        col = t[:, i] - t0
+        print(f"XB   {nm:12s} {col.median():9.0f} [{col.min():9.0f}, {col.max():9.0f}]")
+    print("XB   per-CTA durations (median ns): csync1 %.0f | ph1 %.0f (1st chunk after csync1 %.0f, half-K at %.0f) | attn %.0f | "
+          "o store %.0f | csync2 %.0f | O exchange %.0f | to_out %.0f | y store %.0f" % (
+              (t[:, 1] - t[:, 0]).median(), (t[:, 2] - t[:, 1]).median(), (t[:, 10] - t[:, 1]).median(),
+              (t[:, 11] - t[:, 1]).median(), (t[:, 3] - t[:, 2]).median(), (t[:, 4] - t[:, 3]).median(),
+              (t[:, 5] - t[:, 4]).median(), (t[:, 6] - t[:, 5]).median(), (t[:, 7] - t[:, 6]).median(),
+              (t[:, 8] - t[:, 7]).median()), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "check"):
         for shape in ((1, 128, 1, 128), (2, 32, 2, 128), (1, 128, 2, 2560), (3, 256, 2, 2560), (1, 513, 8, 512),
                       (6, 1024, 8, 2560)):
             check(*shape)
+    if what in ("all", "timeline"):
+        timeline(6, 256, 2, 2560)
+        timeline(6, 1024, 8, 2560)
     if what in ("all", "bench"):
         bench(6, 256, 2, 2560, "C2")
         bench(6, 1024, 8, 2560, "C3")

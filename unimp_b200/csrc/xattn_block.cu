@@ -68,7 +68,18 @@ struct XBlkArgs {
   const int32_t* tt;          // (B,T)
   int T, Ti, n, D, NK, NS, NSH, nsplit;
   float scale, scale_log2;
+  unsigned long long* dbg;    // optional per-CTA phase timestamps (16 x u64 per CTA), NULL = off
 };
+
+__device__ __forceinline__ unsigned long long xb_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define XB_STAMP(slot)                                                                          \
+  do {                                                                                          \
+    if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = xb_now(); \
+  } while (0)
 
 __device__ __forceinline__ uint32_t xb_pack(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -178,10 +189,12 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   const bool uniform = ttr > a.Ti;
   const int blk = (ttr >= 1 && !uniform) ? ttr - 1 : -1;
 
+  if (tid == 0) XB_STAMP(0);
   // cluster barrier #1: every CTA's barriers are initialised before any multicast / remote arrive
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
+  if (tid == 0) XB_STAMP(1);
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int jlo = s_j[0], jhi = s_j[1];
@@ -225,6 +238,8 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
         const int s = k % S1;
         mbar_wait_tag(&full1[s], (k / S1) & 1, T_FULL1 + s);
         tcgen05_fence_after();
+        if (k == 0) XB_STAMP(10);   // first chunk landed
+        if (k == NK / 2) XB_STAMP(11);
         const uint32_t sa = smem_u32(smem + stage1_off(s)), sb = sa + A_BYTES;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
@@ -272,6 +287,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     uint32_t r[32];
     mbar_wait_tag(&bar_qacc, 0, T_QACC);
     tcgen05_fence_after();
+    if (tid == 0) XB_STAMP(2);     // phase 1 done
     __nv_bfloat16* qrow = a.q + ((int64_t)b * a.T + row) * INNER + h * DH;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -334,6 +350,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
       mbar_wait_tag(&bar_o, 0, T_O);
       tcgen05_fence_after();
     }
+    if (tid == 0) XB_STAMP(3);     // attention MMAs done
     __nv_bfloat16* orow = a.o + ((int64_t)b * a.T + row) * INNER + h * DH;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -353,8 +370,10 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
 
   // cluster barrier #2: every head's O tile is in global memory (L2), every CTA is done with its
   // ring / Q / P / K / V buffers and with the Q / S / O accumulator columns
+  if (tid == 0) XB_STAMP(4);       // o stored
   cluster_sync_all();
   tcgen05_fence_after();
+  if (tid == 0) XB_STAMP(5);       // cluster barrier #2 passed
 
   // =============================== phase 3: y slice = O_all . Wout_slice^T ====================
   if (warp == 4) {
@@ -374,6 +393,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   } else if (warp == 5) {
     if (lane == 0) {
       mbar_wait_tag(&full_o, 0, T_FULLO);
+      XB_STAMP(6);                 // all 8 O tiles arrived
       for (int kk = 0; kk < H; ++kk) {
         const int s = kk & 1;
         mbar_wait_tag(&full_w[s], (kk >> 1) & 1, T_FULLW + s);
@@ -393,6 +413,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     uint32_t r[32];
     mbar_wait_tag(&bar_y, 0, T_Y);
     tcgen05_fence_after();
+    if (tid == 0) XB_STAMP(7);     // to_out MMAs done
     __nv_bfloat16* yrow = a.y + ((int64_t)b * a.T + row) * a.D + h * NS;
     for (int c = 0; c < NS; c += 32) {
       tmem_ld32(lane_addr + Y_COL + c, r);
@@ -401,12 +422,16 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     }
     tcgen05_fence_before();
   }
+  if (tid == 0) XB_STAMP(8);       // y stored
   // nobody leaves while a peer may still multicast into its shared memory
   cluster_sync_all();
+  if (tid == 0) XB_STAMP(9);
   if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---- host -------------------------------------------------------------------------------------
+
+static unsigned long long* g_xb_dbg = nullptr;   // test hook: per-CTA phase timestamps
 
 const char* xattn_block_unsupported(int T, int Ti, int n, int Hh, int dh, int D, int dtype) {
   (void)T; (void)Ti;
@@ -458,6 +483,7 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
   a.q = (__nv_bfloat16*)q; a.o = (__nv_bfloat16*)o; a.y = (__nv_bfloat16*)y; a.lse = lse; a.tt = tt;
   a.T = T; a.Ti = Ti; a.n = n; a.D = D; a.NK = D / 64; a.NS = NS; a.NSH = NSH; a.nsplit = nsplit;
   a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  a.dbg = g_xb_dbg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(H, (T + TQ - 1) / TQ, B);
   cfg.blockDim = dim3(THREADS);
@@ -473,3 +499,7 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
 }
 
 }  // namespace unimp
+
+// Test hook (not in the public header): device buffer of 16 x u64 per CTA that the next launches
+// fill with %globaltimer phase stamps; NULL switches it off.
+extern "C" void unimp__xattn_block_debug(unsigned long long* buf) { unimp::g_xb_dbg = buf; }
