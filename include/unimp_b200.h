@@ -147,8 +147,10 @@ int unimp_gate_residual_ln_fwd(const void* branch, const void* x, const void* ga
                                int dtype, void* stream);
 /* Backward.  g_xout / g_ln are the incoming grads of the two outputs (either may be NULL).
  * d_x = g_xout + LNbwd(g_ln);  d_branch = d_x * tanh(gate);
- * d_gate = sum(d_x * branch) * (1 - tanh^2)  ; d_gamma/d_beta = column sums (`dtype`,
- * written not accumulated; any of the three may be NULL).
+ * d_gate = sum(d_x * branch) * (1 - tanh^2)  ; d_gamma/d_beta = column sums (`dtype`; any of
+ * the three may be NULL).  accumulate: bit 0 -> d_gate +=, bit 1 -> d_gamma / d_beta += instead of
+ * = (the outputs are then the optimizer's gradient buffers and an earlier micro-batch of the
+ * step has written them: no separate `grad += d` launches); 0 = write.
  * Ungated residual (branch != NULL, gate == NULL): d_branch == d_x, `branch` is not read and
  * d_branch may be NULL (the caller hands d_x to both inputs); if given it receives a copy.
  * partial is caller scratch of unimp_gate_residual_ln_bwd_workspace() bytes. */
@@ -157,7 +159,7 @@ int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, const void*
                                const void* x_out, const void* gate, const void* gamma,
                                const float* mean, const float* rstd, void* d_x, void* d_branch,
                                void* d_gate, void* d_gamma, void* d_beta, void* partial,
-                               int64_t rows, int D, int dtype, void* stream);
+                               int64_t rows, int D, int accumulate, int dtype, void* stream);
 
 /* ---- a10 / K6: task-weighted focal cross-entropy head ---------------------------------
  * Replaces reference UniMP/mmrec.py:190-213 (shift-by-one CE * weights * (1-pt)^gamma,

@@ -140,7 +140,7 @@ def test_shape_dtype_and_alignment_are_validated_before_launching():
     assert f(None, P + 8, None, P, P, None, P, P, P, 4, 128, 1e-5, 1, None) < 0 and b"aligned" in lib.unimp_last_error_string()
     # K5 backward: a gated branch needs somewhere to put d_branch
     b = lib.unimp_gate_residual_ln_bwd
-    assert b(P, P, P, P, P, P, P, P, P, None, None, None, None, P, 4, 128, 1, None) < 0
+    assert b(P, P, P, P, P, P, P, P, P, None, None, None, None, P, 4, 128, 0, 1, None) < 0
     assert b"d_branch" in lib.unimp_last_error_string()
     # GELU: element count must be whole vectors
     assert lib.unimp_gelu_fwd(P, P, 12, 1, None) < 0 and lib.unimp_gelu_bwd(P, P, P, 12, 1, None) < 0

@@ -106,7 +106,8 @@ def test_masked_cross_attention_fwd_bwd(dtype, tol, B, T, Ti, overflow, simt):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("Bt,Lq,Lk,H", [(4, 64, 320, 8), (2, 257, 257, 16), (3, 17, 17, 1), (1, 64, 80, 8)])
+@pytest.mark.parametrize("Bt,Lq,Lk,H", [(4, 64, 320, 8), (2, 257, 257, 16), (3, 17, 17, 1), (1, 64, 80, 8),
+                                        (1, 300, 577, 4), (2, 128, 64, 2)])
 @pytest.mark.parametrize("simt", [True, False])
 def test_unmasked_attention_fwd_bwd(dtype, tol, Bt, Lq, Lk, H, simt):
     """Perceiver (64x320) and ViT (257x257) shapes plus ragged tails; q/kv as strided views of a
@@ -143,12 +144,14 @@ def test_bf16_attention_never_falls_back_to_cuda_cores_silently():
     kv32 = torch.randn(2, 2 * 32, 2 * H * dh, device=DEV, dtype=torch.bfloat16)     # n_latents = 32
     with pytest.raises(UnimpError, match="n_latents == 64"):
         ops().masked_cross_attention(q, kv32, tt, heads=H, n_latents=32, scale=0.125)
-    kv_long = torch.randn(2, 512, 2 * H * dh, device=DEV, dtype=torch.bfloat16)     # Lk > 384
-    with pytest.raises(UnimpError, match="Lk <= 384"):
-        ops().attention(q, kv_long, heads=H, scale=0.125)
+    q_long = torch.randn(2, 200, H * dh, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    kv = torch.randn(2, 200, 2 * H * dh, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    out = ops().attention(q_long, kv, heads=H, scale=0.125)                         # forward: any Lq, Lk
+    with pytest.raises(UnimpError, match="Lq <= 128"):                              # backward: Perceiver shapes
+        out.sum().backward()
     # the same calls are served in fp32 (parity mode) and through the explicit CUDA-core hook
     ops().masked_cross_attention(q.float(), kv32.float(), tt, heads=H, n_latents=32, scale=0.125)
-    ops().attention(q, kv_long, heads=H, scale=0.125, force_simt=True)
+    ops().attention(q_long, kv, heads=H, scale=0.125, force_simt=True).sum().backward()
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])

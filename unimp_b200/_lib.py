@@ -44,7 +44,7 @@ SIGNATURES = {
     "unimp_gate_residual_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "unimp_gate_residual_ln_bwd_workspace": (_i64, [_i64, _i]),
     "unimp_gate_residual_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                        _i64, _i, _i, _p]),
+                                        _i64, _i, _i, _i, _p]),
     "unimp_focal_ce_workspace": (_i64, [_i, _i, _i, _i]),
     "unimp_focal_ce_fwd": (_i, [_p, _i64, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "unimp_focal_ce_bwd": (_i, [_p, _i64, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _i,

@@ -308,10 +308,12 @@ gate_residual_ln_bwd_kernel(const T* __restrict__ g_xout, const T* __restrict__ 
 }
 
 // Reduce partial[G][2D+1] over G in a fixed order: block = 32 columns x 8 g-lanes.
+// accumulate bit 0: d_gate += ; bit 1: d_gamma / d_beta += (the outputs are the optimizer's gradient
+// buffers and an earlier micro-batch of the step has already written them)
 template <typename T>
 __global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ partial, int G, int D,
                                                    T* __restrict__ d_gate, T* __restrict__ d_gamma,
-                                                   T* __restrict__ d_beta) {
+                                                   T* __restrict__ d_beta, int accumulate) {
   __shared__ float sh[8][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -326,11 +328,11 @@ __global__ void gate_residual_ln_bwd_reduce_kernel(const float* __restrict__ par
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += sh[g][cx];
     if (c < D) {
-      if (d_gamma) d_gamma[c] = Elem<T>::from_f(s);
+      if (d_gamma) d_gamma[c] = Elem<T>::from_f(s + ((accumulate & 2) ? Elem<T>::to_f(d_gamma[c]) : 0.f));
     } else if (c < 2 * D) {
-      if (d_beta) d_beta[c - D] = Elem<T>::from_f(s);
+      if (d_beta) d_beta[c - D] = Elem<T>::from_f(s + ((accumulate & 2) ? Elem<T>::to_f(d_beta[c - D]) : 0.f));
     } else {
-      if (d_gate) d_gate[0] = Elem<T>::from_f(s);
+      if (d_gate) d_gate[0] = Elem<T>::from_f(s + ((accumulate & 1) ? Elem<T>::to_f(d_gate[0]) : 0.f));
     }
   }
 }
@@ -463,7 +465,7 @@ extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, 
                                           const float* mean, const float* rstd, void* d_x,
                                           void* d_branch, void* d_gate, void* d_gamma,
                                           void* d_beta, void* partial, int64_t rows, int D,
-                                          int dtype, void* stream) {
+                                          int accumulate, int dtype, void* stream) {
   UNIMP_CHECK_ARG(d_x && partial, UNIMP_E_NULL, "gate_residual_ln_bwd: d_x/partial NULL");
   UNIMP_CHECK_ARG(g_xout || g_ln, UNIMP_E_NULL, "gate_residual_ln_bwd: no incoming gradient");
   UNIMP_CHECK_ARG(!g_ln || (gamma && x_out && mean && rstd), UNIMP_E_NULL,
@@ -510,10 +512,10 @@ extern "C" int unimp_gate_residual_ln_bwd(const void* g_xout, const void* g_ln, 
   if (dtype == UNIMP_BF16)
     gate_residual_ln_bwd_reduce_kernel<__nv_bfloat16><<<(W + 31) / 32, 256, 0, st>>>(
         (const float*)partial, G, D, (__nv_bfloat16*)d_gate, (__nv_bfloat16*)d_gamma,
-        (__nv_bfloat16*)d_beta);
+        (__nv_bfloat16*)d_beta, accumulate);
   else
     gate_residual_ln_bwd_reduce_kernel<float><<<(W + 31) / 32, 256, 0, st>>>(
-        (const float*)partial, G, D, (float*)d_gate, (float*)d_gamma, (float*)d_beta);
+        (const float*)partial, G, D, (float*)d_gate, (float*)d_gamma, (float*)d_beta, accumulate);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }

@@ -69,6 +69,7 @@ struct XBlkArgs {
   int T, Ti, n, D, NK, NS, NSH, nsplit;
   float scale, scale_log2;
   unsigned long long* dbg;    // optional per-CTA phase timestamps (16 x u64 per CTA), NULL = off
+  int flags;                  // experiments (UNIMP_XB_FLAGS): 1 = no multicast, 2 = skip the x_ln loads (wrong results)
 };
 
 __device__ __forceinline__ unsigned long long xb_now() {
@@ -210,9 +211,16 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
       for (int k = 0; k < NK; ++k) {
         const int s = k % S1;
         if (k >= S1) mbar_wait_tag(&empty1[s], ((k / S1) - 1) & 1, T_EMPTY1 + s);
-        mbar_arrive_expect_tx(&full1[s], STAGE1);
         uint8_t* st = smem + stage1_off(s);
-        if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
+        if (a.flags & 2) {
+          mbar_arrive_expect_tx(&full1[s], B_BYTES);
+        } else if (a.flags & 1) {
+          mbar_arrive_expect_tx(&full1[s], STAGE1);
+          tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);
+        } else {
+          mbar_arrive_expect_tx(&full1[s], STAGE1);
+          if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
+        }
         tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
       }
       // the Wout ring doubles as ring stages 3-5: its first two chunks are fetched once every
@@ -484,6 +492,11 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
   a.T = T; a.Ti = Ti; a.n = n; a.D = D; a.NK = D / 64; a.NS = NS; a.NSH = NSH; a.nsplit = nsplit;
   a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   a.dbg = g_xb_dbg;
+  {
+    static int flags = -1;
+    if (flags < 0) { const char* e = getenv("UNIMP_XB_FLAGS"); flags = e ? atoi(e) : 0; }
+    a.flags = flags;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(H, (T + TQ - 1) / TQ, B);
   cfg.blockDim = dim3(THREADS);

@@ -286,8 +286,14 @@ class GraphedDecoder:
         mask = torch.ones_like(ids) if attention_mask is None else attention_mask.repeat_interleave(nb, dim=0)
         mask = mask.to(torch.int64)
 
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
+        timed = torch.cuda.is_available() and lang_x.device.type == "cuda"   # device-side phase durations
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+
+        def stamp(i):
+            if timed:
+                ev[i].record()
+
+        stamp(0)
         # ---- prefill: the ordinary module path, vision latents cached on the layers --------------
         was_training = model.training
         model.eval()
@@ -339,7 +345,7 @@ class GraphedDecoder:
 
         # step 0 consumes the prefill logits (eagerly); every later token is a graph replay
         advance(first_logits)
-        ev[1].record()
+        stamp(1)
         n_steps = 1
         graph = None
         try:
@@ -348,7 +354,7 @@ class GraphedDecoder:
                 n_steps += 1
             if n_steps < max_new_tokens and bool(search.unfinished()):
                 graph = self._capture(one_token)
-            ev[2].record()
+            stamp(2)
             n_replay = 0
             while graph is not None and n_steps < max_new_tokens:
                 if n_steps % self.sync_every == 0 and not bool(search.unfinished()):
@@ -356,14 +362,14 @@ class GraphedDecoder:
                 graph.replay()
                 n_steps += 1
                 n_replay += 1
-            ev[3].record()
+            stamp(3)
             result = search.result(num_return_sequences)                 # (reads device state: syncs)
-            torch.cuda.synchronize()
-            # device-side durations of the three phases (CUDA events on the launching stream)
-            self.last_timing = {"prefill_ms": ev[0].elapsed_time(ev[1]),
-                                "eager_step_and_capture_ms": ev[1].elapsed_time(ev[2]),
-                                "replay_ms": ev[2].elapsed_time(ev[3]), "replays": n_replay,
-                                "tokens": n_steps}
+            if timed:
+                torch.cuda.synchronize()
+                self.last_timing = {"prefill_ms": ev[0].elapsed_time(ev[1]),
+                                    "eager_step_and_capture_ms": ev[1].elapsed_time(ev[2]),
+                                    "replay_ms": ev[2].elapsed_time(ev[3]), "replays": n_replay,
+                                    "tokens": n_steps}
             self.last_n_steps = n_steps
             self.last_logits_finite = bool(torch.isfinite(S.logits).all())
         finally:

@@ -269,6 +269,7 @@ class _GateResidualLN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, branch, x, gate, gamma, beta, eps):
         dt = _dt(x)
+        beta_param = beta
         x = x.contiguous()
         D = x.shape[-1]
         rows = x.numel() // D
@@ -291,6 +292,7 @@ class _GateResidualLN(torch.autograd.Function):
             "unimp_gate_residual_ln_fwd")
         ctx.save_for_backward(branch, x_out if has_b else x, gate, gamma, mean, rstd)
         ctx.cfg = (has_b, has_ln, rows, D, dt)
+        ctx.beta_ref = beta_param   # the Parameter itself (its value is not needed: only its .grad)
         if has_b and has_ln:
             return x_out, ln_out
         return x_out if has_b else ln_out
@@ -317,18 +319,43 @@ class _GateResidualLN(torch.autograd.Function):
         d_branch = torch.empty_like(xo) if gated else None
         need_gate = has_b and gate is not None and ctx.needs_input_grad[2]
         need_affine = has_ln and g_ln is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
-        d_gate = torch.empty_like(gate) if need_gate else None
-        d_gamma = torch.empty_like(gamma) if need_affine else None   # frozen LN: no column sums
-        d_beta = torch.empty_like(gamma) if need_affine else None
+        # Parameters registered for direct accumulation (FlatAdamW): the fold kernel writes (first
+        # micro-batch of the step) or adds (later ones) straight into their flat-buffer gradients;
+        # autograd gets None and the per-parameter `grad += d` launches disappear.
+        beta = ctx.beta_ref
+        accumulate = 0
+        direct_gate = need_gate and _is_direct(gate)
+        direct_affine = need_affine and _is_direct(gamma) and beta is not None and _is_direct(beta)
+        if direct_gate:
+            d_gate = gate.grad
+            accumulate |= 0 if gate._unimp_fresh else 1
+        else:
+            d_gate = torch.empty_like(gate) if need_gate else None
+        if direct_affine:
+            assert gamma._unimp_fresh == beta._unimp_fresh
+            d_gamma, d_beta = gamma.grad, beta.grad
+            accumulate |= 0 if gamma._unimp_fresh else 2
+        else:
+            d_gamma = torch.empty_like(gamma) if need_affine else None   # frozen LN: no column sums
+            d_beta = torch.empty_like(gamma) if need_affine else None
         ws = torch.empty(lib.unimp_gate_residual_ln_bwd_workspace(rows, D), dtype=torch.uint8,
                          device=xo.device)
         use_ln = has_ln and g_ln is not None
         check(lib.unimp_gate_residual_ln_bwd(
             _ptr(g_xout), _ptr(g_ln) if use_ln else None, _ptr(branch), xo.data_ptr(),
             _ptr(gate), _ptr(gamma) if use_ln else None, _ptr(mean), _ptr(rstd), d_x.data_ptr(),
-            _ptr(d_branch), _ptr(d_gate), _ptr(d_gamma), _ptr(d_beta), ws.data_ptr(), rows, D, dt,
-            _stream()), "unimp_gate_residual_ln_bwd")
-        if has_ln and d_gamma is None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            _ptr(d_branch), _ptr(d_gate), _ptr(d_gamma), _ptr(d_beta), ws.data_ptr(), rows, D,
+            accumulate, dt, _stream()), "unimp_gate_residual_ln_bwd")
+        if direct_gate:
+            gate._unimp_fresh = False
+            _grad_ready(gate)
+            d_gate = None
+        if direct_affine:
+            gamma._unimp_fresh = beta._unimp_fresh = False
+            _grad_ready(gamma)
+            _grad_ready(beta)
+            d_gamma = d_beta = None
+        elif has_ln and d_gamma is None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
             d_gamma = torch.zeros_like(gamma)
             d_beta = torch.zeros_like(gamma)
         return (d_branch if gated else (d_x if has_b else None)), d_x, d_gate, d_gamma, d_beta, None
@@ -563,6 +590,10 @@ def gelu(x):
 
 
 # --------------------------------------------------------------------------- direct grad accumulation
+
+def _is_direct(p) -> bool:
+    return getattr(p, "_unimp_direct", False) and p.grad is not None
+
 
 def _grad_ready(w):
     h = getattr(w, "_unimp_grad_ready", None)

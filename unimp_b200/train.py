@@ -67,6 +67,12 @@ def cosine_with_warmup(step: int, warmup: int, total: int) -> float:
 # flamingo_lm.py): their gradient is written by the backward GEMM / scatter itself
 DIRECT_GRAD_SUFFIXES = ("to_q.weight", "to_kv.weight", "to_out.weight", "ff.1.weight", "ff.3.weight",
                         ".1.1.weight", ".1.3.weight", "embed_in.weight")
+# LayerNorm affine parameters and tanh gates that only ever run through ops.layer_norm /
+# ops.gate_residual_ln / ops.gate_residual (helpers.py): the K5 backward's fold kernel writes their
+# gradients into the flat buffer itself (no `grad += d` launch per parameter: 134 per step at 4B)
+DIRECT_LN_SUFFIXES = ("norm.weight", "norm.bias", "norm_media.weight", "norm_media.bias",
+                      "norm_latents.weight", "norm_latents.bias", "ff.0.weight", "ff.0.bias",
+                      ".1.0.weight", ".1.0.bias", "attn_gate", "ff_gate")
 
 
 class FlatAdamW:
@@ -93,8 +99,9 @@ class FlatAdamW:
                 continue
             # direct-accumulation parameters first, everything else (LN affine, gates, latents)
             # in one tail that zero_grad memsets
-            is_direct = lambda n, p: (direct_grads and p.dim() == 2 and p.is_cuda
-                                      and n.endswith(DIRECT_GRAD_SUFFIXES))
+            is_direct = lambda n, p: direct_grads and p.is_cuda and (
+                (p.dim() == 2 and n.endswith(DIRECT_GRAD_SUFFIXES))
+                or (p.dim() == 1 and n.endswith(DIRECT_LN_SUFFIXES)))
             named = [np for np in named if is_direct(*np)] + [np for np in named if not is_direct(*np)]
             n_direct = sum(1 for np in named if is_direct(*np))
             p0 = named[0][1]
