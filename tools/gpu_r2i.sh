@@ -1,0 +1,5 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+P=${1:-r2i}
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I unimp_b200/csrc -o /tmp/tma_probe tools/probes/tma_probe.cu -lcuda && timeout 120 /tmp/tma_probe > gpurun_out/${P}_tma_probe.log 2>&1
+echo "probe rc=$?"; cat gpurun_out/${P}_tma_probe.log

@@ -92,7 +92,7 @@ def timeline(B, T, Ti, D):
     kv = torch.randn(B, Ti * n, 2 * inner, device=dev, dtype=bf)
     tt = mk_tt(B, T, Ti)
     n_cta = 8 * ((T + 127) // 128) * B
-    buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_cta * 16 + 192, dtype=torch.int64, device=dev)
     f = lib.unimp__xattn_block_debug
     f.argtypes = [ctypes.c_void_p]
     f.restype = None
@@ -104,7 +104,11 @@ def timeline(B, T, Ti, D):
         ops.xattn_block(x, wq, kv, tt, wo, heads=H, n_latents=n, scale=0.125)
         torch.cuda.synchronize()
         f(None)
-    t = buf.view(n_cta, 16).cpu().double()
+    ch = buf[n_cta * 16:].cpu().double()
+    t = buf[:n_cta * 16].view(n_cta, 16).cpu().double()
+    base = t[0, 1]
+    print("XB   CTA 0 per chunk (ns after csync1): k: producer issued / MMA saw it / MMAs issued")
+    print("XB   " + "  ".join(f"{k}:{ch[k] - base:.0f}/{ch[64 + k] - base:.0f}/{ch[128 + k] - base:.0f}" for k in range(0, 40)))
     t0 = t[:, 0].min()
     names = ["start", "csync1", "ph1 done", "attn done", "o stored", "csync2", "O tiles in", "to_out done",
              "y stored", "end", "1st chunk", "half K"]

@@ -64,7 +64,7 @@ def tiny_config() -> FlamingoConfig:
     tok = SpecialTokens(bos=0, eos=0, endofchunk=400, media=401, pad=402, answer=403,
                         first_item=404, n_items=64, first_img=468, n_img=44, n_plain=400)
     return FlamingoConfig(
-        name="tiny", vis_width=64, vis_layers=2, vis_heads=1, vis_mlp=256, image_size=56,
+        name="tiny", vis_width=64, vis_layers=2, vis_heads=4, vis_mlp=256, image_size=56,
         patch_size=14, lm_hidden=128, lm_layers=2, lm_heads=4, lm_ffn=512, vocab=V,
         cross_attn_every_n_layers=1, tokens=tok,
     )

@@ -69,7 +69,9 @@ struct XBlkArgs {
   int T, Ti, n, D, NK, NS, NSH, nsplit;
   float scale, scale_log2;
   unsigned long long* dbg;    // optional per-CTA phase timestamps (16 x u64 per CTA), NULL = off
-  int flags;                  // experiments (UNIMP_XB_FLAGS): 1 = no multicast, 2 = skip the x_ln loads (wrong results)
+  int flags;                  // experiments (UNIMP_XB_FLAGS): 1 = no multicast, 2 = skip the x_ln loads (wrong
+                              // results), 4 = CTA-local ring release (only valid together with 1),
+                              // 8 = skip the phase-1 MMAs, 16 (with 2) = no phase-1 loads at all
 };
 
 __device__ __forceinline__ unsigned long long xb_now() {
@@ -77,6 +79,13 @@ __device__ __forceinline__ unsigned long long xb_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// per-chunk stamps of CTA (0,0,0) only, after the per-CTA table: [0,64) producer issue, [64,128) MMA
+// sees the chunk, [128,192) MMA thread has issued the chunk's MMAs + commit
+#define XB_STAMP_CHUNK(base, k)                                                                  \
+  do {                                                                                          \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (k) < 64)             \
+      a.dbg[gridDim.x * gridDim.y * gridDim.z * 16 + (base) + (k)] = xb_now();                  \
+  } while (0)
 #define XB_STAMP(slot)                                                                          \
   do {                                                                                          \
     if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = xb_now(); \
@@ -141,7 +150,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   if (warp == 4) {
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < S1; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], H); }
+      for (int i = 0; i < S1; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], (a.flags & 4) ? 1 : H); }
       mbar_init(&bar_qacc, 1); mbar_init(&bar_qs, 4);
       mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
       mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1); mbar_init(&bar_o, 1);
@@ -212,6 +221,11 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
         const int s = k % S1;
         if (k >= S1) mbar_wait_tag(&empty1[s], ((k / S1) - 1) & 1, T_EMPTY1 + s);
         uint8_t* st = smem + stage1_off(s);
+        if ((a.flags & 18) == 18) {
+          mbar_arrive(&full1[s]);            // experiment: no loads at all
+          XB_STAMP_CHUNK(0, k);
+          continue;
+        }
         if (a.flags & 2) {
           mbar_arrive_expect_tx(&full1[s], B_BYTES);
         } else if (a.flags & 1) {
@@ -222,6 +236,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
           if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
         }
         tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
+        XB_STAMP_CHUNK(0, k);
       }
       // the Wout ring doubles as ring stages 3-5: its first two chunks are fetched once every
       // phase-1 MMA of this CTA has completed (they arrive while phase 2 runs)
@@ -248,12 +263,17 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
         tcgen05_fence_after();
         if (k == 0) XB_STAMP(10);   // first chunk landed
         if (k == NK / 2) XB_STAMP(11);
+        XB_STAMP_CHUNK(64, k);
         const uint32_t sa = smem_u32(smem + stage1_off(s)), sb = sa + A_BYTES;
+        if (!(a.flags & 8)) {                  // flag 8: experiment, skip the MMAs
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
-                  idesc_s, (k > 0 || k4 > 0));
-        umma_commit_mc(&empty1[s], ALL);       // slot s is free in THIS CTA; all 8 must say so
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
+                    idesc_s, (k > 0 || k4 > 0));
+        }
+        if (a.flags & 4) umma_commit(&empty1[s]);   // experiment: CTA-local ring (needs flag 1: no multicast)
+        else umma_commit_mc(&empty1[s], ALL);       // slot s is free in THIS CTA; all 8 must say so
+        XB_STAMP_CHUNK(128, k);
       }
       umma_commit(&bar_qacc);
       if (nblk > 0) {

@@ -54,7 +54,10 @@ class VisionTransformer(nn.Module):
     def __init__(self, image_size=224, patch_size=14, width=1024, layers=24, heads=16, mlp=4096,
                  quick_gelu=True):
         super().__init__()
-        assert width // heads == 64, "attention kernels are built for head dim 64"
+        assert width % heads == 0 and width // heads <= 64, "head dim must be <= 64"
+        # head dim 64 (ViT-L/14) runs on the attention kernels directly; a smaller head dim (the
+        # tiny CPU-runnable configuration of BASELINE.md: 64-wide, 4 heads x 16) is zero-padded
+        # to 64 per head — the extra coordinates add 0 to every score and their outputs are dropped
         self.image_size, self.patch_size, self.width, self.heads = image_size, patch_size, width, heads
         self.grid = image_size // patch_size
         self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
@@ -68,6 +71,17 @@ class VisionTransformer(nn.Module):
         self.output_tokens = True
         for blk in self.transformer.resblocks:
             nn.init.normal_(blk.attn.in_proj_weight, std=scale)
+
+    def _attention(self, qkv):
+        W, H = self.width, self.heads
+        dh = W // H
+        if dh == 64:
+            return ops.attention(qkv[..., :W], qkv[..., W:], heads=H, scale=0.125)
+        N, L, _ = qkv.shape
+        q, k, v = (F.pad(t, (0, 64 - dh)).reshape(N, L, H * 64)
+                   for t in qkv.view(N, L, 3, H, dh).unbind(2))
+        a = ops.attention(q, torch.cat((k, v), dim=-1), heads=H, scale=dh ** -0.5)
+        return a.view(N, L, H, 64)[..., :dh].reshape(N, L, W)
 
     def _act(self, h):
         return ops.quick_gelu_(h) if self.quick_gelu else F.gelu(h)
@@ -88,7 +102,7 @@ class VisionTransformer(nn.Module):
         W = self.width
         for i, blk in enumerate(blocks):
             qkv = F.linear(h, blk.attn.in_proj_weight, blk.attn.in_proj_bias)  # (N, L, 3W)
-            a = ops.attention(qkv[..., :W], qkv[..., W:], heads=self.heads, scale=0.125)  # K3
+            a = self._attention(qkv)                                                  # K3
             a = blk.attn.out_proj(a)
             x, h = ops.gate_residual_ln(a, x, None, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
             m = blk.mlp.c_proj(self._act(blk.mlp.c_fc(h)))
