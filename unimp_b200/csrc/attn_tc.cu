@@ -92,13 +92,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __shared__ int s_jlo, s_jhi;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool issuer = tid == TQ;        // lane 0 of warp 4
   const bool worker = tid < TQ;         // owns TMEM lane `tid`
   const int row0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const int row = row0 + tid;
   const bool valid = worker && row < a.Lq;
 
-  if (issuer) {
+  if (warp == 4 && elect_one_sync()) {
     mbar_init(&bar_q, 1); mbar_init(&bar_k, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1);
     mbar_init(&bar_p[0], 1); mbar_init(&bar_p[1], 1); mbar_init(&bar_o, 1);
     fence_barrier_init();
@@ -123,7 +122,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
   if constexpr (!MASKED) {
     const int nb = (a.Lk + KB - 1) / KB;
-    if (issuer) {
+    if (warp == 4 && elect_one_sync()) {
       mbar_arrive_expect_tx(&bar_k, nb * KV_BYTES);
       for (int j = 0; j < nb; ++j) tma_load_4d(sK + j * KV_BYTES, &tk, &bar_k, 0, h, j * KB, b);
       mbar_arrive_expect_tx(&bar_v, nb * KV_BYTES);
@@ -179,7 +178,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tcgen05_fence_before();
       }
       __syncthreads();
-      if (issuer) {
+      if (warp == 4 && elect_one_sync()) {
         if (j == 0) mbar_wait(&bar_v, 0);
         tcgen05_fence_after();
 #pragma unroll
@@ -203,12 +202,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     __syncthreads();
     const int jlo = s_jlo, jhi = s_jhi;
     any_mma = jhi >= jlo;
-    if (!any_mma && issuer) mbar_wait(&bar_q, 0);  // never leave a TMA in flight at exit
+    if (!any_mma && warp == 4 && elect_one_sync()) mbar_wait(&bar_q, 0);  // never leave a TMA in flight at exit
     float m_row = 0.f;
     for (int j = jlo; j <= jhi; ++j) {
       const int it = j - jlo;
       const uint32_t ph = it & 1;
-      if (issuer) {
+      if (warp == 4 && elect_one_sync()) {
         // the previous PV MMA (reads sK/sV/sP) has completed: waited on bar_p below
         mbar_arrive_expect_tx(&bar_k, 2 * KV_BYTES);
         tma_load_4d(sK, &tk, &bar_k, 0, h, j * a.n, b);
@@ -255,7 +254,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tcgen05_fence_before();
       }
       __syncthreads();
-      if (issuer) {
+      if (warp == 4 && elect_one_sync()) {
         tcgen05_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < KB / 16; ++k4)
@@ -340,7 +339,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const int row0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_init(&bar_q, 1); mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1);
       mbar_init(&bar_o, 1);
 #pragma unroll
@@ -365,7 +364,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) {
+    if (elect_one_sync()) {
       s_j[0] = lo; s_j[1] = hi;
       const int nb = hi >= lo ? hi - lo + 1 : 0;
       for (int it = 0; it < nb && it < XF_STAGES; ++it) {
@@ -396,8 +395,8 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
   const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);
 
-  if (tid == TQ) {
-    // ---- issuer: one thread issues every MMA and the (rare) K/V refills ----------------------
+  if (warp == 4 && elect_one_sync()) {
+    // ---- issuer: one elected lane issues every MMA and the (rare) K/V refills -----------------
     mbar_wait(&bar_q, 0);
     if (nblk > 0) {
       mbar_wait(&bar_kv[0], 0);
@@ -561,7 +560,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   };
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_init(&bar_q, 1); mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1);
       mbar_init(&bar_o, 1);
 #pragma unroll
@@ -582,7 +581,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
   const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);
 
-  if (tid == TQ) {
+  if (warp == 4 && elect_one_sync()) {
     mbar_wait(&bar_q, 0);
     mbar_wait(&bar_kv[0], 0);
     tcgen05_fence_after();
@@ -964,10 +963,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool issuer = tid == TQ, worker = tid < TQ;
+  const bool worker = tid < TQ;
   const int h = blockIdx.y, b = blockIdx.z;
 
-  if (issuer) {
+  if (warp == 4 && elect_one_sync()) {
     mbar_init(&bar_qdo, 1); mbar_init(&bar_kv, 1); mbar_init(&bar_s, 1); mbar_init(&bar_g, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tdo); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
@@ -1026,7 +1025,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       if (!__syncthreads_or(mine ? 1 : 0)) continue;  // CTA-uniform (non-monotonic text_time only)
     }
     // ---- loads + S / dP ---------------------------------------------------------------
-    if (issuer) {
+    if (warp == 4 && elect_one_sync()) {
       const bool need_qdo = MASKED || !qdo_loaded, need_kv = !MASKED || !kv_loaded;
       if (need_qdo) {
         mbar_arrive_expect_tx(&bar_qdo, 2 * Q_BYTES);
@@ -1106,7 +1105,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     ph_s ^= 1;
     __syncthreads();
     // ---- [dV|dK] += [P|dS]^T [dO|Q]  and  dQ (+)= dS K -------------------------------------
-    if (issuer) {
+    if (warp == 4 && elect_one_sync()) {
       tcgen05_fence_after();
       const bool kv_acc = MASKED ? acc_started : false;   // MASKED: accumulate across tiles
       const bool dq_acc = MASKED ? false : acc_started;   // UNMASKED: accumulate across blocks

@@ -61,6 +61,22 @@ __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, in
   __trap();
 }
 
+// ---- single-lane election ------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor take their operands from UNIFORM registers.
+// Issued under `if (lane == 0)` (a branch ptxas must treat as divergent) every such instruction is
+// wrapped in a waterfall loop (ELECT ... BRA.U.ANY) plus ~10 uniform-datapath instructions of
+// descriptor arithmetic: measured 120 cycles per MMA instead of 32-48.  Issued under elect.sync, in
+// a converged warp, they go out back to back.  Call with all 32 lanes of the warp active.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- thread-block clusters -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

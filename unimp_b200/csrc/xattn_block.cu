@@ -20,7 +20,8 @@
 //            128 x 512 O tile as an A operand, and computes 1/8 of the output columns:
 //            y[:, c*D/8 : (c+1)*D/8] = O_all . Wout[c*D/8 : ...]^T  (Wout streamed by TMA, 2 stages).
 // Warp roles (192 threads): warps 0-3 own one query row / TMEM lane each (conversion, softmax,
-// epilogues); warp 4 lane 0 = TMA producer; warp 5 lane 0 = MMA issuer (warp 5 owns TMEM).
+// epilogues); warp 4 = TMA producer, warp 5 = MMA issuer (warp 5 owns TMEM): one lane of each,
+// chosen by elect.sync so that the uniform-register instructions go out without waterfall loops.
 // Every mbarrier wait is bounded and tagged (a protocol bug traps and names the barrier).
 #include <stdlib.h>
 
@@ -148,7 +149,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   const int NK = a.NK, NS = a.NS, NSH = a.NSH;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
 #pragma unroll
       for (int i = 0; i < S1; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], (a.flags & 4) ? 1 : H); }
       mbar_init(&bar_qacc, 1); mbar_init(&bar_qs, 4);
@@ -177,7 +178,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) {
+    if (elect_one_sync()) {
       s_j[0] = lo; s_j[1] = hi;
       // loads that touch only THIS CTA's barriers may start before the cluster is in step:
       // K/V of the first two image blocks
@@ -216,7 +217,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
 
   // =============================== phases 1 + 2 =============================================
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int k = 0; k < NK; ++k) {
         const int s = k % S1;
         if (k >= S1) mbar_wait_tag(&empty1[s], ((k / S1) - 1) & 1, T_EMPTY1 + s);
@@ -256,7 +257,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int k = 0; k < NK; ++k) {
         const int s = k % S1;
         mbar_wait_tag(&full1[s], (k / S1) & 1, T_FULL1 + s);
@@ -405,7 +406,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
 
   // =============================== phase 3: y slice = O_all . Wout_slice^T ====================
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       fence_proxy_async_all();
       mbar_arrive_expect_tx(&full_o, H * Q_BYTES);
       tma_load_4d_mc(sO + h * Q_BYTES, &to, &full_o, 0, h, t0, b, ALL);
@@ -419,7 +420,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_wait_tag(&full_o, 0, T_FULLO);
       XB_STAMP(6);                 // all 8 O tiles arrived
       for (int kk = 0; kk < H; ++kk) {
