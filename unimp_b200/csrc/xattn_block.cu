@@ -7,7 +7,8 @@
 //
 // One thread-block CLUSTER of 8 CTAs per 128-row query tile, one head per CTA:
 //   phase 1  Q_h (128x64, TMEM) = x_ln tile (128 x D) . Wq_h^T, K = D in 64-wide chunks through a
-//            6-stage ring (144 KB in flight per SM: the loads are L2-latency x bandwidth bound).
+//            ring of 3 stages x 2 chunks (144 KB in flight per SM).  Two chunks per stage because the
+//            MMA issuer pays ~250 cycles per mbarrier wait (measured): one wait per 8 MMAs, not 4.
 //            The x_ln chunk is the same for all 8 heads: CTA (k mod 8) loads chunk k ONCE and
 //            TMA-MULTICASTS it into all 8 CTAs' rings (L2 reads of x_ln / 8); a ring slot is
 //            released by tcgen05.commit multicast to all 8 CTAs' "empty" barriers, because any of
@@ -35,7 +36,8 @@ using namespace tc;
 namespace xb {
 constexpr int TQ = 128, KB = 64, DH = 64, H = 8, INNER = H * DH;
 constexpr int THREADS = 192;
-constexpr int S1 = 6;                                  // phase-1 ring depth (3 stages + 3 in the idle Wout ring)
+constexpr int S1 = 3;                                  // phase-1 ring: 3 stages of TWO K chunks (48 KB) each; the
+                                                       // chunk slots 3-5 live in the idle Wout ring
 constexpr uint32_t A_BYTES = TQ * 64 * 2;              // 16 KB: x_ln chunk (128 rows x 64)
 constexpr uint32_t B_BYTES = 64 * 64 * 2;              // 8 KB: Wq_h chunk
 constexpr uint32_t STAGE1 = A_BYTES + B_BYTES;         // 24 KB
@@ -70,9 +72,8 @@ struct XBlkArgs {
   int T, Ti, n, D, NK, NS, NSH, nsplit;
   float scale, scale_log2;
   unsigned long long* dbg;    // optional per-CTA phase timestamps (16 x u64 per CTA), NULL = off
-  int flags;                  // experiments (UNIMP_XB_FLAGS): 1 = no multicast, 2 = skip the x_ln loads (wrong
-                              // results), 4 = CTA-local ring release (only valid together with 1),
-                              // 8 = skip the phase-1 MMAs, 16 (with 2) = no phase-1 loads at all
+  int flags;                  // A/B switch (UNIMP_XB_FLAGS): 1 = no multicast (every CTA loads its own x_ln
+                              // chunks, CTA-local ring release)
 };
 
 __device__ __forceinline__ unsigned long long xb_now() {
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(xb::THREADS, 1)
 xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_constant__ CUtensorMap twq,
                        const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                        const __grid_constant__ CUtensorMap to, const __grid_constant__ CUtensorMap twout,
+                       const __grid_constant__ CUtensorMap tqo, const __grid_constant__ CUtensorMap ty,
                        const XBlkArgs a) {
   using namespace xb;
   extern __shared__ uint8_t smem_raw[];
@@ -151,7 +153,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   if (warp == 4) {
     if (elect_one_sync()) {
 #pragma unroll
-      for (int i = 0; i < S1; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], (a.flags & 4) ? 1 : H); }
+      for (int i = 0; i < S1; ++i) { mbar_init(&full1[i], 1); mbar_init(&empty1[i], (a.flags & 1) ? 1 : H); }
       mbar_init(&bar_qacc, 1); mbar_init(&bar_qs, 4);
       mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
       mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1); mbar_init(&bar_o, 1);
@@ -218,26 +220,19 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   // =============================== phases 1 + 2 =============================================
   if (warp == 4) {
     if (elect_one_sync()) {
-      for (int k = 0; k < NK; ++k) {
-        const int s = k % S1;
-        if (k >= S1) mbar_wait_tag(&empty1[s], ((k / S1) - 1) & 1, T_EMPTY1 + s);
-        uint8_t* st = smem + stage1_off(s);
-        if ((a.flags & 18) == 18) {
-          mbar_arrive(&full1[s]);            // experiment: no loads at all
-          XB_STAMP_CHUNK(0, k);
-          continue;
+      for (int p = 0; p < NK / 2; ++p) {            // one ring stage = TWO 64-wide K chunks (48 KB)
+        const int s = p % S1;
+        if (p >= S1) mbar_wait_tag(&empty1[s], ((p / S1) - 1) & 1, T_EMPTY1 + s);
+        mbar_arrive_expect_tx(&full1[s], 2 * STAGE1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int k = 2 * p + c;
+          uint8_t* st = smem + stage1_off(2 * s + c);
+          if (a.flags & 1) tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);                 // A/B test: no multicast
+          else if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
+          tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
         }
-        if (a.flags & 2) {
-          mbar_arrive_expect_tx(&full1[s], B_BYTES);
-        } else if (a.flags & 1) {
-          mbar_arrive_expect_tx(&full1[s], STAGE1);
-          tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);
-        } else {
-          mbar_arrive_expect_tx(&full1[s], STAGE1);
-          if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
-        }
-        tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
-        XB_STAMP_CHUNK(0, k);
+        XB_STAMP_CHUNK(0, p);
       }
       // the Wout ring doubles as ring stages 3-5: its first two chunks are fetched once every
       // phase-1 MMA of this CTA has completed (they arrive while phase 2 runs)
@@ -258,23 +253,24 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one_sync()) {
-      for (int k = 0; k < NK; ++k) {
-        const int s = k % S1;
-        mbar_wait_tag(&full1[s], (k / S1) & 1, T_FULL1 + s);
+      for (int p = 0; p < NK / 2; ++p) {
+        const int s = p % S1;
+        mbar_wait_tag(&full1[s], (p / S1) & 1, T_FULL1 + s);
         tcgen05_fence_after();
-        if (k == 0) XB_STAMP(10);   // first chunk landed
-        if (k == NK / 2) XB_STAMP(11);
-        XB_STAMP_CHUNK(64, k);
-        const uint32_t sa = smem_u32(smem + stage1_off(s)), sb = sa + A_BYTES;
-        if (!(a.flags & 8)) {                  // flag 8: experiment, skip the MMAs
+        if (p == 0) XB_STAMP(10);   // first stage landed
+        if (p == NK / 4) XB_STAMP(11);
+        XB_STAMP_CHUNK(64, p);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t sa = smem_u32(smem + stage1_off(2 * s + c)), sb = sa + A_BYTES;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
             umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
-                    idesc_s, (k > 0 || k4 > 0));
+                    idesc_s, (p > 0 || c > 0 || k4 > 0));
         }
-        if (a.flags & 4) umma_commit(&empty1[s]);   // experiment: CTA-local ring (needs flag 1: no multicast)
-        else umma_commit_mc(&empty1[s], ALL);       // slot s is free in THIS CTA; all 8 must say so
-        XB_STAMP_CHUNK(128, k);
+        if (a.flags & 1) umma_commit(&empty1[s]);   // CTA-local ring when nothing is multicast
+        else umma_commit_mc(&empty1[s], ALL);       // the stage is free in THIS CTA; all 8 must say so
+        XB_STAMP_CHUNK(128, p);
       }
       umma_commit(&bar_qacc);
       if (nblk > 0) {
@@ -317,18 +313,23 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     mbar_wait_tag(&bar_qacc, 0, T_QACC);
     tcgen05_fence_after();
     if (tid == 0) XB_STAMP(2);     // phase 1 done
-    __nv_bfloat16* qrow = a.q + ((int64_t)b * a.T + row) * INNER + h * DH;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       tmem_ld32(lane_addr + Q_COL + half * 32, r);
       tmem_ld_wait();
       xb_store_half(sQ, tid, half, r, 1.f);
-      if (valid) xb_store_global32(qrow + half * 32, r, 1.f, 32);
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_qs);
+    // q for backward: the swizzled tile just written IS the TMA box layout -> one bulk store instead of
+    // 128 B of strided STG per thread (rows beyond T are clipped by the tensor map)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 0 && elect_one_sync()) {
+      tma_store_4d(&tqo, sQ, 0, h, t0, b);
+      tma_store_commit();
+    }
 
     // ---- masked row softmax per image block (as xattn_fwd_tc_kernel) ------------------------
     float sum = 0.f, m_row = 0.f;
@@ -394,6 +395,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     }
     if (valid) a.lse[((int64_t)b * H + h) * a.T + row] = lse_val;
     fence_proxy_async_all();      // the O rows just written are read back by TMA (async proxy)
+    if (warp == 0 && elect_one_sync()) tma_store_wait_read();   // q store done with sQ (peers overwrite it next)
     tcgen05_fence_before();
   }
 
@@ -443,11 +445,32 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     mbar_wait_tag(&bar_y, 0, T_Y);
     tcgen05_fence_after();
     if (tid == 0) XB_STAMP(7);     // to_out MMAs done
-    __nv_bfloat16* yrow = a.y + ((int64_t)b * a.T + row) * a.D + h * NS;
-    for (int c = 0; c < NS; c += 32) {
-      tmem_ld32(lane_addr + Y_COL + c, r);
-      tmem_ld_wait();
-      if (valid) xb_store_global32(yrow + c, r, 1.f, NS - c < 32 ? NS - c : 32);
+    if (NS % 64 == 0) {
+      // stage the slice as 64-column swizzled tiles over the (now dead) O tiles and let TMA write
+      // them: full 128-byte lines instead of 40 strided 16-byte stores per thread
+      uint8_t* sY = smem + OFF_O;
+      for (int c64 = 0; c64 < NS / 64; ++c64) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(lane_addr + Y_COL + c64 * 64 + half * 32, r);
+          tmem_ld_wait();
+          xb_store_half(sY + c64 * Q_BYTES, tid, half, r, 1.f);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0 && elect_one_sync()) {
+          tma_store_3d(&ty, sY + c64 * Q_BYTES, h * NS + c64 * 64, t0, b);
+          tma_store_commit();
+        }
+      }
+      if (warp == 0 && elect_one_sync()) tma_store_wait_read();
+    } else {
+      __nv_bfloat16* yrow = a.y + ((int64_t)b * a.T + row) * a.D + h * NS;
+      for (int c = 0; c < NS; c += 32) {
+        tmem_ld32(lane_addr + Y_COL + c, r);
+        tmem_ld_wait();
+        if (valid) xb_store_global32(yrow + c, r, 1.f, NS - c < 32 ? NS - c : 32);
+      }
     }
     tcgen05_fence_before();
   }
@@ -477,7 +500,7 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
                            const int32_t* tt, const void* w_out, void* q, void* o, float* lse, void* y,
                            int B, int T, int Ti, int n, int D, float scale, cudaStream_t st) {
   using namespace xb;
-  CUtensorMap tx, twq, tk, tv, to, twout;
+  CUtensorMap tx, twq, tk, tv, to, twout, tqo, ty;
   int rc;
   const int NS = D / 8, nsplit = NS > 256 ? 2 : 1, NSH = NS / nsplit;
   {
@@ -501,6 +524,13 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
   if ((rc = make_tmap_bhld(&tk, k.ptr, k.batch_stride, k.row_stride, B, Ti * n, H, KB))) return rc;
   if ((rc = make_tmap_bhld(&tv, v.ptr, v.batch_stride, v.row_stride, B, Ti * n, H, KB))) return rc;
   if ((rc = make_tmap_bhld(&to, o, (int64_t)T * INNER, INNER, B, T, H, TQ))) return rc;
+  if ((rc = make_tmap_bhld(&tqo, q, (int64_t)T * INNER, INNER, B, T, H, TQ))) return rc;
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)T, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
+    const uint32_t box[3] = {64, (uint32_t)TQ, 1};
+    if ((rc = make_tmap_tiled(&ty, y, 3, dims, strides, box))) return rc;
+  }
   const int smem = 1024 + SMEM_BYTES;
   static bool attr = false;
   if (!attr) {
@@ -527,7 +557,7 @@ int launch_xattn_block_fwd(const void* x_ln, const void* w_q, unimp_view_t k, un
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = H; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, xattn_block_fwd_kernel, tx, twq, tk, tv, to, twout, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xattn_block_fwd_kernel, tx, twq, tk, tv, to, twout, tqo, ty, a);
   if (e != cudaSuccess) { set_error("xattn_block_fwd launch: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
