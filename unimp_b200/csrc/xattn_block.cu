@@ -220,19 +220,30 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   // =============================== phases 1 + 2 =============================================
   if (warp == 4) {
     if (elect_one_sync()) {
-      for (int p = 0; p < NK / 2; ++p) {            // one ring stage = TWO 64-wide K chunks (48 KB)
-        const int s = p % S1;
-        if (p >= S1) mbar_wait_tag(&empty1[s], ((p / S1) - 1) & 1, T_EMPTY1 + s);
-        mbar_arrive_expect_tx(&full1[s], 2 * STAGE1);
+      // one ring stage = TWO 64-wide K chunks (48 KB).  The stage loop is unrolled by the ring depth so
+      // that every shared-memory offset is a compile-time constant: the elected lane runs on the
+      // uniform datapath, where each extra address instruction costs ~12 cycles.
+      const int NP = NK / 2;
+      uint32_t ph = 1;                                // parity of the "empty" phase to wait for
+      for (int p0 = 0; p0 < NP; p0 += S1) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int k = 2 * p + c;
-          uint8_t* st = smem + stage1_off(2 * s + c);
-          if (a.flags & 1) tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);                 // A/B test: no multicast
-          else if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
-          tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
+        for (int s = 0; s < S1; ++s) {
+          const int p = p0 + s;
+          if (p < NP) {
+            if (p0 > 0) mbar_wait_tag(&empty1[s], ph, T_EMPTY1 + s);
+            mbar_arrive_expect_tx(&full1[s], 2 * STAGE1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int k = 2 * p + c;
+              uint8_t* st = smem + stage1_off(2 * s + c);
+              if (a.flags & 1) tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);               // A/B test: no multicast
+              else if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
+              tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
+            }
+            XB_STAMP_CHUNK(0, p);
+          }
         }
-        XB_STAMP_CHUNK(0, p);
+        ph ^= 1;
       }
       // the Wout ring doubles as ring stages 3-5: its first two chunks are fetched once every
       // phase-1 MMA of this CTA has completed (they arrive while phase 2 runs)
@@ -253,24 +264,33 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one_sync()) {
-      for (int p = 0; p < NK / 2; ++p) {
-        const int s = p % S1;
-        mbar_wait_tag(&full1[s], (p / S1) & 1, T_FULL1 + s);
-        tcgen05_fence_after();
-        if (p == 0) XB_STAMP(10);   // first stage landed
-        if (p == NK / 4) XB_STAMP(11);
-        XB_STAMP_CHUNK(64, p);
+      const int NP = NK / 2;
+      const uint32_t smem_base = smem_u32(smem);
+      uint32_t ph = 0;
+      for (int p0 = 0; p0 < NP; p0 += S1) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t sa = smem_u32(smem + stage1_off(2 * s + c)), sb = sa + A_BYTES;
+        for (int s = 0; s < S1; ++s) {
+          const int p = p0 + s;
+          if (p < NP) {
+            mbar_wait_tag(&full1[s], ph, T_FULL1 + s);
+            tcgen05_fence_after();
+            if (p == 0) XB_STAMP(10);   // first stage landed
+            if (p == NP / 2) XB_STAMP(11);
+            XB_STAMP_CHUNK(64, p);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
-                    idesc_s, (p > 0 || c > 0 || k4 > 0));
+            for (int c = 0; c < 2; ++c) {
+              const uint32_t sa = smem_base + stage1_off(2 * s + c), sb = sa + A_BYTES;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ss(tmem + Q_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
+                        idesc_s, (p > 0 || c > 0 || k4 > 0));
+            }
+            if (a.flags & 1) umma_commit(&empty1[s]);   // CTA-local ring when nothing is multicast
+            else umma_commit_mc(&empty1[s], ALL);       // the stage is free in THIS CTA; all 8 must say so
+            XB_STAMP_CHUNK(128, p);
+          }
         }
-        if (a.flags & 1) umma_commit(&empty1[s]);   // CTA-local ring when nothing is multicast
-        else umma_commit_mc(&empty1[s], ALL);       // the stage is free in THIS CTA; all 8 must say so
-        XB_STAMP_CHUNK(128, p);
+        ph ^= 1;
       }
       umma_commit(&bar_qacc);
       if (nblk > 0) {
@@ -425,16 +445,22 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     if (elect_one_sync()) {
       mbar_wait_tag(&full_o, 0, T_FULLO);
       XB_STAMP(6);                 // all 8 O tiles arrived
-      for (int kk = 0; kk < H; ++kk) {
+      const uint32_t so_base = smem_u32(sO), sw_base = smem_u32(sW);
+      const uint32_t half_off = (uint32_t)NSH * 128u;
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) {              // fully unrolled: constant offsets, constant parities
         const int s = kk & 1;
         mbar_wait_tag(&full_w[s], (kk >> 1) & 1, T_FULLW + s);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(sO + kk * Q_BYTES), sb = smem_u32(sW + s * W_STAGE);
+        const uint32_t sa = so_base + kk * Q_BYTES, sb = sw_base + s * W_STAGE;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          for (int half = 0; half < a.nsplit; ++half)
-            umma_ss(tmem + Y_COL + half * NSH, make_smem_desc(sa + k4 * 32, 16, 1024),
-                    make_smem_desc(sb + half * NSH * 128 + k4 * 32, 16, 1024), idesc_y, (kk > 0 || k4 > 0));
+        for (int k4 = 0; k4 < 4; ++k4) {
+          umma_ss(tmem + Y_COL, make_smem_desc(sa + k4 * 32, 16, 1024), make_smem_desc(sb + k4 * 32, 16, 1024),
+                  idesc_y, (kk > 0 || k4 > 0));
+          if (a.nsplit > 1)
+            umma_ss(tmem + Y_COL + NSH, make_smem_desc(sa + k4 * 32, 16, 1024),
+                    make_smem_desc(sb + half_off + k4 * 32, 16, 1024), idesc_y, (kk > 0 || k4 > 0));
+        }
         umma_commit(&empty_w[s]);
       }
       umma_commit(&bar_y);
