@@ -169,6 +169,31 @@ def _run_xattn(cfg, wl, dtype, eager, rec):
                                             for o, q, kv, g in zip(eos, qs, kvs, gos)]), 2.5 * xb, 2.5 * xf, K)
         del efw, eos
     del qs, kvs, gos, os_, fwd, bwd
+    # ---- K1-fused: to_q -> masked attention -> to_out in one cluster kernel ----------------------
+    x_probe = torch.empty(B, T, D, device=dev, dtype=dtype)
+    kv_probe = torch.empty(B, Ti * n, 2 * inner, device=dev, dtype=dtype)
+    if ops.xattn_block_supported(x_probe, kv_probe, heads=H, n_latents=n):
+        fb = es * (2 * B * T * D + 2 * B * T * inner + 2 * B * Ti * n * inner + 2 * D * inner) + 4 * B * T * H
+        ff = 2.0 * B * T * D * inner * 2 + xf
+        K = _k(fb, cap=24)
+        xs = [torch.randn(B, T, D, device=dev, dtype=dtype) for _ in range(K)]
+        kvs = [torch.randn(B, Ti * n, 2 * inner, device=dev, dtype=dtype) for _ in range(K)]
+        wqs = [(torch.randn(inner, D, device=dev) * D ** -0.5).to(dtype) for _ in range(K)]
+        wos = [(torch.randn(D, inner, device=dev) * inner ** -0.5).to(dtype) for _ in range(K)]
+        with torch.no_grad():
+            rec("xattn_block_fwd", _time_graph([
+                lambda x=x, kv=kv, wq=wq, wo=wo: ops.xattn_block(x, wq, kv, tt, wo, heads=H, n_latents=n, scale=dh ** -0.5)
+                for x, kv, wq, wo in zip(xs, kvs, wqs, wos)]), fb, ff, K)
+            rec("xattn_three_launches", _time_graph([
+                lambda x=x, kv=kv, wq=wq, wo=wo: torch.nn.functional.linear(ops.masked_cross_attention(
+                    torch.nn.functional.linear(x, wq), kv, tt, heads=H, n_latents=n, scale=dh ** -0.5), wo)
+                for x, kv, wq, wo in zip(xs, kvs, wqs, wos)]), fb, ff, K)
+            if eager:
+                rec("eager_xattn_block_fwd", _time_graph([
+                    lambda x=x, kv=kv, wq=wq, wo=wo: torch.nn.functional.linear(_eager_xattn(
+                        torch.nn.functional.linear(x, wq), kv, tt, H, n, dh ** -0.5), wo)
+                    for x, kv, wq, wo in zip(xs, kvs, wqs, wos)]), fb, ff, K)
+        del xs, kvs, wqs, wos
 
 
 def _run_vit_perceiver(cfg, wl, dtype, eager, rec):
