@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--dp", default="zero1", choices=["zero1", "allreduce"],
                     help="N>1: sharded optimizer (reduce-scatter/all-gather) or plain all-reduce")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--no-defer-optimizer", action="store_true",
+                    help="N=1: run clip+AdamW at the end of its own step instead of under the next ViT forward")
     ap.add_argument("--no-fuse-accum", action="store_true",
                     help="run the accumulation window as sequential micro-batches (reference style)")
     ap.add_argument("--ncu-range", action="store_true",
@@ -450,7 +452,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # everything (model build, warm-up, capture, replay, timing events) runs on ONE non-default
     # stream: the legacy default stream cannot take part in a graph capture that contains NCCL
-    torch.cuda.set_stream(torch.cuda.Stream())
+    # (high priority: at N=1 the deferred AdamW pass runs on a low-priority stream underneath it)
+    torch.cuda.set_stream(torch.cuda.Stream(priority=-1))
     assert _lib.load().unimp_device_ok() == 1
     torch.backends.cuda.matmul.allow_tf32 = True
     peaks = load_peaks()
@@ -507,7 +510,8 @@ def main():
         # step's inputs from static device buffers that are refilled before every replay
         try:
             graphed = GraphedTrainStep(model, tk, opt, reducer, dev[:args.accum], gamma=wl.gamma,
-                                       fuse_accum=not args.no_fuse_accum, label_rows=label_rows)
+                                       fuse_accum=not args.no_fuse_accum, label_rows=label_rows,
+                                       defer_optimizer=(world == 1 and not args.no_defer_optimizer))
         except Exception as ex:  # noqa: BLE001  (never fail the bench on a capture problem: say so)
             if world > 1:
                 raise
@@ -515,6 +519,12 @@ def main():
             config["graph_capture_error"] = repr(ex)[:300]
             torch.cuda.synchronize()
     config["launch"] = "cuda-graph replay of the whole step" if use_graph else "eager"
+    if graphed is not None and graphed.deferred:
+        config["optimizer_overlap"] = (
+            "clip + AdamW of step k runs at the start of replay k+1 on a low-priority stream underneath the "
+            "frozen ViT forward (the Perceiver waits for it): every replay still applies exactly one "
+            "optimizer step; identical parameters after flush() (tests/test_model_gpu.py::"
+            "test_deferred_optimizer_graph_equals_eager_steps)")
     config["accum_window"] = (
         f"{args.accum} micro-batches of {wl.B} run as ONE forward/backward over {args.accum * wl.B} samples "
         "(identical arithmetic: per-sample ops, per-micro-batch loss normalisation kept; "
@@ -593,6 +603,8 @@ def main():
     e2e_value = samples_per_step * args.steps / (ms_e2e * 1e-3)
 
     kernels, roofline, roofline_dominant, roofline_core, launches, per_step = {}, None, None, None, None, None
+    if graphed is not None:
+        graphed.flush()
     if not args.no_kernel_profile:
         cnt = LaunchCounter()
         cnt.install()

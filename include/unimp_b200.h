@@ -240,11 +240,15 @@ int unimp_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype
  * UniMP/mmrec.py:247-248).  master/m/v fp32, grad `dtype`; writes the `dtype` working
  * copy `param`.  gnorm_sq: device scalar, sum of squared grads (NULL = no clipping).
  * hyper: DEVICE float[3] = {lr, 1-beta1^t, sqrt(1-beta2^t)} — step-dependent scalars live in
- * device memory so that a captured CUDA graph of the step stays valid across steps. */
+ * device memory so that a captured CUDA graph of the step stays valid across steps.
+ * background != 0: launch geometry for running UNDER other kernels (short-lived CTAs; the caller
+ * puts it on a low-priority stream next to compute-bound work that does not read the parameters:
+ * unimp_b200.train.GraphedTrainStep(defer_optimizer=True) overlaps it with the frozen ViT forward). */
 int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
                      float* exp_avg_sq, int64_t n, const float* hyper, float beta1, float beta2,
                      float eps, float weight_decay, const float* gnorm_sq, float max_norm,
-                     float grad_scale, int dtype, void* stream);
+                     float grad_scale, int background, int dtype,
+                     void* stream);
 /* acc[0] += sum(grad^2) (fp32). */
 int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, void* stream);
 

@@ -463,3 +463,39 @@ def test_reference_style_train_loop_drives_the_product_model():
             for (n, p, _, _) in g["spans"]:
                 t = 5e-4 if p.numel() == 1 else 2e-5
                 assert rel_err(p.grad, g_ref[n]) < t, (label_rows, n, rel_err(p.grad, g_ref[n]))
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_deferred_optimizer_graph_equals_eager_steps(fuse):
+    """GraphedTrainStep(defer_optimizer=True): the clip + AdamW pass of step k runs at the start of
+    replay k+1 on a side stream under the frozen ViT forward.  After flush() the parameters, the
+    AdamW state and the loss trajectory equal K ordinary steps."""
+    from unimp_b200.factory import build_flamingo
+    from unimp_b200.train import FlatAdamW, GraphedTrainStep, get_grouped_params, train_step
+
+    cfg = tiny_config()
+    sets = [[{k: v.cuda() for k, v in make_batch(cfg, WORKLOADS["C1-tiny"], seed=10 * j + i).items()}
+             for i in range(2)] for j in range(3)]
+    scales = [0.25, 0.5, 1.0, 1.0, 0.7]
+
+    def fresh():
+        m = build_flamingo(cfg, dtype=torch.float32, device="cuda", gate=0.5)
+        return m, FlatAdamW(get_grouped_params(m, 0.1), lr=1e-3)
+
+    model, opt = fresh()
+    eager = [float(train_step(model, None, cfg.tokens, opt, None, accum_steps=2, micro_batches=sets[i % 3],
+                              fuse_accum=fuse, lr_scale=scales[i])) for i in range(5)]
+    want = [t.clone() for t in opt.state_tensors()]
+    torch.cuda.set_stream(torch.cuda.Stream(priority=-1))
+    model, opt = fresh()
+    g = GraphedTrainStep(model, cfg.tokens, opt, None, sets[0], fuse_accum=fuse, defer_optimizer=True)
+    assert opt.step_count == 0
+    got = [float(g(sets[i % 3], lr_scale=scales[i])) for i in range(5)]
+    assert opt.step_count == 4                      # the 5th update is still pending
+    g.flush()
+    assert opt.step_count == 5
+    torch.cuda.synchronize()
+    for a, b in zip(got, eager):
+        assert abs(a - b) < 2e-4 * abs(b), (got, eager)
+    for a, b in zip(opt.state_tensors(), want):
+        assert rel_err(a, b) < 1e-4

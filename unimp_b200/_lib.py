@@ -53,7 +53,7 @@ SIGNATURES = {
     "unimp_focal_ce_rows_bwd": (_i, [_p, _i64, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i64, _i, _i,
                                      _i, _i, _p]),
     "unimp_mask_labels": (_i, [_p, _i64, _i64, _i64, _i64, _p, _i, _i, _p]),
-    "unimp_adamw_step": (_i, [_p, _p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _p, _f, _f, _i, _p]),
+    "unimp_adamw_step": (_i, [_p, _p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _p, _f, _f, _i, _i, _p]),
     "unimp_sumsq": (_i, [_p, _i64, _p, _i, _p]),
     "unimp_rotary_qkv_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i, _p]),
     "unimp_rotary_qkv_bwd": (_i, [_p, _p, _p, C.POINTER(C.c_int64), _p, _p, _p, _i, _i, _i, _i, _i,

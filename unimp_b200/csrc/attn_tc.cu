@@ -582,42 +582,54 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);
 
   if (warp == 4 && elect_one_sync()) {
+    // The elected lane runs mostly on the uniform datapath (~12 cycles per dependent instruction):
+    // the step loop is unrolled by the ring depth so that stage offsets and most barrier parities
+    // are compile-time constants.
+    static_assert(XF_STAGES == 2, "the unrolled step loop assumes a 2-stage ring");
+    const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), p_u = smem_u32(sP);
     mbar_wait(&bar_q, 0);
     mbar_wait(&bar_kv[0], 0);
     tcgen05_fence_after();
 #pragma unroll
     for (int k4 = 0; k4 < DH / 16; ++k4)
-      umma_ss(tmem + S_COL, make_smem_desc(smem_u32(sQ) + k4 * 32, 16, 1024),
-              make_smem_desc(smem_u32(sK) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      umma_ss(tmem + S_COL, make_smem_desc(q_u + k4 * 32, 16, 1024), make_smem_desc(k_u + k4 * 32, 16, 1024),
+              idesc_s, k4 > 0);
     umma_commit(&bar_s);
-    for (int s = 0; s < nsteps; ++s) {
-      const int st = s % XF_STAGES;
-      const bool sweep2 = s >= nb;
-      mbar_wait(&bar_p, s & 1);                 // sweep 1: S_s consumed; sweep 2: P_s in shared memory
-      if (sweep2) {
-        tcgen05_fence_after();
+    uint32_t ring_ph = 0;                      // parity of stage 0's current fill; stage 1 lags by one step
+    for (int s0 = 0; s0 < nsteps; s0 += 2) {
 #pragma unroll
-        for (int k4 = 0; k4 < KB / 16; ++k4)
-          umma_ss(tmem + O_COL, make_smem_desc(smem_u32(sP) + k4 * 32, 16, 1024),
-                  make_smem_desc(smem_u32(sV + st * KV_BYTES) + k4 * 2048, 1024, 1024), idesc_o,
-                  (s > nb || k4 > 0));
-        umma_commit(&bar_pv);
-        if (s + 1 == nsteps) umma_commit(&bar_o);
-      }
-      if (s + 1 < nsteps) {
-        const int sn = (s + 1) % XF_STAGES;
-        mbar_wait(&bar_kv[sn], ((s + 1) / XF_STAGES) & 1);
-        tcgen05_fence_after();
+      for (int u = 0; u < 2; ++u) {
+        const int s = s0 + u;                  // stage = u, bar_p parity = u
+        if (s < nsteps) {
+          const bool sweep2 = s >= nb;
+          mbar_wait(&bar_p, u);                // sweep 1: S_s consumed; sweep 2: P_s in shared memory
+          if (sweep2) {
+            tcgen05_fence_after();
 #pragma unroll
-        for (int k4 = 0; k4 < DH / 16; ++k4)
-          umma_ss(tmem + S_COL, make_smem_desc(smem_u32(sQ) + k4 * 32, 16, 1024),
-                  make_smem_desc(smem_u32(sK + sn * KV_BYTES) + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-        umma_commit(&bar_s);
+            for (int k4 = 0; k4 < KB / 16; ++k4)
+              umma_ss(tmem + O_COL, make_smem_desc(p_u + k4 * 32, 16, 1024),
+                      make_smem_desc(v_u + u * KV_BYTES + k4 * 2048, 1024, 1024), idesc_o, (s > nb || k4 > 0));
+            umma_commit(&bar_pv);
+            if (s + 1 == nsteps) umma_commit(&bar_o);
+          }
+          if (s + 1 < nsteps) {
+            // step s+1 lives in stage 1-u; its fill parity: stage 1 (u == 0) shares this round's
+            // parity, stage 0 (u == 1) is one fill ahead
+            mbar_wait(&bar_kv[1 - u], u == 0 ? ring_ph : (ring_ph ^ 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < DH / 16; ++k4)
+              umma_ss(tmem + S_COL, make_smem_desc(q_u + k4 * 32, 16, 1024),
+                      make_smem_desc(k_u + (1 - u) * KV_BYTES + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+            umma_commit(&bar_s);
+          }
+          if (s + XF_STAGES < nsteps) {
+            if (sweep2) mbar_wait(&bar_pv, (s - nb) & 1);   // PV_s has released stage u
+            load_step(s + XF_STAGES);
+          }
+        }
       }
-      if (s + XF_STAGES < nsteps) {
-        if (sweep2) mbar_wait(&bar_pv, (s - nb) & 1);   // PV_s has released stage `st`
-        load_step(s + XF_STAGES);
-      }
+      ring_ph ^= 1;
     }
   }
 

@@ -185,7 +185,8 @@ extern "C" int unimp_sumsq(const void* grad, int64_t n, float* acc, int dtype, v
 extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, float* exp_avg,
                                 float* exp_avg_sq, int64_t n, const float* hyper, float beta1,
                                 float beta2, float eps, float weight_decay, const float* gnorm_sq,
-                                float max_norm, float grad_scale, int dtype, void* stream) {
+                                float max_norm, float grad_scale, int background, int dtype,
+                                void* stream) {
   UNIMP_CHECK_ARG(master && param && grad && exp_avg && exp_avg_sq && hyper, UNIMP_E_NULL,
                   "adamw_step: NULL pointer");
   UNIMP_CHECK_ARG(aligned16(master) && aligned16(exp_avg) && aligned16(exp_avg_sq), UNIMP_E_ALIGN,
@@ -193,7 +194,14 @@ extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, fl
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "adamw_step: dtype");
   if (n <= 0) return 0;
   int64_t blocks = (n / 4 + 255) / 256;
-  if (blocks > 16 * UNIMP_NUM_SMS) blocks = 16 * UNIMP_NUM_SMS;
+  if (background) {
+    // meant to run UNDER other kernels (a low-priority stream beside the frozen ViT forward): many
+    // short-lived CTAs (8 vectors per thread) instead of a resident grid-stride wave, so that the
+    // block scheduler can hand freed SM slots to the higher-priority kernels all the time
+    blocks = (blocks + 7) / 8;
+  } else if (blocks > 16 * UNIMP_NUM_SMS) {
+    blocks = 16 * UNIMP_NUM_SMS;
+  }
   if (blocks < 1) blocks = 1;
   if (dtype == UNIMP_BF16)
     adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(

@@ -43,6 +43,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a descriptor / protocol bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1   // (ptxas unrolls this poll 64x otherwise: kilobytes of instruction cache per wait)
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     if (mbar_try_wait(bar, parity)) return;
   }
@@ -53,6 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Same, tagged: `tag` identifies the barrier in the timeout message (protocol debugging).
 __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     if (mbar_try_wait(bar, parity)) return;
   }

@@ -685,13 +685,14 @@ def sumsq_(grad: torch.Tensor, acc: torch.Tensor):
 
 
 def adamw_step_(master, param, grad, exp_avg, exp_avg_sq, *, hyper, beta1, beta2, eps, weight_decay,
-                gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
-    """hyper: device float32[3] = (lr, 1-beta1^t, sqrt(1-beta2^t)); see adamw_hyper()."""
+                gnorm_sq=None, max_norm=0.0, grad_scale=1.0, background=False):
+    """hyper: device float32[3] = (lr, 1-beta1^t, sqrt(1-beta2^t)); see adamw_hyper().
+    `background`: launch geometry for running under other kernels on a low-priority stream."""
     check(_lib.load().unimp_adamw_step(master.data_ptr(), param.data_ptr(), grad.data_ptr(),
                                        exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
                                        hyper.data_ptr(), float(beta1), float(beta2), float(eps),
                                        float(weight_decay), _ptr(gnorm_sq), float(max_norm),
-                                       float(grad_scale), _dt(param), _stream()),
+                                       float(grad_scale), int(background), _dt(param), _stream()),
           "unimp_adamw_step")
 
 

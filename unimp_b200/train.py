@@ -215,8 +215,9 @@ class FlatAdamW:
             self._hyper_events[slot] = ev
 
     @torch.no_grad()
-    def step_kernels(self, grad_scale: float = 1.0):
-        """Device side of a step (capturable): grad-norm, clip, AdamW. No host sync."""
+    def step_kernels(self, grad_scale: float = 1.0, background: bool = False):
+        """Device side of a step (capturable): grad-norm, clip, AdamW. No host sync.
+        `background`: AdamW launch geometry for running under other kernels (deferred mode)."""
         self._zero_unwritten()
         self.gnorm_sq.zero_()
         for g in self.groups:
@@ -226,7 +227,13 @@ class FlatAdamW:
                             hyper=self.hyper, beta1=self.betas[0], beta2=self.betas[1],
                             eps=self.eps, weight_decay=g["weight_decay"],
                             gnorm_sq=self.gnorm_sq if self.max_grad_norm > 0 else None,
-                            max_norm=self.max_grad_norm, grad_scale=grad_scale)
+                            max_norm=self.max_grad_norm, grad_scale=grad_scale, background=background)
+
+    def upload_noop_hyper(self):
+        """lr = 0 with valid bias corrections: an AdamW pass over ZERO gradients that changes
+        nothing (deferred mode's first replay has no gradients to apply yet)."""
+        h = ops.adamw_hyper(0.0, self.betas[0], self.betas[1], 1)
+        self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
 
     def step(self, *, lr_scale: float = 1.0, grad_scale: float = 1.0):
         """clip_grad_norm_(max_grad_norm) over ALL groups, then AdamW."""
@@ -549,12 +556,28 @@ class GraphedTrainStep:
 
     def __init__(self, model, tokens, opt: FlatAdamW, reducer, example_mbs, *, gamma=2.0,
                  use_reweight=True, warmup_iters=3, capture_error_mode=None, fuse_accum=False,
-                 label_rows=None):
-        """`label_rows`: static capacity (int) of the head + loss fusion's row gather — an upper
+                 label_rows=None, defer_optimizer=False):
+        """`defer_optimizer` (single GPU): the clip + AdamW pass of step k (5.3 ms of pure HBM traffic
+        at 4B) is not run at the end of step k but at the START of step k+1, on a low-priority side
+        stream underneath the frozen ViT forward (compute-bound, reads no trainable parameter); the
+        Perceiver's forward waits for it.  Same arithmetic, same order of updates — every parameter is
+        updated before it is next read; call `flush()` after the last step (before evaluating /
+        checkpointing) to apply the pending update.  The first replay applies a no-op update.
+        `label_rows`: static capacity (int) of the head + loss fusion's row gather — an upper
         bound on the number of valid labels per forward (per window when `fuse_accum`); None keeps
         dense logits.  `True` is not allowed here (its exact gather needs a host sync)."""
         assert label_rows is None or (label_rows is not True and int(label_rows) > 0)
         self.label_rows = label_rows
+        self.deferred = bool(defer_optimizer)
+        self._in_body = self._forked = False
+        self._pending = None                 # lr_scale of the step whose gradients await their update
+        if self.deferred:
+            assert reducer is None or reducer.world == 1, "defer_optimizer is the single-GPU arrangement"
+            self._opt_stream = torch.cuda.Stream(priority=0)      # lowest priority: fills idle SM slots
+            self._hooks = [
+                model.vision_encoder.register_forward_pre_hook(lambda m, a: self._fork_optimizer()),
+                model.perceiver.register_forward_pre_hook(lambda m, a: self._join_optimizer()),
+            ]
         self.fuse_accum = fuse_accum and len(example_mbs) > 1
         # NOTE: with NCCL in the graph, run the whole process on a NON-default stream
         # (`torch.cuda.set_stream(torch.cuda.Stream())` before building the model): gradient
@@ -583,6 +606,10 @@ class GraphedTrainStep:
             for _ in range(warmup_iters):
                 self.opt.prepare_step(0.0)
                 self._body()
+            if self.deferred:
+                side.wait_stream(self._opt_stream)
+                for g in opt.groups:
+                    g["flat_g"].zero_()      # the first replay's (no-op) update must see zero gradients
             # (deferred all-gather mode: the reducer is left "params stale" on purpose, so that the
             # capture below records the gather at the ViT entry; the restore makes every rank's
             # full parameter buffer current regardless)
@@ -597,7 +624,31 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = self._body()
 
+    # ---- deferred optimizer: fork at the ViT, join at the Perceiver ----------------------------
+    def _fork_optimizer(self):
+        if not self._in_body or self._forked:
+            return
+        side = self._opt_stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.opt.step_kernels(self.grad_scale, background=True)   # the PREVIOUS step's gradients
+            self.opt.zero_grad()                                      # then make room for this step's
+        self._forked = True
+
+    def _join_optimizer(self):
+        if self._in_body and self._forked:
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
+
+    def flush(self):
+        """Deferred mode: apply the update of the last step (its gradients are still pending)."""
+        if self.deferred and self._pending is not None:
+            self.opt.prepare_step(self._pending)
+            self.opt.step_kernels(self.grad_scale)
+            self._pending = None
+
     def _body(self):
+        if self.deferred:
+            return self._body_deferred()
         if self.reducer is not None and self.reducer.sharded:
             self.reducer.begin_step()
         self.opt.zero_grad()
@@ -619,10 +670,35 @@ class GraphedTrainStep:
         self.opt.step_with(self.reducer)
         return loss.detach()
 
+    def _body_deferred(self):
+        self._in_body, self._forked = True, False
+        try:
+            if self.fuse_accum:
+                loss, _ = unimp_loss_fused(self.model, self.static, self.tokens, gamma=self.gamma,
+                                           use_reweight=self.use_reweight, label_rows=self.label_rows)
+                loss.backward()
+            else:
+                loss = None
+                for mb in self.static:
+                    loss, _, _ = unimp_loss(self.model, mb, self.tokens, gamma=self.gamma,
+                                            use_reweight=self.use_reweight, label_rows=self.label_rows)
+                    (loss / self.accum if self.accum > 1 else loss).backward()
+            assert self._forked, "the model never ran its vision encoder: nothing applied the pending update"
+        finally:
+            self._in_body = False
+        return loss.detach()
+
     def __call__(self, mbs, lr_scale: float = 1.0):
         for st, mb in zip(self.static, mbs):
             for k, v in mb.items():
                 st[k].copy_(v, non_blocking=True)
-        self.opt.prepare_step(lr_scale)
+        if not self.deferred:
+            self.opt.prepare_step(lr_scale)
+        elif self._pending is None:
+            self.opt.upload_noop_hyper()             # first replay: nothing to apply yet
+        else:
+            self.opt.prepare_step(self._pending)     # the update of the PREVIOUS step's gradients
         self.graph.replay()
+        if self.deferred:
+            self._pending = lr_scale
         return self.loss
