@@ -297,10 +297,11 @@ def test_focal_ce_all_ignored_is_nan_like_reference():
 
 # ------------------------------------------------------------------ optimizer kernels
 
+@pytest.mark.parametrize("background", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_fused_adamw_matches_torch(dtype):
+def test_fused_adamw_matches_torch(dtype, background):
     torch.manual_seed(0)
-    n = 10007
+    n = 10007 if not background else 2 * 148 * 256 * 4 * 5 + 1003   # background: several strides + a ragged tail
     p0 = torch.randn(n)
     ref_p = p0.clone().requires_grad_(True)
     opt = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
@@ -319,7 +320,7 @@ def test_fused_adamw_matches_torch(dtype):
         assert abs(float(acc) - float(g.float().pow(2).sum())) / float(acc) < 1e-5
         hyper = torch.tensor(ops().adamw_hyper(1e-2, 0.9, 0.999, step), device=DEV)
         ops().adamw_step_(master, param, gd, m, v, hyper=hyper, beta1=0.9, beta2=0.999, eps=1e-8,
-                          weight_decay=0.1, gnorm_sq=acc, max_norm=1.0)
+                          weight_decay=0.1, gnorm_sq=acc, max_norm=1.0, background=background)
     assert torch.allclose(master.cpu(), ref_p.detach(), rtol=1e-5, atol=2e-6)
     assert rel_err(param, ref_p.detach()) < (1e-6 if dtype == torch.float32 else 4e-3)
 

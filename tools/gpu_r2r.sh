@@ -16,4 +16,4 @@ for n in ("defer", "nodefer"):
     except Exception as e:
         print(n, "no json", e)
 PY
-timeout 200 python tools/kbench_cli.py --workload C2-rec --only vit --no-eager --tag v2b 2>&1 | grep "^KB"
+timeout 200 python tools/kbench_cli.py --workload C2-rec --only misc --no-eager --tag bg 2>&1 | grep "^KB"

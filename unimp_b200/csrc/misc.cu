@@ -87,7 +87,26 @@ sumsq_kernel(const T* __restrict__ g, int64_t n, float* __restrict__ acc) {
 }
 
 // One pass: read grad, master, m, v; write master, m, v and the T working copy.
+// U = vectors (4 parameters each) a thread keeps in flight per iteration: 1 for the resident
+// grid-stride wave; 4 for the BACKGROUND geometry (2 small CTAs per SM that leave room for
+// concurrently running compute-bound kernels: every load of the 4 vectors is issued before the
+// first use, 4 x 56 B per thread in flight).
 template <typename T>
+__device__ __forceinline__ void adamw_update4(float* p, float* mm, float* vv, const float* g4, float clip,
+                                              float lr, float wd, float b1, float b2, float eps, float bc1,
+                                              float bc2_sqrt) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float g = g4[i] * clip;
+    p[i] *= 1.f - lr * wd;                       // decoupled weight decay
+    mm[i] = b1 * mm[i] + (1.f - b1) * g;
+    vv[i] = b2 * vv[i] + (1.f - b2) * g * g;
+    const float denom = sqrtf(vv[i]) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mm[i] / denom);
+  }
+}
+
+template <typename T, int U>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ master, T* __restrict__ param, const T* __restrict__ grad,
              float* __restrict__ m, float* __restrict__ v, int64_t n, const float* __restrict__ hyper,
@@ -101,35 +120,42 @@ adamw_kernel(float* __restrict__ master, T* __restrict__ param, const T* __restr
     clip *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
-    if (i0 + 4 <= n) {
-      float4 p4 = *reinterpret_cast<float4*>(master + i0);
-      float4 m4 = *reinterpret_cast<float4*>(m + i0);
-      float4 v4 = *reinterpret_cast<float4*>(v + i0);
-      float p[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w},
-            vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride * U) {
+    float4 p4[U], m4[U], v4[U];
+    float g4[U][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float g = Elem<T>::to_f(grad[i0 + i]) * clip;
-        p[i] *= 1.f - lr * wd;                       // decoupled weight decay
-        mm[i] = b1 * mm[i] + (1.f - b1) * g;
-        vv[i] = b2 * vv[i] + (1.f - b2) * g * g;
-        const float denom = sqrtf(vv[i]) / bc2_sqrt + eps;
-        p[i] -= (lr / bc1) * (mm[i] / denom);
-        param[i0 + i] = Elem<T>::from_f(p[i]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i + 4 <= n) {
+        p4[u] = *reinterpret_cast<float4*>(master + i);
+        m4[u] = *reinterpret_cast<float4*>(m + i);
+        v4[u] = *reinterpret_cast<float4*>(v + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g4[u][e] = Elem<T>::to_f(grad[i + e]);
       }
-      *reinterpret_cast<float4*>(master + i0) = make_float4(p[0], p[1], p[2], p[3]);
-      *reinterpret_cast<float4*>(m + i0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-      *reinterpret_cast<float4*>(v + i0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    } else {
-      for (int64_t i = i0; i < n; ++i) {
-        const float g = Elem<T>::to_f(grad[i]) * clip;
-        float p = master[i] * (1.f - lr * wd);
-        const float mm = b1 * m[i] + (1.f - b1) * g;
-        const float vv = b2 * v[i] + (1.f - b2) * g * g;
-        p -= (lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + eps));
-        master[i] = p; m[i] = mm; v[i] = vv;
-        param[i] = Elem<T>::from_f(p);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i + 4 <= n) {
+        float p[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w}, mm[4] = {m4[u].x, m4[u].y, m4[u].z, m4[u].w},
+              vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+        adamw_update4<T>(p, mm, vv, g4[u], clip, lr, wd, b1, b2, eps, bc1, bc2_sqrt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) param[i + e] = Elem<T>::from_f(p[e]);
+        *reinterpret_cast<float4*>(master + i) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      } else if (i < n) {
+        for (int64_t j = i; j < n; ++j) {
+          const float g = Elem<T>::to_f(grad[j]) * clip;
+          float p = master[j] * (1.f - lr * wd);
+          const float mm = b1 * m[j] + (1.f - b1) * g;
+          const float vv = b2 * v[j] + (1.f - b2) * g * g;
+          p -= (lr / bc1) * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+          master[j] = p; m[j] = mm; v[j] = vv;
+          param[j] = Elem<T>::from_f(p);
+        }
       }
     }
   }
@@ -194,21 +220,32 @@ extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, fl
   UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "adamw_step: dtype");
   if (n <= 0) return 0;
   int64_t blocks = (n / 4 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
   if (background) {
-    // meant to run UNDER other kernels (a low-priority stream beside the frozen ViT forward): many
-    // short-lived CTAs (8 vectors per thread) instead of a resident grid-stride wave, so that the
-    // block scheduler can hand freed SM slots to the higher-priority kernels all the time
-    blocks = (blocks + 7) / 8;
-  } else if (blocks > 16 * UNIMP_NUM_SMS) {
-    blocks = 16 * UNIMP_NUM_SMS;
+    // Meant to run UNDER other kernels (beside the frozen ViT forward): a grid the block scheduler
+    // dispatches at once (2 CTAs of 256 threads per SM, ~25 % of an SM's thread slots and registers),
+    // so that the CTAs of the concurrently running compute-bound kernels fit next to it; 4 vectors
+    // per thread in flight keep the HBM pipe full from that small footprint.
+    if (blocks > 2 * UNIMP_NUM_SMS) blocks = 2 * UNIMP_NUM_SMS;
+    if (dtype == UNIMP_BF16)
+      adamw_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, 256, 0, st>>>(
+          master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, hyper, beta1,
+          beta2, eps, weight_decay, gnorm_sq, max_norm, grad_scale);
+    else
+      adamw_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>(
+          master, (float*)param, (const float*)grad, exp_avg, exp_avg_sq, n, hyper, beta1, beta2, eps,
+          weight_decay, gnorm_sq, max_norm, grad_scale);
+    UNIMP_CHECK_LAUNCH();
+    return 0;
   }
+  if (blocks > 16 * UNIMP_NUM_SMS) blocks = 16 * UNIMP_NUM_SMS;
   if (blocks < 1) blocks = 1;
   if (dtype == UNIMP_BF16)
-    adamw_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    adamw_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, st>>>(
         master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, hyper,
         beta1, beta2, eps, weight_decay, gnorm_sq, max_norm, grad_scale);
   else
-    adamw_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    adamw_kernel<float, 1><<<(unsigned)blocks, 256, 0, st>>>(
         master, (float*)param, (const float*)grad, exp_avg, exp_avg_sq, n, hyper, beta1, beta2, eps,
         weight_decay, gnorm_sq, max_norm, grad_scale);
   UNIMP_CHECK_LAUNCH();

@@ -363,5 +363,9 @@ def _run_misc(cfg, wl, dtype, rec):
                                                                  beta2=0.999, eps=1e-8, weight_decay=0.1,
                                                                  gnorm_sq=gn, max_norm=1.0)] * 3),
         npar * (2 * es + 6 * 4), 0.0, 3)
+    rec("adamw_clip_step_background", _time_graph([lambda: ops.adamw_step_(ma, pw, pg, m1, m2, hyper=hyper, beta1=0.9,
+                                                                            beta2=0.999, eps=1e-8, weight_decay=0.1,
+                                                                            gnorm_sq=gn, max_norm=1.0, background=True)] * 3),
+        npar * (2 * es + 6 * 4), 0.0, 3)
     rec("grad_sumsq", _time_graph([lambda: ops.sumsq_(pg, gn)] * 3), npar * es, 0.0, 3)
     del pw, pg, ma, m1, m2
