@@ -227,6 +227,16 @@ extern "C" int unimp_adamw_step(float* master, void* param, const void* grad, fl
     // so that the CTAs of the concurrently running compute-bound kernels fit next to it; 4 vectors
     // per thread in flight keep the HBM pipe full from that small footprint.
     if (blocks > 2 * UNIMP_NUM_SMS) blocks = 2 * UNIMP_NUM_SMS;
+    // the kernels it runs beside (cuBLAS GEMMs, the attention kernels) want the largest shared-memory
+    // carve-out; an SM cannot host CTAs with different carve-outs at once, so ask for the same one
+    static bool carve = false;
+    if (!carve) {
+      cudaFuncSetAttribute(adamw_kernel<__nv_bfloat16, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(adamw_kernel<float, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carve = true;
+    }
     if (dtype == UNIMP_BF16)
       adamw_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, 256, 0, st>>>(
           master, (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, exp_avg, exp_avg_sq, n, hyper, beta1,
