@@ -166,7 +166,7 @@ def _cpu_optimizer_kernels():
         acc += grad.float().pow(2).sum()
 
     def adamw_step_(master, param, grad, m, v, *, hyper, beta1, beta2, eps, weight_decay, gnorm_sq=None,
-                    max_norm=0.0, grad_scale=1.0):
+                    max_norm=0.0, grad_scale=1.0, background=False):
         lr, bc1, bc2_sqrt = (float(x) for x in hyper)
         clip = grad_scale
         if gnorm_sq is not None:
