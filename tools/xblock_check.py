@@ -124,12 +124,50 @@ def timeline(B, T, Ti, D):
               (t[:, 8] - t[:, 7]).median()), flush=True)
 
 
+def core_timeline(B, T, Ti):
+    """Per-CTA phase timestamps of one launch of the standalone core (unimp__xattn_fwd_debug hook)."""
+    import ctypes
+    lib = _lib.load()
+    inner = H * dh
+    q = torch.randn(B, T, inner, device=dev, dtype=bf)
+    kv = torch.randn(B, Ti * n, 2 * inner, device=dev, dtype=bf)
+    tt = mk_tt(B, T, Ti)
+    n_cta = ((T + 127) // 128) * H * B
+    buf = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
+    f = lib.unimp__xattn_fwd_debug
+    f.argtypes = [ctypes.c_void_p]
+    f.restype = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            ops.masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=0.125)
+        flush.zero_()                      # cold L2, like the back-to-back cold sets of kbench
+        torch.cuda.synchronize()
+        f(buf.data_ptr())
+        ops.masked_cross_attention(q, kv, tt, heads=H, n_latents=n, scale=0.125)
+        torch.cuda.synchronize()
+        f(None)
+    t = buf.view(n_cta, 8).cpu().double()
+    t0 = t[:, 0].min()
+    names = ["start", "prologue", "S ready", "P written", "softmax", "O ready", "stored"]
+    print(f"XF timeline B={B} T={T} Ti={Ti} ({n_cta} CTAs, cold L2); ns since the first CTA's start: median [min, max]")
+    for i, nm in enumerate(names):
+        col = t[:, i] - t0
+        print(f"XF   {nm:10s} {col.median():8.0f} [{col.min():8.0f}, {col.max():8.0f}]")
+    d = lambda i, j: (t[:, i] - t[:, j]).median()
+    print("XF   per-CTA durations (median ns): prologue %.0f | loads+first S %.0f | softmax(1st) %.0f | rest %.0f | PV+wait %.0f | "
+          "store %.0f | CTA total %.0f" % (d(1, 0), d(2, 1), d(3, 2), d(4, 3), d(5, 4), d(6, 5), d(6, 0)), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "check"):
         for shape in ((1, 128, 1, 128), (2, 32, 2, 128), (1, 128, 2, 2560), (3, 256, 2, 2560), (1, 513, 8, 512),
                       (6, 1024, 8, 2560)):
             check(*shape)
+    if what in ("all", "core"):
+        core_timeline(6, 256, 2)
+        core_timeline(6, 1024, 8)
     if what in ("all", "timeline"):
         timeline(6, 256, 2, 2560)
         timeline(6, 1024, 8, 2560)

@@ -33,6 +33,7 @@ constexpr uint32_t KV_BYTES = KB * DH * 2;   // 8 KB
 constexpr uint32_t P_BYTES = TQ * KB * 2;    // 16 KB
 
 struct FwdArgs {
+  unsigned long long* dbg;   // test hook: per-CTA phase timestamps (8 x u64 per CTA), NULL = off
   __nv_bfloat16* o;
   int64_t o_bs, o_rs;
   float* lse;
@@ -89,6 +90,16 @@ constexpr int FWD_THREADS = TQ + 32;  // warps 0-3: one query row per thread; wa
 // ---------------------------------------------------------------------------------------------
 constexpr int XF_STAGES = 2;
 
+__device__ __forceinline__ unsigned long long xf_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define XF_STAMP(slot)                                                                                   \
+  do {                                                                                                   \
+    if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = xf_now(); \
+  } while (0)
+
 __global__ void __launch_bounds__(FWD_THREADS, 3)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                     const __grid_constant__ CUtensorMap tv, const FwdArgs a) {
@@ -106,6 +117,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = tid < TQ;
   const int row0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  if (tid == 0) XF_STAMP(0);                       // CTA started
 
   if (warp == 4) {
     if (elect_one_sync()) {
@@ -156,6 +168,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (tid == 0) XF_STAMP(1);                       // prologue done (TMEM allocated, loads issued)
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int jlo = s_j[0], jhi = s_j[1];
@@ -213,6 +226,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       const int j = jlo + it;
       mbar_wait(&bar_s, it & 1);
       tcgen05_fence_after();
+      if (tid == 0 && it == 0) XF_STAMP(2);        // first S ready (Q, K landed, MMA done)
       const bool mine = uniform || blk == j;
       const bool warp_any = __any_sync(0xffffffffu, mine);
       float m = -INFINITY;
@@ -249,7 +263,9 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p);
+      if (tid == 0 && it == 0) XF_STAMP(3);        // first P written
     }
+    if (tid == 0) XF_STAMP(4);                     // all softmax done
     // ---- epilogue: O / sum -> global -----------------------------------------------------
     const float lse_val = sum > 0.f ? m_row * a.scale + logf(sum) : -INFINITY;
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
@@ -257,6 +273,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       mbar_wait(&bar_o, 0);
       tcgen05_fence_after();
     }
+    if (tid == 0) XF_STAMP(5);                     // O complete
     __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -280,6 +297,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     }
     if (valid) a.lse[((int64_t)b * a.H + h) * a.Lq + row] = lse_val;
     tcgen05_fence_before();
+    if (tid == 0) XF_STAMP(6);                     // stores issued
   }
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
@@ -601,6 +619,7 @@ static int launch_attn_fwd2(unimp_view_t q, unimp_view_t k, unimp_view_t v, unim
     attr = true;
   }
   FwdArgs a;
+  a.dbg = nullptr;
   a.o = (__nv_bfloat16*)o.ptr; a.o_bs = o.batch_stride; a.o_rs = o.row_stride;
   a.lse = lse; a.tt = nullptr; a.Lq = Lq; a.Lk = Lk; a.H = H; a.n = Lk; a.Ti = 1;
   a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
@@ -609,6 +628,8 @@ static int launch_attn_fwd2(unimp_view_t q, unimp_view_t k, unimp_view_t v, unim
   UNIMP_CHECK_LAUNCH();
   return 0;
 }
+
+static unsigned long long* g_xf_dbg = nullptr;   // test hook (unimp__xattn_fwd_debug)
 
 static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
                             unimp_mview_t o, float* lse, int B, int Lq, int Lk, int H, int n, int Ti,
@@ -629,6 +650,7 @@ static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, cons
     attr = true;
   }
   FwdArgs a;
+  a.dbg = g_xf_dbg;
   a.o = (__nv_bfloat16*)o.ptr; a.o_bs = o.batch_stride; a.o_rs = o.row_stride;
   a.lse = lse; a.tt = tt; a.Lq = Lq; a.Lk = Lk; a.H = H; a.n = n; a.Ti = Ti;
   a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
@@ -988,3 +1010,7 @@ int launch_attn_bwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int
 }
 
 }  // namespace unimp
+
+// Test hook (not in the public header): device buffer of 8 x u64 per CTA that the next
+// unimp_xattn_fwd launches fill with %globaltimer phase stamps; NULL switches it off.
+extern "C" void unimp__xattn_fwd_debug(unsigned long long* buf) { unimp::g_xf_dbg = buf; }
