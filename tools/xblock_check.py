@@ -104,22 +104,18 @@ def timeline(B, T, Ti, D):
         ops.xattn_block(x, wq, kv, tt, wo, heads=H, n_latents=n, scale=0.125)
         torch.cuda.synchronize()
         f(None)
-    ch = buf[n_cta * 16:].cpu().double()
     t = buf[:n_cta * 16].view(n_cta, 16).cpu().double()
-    base = t[0, 1]
-    print("XB   CTA 0 per chunk (ns after csync1): k: producer issued / MMA saw it / MMAs issued")
-    print("XB   " + "  ".join(f"{k}:{ch[k] - base:.0f}/{ch[64 + k] - base:.0f}/{ch[128 + k] - base:.0f}" for k in range(0, 40)))
     t0 = t[:, 0].min()
     names = ["start", "csync1", "ph1 done", "attn done", "o stored", "csync2", "O tiles in", "to_out done",
-             "y stored", "end", "1st chunk", "half K"]
+             "y stored", "end"]
     print(f"XB timeline B={B} T={T} Ti={Ti} D={D} ({n_cta} CTAs); ns since the first CTA's start: median [min, max]")
     for i, nm in enumerate(names):
         col = t[:, i] - t0
         print(f"XB   {nm:12s} {col.median():9.0f} [{col.min():9.0f}, {col.max():9.0f}]")
-    print("XB   per-CTA durations (median ns): csync1 %.0f | ph1 %.0f (1st chunk after csync1 %.0f, half-K at %.0f) | attn %.0f | "
+    print("XB   per-CTA durations (median ns): csync1 %.0f | ph1 %.0f | attn %.0f | "
           "o store %.0f | csync2 %.0f | O exchange %.0f | to_out %.0f | y store %.0f" % (
-              (t[:, 1] - t[:, 0]).median(), (t[:, 2] - t[:, 1]).median(), (t[:, 10] - t[:, 1]).median(),
-              (t[:, 11] - t[:, 1]).median(), (t[:, 3] - t[:, 2]).median(), (t[:, 4] - t[:, 3]).median(),
+              (t[:, 1] - t[:, 0]).median(), (t[:, 2] - t[:, 1]).median(),
+              (t[:, 3] - t[:, 2]).median(), (t[:, 4] - t[:, 3]).median(),
               (t[:, 5] - t[:, 4]).median(), (t[:, 6] - t[:, 5]).median(), (t[:, 7] - t[:, 6]).median(),
               (t[:, 8] - t[:, 7]).median()), flush=True)
 

@@ -81,13 +81,6 @@ __device__ __forceinline__ unsigned long long xb_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// per-chunk stamps of CTA (0,0,0) only, after the per-CTA table: [0,64) producer issue, [64,128) MMA
-// sees the chunk, [128,192) MMA thread has issued the chunk's MMAs + commit
-#define XB_STAMP_CHUNK(base, k)                                                                  \
-  do {                                                                                          \
-    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (k) < 64)             \
-      a.dbg[gridDim.x * gridDim.y * gridDim.z * 16 + (base) + (k)] = xb_now();                  \
-  } while (0)
 #define XB_STAMP(slot)                                                                          \
   do {                                                                                          \
     if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = xb_now(); \
@@ -240,7 +233,6 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
               else if ((k & (H - 1)) == h) tma_load_3d_mc(st, &tx, &full1[s], k * 64, t0, b, ALL);
               tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
             }
-            XB_STAMP_CHUNK(0, p);
           }
         }
         ph ^= 1;
@@ -274,9 +266,6 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
           if (p < NP) {
             mbar_wait_tag(&full1[s], ph, T_FULL1 + s);
             tcgen05_fence_after();
-            if (p == 0) XB_STAMP(10);   // first stage landed
-            if (p == NP / 2) XB_STAMP(11);
-            XB_STAMP_CHUNK(64, p);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               const uint32_t sa = smem_base + stage1_off(2 * s + c), sb = sa + A_BYTES;
@@ -287,7 +276,6 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
             }
             if (a.flags & 1) umma_commit(&empty1[s]);   // CTA-local ring when nothing is multicast
             else umma_commit_mc(&empty1[s], ALL);       // the stage is free in THIS CTA; all 8 must say so
-            XB_STAMP_CHUNK(128, p);
           }
         }
         ph ^= 1;
