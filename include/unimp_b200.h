@@ -224,6 +224,27 @@ int unimp_rotary_qkv_fwd(const void* qkv, void* out, const void* cos, const void
 int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const int64_t* strides9,
                          const void* cos, const void* sin, void* d_qkv, int B, int T, int H, int dh,
                          int rot, int64_t cs_batch_stride, int dtype, void* stream);
+/* ---- f3 / K4: causal self-attention of the GPT-NeoX decoder layers, head dim 80 -----------
+ * Replaces the attention core of HF `GPTNeoXAttention.forward` (transformers gpt_neox, reached
+ * through upstream `FlamingoLayer.forward` -> `self.decoder_layer(...)`; call site reference
+ * UniMP/mmrec.py:177-181): softmax(scale * q k^T + mask) v per head, where key j is visible to
+ * query i iff j <= i and bit j of key_bits[b] is set (what HF builds from a 2-D attention_mask;
+ * key_bits == NULL: causal only).  q,k,v: (B,T,H,dh) views that share batch/row/head strides
+ * (elements) — the rotated packed projection; o, d_o: (B,T,H*dh) contiguous; lse (B,H,T) fp32.
+ * unimp_key_bits packs an attention_mask (B,T) of bool/uint8 (elem_size 1) or int64 (8),
+ * nonzero = real token, into (B, 2*ceil(T/64)) words of 32 keys.
+ * Backward: dq32 (B,T,H,dh) fp32 (zeroed and accumulated by the call), dk, dv (B,T,H,dh) in
+ * `dtype`, contiguous.  bf16, dh == 80 only (unimp_lm_attn_supported); rows that see no key
+ * give o = 0. */
+int unimp_lm_attn_supported(int T, int H, int dh, int dtype);
+int unimp_key_bits(const void* mask, int elem_size, uint32_t* bits, int B, int T, void* stream);
+int unimp_lm_attn_fwd(const void* q, const void* k, const void* v, int64_t batch_stride,
+                      int64_t row_stride, int64_t head_stride, const uint32_t* key_bits, void* o,
+                      float* lse, int B, int T, int H, int dh, float scale, int dtype, void* stream);
+int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, int64_t batch_stride,
+                      int64_t row_stride, int64_t head_stride, const uint32_t* key_bits,
+                      const void* o, const void* d_o, const float* lse, float* dq32, void* dk,
+                      void* dv, int B, int T, int H, int dh, float scale, int dtype, void* stream);
 /* CLIP QuickGELU x*sigmoid(1.702x), in place (ViT MLP; forward only: the tower is frozen). */
 int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream);
 /* Exact (erf) GELU of the FeedForward blocks: open_flamingo helpers.FeedForward's nn.GELU()

@@ -98,8 +98,9 @@ def test_ctypes_signatures_match_the_header_prototypes():
 
 
 def _entry_points():
-    skip = {"unimp_version", "unimp_last_error_string", "unimp_device_ok", "unimp_xattn_block_supported"}
-    return sorted(n for n in _lib.SIGNATURES if n not in skip and not n.endswith("_workspace"))
+    skip = {"unimp_version", "unimp_last_error_string", "unimp_device_ok"}
+    return sorted(n for n in _lib.SIGNATURES
+                  if n not in skip and not n.endswith("_workspace") and not n.endswith("_supported"))
 
 
 def _null_args(name):

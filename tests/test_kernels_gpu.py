@@ -410,6 +410,150 @@ def test_fused_neox_layer_matches_hf_layer(dtype, tol, parallel):
     assert rel_err(xb.grad, xa.grad) < tol
 
 
+# ------------------------------------------------------------------ K4: LM causal attention, head dim 80
+
+def _key_mask(kind, B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "none":
+        return None
+    m = torch.ones(B, T, dtype=torch.int64)
+    for b in range(B):
+        n = int(torch.randint(1, max(2, T // 2), (1,), generator=g))
+        if kind == "right":
+            m[b, T - n:] = 0
+        elif kind == "left":
+            m[b, :n] = 0
+        else:  # holes: any 2-D mask is legal input
+            m[b] = (torch.rand(T, generator=g) > 0.3).long()
+            m[b, 0] = 1
+    if kind == "right":
+        m[0] = 1  # one full-length sample, like a real batch
+    return m
+
+
+def _lm_attn_ref(packed, H, dh, key_mask, scale):
+    """fp64 dense softmax(scale q k^T + causal & key mask) v on the packed (B,T,H,3,dh) projection;
+    rows that see no key give 0 (HF/SDPA would give NaN there; such rows are padding)."""
+    B, T, _ = packed.shape
+    q, k, v = (packed.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+    sim = (q @ k.transpose(-1, -2)) * scale
+    vis = torch.ones(T, T, dtype=torch.bool, device=packed.device).tril()[None, None]
+    if key_mask is not None:
+        vis = vis & key_mask.bool()[:, None, None, :]
+    sim = sim.masked_fill(~vis, float("-inf"))
+    none = ~vis.any(-1, keepdim=True)
+    p = torch.softmax(sim.masked_fill(none, 0.0), -1).masked_fill(none, 0.0)
+    return (p @ v).transpose(1, 2).reshape(B, T, H * dh), none.expand(B, H, T, 1)[..., 0]
+
+
+@pytest.mark.parametrize("kind", ["none", "right", "left", "holes"])
+@pytest.mark.parametrize("B,T,H", [(2, 24, 4), (1, 200, 3), (3, 256, 32), (2, 513, 2)])
+def test_lm_attention_matches_fp64_dense_reference(B, T, H, kind):
+    """unimp_lm_attn_fwd/bwd (tcgen05, head dim 80 as two TMA panels) vs the fp64 dense form of
+    HF GPTNeoXAttention's core, on q/k/v views of ONE packed projection (the real strides), with
+    no / right / left padding and an arbitrary 2-D mask.  bf16 bar 2e-2 (north star)."""
+    dh = 80
+    torch.manual_seed(T + H)
+    packed = torch.randn(B, T, H * 3 * dh, device=DEV, dtype=torch.bfloat16)
+    go = torch.randn(B, T, H * dh, device=DEV, dtype=torch.bfloat16)
+    km = _key_mask(kind, B, T, seed=T)
+    km_d = km.to(DEV) if km is not None else None
+    bits = ops().key_bits(km_d) if km is not None else None
+    if km is not None:  # the packing itself, bit-exact
+        w = bits.cpu().long() & 0xffffffff
+        for b in range(B):
+            for j in range(T):
+                assert ((int(w[b, j // 32]) >> (j % 32)) & 1) == int(km[b, j])
+    pk = packed.clone().requires_grad_(True)
+    q, k, v = (pk.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+    o = ops().lm_attention(q, k, v, bits, scale=dh ** -0.5)
+    o.backward(go)
+    r = packed.double().requires_grad_(True)
+    want, none = _lm_attn_ref(r, H, dh, km_d, dh ** -0.5)
+    want.backward(go.double())
+    assert torch.isfinite(o).all() and torch.isfinite(pk.grad).all()
+    assert_close(o, want, 2e-2, f"o {kind}")
+    assert_close(pk.grad, r.grad, 2e-2, f"d_qkv {kind}")
+    dead = none.transpose(1, 2)[..., None].expand(B, T, H, dh).reshape(B, T, H * dh)
+    assert o.detach()[dead].abs().max().item() == 0 if dead.any() else True
+
+
+def test_lm_attention_full_size_and_causality():
+    """configs[2] shape (6 fused samples, T=1024, 32 heads x 80): fp64 dense reference on a slice of
+    heads, and the size-independent property that changing token t changes no output row before t."""
+    B, T, H, dh = 6, 1024, 32, 80
+    torch.manual_seed(3)
+    packed = torch.randn(B, T, H * 3 * dh, device=DEV, dtype=torch.bfloat16)
+    km = _key_mask("right", B, T, seed=5).to(DEV)
+    bits = ops().key_bits(km)
+    pk = packed.clone().requires_grad_(True)
+    q, k, v = (pk.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+    o = ops().lm_attention(q, k, v, bits, scale=dh ** -0.5)
+    go = torch.randn_like(o)
+    o.backward(go)
+    for h0 in (0, 17, 31):  # fp64 dense on single heads (B x T x T doubles each)
+        sl = packed.view(B, T, H, 3 * dh)[:, :, h0].double().requires_grad_(True)
+        want, _ = _lm_attn_ref(sl, 1, dh, km, dh ** -0.5)
+        gsl = go.view(B, T, H, dh)[:, :, h0].double()
+        want.backward(gsl)
+        assert_close(o.view(B, T, H, dh)[:, :, h0], want, 2e-2, f"o head {h0}")
+        assert_close(pk.grad.view(B, T, H, 3 * dh)[:, :, h0], sl.grad, 2e-2, f"d_qkv head {h0}")
+    t = 700
+    p2 = packed.clone()
+    p2[:, t] += 1.0
+    q2, k2, v2 = (p2.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+    o2 = ops().lm_attention(q2, k2, v2, bits, scale=dh ** -0.5)
+    assert torch.equal(o2[:, :t], o.detach()[:, :t])
+    assert (o2[:, t] != o.detach()[:, t]).any()
+
+
+@pytest.mark.parametrize("pad", [False, True])
+def test_fused_neox_layer_with_own_attention_matches_hf_layer(pad):
+    """fused_neox_layer on `unimp_lm_attn_*` (bf16, 32 heads x 80, the RedPajama-3B geometry at
+    reduced width) == HF GPTNeoXLayer with the 4-D mask HF builds from a right-padded 2-D mask."""
+    from transformers import GPTNeoXConfig
+    from transformers.models.gpt_neox.modeling_gpt_neox import GPTNeoXLayer, GPTNeoXRotaryEmbedding
+
+    from unimp_b200 import flamingo_lm
+    from unimp_b200.flamingo_lm import fused_neox_layer
+
+    torch.manual_seed(0)
+    cfg = GPTNeoXConfig(hidden_size=320, num_hidden_layers=1, num_attention_heads=4, intermediate_size=640,
+                        vocab_size=128, use_parallel_residual=False, hidden_dropout=0.0, attention_dropout=0.0,
+                        rotary_pct=1.0)
+    cfg._attn_implementation = "sdpa"
+    dt = torch.bfloat16
+    layer = GPTNeoXLayer(cfg, 0).to(DEV, dt)
+    rope = GPTNeoXRotaryEmbedding(cfg).to(DEV)
+    B, T = 3, 200
+    x = torch.randn(B, T, 320, device=DEV, dtype=dt)
+    pe = rope(x, torch.arange(T, device=DEV)[None])
+    g = torch.randn_like(x)
+    km = torch.ones(B, T, dtype=torch.int64, device=DEV)
+    if pad:
+        km[1, 150:] = 0
+        km[2, 37:] = 0
+    mask4 = (torch.ones(T, T, dtype=torch.bool, device=DEV).tril()[None, None] & km.bool()[:, None, None, :]) \
+        if pad else None
+    xa = x.clone().requires_grad_(True)
+    ya = layer(xa, attention_mask=mask4, position_embeddings=pe)
+    ya.backward(g * km[..., None].to(dt))      # padded rows carry no loss
+    xb = x.clone().requires_grad_(True)
+    assert flamingo_lm.LM_ATTN
+    calls = []
+    orig = ops().lm_attention
+    ops().lm_attention = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        yb = fused_neox_layer(layer, xb, mask4, pe, key_bits=ops().key_bits(km) if pad else True)
+    finally:
+        ops().lm_attention = orig
+    assert calls, "the layer did not run on unimp_lm_attn_fwd"
+    yb.backward(g * km[..., None].to(dt))
+    keep = km.bool()
+    assert rel_err(yb[keep], ya[keep]) < 2e-2
+    assert rel_err(xb.grad[keep], xa.grad[keep]) < 2e-2
+
+
 # ------------------------------------------------------------------ full-size property checks
 
 def test_xattn_full_size_tc_equals_fp64_dense_oracle_and_blocks_are_independent():

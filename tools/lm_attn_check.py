@@ -1,0 +1,100 @@
+"""On-GPU check + timing of the K4 kernels (unimp_lm_attn_fwd/bwd) against fp64 dense / cuDNN SDPA.
+usage: python tools/lm_attn_check.py [check] [bench]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unimp_b200 import ops  # noqa: E402
+
+dev, bf, dh = "cuda", torch.bfloat16, 80
+
+
+def views(pk, B, T, H):
+    return tuple(pk.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+
+
+def ref(packed, H, km, scale):
+    B, T, _ = packed.shape
+    q, k, v = views(packed, B, T, H)
+    sim = (q @ k.transpose(-1, -2)) * scale
+    vis = torch.ones(T, T, dtype=torch.bool, device=packed.device).tril()[None, None]
+    if km is not None:
+        vis = vis & km.bool()[:, None, None, :]
+    sim = sim.masked_fill(~vis, float("-inf"))
+    none = ~vis.any(-1, keepdim=True)
+    p = torch.softmax(sim.masked_fill(none, 0.0), -1).masked_fill(none, 0.0)
+    return (p @ v).transpose(1, 2).reshape(B, T, H * dh)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def check(B, T, H, pad):
+    torch.manual_seed(T)
+    packed = torch.randn(B, T, H * 3 * dh, device=dev, dtype=bf)
+    go = torch.randn(B, T, H * dh, device=dev, dtype=bf)
+    km = None
+    if pad:
+        km = torch.ones(B, T, dtype=torch.int64, device=dev)
+        for b in range(1, B):
+            km[b, T - (b * 37) % (T // 2) - 1:] = 0
+    bits = ops.key_bits(km) if pad else None
+    pk = packed.clone().requires_grad_(True)
+    o = ops.lm_attention(*views(pk, B, T, H), bits, scale=dh ** -0.5)
+    o.backward(go)
+    torch.cuda.synchronize()
+    r = packed.double().requires_grad_(True)
+    want = ref(r, H, km, dh ** -0.5)
+    want.backward(go.double())
+    g, gr = pk.grad.view(B, T, H, 3, dh), r.grad.view(B, T, H, 3, dh)
+    print(f"LM check B={B} T={T} H={H} pad={pad}: o {rel(o, want):.2e}  dq {rel(g[..., 0, :], gr[..., 0, :]):.2e}  "
+          f"dk {rel(g[..., 1, :], gr[..., 1, :]):.2e}  dv {rel(g[..., 2, :], gr[..., 2, :]):.2e}  "
+          f"nan {int(torch.isnan(o).sum())}/{int(torch.isnan(pk.grad).sum())}", flush=True)
+
+
+def bench(B, T, H, sets=8, iters=5):
+    F = torch.nn.functional
+    packs = [torch.randn(B, T, H * 3 * dh, device=dev, dtype=bf, requires_grad=True) for _ in range(sets)]
+    gos = [torch.randn(B, T, H * dh, device=dev, dtype=bf) for _ in range(sets)]
+
+    def run(fn):
+        outs = [fn(p) for p in packs]                      # warm-up + graphs for backward timing
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        for _ in range(iters):
+            outs = [fn(p) for p in packs]
+        e[1].record()
+        torch.cuda.synchronize()
+        fwd = e[0].elapsed_time(e[1]) / (iters * sets) * 1e3
+        e[2].record()
+        for _ in range(iters):
+            for o, p, g in zip(outs, packs, gos):
+                torch.autograd.grad(o, p, g, retain_graph=True)
+        e[3].record()
+        torch.cuda.synchronize()
+        return fwd, e[2].elapsed_time(e[3]) / (iters * sets) * 1e3
+
+    ours = run(lambda p: ops.lm_attention(*views(p, B, T, H), None, scale=dh ** -0.5))
+    sdpa = run(lambda p: F.scaled_dot_product_attention(*views(p, B, T, H), is_causal=True, scale=dh ** -0.5)
+               .transpose(1, 2).reshape(B, T, H * dh))
+    flops = 4 * B * H * T * T * dh / 2
+    print(f"LM bench B={B} T={T} H={H}: ours fwd {ours[0]:.1f} us ({flops / ours[0] / 1e6:.0f} TFLOP/s) "
+          f"fwd+bwd-launch {ours[1]:.1f} us | SDPA fwd {sdpa[0]:.1f} us bwd {sdpa[1]:.1f} us "
+          f"(eager loops: launch overhead included on both sides)", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["check", "bench"]
+    if "check" in what:
+        for B, T, H, pad in [(1, 64, 1, False), (1, 128, 1, False), (2, 24, 4, False), (1, 200, 3, True),
+                             (3, 256, 32, True), (2, 513, 2, True), (6, 1024, 32, True)]:
+            check(B, T, H, pad)
+    if "bench" in what:
+        with torch.no_grad():
+            pass
+        bench(6, 256, 32)
+        bench(6, 1024, 32, sets=4, iters=3)

@@ -11,6 +11,8 @@ from the one-pass focal-CE kernel rather than HF's fp32 upcast + CrossEntropyLos
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Optional
 
@@ -169,6 +171,9 @@ def _is_exact_gelu(act) -> bool:
     return isinstance(act, torch.nn.GELU) and act.approximate == "none"
 
 
+# K4 on our own kernel (bf16, head dim 80); UNIMP_LM_ATTN=0 keeps cuDNN SDPA for A/B runs
+LM_ATTN = os.environ.get("UNIMP_LM_ATTN", "1") != "0"
+
 _MASK_CACHE = [None, None, None]   # (bool mask object, (dtype, version), additive mask)
 
 
@@ -185,12 +190,15 @@ def _additive_mask(mask, dtype):
     return _MASK_CACHE[2]
 
 
-def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None, kv_step=None):
+def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, next_ln=None, kv_step=None,
+                     key_bits=None):
     """HF `GPTNeoXLayer.forward` (transformers gpt_neox, no cache) with its elementwise glue on
-    our kernels: LayerNorms and residual adds are K5 launches, rotary runs in place on the packed
-    qkv projection (`unimp_rotary_qkv_*`), q/k/v reach SDPA as strided views.  GEMMs stay on
-    cuBLAS and the causal attention core on cuDNN SDPA (K4: not in the north star).  Same
-    parameters, same arithmetic; ~11 launches instead of ~30 per layer.
+    our kernels: LayerNorms and residual adds are K5 launches, rotary runs on the packed qkv
+    projection (`unimp_rotary_qkv_*`), the causal attention core is `unimp_lm_attn_*` (K4: bf16,
+    head dim 80, `key_bits` given) and otherwise SDPA over strided views.  GEMMs stay on cuBLAS.
+    Same parameters, same arithmetic; ~11 launches instead of ~30 per layer.
+    `key_bits`: True = causal only, or `ops.key_bits(attention_mask_2d)`; the caller vouches that
+    `attention_mask` (the 4-D mask HF built) is exactly causal & those key bits.
     `h1`: input_layernorm(x) if the caller already produced it in a fused epilogue.
     `next_ln`: the LayerNorm that reads this layer's output first (next layer's x-attn norm or
     input_layernorm); if given, returns (y, next_ln(y)) from the same launch as the last residual.
@@ -208,16 +216,20 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     cos, sin = position_embeddings
     q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
                              rotary_dim=rot)
-    attention_mask = _additive_mask(attention_mask, x.dtype)
-    if kv_step is not None:
-        k_cache, v_cache, cursor = kv_step
-        k_cache.index_copy_(2, cursor, k)
-        v_cache.index_copy_(2, cursor, v)
-        k, v = k_cache, v_cache
-    a = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0,
-                                       is_causal=attention_mask is None and T > 1 and kv_step is None,
-                                       scale=att.scaling)
-    o = F.linear(a.transpose(1, 2).reshape(B, T, D), att.dense.weight, att.dense.bias)
+    if key_bits is not None and kv_step is None and LM_ATTN and ops.lm_attention_supported(q):
+        a = ops.lm_attention(q, k, v, None if key_bits is True else key_bits, scale=att.scaling)
+    else:
+        attention_mask = _additive_mask(attention_mask, x.dtype)
+        if kv_step is not None:
+            k_cache, v_cache, cursor = kv_step
+            k_cache.index_copy_(2, cursor, k)
+            v_cache.index_copy_(2, cursor, v)
+            k, v = k_cache, v_cache
+        a = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0,
+                                           is_causal=attention_mask is None and T > 1 and kv_step is None,
+                                           scale=att.scaling)
+        a = a.transpose(1, 2).reshape(B, T, D)
+    o = F.linear(a, att.dense.weight, att.dense.bias)
     mlp = layer.mlp
     act = ops.gelu if _is_exact_gelu(mlp.act) else mlp.act
     if layer.use_parallel_residual:
@@ -243,6 +255,7 @@ class FlamingoLayer(nn.Module):
         self.media_locations = None
         self.text_time = None
         self.use_cached_media = False
+        self.lm_key_bits = None      # set per forward by FlamingoLMMixin.forward (fused_neox_layer)
         self._next_holder = [None]   # next FlamingoLayer (a list: not a registered submodule)
         self._pre = None             # (x, first_ln(x)) handed over by the previous layer
 
@@ -289,7 +302,8 @@ class FlamingoLayer(nn.Module):
             lang_x, h1 = out if fuse else (out, None)
         if fuse:
             out = fused_neox_layer(self.decoder_layer, lang_x, attention_mask,
-                                   decoder_layer_kwargs["position_embeddings"], h1, next_ln)
+                                   decoder_layer_kwargs["position_embeddings"], h1, next_ln,
+                                   key_bits=self.lm_key_bits)
             if next_ln is not None:
                 y, y_ln = out
                 nxt._pre = (y, y_ln)   # consumed (and cleared) by the next layer's forward
@@ -365,9 +379,23 @@ class FlamingoLMMixin(nn.Module):
         else:
             kwargs["input_ids"] = input_ids
         kwargs["attention_mask"] = attention_mask
-        if label_rows is not None and label_rows is not False:
-            return self._forward_label_rows(labels, label_rows, kwargs)
-        out = super().forward(**kwargs)  # HF forward without labels: no fp32 logits copy
+        # K4: with no KV cache HF's 4-D mask is exactly causal & key padding; hand the layers the
+        # padding as one bit per key (they fall back to SDPA with HF's mask for anything else)
+        kb = None
+        if input_ids.is_cuda and kwargs.get("past_key_values") is None and not use_cached:
+            if attention_mask is None:
+                kb = True
+            elif attention_mask.dim() == 2 and attention_mask.shape == input_ids.shape:
+                kb = ops.key_bits(attention_mask)
+        for layer in layers:
+            layer.lm_key_bits = kb
+        try:
+            if label_rows is not None and label_rows is not False:
+                return self._forward_label_rows(labels, label_rows, kwargs)
+            out = super().forward(**kwargs)  # HF forward without labels: no fp32 logits copy
+        finally:
+            for layer in layers:
+                layer.lm_key_bits = None
         if labels is None:
             return out
         logits = out.logits

@@ -556,6 +556,68 @@ def rotary_qkv(qkv, cos, sin, *, heads: int, head_dim: int, rotary_dim: int):
     return _RotaryQKV.apply(qkv, cos, sin, heads, head_dim, rotary_dim)
 
 
+class _LMAttention(torch.autograd.Function):
+    """K4: causal (+ key padding) self-attention of a GPT-NeoX layer, head dim 80, bf16
+    (`unimp_lm_attn_fwd/bwd`).  q,k,v: (B,H,T,dh) views of the rotated packed projection."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_bits, scale):
+        B, H, T, dh = q.shape
+        assert q.stride() == k.stride() == v.stride() and q.stride(3) == 1
+        o = torch.empty((B, T, H * dh), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+        kb = key_bits.data_ptr() if key_bits is not None else None
+        check(_lib.load().unimp_lm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), q.stride(2),
+                                            q.stride(1), kb, o.data_ptr(), lse.data_ptr(), B, T, H, dh,
+                                            float(scale), _dt(q), _stream()), "unimp_lm_attn_fwd")
+        ctx.save_for_backward(q, k, v, o, lse, key_bits)
+        ctx.scale = float(scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse, key_bits = ctx.saved_tensors
+        B, H, T, dh = q.shape
+        d_o = d_o.contiguous()
+        dq32 = torch.empty((B, T, H, dh), dtype=torch.float32, device=q.device)
+        dk = torch.empty((B, T, H, dh), dtype=q.dtype, device=q.device)
+        dv = torch.empty_like(dk)
+        kb = key_bits.data_ptr() if key_bits is not None else None
+        check(_lib.load().unimp_lm_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), q.stride(2),
+                                            q.stride(1), kb, o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                            dq32.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, H, dh,
+                                            ctx.scale, _dt(q), _stream()), "unimp_lm_attn_bwd")
+        return (dq32.to(q.dtype).transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None)
+
+
+def lm_attention_supported(q) -> bool:
+    """bf16, head dim 80 (RedPajama-INCITE 3B: 32 heads x 80)."""
+    B, H, T, dh = q.shape
+    return q.is_cuda and bool(_lib.load().unimp_lm_attn_supported(T, H, dh, _dt(q)))
+
+
+def key_bits(attention_mask):
+    """(B,T) attention_mask (bool / uint8 / int64; nonzero = real token) -> (B, 2*ceil(T/64)) int32
+    words of 32 keys for `lm_attention`."""
+    m = attention_mask
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    elif m.dtype not in (torch.uint8, torch.int64):
+        m = m.to(torch.int64)
+    m = m.contiguous()
+    B, T = m.shape
+    bits = torch.empty((B, 2 * ((T + 63) // 64)), dtype=torch.int32, device=m.device)
+    check(_lib.load().unimp_key_bits(m.data_ptr(), m.element_size(), bits.data_ptr(), B, T, _stream()),
+          "unimp_key_bits")
+    return bits
+
+
+def lm_attention(q, k, v, key_bits=None, *, scale: float):
+    """softmax(scale*q k^T + causal & key-padding mask) v; q,k,v (B,H,T,dh) strided views sharing one
+    layout -> (B,T,H*dh) contiguous (what `GPTNeoXAttention.dense` consumes)."""
+    return _LMAttention.apply(q, k, v, key_bits, scale)
+
+
 def quick_gelu_(x):
     """In-place CLIP QuickGELU (no autograd: used inside the frozen, no_grad vision tower)."""
     assert x.is_contiguous()
