@@ -233,8 +233,8 @@ int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const i
  * (elements) — the rotated packed projection; o, d_o: (B,T,H*dh) contiguous; lse (B,H,T) fp32.
  * unimp_key_bits packs an attention_mask (B,T) of bool/uint8 (elem_size 1) or int64 (8),
  * nonzero = real token, into (B, 2*ceil(T/64)) words of 32 keys.
- * Backward: dq32 (B,T,H,dh) fp32 (zeroed and accumulated by the call), dk, dv (B,T,H,dh) in
- * `dtype`, contiguous.  bf16, dh == 80 only (unimp_lm_attn_supported); rows that see no key
+ * Backward: dq32 (B,H,Tp,84) fp32 scratch, Tp = T rounded up to 128 (zeroed and accumulated by
+ * the call; dq = dq32[:, :, :T, :80]), dk, dv (B,T,H,dh) in `dtype`, contiguous.  bf16, dh == 80 only (unimp_lm_attn_supported); rows that see no key
  * give o = 0. */
 int unimp_lm_attn_supported(int T, int H, int dh, int dtype);
 int unimp_key_bits(const void* mask, int elem_size, uint32_t* bits, int B, int T, void* stream);

@@ -3,5 +3,7 @@ mkdir -p gpurun_out
 P=${1:-lm}
 timeout 300 python tools/lm_attn_check.py check > gpurun_out/${P}_lm_check.log 2>&1
 grep -E "LM check|unimp|Error|error" gpurun_out/${P}_lm_check.log | head -20
-timeout 300 python tools/lm_attn_check.py bench > gpurun_out/${P}_lm_bench.log 2>&1
-grep -E "LM bench|unimp|Error|error" gpurun_out/${P}_lm_bench.log | head
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "attention or attn or perceiver or vit or lm_" > gpurun_out/${P}_pytest.log 2>&1
+tail -5 gpurun_out/${P}_pytest.log
+timeout 300 python tools/kbench_cli.py --workload C2-rec --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB"
+timeout 300 python tools/kbench_cli.py --workload C3-multitask --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB"

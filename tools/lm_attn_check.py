@@ -88,7 +88,7 @@ def bench(B, T, H, sets=8, iters=5):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["check", "bench"]
+    what = sys.argv[1:] or ["check"]
     if "check" in what:
         for B, T, H, pad in [(1, 64, 1, False), (1, 128, 1, False), (2, 24, 4, False), (1, 200, 3, True),
                              (3, 256, 32, True), (2, 513, 2, True), (6, 1024, 32, True)]:
@@ -98,3 +98,52 @@ if __name__ == "__main__":
             pass
         bench(6, 256, 32)
         bench(6, 1024, 32, sets=4, iters=3)
+
+
+def timeline(kind):
+    """Per-CTA step stamps of one flash_fwd launch (unimp__flash_fwd_debug hook)."""
+    import ctypes
+    from unimp_b200 import _lib
+    lib = _lib.load()
+    f = lib.unimp__flash_fwd_debug
+    f.argtypes = [ctypes.c_void_p]
+    f.restype = None
+    if kind == "lm":
+        B, T, H = 6, 1024, 32
+        pk = torch.randn(B, T, H * 3 * dh, device=dev, dtype=bf)
+        run = lambda: ops.lm_attention(*views(pk, B, T, H), None, scale=dh ** -0.5)
+        n_cta = (T // 128) * H * B
+    else:
+        Bt, L, Hh = 48, 257, 16
+        q = torch.randn(Bt, L, Hh * 64, device=dev, dtype=bf)
+        kv = torch.randn(Bt, L, 2 * Hh * 64, device=dev, dtype=bf)
+        run = lambda: ops.attention(q, kv, heads=Hh, scale=0.125)
+        n_cta = 3 * Hh * Bt
+    buf = torch.zeros(n_cta * 64, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        f(buf.data_ptr())
+        run()
+        torch.cuda.synchronize()
+        f(None)
+    t = buf.view(n_cta, 64).cpu().double()
+    t0 = t[:, 0].min()
+    span = (t[:, 3].max() - t0)
+    print(f"FF timeline {kind}: {n_cta} CTAs, first start to last end {span:.0f} ns; per-CTA start->ready "
+          f"{(t[:, 1] - t[:, 0]).median():.0f}, ready->last PV {(t[:, 2] - t[:, 1]).median():.0f}, epilogue "
+          f"{(t[:, 3] - t[:, 2]).median():.0f}")
+    full = t[t[:, 8 + 4 * 6 + 5] > 0]      # CTAs with >= 5 steps
+    print(f"FF   {len(full)} CTAs with >= 5 steps; medians over them, ns relative to the CTA's 'ready' stamp:")
+    for j in range(5):
+        s = 8 + j * 6
+        rel = lambda k: (full[:, s + k] - full[:, 1]).median()
+        print(f"FF   step {j}: worker S ready {rel(2):7.0f} | exps done {rel(3):7.0f} | PV(j-1) seen "
+              f"{rel(4) if j else float('nan'):7.0f} | arrived {rel(5):7.0f} || issuer got P {rel(0):7.0f} | "
+              f"issuer step done {rel(1):7.0f}", flush=True)
+
+
+if "timeline" in sys.argv[1:]:
+    timeline("lm")
+    timeline("vit")

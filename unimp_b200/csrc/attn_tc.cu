@@ -557,10 +557,10 @@ int make_tmap_bhld(CUtensorMap* out, const void* base, int64_t batch_stride, int
   return 0;
 }
 
-// Generic bf16 tiled map, SWIZZLE_128B (box inner extent = 64 elements = 128 bytes), zero fill out
-// of range.  dims / box: innermost first; strides_bytes: rank-1 entries (dims 1..rank-1).
-int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box) {
+// Generic bf16 tiled map, zero fill out of range.  dims / box: innermost first; strides_bytes:
+// rank-1 entries (dims 1..rank-1).  swizzle_bytes: 128 (box inner extent 64 elements) or 32 (16).
+int make_tmap_tiled_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return UNIMP_E_DEVICE; }
   static thread_local bool ctx_bound = false;
@@ -575,7 +575,8 @@ int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, bx,
-                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=%llu,%llu", (int)r, base, rank,
@@ -583,6 +584,11 @@ int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t
     return UNIMP_E_SHAPE;
   }
   return 0;
+}
+
+int make_tmap_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_tiled_sw(out, base, rank, dims, strides_bytes, box, 128);
 }
 
 static bool view_ok(const void* p, int64_t bs, int64_t rs) {
@@ -660,10 +666,17 @@ static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, cons
   return 0;
 }
 
+int launch_flash_fwd_64(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o, float* lse, int B,
+                        int Lq, int Lk, int H, float scale, cudaStream_t st);
+
 int launch_attn_fwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt, unimp_mview_t o,
                        float* lse, int B, int Lq, int Lk, int H, int n, int Ti, float scale,
                        cudaStream_t st) {
   if (tt) return launch_xattn_fwd(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
+  // one-sweep kernel (flash_fwd.cu); UNIMP_ATTN_FWD2=1 keeps the two-sweep kernel for A/B runs
+  static const bool two_sweep = getenv("UNIMP_ATTN_FWD2") && atoi(getenv("UNIMP_ATTN_FWD2")) != 0;
+  if (!two_sweep && k.batch_stride == v.batch_stride && k.row_stride == v.row_stride)
+    return launch_flash_fwd_64(q, k, v, o, lse, B, Lq, Lk, H, scale, st);
   return launch_attn_fwd2(q, k, v, o, lse, B, Lq, Lk, H, scale, st);
 }
 

@@ -1,0 +1,452 @@
+// One-sweep attention forward on tcgen05 (round 2, second generation of the unmasked / causal cores).
+//
+//   K2  Perceiver latent attention 64 x 320, K3 ViT-L/14 self-attention 257 x 257  (DH = 64)
+//   K4  GPT-NeoX causal self-attention with key padding                            (DH = 80)
+//
+// vs attn_fwd2_tc_kernel (two sweeps, S recomputed) and the first lm_attn_fwd_kernel:
+//   * ONE sweep over the key blocks with an online softmax; O is rescaled in TMEM only when a row's
+//     running maximum grows by more than 2^8 (rare after the first blocks), so the common step is
+//     S -> registers -> exp2 -> P (bf16, shared) with no TMEM round trip of O;
+//   * S is double-buffered in TMEM (2 x 64 columns): S_{j+1} = Q K_{j+1}^T runs on the tensor pipe
+//     while the 128 softmax threads work on S_j, and PV_j runs while they work on S_{j+1};
+//   * K and V travel through separate TMA rings (4 and 3 stages): K_{j+4} is requested as soon as
+//     S_j has been consumed, V_{j+3} as soon as PV_j has finished — two steps of slack each;
+//   * head dim 80 = a 64-column SWIZZLE_128B panel + a 16-column SWIZZLE_32B panel (2 KB per 64-row
+//     tile instead of the 8 KB a zero-padded 128-byte panel costs): 106 KB of shared memory, two
+//     CTAs per SM.
+// CTA = (128-query tile, head, sample); warps 0-3: one query row per thread (TMEM lane = row);
+// warp 4: one elected lane issues every TMA and tcgen05.mma.  All mbarrier waits are bounded.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace unimp {
+namespace ff {
+
+using namespace tc;
+
+constexpr int TQ = 128, KB = 64, THREADS = TQ + 32;
+constexpr int NK = 4, NV = 3;                 // K / V ring depths
+constexpr uint32_t QP0 = TQ * 128;            // [128][64] bf16, SWIZZLE_128B
+constexpr uint32_t QP1 = TQ * 32;             // [128][16] bf16, SWIZZLE_32B
+constexpr uint32_t KP0 = KB * 128, KP1 = KB * 32;
+constexpr uint32_t PB = TQ * 128;
+
+struct Args {
+  unsigned long long* dbg;   // test hook (unimp__flash_fwd_debug): 64 x u64 %globaltimer stamps per CTA, NULL = off
+  __nv_bfloat16* o;
+  int64_t o_bs, o_rs;        // o[b][row][h*DH + d]
+  float* lse;                // (B,H,Lq)
+  const uint32_t* kbits;     // (B, kwords) key-valid bits or NULL
+  int kwords;
+  int Lq, Lk, H;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// stamp slot: step j < 8 -> 8 + j*6 + k ; k: 0 issuer got P_j, 1 issuer done with step j,
+// 2 worker got S_j, 3 worker exps done, 4 worker got PV_{j-1}, 5 worker arrived
+#define FF_STAMP(slot)                                                                                   \
+  do {                                                                                                   \
+    if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = now_ns(); \
+  } while (0)
+
+// SWIZZLE_32B shared-memory descriptor (layout type 6): rows of 32 bytes, 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void store_half(uint8_t* tile, int row, int half, const float* p) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v;
+    v.x = pack2(p[8 * c + 0], p[8 * c + 1]);
+    v.y = pack2(p[8 * c + 2], p[8 * c + 3]);
+    v.z = pack2(p[8 * c + 4], p[8 * c + 5]);
+    v.w = pack2(p[8 * c + 6], p[8 * c + 7]);
+    *reinterpret_cast<uint4*>(tile + sw128_offset(row, half * 4 + c)) = v;
+  }
+}
+__device__ __forceinline__ void store_bf16(__nv_bfloat16* dst, const uint32_t* r, int n, float mul) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c * 8 < n) {
+      uint4 v;
+      v.x = pack2(__uint_as_float(r[8 * c + 0]) * mul, __uint_as_float(r[8 * c + 1]) * mul);
+      v.y = pack2(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul);
+      v.z = pack2(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul);
+      v.w = pack2(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul);
+      *reinterpret_cast<uint4*>(dst + c * 8) = v;
+    }
+  }
+}
+
+template <bool CAUSAL>
+__device__ __forceinline__ uint64_t visible(const Args& a, int b, int j, int row) {
+  uint64_t m = ~0ull;
+  if (CAUSAL) {
+    const int d = row - j * KB;
+    m = d < 0 ? 0ull : (d >= 63 ? ~0ull : ((2ull << d) - 1ull));
+  }
+  const int rem = a.Lk - j * KB;               // keys of this block that exist
+  if (rem < KB) m &= rem <= 0 ? 0ull : ((1ull << rem) - 1ull);
+  if (a.kbits) {
+    const uint32_t* w = a.kbits + (int64_t)b * a.kwords + 2 * j;
+    m &= (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+  }
+  return m;
+}
+
+template <int DH>
+struct Smem {
+  static constexpr bool P1 = DH > 64;
+  static constexpr uint32_t KST = KP0 + (P1 ? KP1 : 0);       // one K (or V) stage
+  static constexpr uint32_t Q0 = 0, Q1 = QP0, KR = Q1 + (P1 ? QP1 : 0), VR = KR + NK * KST,
+                            P = VR + NV * KST, BAR = P + PB, TOTAL = BAR + 128;
+};
+
+template <int DH, bool CAUSAL>
+__global__ void __launch_bounds__(THREADS, 2)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tq1,
+                 const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1, const Args a) {
+  using L = Smem<DH>;
+  constexpr bool P1 = L::P1;
+  constexpr uint32_t S_COL = 0, O0_COL = 128, O1_COL = 192, TMEM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 1 + NK, *bar_s = bars + 1 + NK + NV,
+           *bar_p = bar_s + 2, *bar_pv = bar_s + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = tid < TQ;
+  if (tid == 0) FF_STAMP(0);
+  const int qt = CAUSAL ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;   // causal: long tiles first
+  const int row0 = qt * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int nb_all = (a.Lk + KB - 1) / KB;
+  const int nb = CAUSAL ? min(nb_all, (row0 + TQ) / KB) : nb_all;
+
+  auto load_k = [&](int j) {
+    const int st = j % NK;
+    uint8_t* dst = smem + L::KR + st * L::KST;
+    mbar_arrive_expect_tx(&bar_k[st], L::KST);
+    tma_load_4d(dst, &tk, &bar_k[st], 0, h, j * KB, b);
+    if (P1) tma_load_4d(dst + KP0, &tk1, &bar_k[st], 64, h, j * KB, b);
+  };
+  auto load_v = [&](int j) {
+    const int st = j % NV;
+    uint8_t* dst = smem + L::VR + st * L::KST;
+    mbar_arrive_expect_tx(&bar_v[st], L::KST);
+    tma_load_4d(dst, &tv, &bar_v[st], 0, h, j * KB, b);
+    if (P1) tma_load_4d(dst + KP0, &tv1, &bar_v[st], 64, h, j * KB, b);
+  };
+
+  if (warp == 4) {
+    if (elect_one_sync()) {
+      if (smem_u32(smem) & 1023u) {
+        printf("unimp: flash_fwd: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+      }
+      mbar_init(bar_q, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 4);
+      mbar_init(bar_pv, 1);
+#pragma unroll
+      for (int i = 0; i < NK; ++i) mbar_init(&bar_k[i], 1);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) mbar_init(&bar_v[i], 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(bar_q, QP0 + (P1 ? QP1 : 0));
+      tma_load_4d(smem + L::Q0, &tq, bar_q, 0, h, row0, b);
+      if (P1) tma_load_4d(smem + L::Q1, &tq1, bar_q, 64, h, row0, b);
+      for (int j = 0; j < nb && j < NK; ++j) load_k(j);
+      for (int j = 0; j < nb && j < NV; ++j) load_v(j);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  if (tid == 0) FF_STAMP(1);
+
+  if (warp == 4 && elect_one_sync()) {
+    constexpr uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
+    constexpr uint32_t idesc_o0 = make_idesc(TQ, 64, 0, 1);
+    constexpr uint32_t idesc_o1 = make_idesc(TQ, 16, 0, 1);
+    const uint32_t su = smem_u32(smem);
+    auto issue_s = [&](int j) {                     // S_j = Q K_j^T into buffer j & 1
+      const uint32_t k_u = su + L::KR + (j % NK) * L::KST;
+      const uint32_t d = tmem + S_COL + (j & 1) * 64;
+      mbar_wait(&bar_k[j % NK], (j / NK) & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(d, make_smem_desc(su + L::Q0 + k4 * 32, 16, 1024), make_smem_desc(k_u + k4 * 32, 16, 1024),
+                idesc_s, k4 > 0);
+      if (P1) umma_ss(d, make_smem_desc32(su + L::Q1, 16, 256), make_smem_desc32(k_u + KP0, 16, 256), idesc_s, 1);
+      umma_commit(&bar_s[j & 1]);
+    };
+    mbar_wait(bar_q, 0);
+    issue_s(0);
+    if (nb > 1) issue_s(1);
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(bar_p, j & 1);                      // P_j in shared memory, S_j consumed
+      if (j < 8) FF_STAMP(8 + j * 6 + 0);
+      if (j > 0) mbar_wait(bar_pv, (j - 1) & 1);    // (long done: the workers waited for it too)
+      mbar_wait(&bar_v[j % NV], (j / NV) & 1);
+      tcgen05_fence_after();
+      const uint32_t v_u = su + L::VR + (j % NV) * L::KST;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(tmem + O0_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (j > 0 || k4 > 0));
+      if (P1) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_ss(tmem + O1_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                  make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (j > 0 || k4 > 0));
+      }
+      umma_commit(bar_pv);
+      if (j + 2 < nb) issue_s(j + 2);               // into the S buffer the workers just released
+      if (j + NK < nb) load_k(j + NK);              // S_j is done: its K stage is free
+      if (j >= 1 && j - 1 + NV < nb) load_v(j - 1 + NV);   // PV_{j-1} is done: its V stage is free
+      if (j < 8) FF_STAMP(8 + j * 6 + 1);
+    }
+  }
+
+  if (worker) {
+    const int row = row0 + tid;
+    const bool valid = row < a.Lq;
+    const bool active = row0 + (warp << 5) < a.Lq;   // warp-uniform: any valid row in this warp
+    float m_ref = -INFINITY, sum = 0.f;              // m_ref: the maximum the stored exponents refer to (raw S units)
+    const float tau = 8.f / a.scale_log2;            // rescale O only when the maximum grows by > 2^8
+    uint32_t s0[32], s1[32];
+    for (int j = 0; j < nb; ++j) {
+      const uint64_t vis = (active && valid) ? visible<CAUSAL>(a, b, j, row) : 0ull;
+      const bool any = __any_sync(0xffffffffu, vis != 0ull);
+      mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+      tcgen05_fence_after();
+      if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 2);
+      float alpha = 1.f;
+      bool grow = false;
+      if (any) {
+        const uint32_t sc = lane_addr + S_COL + (j & 1) * 64;
+        tmem_ld32(sc, s0);
+        tmem_ld32(sc + 32, s1);
+        tmem_ld_wait();
+        const uint32_t v0 = (uint32_t)vis, v1 = (uint32_t)(vis >> 32);
+        float bm = -INFINITY;
+        if (vis == ~0ull) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) bm = fmaxf(bm, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if ((v0 >> c) & 1u) bm = fmaxf(bm, __uint_as_float(s0[c]));
+            if ((v1 >> c) & 1u) bm = fmaxf(bm, __uint_as_float(s1[c]));
+          }
+        }
+        if (bm > m_ref + tau || (m_ref == -INFINITY && bm > -INFINITY)) {
+          grow = m_ref > -INFINITY;                  // O holds something to rescale
+          alpha = grow ? exp2f((m_ref - bm) * a.scale_log2) : 1.f;
+          m_ref = bm;
+        }
+        const float ms = m_ref > -INFINITY ? m_ref * a.scale_log2 : 0.f;
+        float psum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float p0 = ((v0 >> c) & 1u) ? exp2f(__uint_as_float(s0[c]) * a.scale_log2 - ms) : 0.f;
+          const float p1 = ((v1 >> c) & 1u) ? exp2f(__uint_as_float(s1[c]) * a.scale_log2 - ms) : 0.f;
+          s0[c] = __float_as_uint(p0);
+          s1[c] = __float_as_uint(p1);
+          psum += p0 + p1;
+        }
+        sum = sum * alpha + psum;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { s0[c] = 0u; s1[c] = 0u; }
+      }
+      // sP and O are free once PV_{j-1} has finished
+      if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 3);
+      if (j > 0) {
+        mbar_wait(bar_pv, (j - 1) & 1);
+        tcgen05_fence_after();
+        if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 4);
+        if (__any_sync(0xffffffffu, grow)) {
+          uint32_t t[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(lane_addr + O0_COL + half * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) t[c] = __float_as_uint(__uint_as_float(t[c]) * alpha);
+            tmem_st32(lane_addr + O0_COL + half * 32, t);
+          }
+          if (P1) {
+            tmem_ld16(lane_addr + O1_COL, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = __float_as_uint(__uint_as_float(t[c]) * alpha);
+            tmem_st16(lane_addr + O1_COL, t);
+          }
+          tmem_st_wait();
+        }
+      }
+      if (active) {
+        store_half(smem + L::P, tid, 0, reinterpret_cast<const float*>(s0));
+        store_half(smem + L::P, tid, 1, reinterpret_cast<const float*>(s1));
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 5);
+    }
+    mbar_wait(bar_pv, (nb - 1) & 1);
+    tcgen05_fence_after();
+    if (tid == 0) FF_STAMP(2);
+    if (active) {
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(lane_addr + O0_COL + half * 32, s0);
+        tmem_ld_wait();
+        if (valid) store_bf16(orow + half * 32, s0, 32, inv);
+      }
+      if (P1) {
+        tmem_ld16(lane_addr + O1_COL, s0);
+        tmem_ld_wait();
+        if (valid) store_bf16(orow + 64, s0, 16, inv);
+      }
+      if (valid) a.lse[((int64_t)b * a.H + h) * a.Lq + row] = sum > 0.f ? m_ref * a.scale + logf(sum) : -INFINITY;
+    }
+    tcgen05_fence_before();
+    if (tid == 0) FF_STAMP(3);
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+static unsigned long long* g_dbg = nullptr;
+
+}  // namespace ff
+
+// ---- host -----------------------------------------------------------------------------------
+int make_tmap_tiled_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+// q, k, v: (B, L, H, dh) views given by (batch, row, head) strides in elements.
+template <int DH, bool CAUSAL>
+static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, const void* v,
+                        int64_t k_bs, int64_t k_rs, int64_t k_hs, const uint32_t* kbits, void* o, int64_t o_bs,
+                        int64_t o_rs, float* lse, int B, int Lq, int Lk, int H, float scale, cudaStream_t st) {
+  using L = ff::Smem<DH>;
+  CUtensorMap m[6];
+  auto mk = [&](CUtensorMap* out, const void* base, int64_t bs, int64_t rs, int64_t hs, int Ln, int rows,
+                bool p1) -> int {
+    if (B == 1) bs = rs * (int64_t)Ln;
+    const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)H, (uint64_t)Ln, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
+    const uint32_t box[4] = {p1 ? 16u : 64u, 1, (uint32_t)rows, 1};
+    return make_tmap_tiled_sw(out, base, 4, dims, strides, box, p1 ? 32 : 128);
+  };
+  int rc;
+  if ((rc = mk(&m[0], q, q_bs, q_rs, q_hs, Lq, ff::TQ, false))) return rc;
+  if ((rc = mk(&m[1], k, k_bs, k_rs, k_hs, Lk, ff::KB, false))) return rc;
+  if ((rc = mk(&m[2], v, k_bs, k_rs, k_hs, Lk, ff::KB, false))) return rc;
+  if (L::P1) {
+    if ((rc = mk(&m[3], q, q_bs, q_rs, q_hs, Lq, ff::TQ, true))) return rc;
+    if ((rc = mk(&m[4], k, k_bs, k_rs, k_hs, Lk, ff::KB, true))) return rc;
+    if ((rc = mk(&m[5], v, k_bs, k_rs, k_hs, Lk, ff::KB, true))) return rc;
+  } else {
+    m[3] = m[0]; m[4] = m[1]; m[5] = m[2];
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+    if (e != cudaSuccess) { set_error("flash_fwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    attr = true;
+  }
+  ff::Args a{};
+  a.dbg = ff::g_dbg;
+  a.o = (__nv_bfloat16*)o; a.o_bs = o_bs; a.o_rs = o_rs; a.lse = lse;
+  a.kbits = kbits; a.kwords = 2 * ((Lk + 63) / 64);
+  a.Lq = Lq; a.Lk = Lk; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + ff::TQ - 1) / ff::TQ, H, B);
+  ff::flash_fwd_kernel<DH, CAUSAL><<<grid, ff::THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+// dh = 64, unmasked (Perceiver / ViT): q (B,Lq,H,64), k/v (B,Lk,H,64) with head stride 64
+int launch_flash_fwd_64(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o, float* lse, int B,
+                        int Lq, int Lk, int H, float scale, cudaStream_t st) {
+  return launch_flash<64, false>(q.ptr, q.batch_stride, q.row_stride, 64, k.ptr, v.ptr, k.batch_stride,
+                                 k.row_stride, 64, nullptr, o.ptr, o.batch_stride, o.row_stride, lse, B, Lq, Lk,
+                                 H, scale, st);
+}
+
+// dh = 80, causal + key bits (GPT-NeoX)
+int launch_flash_fwd_80(const void* q, const void* k, const void* v, int64_t bs, int64_t rs, int64_t hs,
+                        const uint32_t* kbits, void* o, float* lse, int B, int T, int H, float scale,
+                        cudaStream_t st) {
+  return launch_flash<80, true>(q, bs, rs, hs, k, v, bs, rs, hs, kbits, o, (int64_t)T * H * 80, (int64_t)H * 80,
+                                lse, B, T, T, H, scale, st);
+}
+
+}  // namespace unimp
+
+// Test hook (not in the public header): device buffer of 64 x u64 per CTA that the next flash_fwd
+// launches fill with %globaltimer stamps; NULL switches it off.
+extern "C" void unimp__flash_fwd_debug(unsigned long long* buf) { unimp::ff::g_dbg = buf; }

@@ -17,8 +17,11 @@
 // Forward : CTA = (128-query tile, head, sample), two sweeps over the tile's key blocks like
 //           attn_fwd2_tc_kernel (row max, then exp + PV with S recomputed); 2 CTAs per SM.
 // Backward: CTA = (64-key block, head, sample) walks the query tiles at or below the diagonal;
-//           dK/dV accumulate in TMEM across tiles, dQ tiles are added into an fp32 buffer with
-//           vector atomics (one CTA per key block contributes to each query row).
+//           dK/dV accumulate in TMEM across tiles; each pair's dQ tile is staged in shared memory and
+//           added into an fp32 buffer (B,H,Tp,84) with ONE bulk reduce (cp.reduce.async.bulk .add.f32,
+//           43 KB, asynchronous) — per-thread vector atomics were L2-bound (917 us at T=1024).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -40,7 +43,7 @@ struct Args {
   float* lse;                // (B,H,T)
   const uint32_t* kbits;     // (B, kwords) or NULL
   int kwords;
-  float* dq32;               // bwd: (B,T,H,80) fp32, zeroed by the launcher
+  float* dq32;               // bwd: (B,H,Tp,84) fp32 (Tp = T rounded up to 128), zeroed by the launcher
   __nv_bfloat16 *dk, *dv;    // bwd: (B,T,H,80) bf16 contiguous
   int T, H;
   float scale, scale_log2;
@@ -293,13 +296,24 @@ lm_attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // Backward.  Per (query tile i, key block j) pair, with S, dP, P, dS as in attn_bwd_tc_kernel:
 //   [dV_j | dK_j] += [P | dS]^T [dO_i | Q_i]   per 64-column panel (two M=N=128 MMAs chains)
-//   dQ_i += dS K_j                              per panel, flushed to dq32 with fp32 vector atomics
-// Shared memory: [dO p0][Q p0][dO p1][Q p1] (B operand chunks 16 KB apart), [P][dS], K p0/p1, V p0/p1.
+//   dQ_i += dS K_j                              per panel; staged as fp32 [128][84] (336-byte pitch:
+//                                               conflict-free float4 stores) and bulk-reduced into dq32
+// Shared memory: [dO p0][Q p0][dO p1][Q p1] (B operand chunks 16 KB apart), [P][dS], K p0/p1, V p0/p1,
+// dQ staging.
 // TMEM: S 64 | dP 64 | dQ p0 64 | dQ p1 64 | dKV p0 128 | dKV p1 128 = 512 columns, one CTA per SM.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t B_DO0 = 0, B_Q0 = QP, B_DO1 = 2 * QP, B_Q1 = 3 * QP, B_P = 4 * QP, B_DS = B_P + PB,
                    B_K0 = B_DS + PB, B_K1 = B_K0 + KP, B_V0 = B_K1 + KP, B_V1 = B_V0 + KP,
-                   B_BAR = B_V1 + KP, B_SMEM = B_BAR + 128;
+                   B_STG = B_V1 + KP, DQ_PITCH = 84, STG_BYTES = TQ * DQ_PITCH * 4,
+                   B_BAR = B_STG + STG_BYTES, B_SMEM = B_BAR + 128;
+
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               :
+               : "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
@@ -324,7 +338,8 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         printf("unimp: lm_attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
         __trap();
       }
-      mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_g, 1);
+      mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
+      mbar_init(bar_g, 2);     // MMAs of the pair done (tcgen05.commit) + dQ staging free (issuer)
       fence_barrier_init();
       mbar_arrive_expect_tx(bar_kv, 4 * KP);
       tma_load_4d(smem + B_K0, &tk, bar_kv, 0, h, kb * KB, b);
@@ -353,12 +368,20 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
   uint32_t ph = 0;
   uint32_t r[32];
+  float* stg = reinterpret_cast<float*>(smem + B_STG);
+  const int Tp = nq * TQ;
+  float* dq_head = a.dq32 + ((int64_t)b * a.H + h) * Tp * DQ_PITCH;
+  if (worker) *reinterpret_cast<float4*>(stg + tid * DQ_PITCH + DH) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int qt = q_lo; qt < nq; ++qt) {
     const int it = qt - q_lo;
     const int row = qt * TQ + tid;
     const bool valid = worker && row < a.T;
     // ---- S and dP ------------------------------------------------------------------------
     if (warp == 4 && elect_one_sync()) {
+      if (it > 0) {            // the previous pair's dQ tile (staged before the loop-end barrier)
+        bulk_reduce_add_f32(dq_head + (int64_t)(qt - 1) * TQ * DQ_PITCH, stg, STG_BYTES);
+        tma_store_commit();
+      }
       if (it == 0) mbar_wait(bar_kv, 0);
       mbar_wait(bar_qdo, ph);
       tcgen05_fence_after();
@@ -441,6 +464,8 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         umma_ss(tmem + DQ1_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
                 make_smem_desc(su + B_K1 + k4 * 2048, 1024, 1024), idesc_dq, k4 > 0);
       umma_commit(bar_g);
+      tma_store_wait_read();             // the previous dQ reduce has left the staging buffer
+      mbar_arrive(bar_g);
       mbar_wait(bar_g, ph);              // the Q/dO panels are free: fetch the next tile's
       if (qt + 1 < nq) {
         mbar_arrive_expect_tx(bar_qdo, 4 * QP);
@@ -453,19 +478,18 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     if (worker) {
       mbar_wait(bar_g, ph);
       tcgen05_fence_after();
-      float* dst = a.dq32 + (((int64_t)b * a.T + row) * a.H + h) * DH;
+      float* dst = stg + tid * DQ_PITCH;
 #pragma unroll
       for (int part = 0; part < 3; ++part) {      // dQ p0 cols 0-31, 32-63, p1 cols 0-15
         tmem_ld32(lane_addr + (part < 2 ? DQ0_COL + part * 32 : DQ1_COL), r);
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int c = 0; c < (part < 2 ? 8 : 4); ++c)
-            atomicAdd(reinterpret_cast<float4*>(dst + part * 32 + c * 4),
-                      make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                  __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])));
-        }
+        for (int c = 0; c < (part < 2 ? 8 : 4); ++c)
+          *reinterpret_cast<float4*>(dst + part * 32 + c * 4) =
+              make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                          __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
       }
+      fence_proxy_async_smem();
       tcgen05_fence_before();
     }
     ph ^= 1;
@@ -473,6 +497,11 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     tcgen05_fence_after();
   }
 
+  if (warp == 4 && elect_one_sync()) {          // the last pair's dQ tile
+    bulk_reduce_add_f32(dq_head + (int64_t)(nq - 1) * TQ * DQ_PITCH, stg, STG_BYTES);
+    tma_store_commit();
+    bulk_wait_all();
+  }
   // ---- flush dV (lanes 0-63) and dK (lanes 64-127) of this key block -----------------------
   if (worker) {
     const int key = kb * KB + (tid & 63);
@@ -528,6 +557,12 @@ static const char* unsupported(const void* q, const void* k, const void* v, int6
 }  // namespace lm
 }  // namespace unimp
 
+namespace unimp {
+int launch_flash_fwd_80(const void* q, const void* k, const void* v, int64_t bs, int64_t rs, int64_t hs,
+                        const uint32_t* kbits, void* o, float* lse, int B, int T, int H, float scale,
+                        cudaStream_t st);
+}
+
 using namespace unimp;
 
 extern "C" int unimp_lm_attn_supported(int T, int H, int dh, int dtype) {
@@ -556,6 +591,11 @@ extern "C" int unimp_lm_attn_fwd(const void* q, const void* k, const void* v, in
   const char* why = lm::unsupported(q, k, v, batch_stride, row_stride, head_stride, dh, dtype);
   UNIMP_CHECK_ARG(!why, UNIMP_E_SHAPE, "unimp_lm_attn_fwd: %s", why);
   UNIMP_CHECK_ARG(aligned16(o), UNIMP_E_ALIGN, "unimp_lm_attn_fwd: o must be 16-byte aligned");
+  // one-sweep kernel (flash_fwd.cu); UNIMP_LM_FWD1=1 keeps the two-sweep kernel below for A/B runs
+  static const bool two_sweep = getenv("UNIMP_LM_FWD1") && atoi(getenv("UNIMP_LM_FWD1")) != 0;
+  if (!two_sweep)
+    return launch_flash_fwd_80(q, k, v, batch_stride, row_stride, head_stride, key_bits, o, lse, B, T, H, scale,
+                               (cudaStream_t)stream);
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = lm::make_map(&tq, q, batch_stride, row_stride, head_stride, B, T, H, lm::TQ))) return rc;
@@ -607,7 +647,8 @@ extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, in
     if (e != cudaSuccess) { set_error("lm_attn_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr = true;
   }
-  cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * T * D * sizeof(float), st);
+  const int Tp = (T + lm::TQ - 1) / lm::TQ * lm::TQ;
+  cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * H * Tp * lm::DQ_PITCH * sizeof(float), st);
   if (e != cudaSuccess) { set_error("lm_attn_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
   lm::Args a{};
   a.o = (__nv_bfloat16*)const_cast<void*>(o); a.d_o = (const __nv_bfloat16*)d_o;

@@ -118,6 +118,8 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True, 
         _run_vit_perceiver(cfg, wl, dtype, eager, rec)
     if want("k5") or want("gelu"):
         _run_k5_gelu(cfg, wl, dtype, eager, rec)
+    if want("lm"):
+        _run_lm_attn(cfg, wl, dtype, eager, rec)
     if want("focal"):
         _run_focal(cfg, wl, dtype, eager, rec, out, n_valid_rows)
     if want("misc"):
@@ -194,6 +196,38 @@ def _run_xattn(cfg, wl, dtype, eager, rec):
                         torch.nn.functional.linear(x, wq), kv, tt, H, n, dh ** -0.5), wo)
                     for x, kv, wq, wo in zip(xs, kvs, wqs, wos)]), fb, ff, K)
         del xs, kvs, wqs, wos
+
+
+def _run_lm_attn(cfg, wl, dtype, eager, rec):
+    """K4: causal self-attention of one GPT-NeoX layer on the packed, rotated qkv projection
+    (B, T, H, 3, dh); eager column = what the reference runs (HF sdpa attention -> cuDNN flash)."""
+    dev, es, B, T = "cuda", 2, wl.B, wl.T
+    H, dh = cfg.lm_heads, cfg.lm_hidden // cfg.lm_heads
+    probe = torch.empty(B, H, T, dh, device=dev, dtype=dtype)
+    if dtype != torch.bfloat16 or not ops.lm_attention_supported(probe):
+        return
+    byts = es * 4 * B * T * H * dh + 4 * B * H * T          # q, k, v, o + lse
+    fl = 4.0 * B * H * dh * T * (T + 1) / 2                 # causal half
+    K = _k(byts, cap=16)
+    packs = [torch.randn(B, T, H * 3 * dh, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    gos = [torch.randn(B, T, H * dh, device=dev, dtype=dtype) for _ in range(K)]
+
+    def views(p):
+        return tuple(p.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+
+    fwd = [lambda p=p: ops.lm_attention(*views(p), None, scale=dh ** -0.5) for p in packs]
+    rec("lm_attn_fwd", _time_graph(fwd), byts, fl, K)
+    os_ = [f() for f in fwd]
+    bwd = [lambda o=o, p=p, g=g: torch.autograd.grad(o, p, g, retain_graph=True) for o, p, g in zip(os_, packs, gos)]
+    rec("lm_attn_bwd", _time_graph(bwd), 2.5 * byts, 2.5 * fl, K)
+    if eager:
+        F = torch.nn.functional
+        efw = [lambda p=p: F.scaled_dot_product_attention(*views(p), is_causal=True, scale=dh ** -0.5)
+               .transpose(1, 2).reshape(B, T, H * dh) for p in packs]
+        rec("eager_lm_attn_fwd", _time_graph(efw), byts, fl, K)
+        eos = [f() for f in efw]
+        rec("eager_lm_attn_bwd", _time_graph([lambda o=o, p=p, g=g: torch.autograd.grad(o, p, g, retain_graph=True)
+                                              for o, p, g in zip(eos, packs, gos)]), 2.5 * byts, 2.5 * fl, K)
 
 
 def _run_vit_perceiver(cfg, wl, dtype, eager, rec):

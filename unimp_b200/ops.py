@@ -579,7 +579,7 @@ class _LMAttention(torch.autograd.Function):
         q, k, v, o, lse, key_bits = ctx.saved_tensors
         B, H, T, dh = q.shape
         d_o = d_o.contiguous()
-        dq32 = torch.empty((B, T, H, dh), dtype=torch.float32, device=q.device)
+        dq32 = torch.empty((B, H, (T + 127) // 128 * 128, 84), dtype=torch.float32, device=q.device)
         dk = torch.empty((B, T, H, dh), dtype=q.dtype, device=q.device)
         dv = torch.empty_like(dk)
         kb = key_bits.data_ptr() if key_bits is not None else None
@@ -587,7 +587,7 @@ class _LMAttention(torch.autograd.Function):
                                             q.stride(1), kb, o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
                                             dq32.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, H, dh,
                                             ctx.scale, _dt(q), _stream()), "unimp_lm_attn_bwd")
-        return (dq32.to(q.dtype).transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None)
+        return (dq32[:, :, :T, :dh].to(q.dtype), dk.transpose(1, 2), dv.transpose(1, 2), None, None)
 
 
 def lm_attention_supported(q) -> bool:
