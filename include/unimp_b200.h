@@ -234,7 +234,8 @@ int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const i
  * unimp_key_bits packs an attention_mask (B,T) of bool/uint8 (elem_size 1) or int64 (8),
  * nonzero = real token, into (B, 2*ceil(T/64)) words of 32 keys.
  * Backward: dq32 (B,H,Tp,84) fp32 scratch, Tp = T rounded up to 128 (zeroed and accumulated by
- * the call; dq = dq32[:, :, :T, :80]), dk, dv (B,T,H,dh) in `dtype`, contiguous.  bf16, dh == 80 only (unimp_lm_attn_supported); rows that see no key
+ * the call; dq = dq32[:, :, :T, :80]), delta (B,H,T) fp32 scratch (rowsum(dO o O), written by the
+ * call), dk, dv (B,T,H,dh) in `dtype`, contiguous.  bf16, dh == 80 only (unimp_lm_attn_supported); rows that see no key
  * give o = 0. */
 int unimp_lm_attn_supported(int T, int H, int dh, int dtype);
 int unimp_key_bits(const void* mask, int elem_size, uint32_t* bits, int B, int T, void* stream);
@@ -243,8 +244,9 @@ int unimp_lm_attn_fwd(const void* q, const void* k, const void* v, int64_t batch
                       float* lse, int B, int T, int H, int dh, float scale, int dtype, void* stream);
 int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, int64_t batch_stride,
                       int64_t row_stride, int64_t head_stride, const uint32_t* key_bits,
-                      const void* o, const void* d_o, const float* lse, float* dq32, void* dk,
-                      void* dv, int B, int T, int H, int dh, float scale, int dtype, void* stream);
+                      const void* o, const void* d_o, const float* lse, float* dq32, float* delta,
+                      void* dk, void* dv, int B, int T, int H, int dh, float scale, int dtype,
+                      void* stream);
 /* CLIP QuickGELU x*sigmoid(1.702x), in place (ViT MLP; forward only: the tower is frozen). */
 int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream);
 /* Exact (erf) GELU of the FeedForward blocks: open_flamingo helpers.FeedForward's nn.GELU()

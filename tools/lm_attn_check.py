@@ -131,18 +131,68 @@ def timeline(kind):
     t = buf.view(n_cta, 64).cpu().double()
     t0 = t[:, 0].min()
     span = (t[:, 3].max() - t0)
+    occ = lib.unimp__flash_fwd_occupancy(80 if kind == "lm" else 64)
+    print(f"FF occupancy query: {occ} CTAs/SM; measured concurrency "
+          f"{float((t[:, 3] - t[:, 0]).sum() / span / 148):.2f} CTAs/SM (sum of CTA lifetimes / span / 148)")
     print(f"FF timeline {kind}: {n_cta} CTAs, first start to last end {span:.0f} ns; per-CTA start->ready "
           f"{(t[:, 1] - t[:, 0]).median():.0f}, ready->last PV {(t[:, 2] - t[:, 1]).median():.0f}, epilogue "
           f"{(t[:, 3] - t[:, 2]).median():.0f}")
     full = t[t[:, 8 + 4 * 6 + 5] > 0]      # CTAs with >= 5 steps
-    print(f"FF   {len(full)} CTAs with >= 5 steps; medians over them, ns relative to the CTA's 'ready' stamp:")
+    print(f"FF   {len(full)} CTAs with >= 5 steps; medians over them, SM CYCLES since the CTA's 'ready' stamp:")
     for j in range(5):
         s = 8 + j * 6
-        rel = lambda k: (full[:, s + k] - full[:, 1]).median()
+        rel = lambda k: (full[:, s + k] - full[:, 4]).median()
         print(f"FF   step {j}: worker S ready {rel(2):7.0f} | exps done {rel(3):7.0f} | PV(j-1) seen "
               f"{rel(4) if j else float('nan'):7.0f} | arrived {rel(5):7.0f} || issuer got P {rel(0):7.0f} | "
               f"issuer step done {rel(1):7.0f}", flush=True)
 
+
+def bwd_timeline(B, T, H):
+    """Per-CTA pair stamps of one unimp_lm_attn_bwd launch (unimp__lm_bwd_debug hook)."""
+    import ctypes
+    from unimp_b200 import _lib
+    lib = _lib.load()
+    f = lib.unimp__lm_bwd_debug
+    f.argtypes = [ctypes.c_void_p]
+    f.restype = None
+    pk = torch.randn(B, T, H * 3 * dh, device=dev, dtype=bf)
+    qkv = tuple(x.requires_grad_() for x in views(pk, B, T, H))
+    o = ops.lm_attention(*qkv, None, scale=dh ** -0.5)
+    go = torch.randn_like(o)
+    n_cta = ((T + 63) // 64) * H * B
+    buf = torch.zeros(n_cta * 64, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        torch.autograd.grad(o, qkv, go, retain_graph=True)
+    torch.cuda.synchronize()
+    f(buf.data_ptr())
+    torch.autograd.grad(o, qkv, go, retain_graph=True)
+    torch.cuda.synchronize()
+    f(None)
+    t = buf.view(n_cta, 64).cpu().double()
+    span = t[:, 3].max() - t[:, 0].min()
+    life = t[:, 3] - t[:, 0]
+    print(f"BW timeline B={B} T={T} H={H}: {n_cta} CTAs, span {span:.0f} ns, concurrency "
+          f"{float(life.sum() / span / 148):.2f} CTAs/SM, CTA lifetime median {life.median():.0f} ns; start->ready "
+          f"{(t[:, 1] - t[:, 0]).median():.0f} ns; last gradients -> end {(t[:, 3] - t[:, 2]).median():.0f} ns "
+          f"({(t[:, 6] - t[:, 5]).median():.0f} cycles)")
+    for npairs in (1, 2, 4, 8):
+        sel = t[(t[:, 8 + (npairs - 1) * 8 + 5] > 0) & ((t[:, 8 + npairs * 8 + 5] == 0) if npairs < 6 else True)]
+        if len(sel) == 0:
+            continue
+        print(f"BW   CTAs with {'>=6' if npairs >= 6 else npairs} pairs: {len(sel)}; lifetime median "
+              f"{(sel[:, 3] - sel[:, 0]).median():.0f} ns; cycles since 'ready':")
+        for i in range(min(npairs, 6)):
+            s_ = 8 + i * 8
+            rel = lambda k: (sel[:, s_ + k] - sel[:, 4]).median()
+            print(f"BW     pair {i}: S/dP ready {rel(2):6.0f} | math done {rel(3):6.0f} | prev grads seen {rel(4):6.0f} | "
+                  f"arrived {rel(5):6.0f} | prev dQ staged {rel(6):6.0f} || MMA got P {rel(0):6.0f} | MMA issued {rel(1):6.0f}",
+                  flush=True)
+        print(f"BW     flush start {(sel[:, 5] - sel[:, 4]).median():6.0f} | end {(sel[:, 6] - sel[:, 4]).median():6.0f}")
+
+
+if "bwd_timeline" in sys.argv[1:]:
+    bwd_timeline(6, 256, 32)
+    bwd_timeline(6, 1024, 32)
 
 if "timeline" in sys.argv[1:]:
     timeline("lm")

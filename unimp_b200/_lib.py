@@ -61,7 +61,7 @@ SIGNATURES = {
     "unimp_lm_attn_supported": (_i, [_i, _i, _i, _i]),
     "unimp_key_bits": (_i, [_p, _i, _p, _i, _i, _p]),
     "unimp_lm_attn_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
-    "unimp_lm_attn_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p,
+    "unimp_lm_attn_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p,
                                _i, _i, _i, _i, _f, _i, _p]),
     "unimp_quick_gelu": (_i, [_p, _i64, _i, _p]),
     "unimp_gelu_fwd": (_i, [_p, _p, _i64, _i, _p]),

@@ -9,13 +9,15 @@
 //     S -> registers -> exp2 -> P (bf16, shared) with no TMEM round trip of O;
 //   * S is double-buffered in TMEM (2 x 64 columns): S_{j+1} = Q K_{j+1}^T runs on the tensor pipe
 //     while the 128 softmax threads work on S_j, and PV_j runs while they work on S_{j+1};
-//   * K and V travel through separate TMA rings (4 and 3 stages): K_{j+4} is requested as soon as
-//     S_j has been consumed, V_{j+3} as soon as PV_j has finished — two steps of slack each;
+//   * K and V travel through two 3-stage TMA rings fed by a dedicated producer lane (full / empty
+//     mbarriers: tcgen05.commit releases a stage): K_{j+3} is requested as soon as S_j has run,
+//     V_{j+3} as soon as PV_j has;
 //   * head dim 80 = a 64-column SWIZZLE_128B panel + a 16-column SWIZZLE_32B panel (2 KB per 64-row
 //     tile instead of the 8 KB a zero-padded 128-byte panel costs): 106 KB of shared memory, two
 //     CTAs per SM.
 // CTA = (128-query tile, head, sample); warps 0-3: one query row per thread (TMEM lane = row);
-// warp 4: one elected lane issues every TMA and tcgen05.mma.  All mbarrier waits are bounded.
+// warp 4: one elected lane issues every tcgen05.mma; warp 5: one elected lane issues every TMA.
+// All mbarrier waits are bounded.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -24,8 +26,9 @@ namespace ff {
 
 using namespace tc;
 
-constexpr int TQ = 128, KB = 64, THREADS = TQ + 32;
-constexpr int NK = 4, NV = 3;                 // K / V ring depths
+constexpr int TQ = 128, KB = 64, THREADS = TQ + 64;   // 4 softmax warps + MMA warp + TMA warp
+constexpr int W_MMA = 4, W_TMA = 5;
+constexpr int NST = 3;                        // K and V ring depth
 constexpr uint32_t QP0 = TQ * 128;            // [128][64] bf16, SWIZZLE_128B
 constexpr uint32_t QP1 = TQ * 32;             // [128][16] bf16, SWIZZLE_32B
 constexpr uint32_t KP0 = KB * 128, KP1 = KB * 32;
@@ -51,51 +54,9 @@ __device__ __forceinline__ unsigned long long now_ns() {
 // 2 worker got S_j, 3 worker exps done, 4 worker got PV_{j-1}, 5 worker arrived
 #define FF_STAMP(slot)                                                                                   \
   do {                                                                                                   \
-    if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = now_ns(); \
+    if (a.dbg) a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] =            \
+        (slot) < 4 ? now_ns() : (unsigned long long)clock64();                                          \
   } while (0)
-
-// SWIZZLE_32B shared-memory descriptor (layout type 6): rows of 32 bytes, 8-row groups 256 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -146,8 +107,8 @@ template <int DH>
 struct Smem {
   static constexpr bool P1 = DH > 64;
   static constexpr uint32_t KST = KP0 + (P1 ? KP1 : 0);       // one K (or V) stage
-  static constexpr uint32_t Q0 = 0, Q1 = QP0, KR = Q1 + (P1 ? QP1 : 0), VR = KR + NK * KST,
-                            P = VR + NV * KST, BAR = P + PB, TOTAL = BAR + 128;
+  static constexpr uint32_t Q0 = 0, Q1 = QP0, KR = Q1 + (P1 ? QP1 : 0), VR = KR + NST * KST,
+                            P = VR + NST * KST, BAR = P + PB, TOTAL = BAR + 256;
 };
 
 template <int DH, bool CAUSAL>
@@ -160,8 +121,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
   constexpr uint32_t S_COL = 0, O0_COL = 128, O1_COL = 192, TMEM_COLS = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
-  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 1 + NK, *bar_s = bars + 1 + NK + NV,
-           *bar_p = bar_s + 2, *bar_pv = bar_s + 3;
+  // full barriers (TMA -> MMA), empty barriers (tcgen05.commit -> TMA producer), S / P / PV handshakes
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bar_k + NST, *k_free = bar_v + NST, *v_free = k_free + NST,
+           *bar_s = v_free + NST, *bar_p = bar_s + 2, *bar_pv = bar_s + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,22 +134,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
   const int nb_all = (a.Lk + KB - 1) / KB;
   const int nb = CAUSAL ? min(nb_all, (row0 + TQ) / KB) : nb_all;
 
-  auto load_k = [&](int j) {
-    const int st = j % NK;
-    uint8_t* dst = smem + L::KR + st * L::KST;
-    mbar_arrive_expect_tx(&bar_k[st], L::KST);
-    tma_load_4d(dst, &tk, &bar_k[st], 0, h, j * KB, b);
-    if (P1) tma_load_4d(dst + KP0, &tk1, &bar_k[st], 64, h, j * KB, b);
-  };
-  auto load_v = [&](int j) {
-    const int st = j % NV;
-    uint8_t* dst = smem + L::VR + st * L::KST;
-    mbar_arrive_expect_tx(&bar_v[st], L::KST);
-    tma_load_4d(dst, &tv, &bar_v[st], 0, h, j * KB, b);
-    if (P1) tma_load_4d(dst + KP0, &tv1, &bar_v[st], 64, h, j * KB, b);
-  };
-
-  if (warp == 4) {
+  if (warp == W_MMA) {
     if (elect_one_sync()) {
       if (smem_u32(smem) & 1023u) {
         printf("unimp: flash_fwd: dynamic shared memory is not 1024-byte aligned\n");
@@ -196,15 +143,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
       mbar_init(bar_q, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 4);
       mbar_init(bar_pv, 1);
 #pragma unroll
-      for (int i = 0; i < NK; ++i) mbar_init(&bar_k[i], 1);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) mbar_init(&bar_v[i], 1);
+      for (int i = 0; i < NST; ++i) {
+        mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_free[i], 1);
+      }
       fence_barrier_init();
-      mbar_arrive_expect_tx(bar_q, QP0 + (P1 ? QP1 : 0));
-      tma_load_4d(smem + L::Q0, &tq, bar_q, 0, h, row0, b);
-      if (P1) tma_load_4d(smem + L::Q1, &tq1, bar_q, 64, h, row0, b);
-      for (int j = 0; j < nb && j < NK; ++j) load_k(j);
-      for (int j = 0; j < nb && j < NV; ++j) load_v(j);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -214,60 +156,104 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  if (tid == 0) FF_STAMP(1);
+  if (tid == 0) { FF_STAMP(1); FF_STAMP(4); }
 
-  if (warp == 4 && elect_one_sync()) {
+  // The two single-lane roles run mostly on the uniform datapath (~12 cycles per dependent
+  // instruction): their loops are unrolled by 6 = lcm(ring depth 3, 2 S buffers) so that every
+  // stage offset, S buffer and most barrier parities are compile-time constants.
+  if (warp == W_TMA && elect_one_sync()) {
+    // ---- TMA producer: Q, then K_j / V_j as their ring stages are released -----------------
+    mbar_arrive_expect_tx(bar_q, QP0 + (P1 ? QP1 : 0));
+    tma_load_4d(smem + L::Q0, &tq, bar_q, 0, h, row0, b);
+    if (P1) tma_load_4d(smem + L::Q1, &tq1, bar_q, 64, h, row0, b);
+    for (int j0 = 0; j0 < nb; j0 += 6) {
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int j = j0 + u;
+        if (j < nb) {
+          const int st = u % NST;                                  // compile-time after unrolling
+          const uint32_t free_par = ((u / NST) + 1) & 1;           // parity of fill (j / NST) - 1
+          uint8_t* kd = smem + L::KR + st * L::KST;
+          uint8_t* vd = smem + L::VR + st * L::KST;
+          if (j >= NST) mbar_wait(&k_free[st], free_par);
+          mbar_arrive_expect_tx(&bar_k[st], L::KST);
+          tma_load_4d(kd, &tk, &bar_k[st], 0, h, j * KB, b);
+          if (P1) tma_load_4d(kd + KP0, &tk1, &bar_k[st], 64, h, j * KB, b);
+          if (j >= NST) mbar_wait(&v_free[st], free_par);
+          mbar_arrive_expect_tx(&bar_v[st], L::KST);
+          tma_load_4d(vd, &tv, &bar_v[st], 0, h, j * KB, b);
+          if (P1) tma_load_4d(vd + KP0, &tv1, &bar_v[st], 64, h, j * KB, b);
+        }
+      }
+    }
+  } else if (warp == W_MMA && elect_one_sync()) {
+    // ---- MMA issuer -------------------------------------------------------------------------
     constexpr uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
     constexpr uint32_t idesc_o0 = make_idesc(TQ, 64, 0, 1);
     constexpr uint32_t idesc_o1 = make_idesc(TQ, 16, 0, 1);
     const uint32_t su = smem_u32(smem);
-    auto issue_s = [&](int j) {                     // S_j = Q K_j^T into buffer j & 1
-      const uint32_t k_u = su + L::KR + (j % NK) * L::KST;
-      const uint32_t d = tmem + S_COL + (j & 1) * 64;
-      mbar_wait(&bar_k[j % NK], (j / NK) & 1);
+    // S_j = Q K_j^T into S buffer (j & 1); st = j % NST, par = parity of that stage's fill
+    auto issue_s = [&](int st, int buf, uint32_t par) {
+      const uint32_t k_u = su + L::KR + st * L::KST;
+      const uint32_t d = tmem + S_COL + buf * 64;
+      mbar_wait(&bar_k[st], par);
       tcgen05_fence_after();
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4)
         umma_ss(d, make_smem_desc(su + L::Q0 + k4 * 32, 16, 1024), make_smem_desc(k_u + k4 * 32, 16, 1024),
                 idesc_s, k4 > 0);
       if (P1) umma_ss(d, make_smem_desc32(su + L::Q1, 16, 256), make_smem_desc32(k_u + KP0, 16, 256), idesc_s, 1);
-      umma_commit(&bar_s[j & 1]);
+      umma_commit(&bar_s[buf]);
+      umma_commit(&k_free[st]);
     };
     mbar_wait(bar_q, 0);
-    issue_s(0);
-    if (nb > 1) issue_s(1);
-    for (int j = 0; j < nb; ++j) {
-      mbar_wait(bar_p, j & 1);                      // P_j in shared memory, S_j consumed
-      if (j < 8) FF_STAMP(8 + j * 6 + 0);
-      if (j > 0) mbar_wait(bar_pv, (j - 1) & 1);    // (long done: the workers waited for it too)
-      mbar_wait(&bar_v[j % NV], (j / NV) & 1);
-      tcgen05_fence_after();
-      const uint32_t v_u = su + L::VR + (j % NV) * L::KST;
+    issue_s(0, 0, 0);
+    if (nb > 1) issue_s(1, 1, 0);
+    for (int j0 = 0; j0 < nb; j0 += 6) {
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + O0_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
-                make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (j > 0 || k4 > 0));
-      if (P1) {
+      for (int u = 0; u < 6; ++u) {
+        const int j = j0 + u;
+        if (j < nb) {
+          const int st = u % NST;
+          mbar_wait(bar_p, u & 1);                       // P_j in shared memory, S_j consumed
+          if (j < 8) FF_STAMP(8 + j * 6 + 0);
+          mbar_wait(&bar_v[st], (u / NST) & 1);
+          tcgen05_fence_after();
+          const uint32_t v_u = su + L::VR + st * L::KST;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          umma_ss(tmem + O1_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
-                  make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (j > 0 || k4 > 0));
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_ss(tmem + O0_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                    make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (j > 0 || k4 > 0));
+          if (P1) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_ss(tmem + O1_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                      make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (j > 0 || k4 > 0));
+          }
+          umma_commit(bar_pv);
+          umma_commit(&v_free[st]);
+          // S_{j+2} into the buffer the workers just released; stage (u+2) % 3, fill (j+2) / 3
+          if (j + 2 < nb) issue_s((u + 2) % NST, u & 1, ((u + 2) / NST) & 1);
+          if (j < 8) FF_STAMP(8 + j * 6 + 1);
+        }
       }
-      umma_commit(bar_pv);
-      if (j + 2 < nb) issue_s(j + 2);               // into the S buffer the workers just released
-      if (j + NK < nb) load_k(j + NK);              // S_j is done: its K stage is free
-      if (j >= 1 && j - 1 + NV < nb) load_v(j - 1 + NV);   // PV_{j-1} is done: its V stage is free
-      if (j < 8) FF_STAMP(8 + j * 6 + 1);
     }
   }
 
   if (worker) {
+    // One thread per query row (TMEM lane = row).  A second thread per row on the other 32 columns
+    // was tried: it needs the row maximum over all 64 scores, i.e. a second TMEM read of S, and the
+    // TMEM read port (64 B/cycle: 512 cycles per 128 x 64 fp32 block) is what bounds the step —
+    // 104 -> 109 us at T=1024 (profiles/r2_flash_fwd_timeline_two_threads_per_row.log).
     const int row = row0 + tid;
     const bool valid = row < a.Lq;
     const bool active = row0 + (warp << 5) < a.Lq;   // warp-uniform: any valid row in this warp
     float m_ref = -INFINITY, sum = 0.f;              // m_ref: the maximum the stored exponents refer to (raw S units)
     const float tau = 8.f / a.scale_log2;            // rescale O only when the maximum grows by > 2^8
-    uint32_t s0[32], s1[32];
+    const float sl2 = a.scale_log2;
+    float f0[32], f1[32];
+    uint32_t* s0 = reinterpret_cast<uint32_t*>(f0);
+    uint32_t* s1 = reinterpret_cast<uint32_t*>(f1);
     for (int j = 0; j < nb; ++j) {
       const uint64_t vis = (active && valid) ? visible<CAUSAL>(a, b, j, row) : 0ull;
       const bool any = __any_sync(0xffffffffu, vis != 0ull);
@@ -276,42 +262,44 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
       if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 2);
       float alpha = 1.f;
       bool grow = false;
+      uint4 pk[8];                                   // this row's 64 probabilities, bf16
       if (any) {
         const uint32_t sc = lane_addr + S_COL + (j & 1) * 64;
         tmem_ld32(sc, s0);
         tmem_ld32(sc + 32, s1);
         tmem_ld_wait();
-        const uint32_t v0 = (uint32_t)vis, v1 = (uint32_t)(vis >> 32);
-        float bm = -INFINITY;
-        if (vis == ~0ull) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) bm = fmaxf(bm, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])));
-        } else {
+        if (vis != ~0ull) {                          // diagonal / ragged / padded block: hide the masked keys
+          const uint32_t v0 = (uint32_t)vis, v1 = (uint32_t)(vis >> 32);
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            if ((v0 >> c) & 1u) bm = fmaxf(bm, __uint_as_float(s0[c]));
-            if ((v1 >> c) & 1u) bm = fmaxf(bm, __uint_as_float(s1[c]));
+            if (!(v0 & (1u << c))) f0[c] = -INFINITY;
+            if (!(v1 & (1u << c))) f1[c] = -INFINITY;
           }
         }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx[c & 3] = fmaxf(mx[c & 3], fmaxf(f0[c], f1[c]));
+        const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         if (bm > m_ref + tau || (m_ref == -INFINITY && bm > -INFINITY)) {
           grow = m_ref > -INFINITY;                  // O holds something to rescale
-          alpha = grow ? exp2f((m_ref - bm) * a.scale_log2) : 1.f;
+          alpha = grow ? exp2f((m_ref - bm) * sl2) : 1.f;
           m_ref = bm;
         }
-        const float ms = m_ref > -INFINITY ? m_ref * a.scale_log2 : 0.f;
-        float psum = 0.f;
+        const float nms = m_ref > -INFINITY ? -m_ref * sl2 : 0.f;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float p0 = ((v0 >> c) & 1u) ? exp2f(__uint_as_float(s0[c]) * a.scale_log2 - ms) : 0.f;
-          const float p1 = ((v1 >> c) & 1u) ? exp2f(__uint_as_float(s1[c]) * a.scale_log2 - ms) : 0.f;
-          s0[c] = __float_as_uint(p0);
-          s1[c] = __float_as_uint(p1);
-          psum += p0 + p1;
+        for (int c = 0; c < 32; c += 2) {
+          const float e0 = exp2f(fmaf(f0[c], sl2, nms)), e1 = exp2f(fmaf(f0[c + 1], sl2, nms));
+          const float g0 = exp2f(fmaf(f1[c], sl2, nms)), g1 = exp2f(fmaf(f1[c + 1], sl2, nms));
+          ps[(c >> 1) & 3] += (e0 + e1) + (g0 + g1);
+          pw[c >> 1] = pack2(e0, e1);
+          pw[16 + (c >> 1)] = pack2(g0, g1);
         }
-        sum = sum * alpha + psum;
+        sum = sum * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { s0[c] = 0u; s1[c] = 0u; }
+        for (int c = 0; c < 8; ++c) pk[c] = make_uint4(0u, 0u, 0u, 0u);
       }
       // sP and O are free once PV_{j-1} has finished
       if (tid == 0 && j < 8) FF_STAMP(8 + j * 6 + 3);
@@ -340,8 +328,8 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         }
       }
       if (active) {
-        store_half(smem + L::P, tid, 0, reinterpret_cast<const float*>(s0));
-        store_half(smem + L::P, tid, 1, reinterpret_cast<const float*>(s1));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(smem + L::P + sw128_offset(tid, c)) = pk[c];
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
@@ -372,7 +360,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     if (tid == 0) FF_STAMP(3);
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 static unsigned long long* g_dbg = nullptr;
@@ -450,3 +438,24 @@ int launch_flash_fwd_80(const void* q, const void* k, const void* v, int64_t bs,
 // Test hook (not in the public header): device buffer of 64 x u64 per CTA that the next flash_fwd
 // launches fill with %globaltimer stamps; NULL switches it off.
 extern "C" void unimp__flash_fwd_debug(unsigned long long* buf) { unimp::ff::g_dbg = buf; }
+
+// Test hook: resident CTAs per SM the runtime grants the kernel (dh = 64 or 80).
+extern "C" int unimp__flash_fwd_occupancy(int dh) {
+  int n = -1;
+  if (dh == 80) {
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)unimp::ff::Smem<80>::TOTAL);
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<80, true>, unimp::ff::THREADS,
+                                                  unimp::ff::Smem<80>::TOTAL);
+  } else {
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)unimp::ff::Smem<64>::TOTAL);
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<64, false>, unimp::ff::THREADS,
+                                                  unimp::ff::Smem<64>::TOTAL);
+  }
+  return n;
+}

@@ -26,6 +26,8 @@
 #include "tc_common.cuh"
 
 namespace unimp {
+int make_tmap_tiled_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 namespace lm {
 
 using namespace tc;
@@ -37,10 +39,12 @@ constexpr uint32_t PB = TQ * 128;     // P / dS: [128 rows][64 keys], 16 KB
 constexpr int THREADS = TQ + 32;
 
 struct Args {
+  unsigned long long* dbg;   // test hook (unimp__lm_bwd_debug): 64 x u64 stamps per CTA, NULL = off
   __nv_bfloat16* o;          // fwd: out (B,T,H*80); bwd: forward output (read)
   const __nv_bfloat16* d_o;  // bwd
   int64_t o_bs, o_rs;        // shared by o and d_o (both (B,T,H*80) contiguous views)
   float* lse;                // (B,H,T)
+  const float* delta;        // bwd: (B,H,T) rowsum(dO o O), written by lm_delta_kernel
   const uint32_t* kbits;     // (B, kwords) or NULL
   int kwords;
   float* dq32;               // bwd: (B,H,Tp,84) fp32 (Tp = T rounded up to 128), zeroed by the launcher
@@ -294,18 +298,41 @@ lm_attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// Backward.  Per (query tile i, key block j) pair, with S, dP, P, dS as in attn_bwd_tc_kernel:
-//   [dV_j | dK_j] += [P | dS]^T [dO_i | Q_i]   per 64-column panel (two M=N=128 MMAs chains)
-//   dQ_i += dS K_j                              per panel; staged as fp32 [128][84] (336-byte pitch:
-//                                               conflict-free float4 stores) and bulk-reduced into dq32
-// Shared memory: [dO p0][Q p0][dO p1][Q p1] (B operand chunks 16 KB apart), [P][dS], K p0/p1, V p0/p1,
-// dQ staging.
-// TMEM: S 64 | dP 64 | dQ p0 64 | dQ p1 64 | dKV p0 128 | dKV p1 128 = 512 columns, one CTA per SM.
+// Backward, pipelined.  CTA = (64-key block j, head, sample) walks the query tiles i at or below the
+// diagonal.  Per pair, with lse and delta = rowsum(dO o O) precomputed per row:
+//     S  = Q_i K_j^T            dP = dO_i V_j^T                          (128 x 64, K = 80)
+//     P  = exp(scale*S - lse),  dS = scale * P o (dP - delta)            (threads)
+//     [dV_j | dK_j] += [P | dS]^T [dO_i | Q_i]  per column panel (M = 128; N = 128 and N = 32)
+//     dQ_i  = dS K_j             per panel; staged as fp32 [128][84] and added into dq32 with ONE
+//                                asynchronous bulk reduce (cp.reduce.async.bulk .add.f32, 43 KB)
+// Roles (320 threads): warps 0-7 = two threads per query row, each owns 32 of the 64 key columns;
+// warp 8 = one elected lane issues every tcgen05.mma; warp 9 = one elected lane issues every TMA.
+// Pipeline: Q/dO tiles travel through a 3-stage ring (full / empty mbarriers); S and dP are
+// double-buffered in TMEM, so S/dP of pair i+1 run while the threads work on pair i and the
+// gradient MMAs of pair i run while they stage dQ of pair i-1.
+// TMEM (512 columns): S 2x64 | dP 2x64 | dKV p0 128 | dQ p0 64 | dKV p1 32 | dQ p1 16.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t B_DO0 = 0, B_Q0 = QP, B_DO1 = 2 * QP, B_Q1 = 3 * QP, B_P = 4 * QP, B_DS = B_P + PB,
-                   B_K0 = B_DS + PB, B_K1 = B_K0 + KP, B_V0 = B_K1 + KP, B_V1 = B_V0 + KP,
-                   B_STG = B_V1 + KP, DQ_PITCH = 84, STG_BYTES = TQ * DQ_PITCH * 4,
-                   B_BAR = B_STG + STG_BYTES, B_SMEM = B_BAR + 128;
+// stamps: 0 start (ns), 1 ready (ns), 2 last pair's gradients seen (ns), 3 end (ns), 4 ready (cycles),
+// 5 flush start (cycles), 6 end (cycles); pair i < 6 -> 8 + i*8 + k (cycles): 0 MMA lane got P_i,
+// 1 MMA lane done with pair i, 2 worker S/dP ready, 3 math done, 4 previous gradients seen,
+// 5 arrived, 6 dQ of the previous pair staged
+#define BW_STAMP(slot)                                                                                   \
+  do {                                                                                                   \
+    if (a.dbg) {                                                                                         \
+      unsigned long long t__;                                                                            \
+      if ((slot) < 4) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
+      else t__ = (unsigned long long)clock64();                                                          \
+      a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = t__;        \
+    }                                                                                                    \
+  } while (0)
+
+constexpr int NQS = 3, BW_THREADS = 2 * TQ + 64, BW_MMA = 8, BW_TMA = 9;
+constexpr uint32_t QP1 = TQ * 32, KP1 = KB * 32;                   // 16-column SWIZZLE_32B panels
+constexpr uint32_t ST_DO0 = 0, ST_Q0 = QP, ST_DO1 = 2 * QP, ST_Q1 = 2 * QP + QP1, ST_BYTES = 2 * QP + 2 * QP1;
+constexpr uint32_t B_RING = 0, B_P = NQS * ST_BYTES, B_DS = B_P + PB, B_K0 = B_DS + PB, B_K1 = B_K0 + KP,
+                   B_V0 = B_K1 + KP1, B_V1 = B_V0 + KP, B_STG = B_V1 + KP1, DQ_PITCH = 84,
+                   STG_BYTES = TQ * DQ_PITCH * 4, B_BAR = B_STG + STG_BYTES, B_SMEM = B_BAR + 256;
+static_assert(B_K1 % 1024 == 0 && B_V0 % 1024 == 0 && B_V1 % 1024 == 0 && B_STG % 1024 == 0, "tile alignment");
 
 __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
@@ -314,43 +341,65 @@ __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssr
                : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// delta[b][h][t] = sum_d o[b][t][h][d] * d_o[b][t][h][d]   (one thread per row, t fastest)
+__global__ void __launch_bounds__(256) lm_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                       const __nv_bfloat16* __restrict__ d_o,
+                                                       float* __restrict__ delta, int T, int H, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = (int)(i % T);
+  const int64_t bh = i / T;
+  const int h = (int)(bh % H);
+  const int64_t b = bh / H;
+  const int64_t off = ((b * T + t) * H + h) * DH;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < DH / 8; ++c) {
+    Vec16<__nv_bfloat16> ov, gv;
+    float of[8], gf[8];
+    ov.load(o + off + c * 8); gv.load(d_o + off + c * 8);
+    ov.unpack(of); gv.unpack(gf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc = fmaf(of[e], gf[e], acc);
+  }
+  delta[i] = acc;
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1)
 lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                   const __grid_constant__ CUtensorMap tq1, const __grid_constant__ CUtensorMap tdo1,
+                   const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
                    const Args a) {
-  constexpr uint32_t S_COL = 0, DP_COL = 64, DQ0_COL = 128, DQ1_COL = 192, DKV0_COL = 256, DKV1_COL = 384,
+  constexpr uint32_t S_COL = 0, DP_COL = 128, DKV0_COL = 256, DQ0_COL = 384, DKV1_COL = 448, DQ1_COL = 480,
                      TMEM_COLS = 512;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BAR);
-  uint64_t *bar_qdo = bars, *bar_kv = bars + 1, *bar_s = bars + 2, *bar_g = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t *bar_kv = bars, *qdo_full = bars + 1, *qdo_free = qdo_full + NQS, *bar_s = qdo_free + NQS,
+           *bar_p = bar_s + 2, *bar_g = bar_s + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const bool worker = tid < TQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = tid < 2 * TQ;
+  if (tid == 0) BW_STAMP(0);
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nq = (a.T + TQ - 1) / TQ;
   const int q_lo = (kb * KB) / TQ;            // first query tile with a row at or after key kb*64
+  const int n = nq - q_lo;                    // pairs of this CTA (>= 1)
 
-  if (warp == 4) {
+  if (warp == BW_MMA) {
     if (elect_one_sync()) {
       if (smem_u32(smem) & 1023u) {
         printf("unimp: lm_attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
         __trap();
       }
-      mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_g, 2);     // MMAs of the pair done (tcgen05.commit) + dQ staging free (issuer)
+      mbar_init(bar_kv, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 8);
+      mbar_init(bar_g, 1);
+#pragma unroll
+      for (int i = 0; i < NQS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_free[i], 1); }
       fence_barrier_init();
-      mbar_arrive_expect_tx(bar_kv, 4 * KP);
-      tma_load_4d(smem + B_K0, &tk, bar_kv, 0, h, kb * KB, b);
-      tma_load_4d(smem + B_K1, &tk, bar_kv, 64, h, kb * KB, b);
-      tma_load_4d(smem + B_V0, &tv, bar_kv, 0, h, kb * KB, b);
-      tma_load_4d(smem + B_V1, &tv, bar_kv, 64, h, kb * KB, b);
-      mbar_arrive_expect_tx(bar_qdo, 4 * QP);
-      tma_load_4d(smem + B_DO0, &tdo, bar_qdo, 0, h, q_lo * TQ, b);
-      tma_load_4d(smem + B_DO1, &tdo, bar_qdo, 64, h, q_lo * TQ, b);
-      tma_load_4d(smem + B_Q0, &tq, bar_qdo, 0, h, q_lo * TQ, b);
-      tma_load_4d(smem + B_Q1, &tq, bar_qdo, 64, h, q_lo * TQ, b);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -361,166 +410,215 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t su = smem_u32(smem);
-  const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);       // S, dP
-  const uint32_t idesc_dq = make_idesc(TQ, 64, 0, 1);      // dQ = dS K   (B = K panel, MN-major)
-  const uint32_t idesc_dkv = make_idesc(128, 128, 1, 1);   // [P|dS]^T [dO|Q]
-  const float l2e = 1.4426950408889634f;
+  if (tid == 0) { BW_STAMP(1); BW_STAMP(4); }
 
-  uint32_t ph = 0;
-  uint32_t r[32];
-  float* stg = reinterpret_cast<float*>(smem + B_STG);
-  const int Tp = nq * TQ;
-  float* dq_head = a.dq32 + ((int64_t)b * a.H + h) * Tp * DQ_PITCH;
-  if (worker) *reinterpret_cast<float4*>(stg + tid * DQ_PITCH + DH) = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int qt = q_lo; qt < nq; ++qt) {
-    const int it = qt - q_lo;
-    const int row = qt * TQ + tid;
-    const bool valid = worker && row < a.T;
-    // ---- S and dP ------------------------------------------------------------------------
-    if (warp == 4 && elect_one_sync()) {
-      if (it > 0) {            // the previous pair's dQ tile (staged before the loop-end barrier)
-        bulk_reduce_add_f32(dq_head + (int64_t)(qt - 1) * TQ * DQ_PITCH, stg, STG_BYTES);
+  // The single-lane loops are unrolled by 6 = lcm(3 ring stages, 2 S/dP buffers): stage offsets,
+  // TMEM buffers and most barrier parities are compile-time constants (uniform-datapath code).
+  if (warp == BW_TMA && elect_one_sync()) {
+    mbar_arrive_expect_tx(bar_kv, 2 * KP + 2 * KP1);
+    tma_load_4d(smem + B_K0, &tk, bar_kv, 0, h, kb * KB, b);
+    tma_load_4d(smem + B_K1, &tk1, bar_kv, 64, h, kb * KB, b);
+    tma_load_4d(smem + B_V0, &tv, bar_kv, 0, h, kb * KB, b);
+    tma_load_4d(smem + B_V1, &tv1, bar_kv, 64, h, kb * KB, b);
+    for (int i0 = 0; i0 < n; i0 += 6) {
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u;
+        if (i < n) {
+          const int st = u % NQS;
+          uint8_t* d = smem + B_RING + st * ST_BYTES;
+          const int r0 = (q_lo + i) * TQ;
+          if (i >= NQS) mbar_wait(&qdo_free[st], ((u / NQS) + 1) & 1);
+          mbar_arrive_expect_tx(&qdo_full[st], ST_BYTES);
+          tma_load_4d(d + ST_Q0, &tq, &qdo_full[st], 0, h, r0, b);
+          tma_load_4d(d + ST_Q1, &tq1, &qdo_full[st], 64, h, r0, b);
+          tma_load_4d(d + ST_DO0, &tdo, &qdo_full[st], 0, h, r0, b);
+          tma_load_4d(d + ST_DO1, &tdo1, &qdo_full[st], 64, h, r0, b);
+        }
+      }
+    }
+  } else if (warp == BW_MMA && elect_one_sync()) {
+    constexpr uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);         // S, dP
+    constexpr uint32_t idesc_dq0 = make_idesc(TQ, 64, 0, 1);       // dQ = dS K   (B = K panel, MN-major)
+    constexpr uint32_t idesc_dq1 = make_idesc(TQ, 16, 0, 1);
+    constexpr uint32_t idesc_dkv0 = make_idesc(128, 128, 1, 1);    // [P|dS]^T [dO|Q] panel 0
+    constexpr uint32_t idesc_dkv1 = make_idesc(128, 32, 1, 1);     // panel 1: N = 16 + 16
+    auto issue_sdp = [&](int st, int buf, uint32_t par) {
+      const uint32_t t_u = su + B_RING + st * ST_BYTES;
+      mbar_wait(&qdo_full[st], par);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(tmem + S_COL + buf * 64, make_smem_desc(t_u + ST_Q0 + k4 * 32, 16, 1024),
+                make_smem_desc(su + B_K0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      umma_ss(tmem + S_COL + buf * 64, make_smem_desc32(t_u + ST_Q1, 16, 256), make_smem_desc32(su + B_K1, 16, 256),
+              idesc_s, 1);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(tmem + DP_COL + buf * 64, make_smem_desc(t_u + ST_DO0 + k4 * 32, 16, 1024),
+                make_smem_desc(su + B_V0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      umma_ss(tmem + DP_COL + buf * 64, make_smem_desc32(t_u + ST_DO1, 16, 256),
+              make_smem_desc32(su + B_V1, 16, 256), idesc_s, 1);
+      umma_commit(&bar_s[buf]);
+    };
+    mbar_wait(bar_kv, 0);
+    issue_sdp(0, 0, 0);
+    if (n > 1) issue_sdp(1, 1, 0);
+    for (int i0 = 0; i0 < n; i0 += 6) {
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u;
+        if (i < n) {
+          const int st = u % NQS;
+          const uint32_t t_u = su + B_RING + st * ST_BYTES;
+          mbar_wait(bar_p, u & 1);          // P_i / dS_i in shared memory, S/dP buffer and dQ columns released
+          if (i < 6) BW_STAMP(8 + i * 8 + 0);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k8 = 0; k8 < TQ / 16; ++k8)
+            umma_ss(tmem + DKV0_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
+                    make_smem_desc(t_u + ST_DO0 + k8 * 2048, QP, 1024), idesc_dkv0, (i > 0 || k8 > 0));
+#pragma unroll
+          for (int k8 = 0; k8 < TQ / 16; ++k8)
+            umma_ss(tmem + DKV1_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
+                    make_smem_desc32(t_u + ST_DO1 + k8 * 512, QP1, 256), idesc_dkv1, (i > 0 || k8 > 0));
+#pragma unroll
+          for (int k4 = 0; k4 < KB / 16; ++k4)
+            umma_ss(tmem + DQ0_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
+                    make_smem_desc(su + B_K0 + k4 * 2048, 1024, 1024), idesc_dq0, k4 > 0);
+#pragma unroll
+          for (int k4 = 0; k4 < KB / 16; ++k4)
+            umma_ss(tmem + DQ1_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
+                    make_smem_desc32(su + B_K1 + k4 * 512, 256, 256), idesc_dq1, k4 > 0);
+          umma_commit(bar_g);
+          umma_commit(&qdo_free[st]);
+          if (i + 2 < n) issue_sdp((u + 2) % NQS, u & 1, ((u + 2) / NQS) & 1);
+          if (i < 6) BW_STAMP(8 + i * 8 + 1);
+        }
+      }
+    }
+  }
+
+  if (worker) {
+    const int r = tid & (TQ - 1), hs = tid >> 7;          // row in the tile, 32-column half
+    const float l2e = 1.4426950408889634f;
+    float* stg = reinterpret_cast<float*>(smem + B_STG);
+    const int Tp = nq * TQ;
+    float* dq_head = a.dq32 + ((int64_t)b * a.H + h) * Tp * DQ_PITCH;
+    const float* lse_h = a.lse + ((int64_t)b * a.H + h) * a.T;
+    const float* del_h = a.delta + ((int64_t)b * a.H + h) * a.T;
+    if (hs == 1) *reinterpret_cast<float4*>(stg + r * DQ_PITCH + DH) = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t q0[32], q1[16];                              // dQ of the previous pair, on its way to staging
+
+    // dQ tile `qt` (already in q0 / q1) -> staging -> one bulk reduce into dq32
+    auto stage_dq = [&](int qt) {
+      if (tid == 0) tma_store_wait_read();                // the previous reduce has left the staging buffer
+      workers_sync();
+      float* dst = stg + r * DQ_PITCH + hs * 32;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(dst + c * 4) = make_float4(__uint_as_float(q0[4 * c]), __uint_as_float(q0[4 * c + 1]),
+                                                              __uint_as_float(q0[4 * c + 2]), __uint_as_float(q0[4 * c + 3]));
+      if (hs == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(stg + r * DQ_PITCH + 64 + c * 4) =
+              make_float4(__uint_as_float(q1[4 * c]), __uint_as_float(q1[4 * c + 1]), __uint_as_float(q1[4 * c + 2]),
+                          __uint_as_float(q1[4 * c + 3]));
+      }
+      fence_proxy_async_smem();
+      workers_sync();
+      if (tid == 0) {
+        bulk_reduce_add_f32(dq_head + (int64_t)qt * TQ * DQ_PITCH, stg, STG_BYTES);
         tma_store_commit();
       }
-      if (it == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_qdo, ph);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + S_COL, make_smem_desc(su + B_Q0 + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_K0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-      umma_ss(tmem + S_COL, make_smem_desc(su + B_Q1, 16, 1024), make_smem_desc(su + B_K1, 16, 1024), idesc_s, 1);
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + DP_COL, make_smem_desc(su + B_DO0 + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_V0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-      umma_ss(tmem + DP_COL, make_smem_desc(su + B_DO1, 16, 1024), make_smem_desc(su + B_V1, 16, 1024), idesc_s, 1);
-      umma_commit(bar_s);
-    }
-    if (worker) {
-      // delta = rowsum(dO o O) and lse for this row while the MMAs run
-      float delta = 0.f, lse_l2 = 0.f;
-      uint64_t vis = 0ull;
-      if (valid) {
-        const __nv_bfloat16* op = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
-        const __nv_bfloat16* gp = a.d_o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
-#pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          Vec16<__nv_bfloat16> ov, gv;
-          float of[8], gf[8];
-          ov.load(op + c * 8); gv.load(gp + c * 8);
-          ov.unpack(of); gv.unpack(gf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) delta = fmaf(of[e], gf[e], delta);
-        }
-        const float lse = a.lse[((int64_t)b * a.H + h) * a.T + row];
-        lse_l2 = lse * l2e;
-        if (lse > -INFINITY) vis = visible(a, b, kb, row);
-      }
-      mbar_wait(bar_s, ph);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t rp[32];
-        tmem_ld32(lane_addr + S_COL + half * 32, r);
-        tmem_ld32(lane_addr + DP_COL + half * 32, rp);
-        tmem_ld_wait();
-        const uint32_t vh = (uint32_t)(vis >> (32 * half));
-        float pv[32], dsv[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float p = 0.f, ds = 0.f;
-          if ((vh >> c) & 1u) {
-            p = exp2f(__uint_as_float(r[c]) * a.scale_log2 - lse_l2);
-            ds = p * (__uint_as_float(rp[c]) - delta) * a.scale;
-          }
-          pv[c] = p;
-          dsv[c] = ds;
-        }
-        store_half(smem + B_P, tid, half, pv);
-        store_half(smem + B_DS, tid, half, dsv);
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-    }
-    __syncthreads();
-    // ---- [dV|dK] += [P|dS]^T [dO|Q] per panel, dQ = dS K per panel -------------------------
-    if (warp == 4 && elect_one_sync()) {
-      tcgen05_fence_after();
-#pragma unroll
-      for (int k8 = 0; k8 < TQ / 16; ++k8)
-        umma_ss(tmem + DKV0_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
-                make_smem_desc(su + B_DO0 + k8 * 2048, QP, 1024), idesc_dkv, (it > 0 || k8 > 0));
-#pragma unroll
-      for (int k8 = 0; k8 < TQ / 16; ++k8)
-        umma_ss(tmem + DKV1_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
-                make_smem_desc(su + B_DO1 + k8 * 2048, QP, 1024), idesc_dkv, (it > 0 || k8 > 0));
-#pragma unroll
-      for (int k4 = 0; k4 < KB / 16; ++k4)
-        umma_ss(tmem + DQ0_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_K0 + k4 * 2048, 1024, 1024), idesc_dq, k4 > 0);
-#pragma unroll
-      for (int k4 = 0; k4 < KB / 16; ++k4)
-        umma_ss(tmem + DQ1_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_K1 + k4 * 2048, 1024, 1024), idesc_dq, k4 > 0);
-      umma_commit(bar_g);
-      tma_store_wait_read();             // the previous dQ reduce has left the staging buffer
-      mbar_arrive(bar_g);
-      mbar_wait(bar_g, ph);              // the Q/dO panels are free: fetch the next tile's
-      if (qt + 1 < nq) {
-        mbar_arrive_expect_tx(bar_qdo, 4 * QP);
-        tma_load_4d(smem + B_DO0, &tdo, bar_qdo, 0, h, (qt + 1) * TQ, b);
-        tma_load_4d(smem + B_DO1, &tdo, bar_qdo, 64, h, (qt + 1) * TQ, b);
-        tma_load_4d(smem + B_Q0, &tq, bar_qdo, 0, h, (qt + 1) * TQ, b);
-        tma_load_4d(smem + B_Q1, &tq, bar_qdo, 64, h, (qt + 1) * TQ, b);
-      }
-    }
-    if (worker) {
-      mbar_wait(bar_g, ph);
-      tcgen05_fence_after();
-      float* dst = stg + tid * DQ_PITCH;
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {      // dQ p0 cols 0-31, 32-63, p1 cols 0-15
-        tmem_ld32(lane_addr + (part < 2 ? DQ0_COL + part * 32 : DQ1_COL), r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < (part < 2 ? 8 : 4); ++c)
-          *reinterpret_cast<float4*>(dst + part * 32 + c * 4) =
-              make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                          __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-    }
-    ph ^= 1;
-    __syncthreads();   // TMEM reads done before the next pair's MMAs overwrite S / dP / dQ
-    tcgen05_fence_after();
-  }
-
-  if (warp == 4 && elect_one_sync()) {          // the last pair's dQ tile
-    bulk_reduce_add_f32(dq_head + (int64_t)(nq - 1) * TQ * DQ_PITCH, stg, STG_BYTES);
-    tma_store_commit();
-    bulk_wait_all();
-  }
-  // ---- flush dV (lanes 0-63) and dK (lanes 64-127) of this key block -----------------------
-  if (worker) {
-    const int key = kb * KB + (tid & 63);
-    const bool is_k = tid >= 64;
-    __nv_bfloat16* dst = (is_k ? a.dk : a.dv) + (((int64_t)b * a.T + key) * a.H + h) * DH;
-    const uint32_t c0 = DKV0_COL + (is_k ? 64 : 0), c1 = DKV1_COL + (is_k ? 64 : 0);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      tmem_ld32(lane_addr + c0 + half * 32, r);
+    };
+    auto read_dq = [&]() {
+      tmem_ld32(lane_addr + DQ0_COL + hs * 32, q0);
+      if (hs == 1) tmem_ld16(lane_addr + DQ1_COL, q1);
       tmem_ld_wait();
-      if (key < a.T) store_bf16(dst + half * 32, r, 32, 1.f);
+    };
+
+    for (int i = 0; i < n; ++i) {
+      const int row = (q_lo + i) * TQ + r;
+      const bool valid = row < a.T;
+      float lse_l2 = 0.f, delta = 0.f;
+      uint32_t vh = 0u;
+      if (valid) {
+        const float lse = lse_h[row];
+        delta = del_h[row];
+        lse_l2 = lse * l2e;
+        if (lse > -INFINITY) vh = (uint32_t)(visible(a, b, kb, row) >> (32 * hs));
+      }
+      mbar_wait(&bar_s[i & 1], (i >> 1) & 1);
+      tcgen05_fence_after();
+      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 2);
+      uint32_t sv[32], dp[32];
+      tmem_ld32(lane_addr + S_COL + (i & 1) * 64 + hs * 32, sv);
+      tmem_ld32(lane_addr + DP_COL + (i & 1) * 64 + hs * 32, dp);
+      tmem_ld_wait();
+      uint4 pp[4], dd[4];
+      uint32_t* pw = reinterpret_cast<uint32_t*>(pp);
+      uint32_t* dw = reinterpret_cast<uint32_t*>(dd);
+      const float nd = -delta;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = exp2f(fmaf(__uint_as_float(sv[c]), a.scale_log2, -lse_l2));
+        float p1 = exp2f(fmaf(__uint_as_float(sv[c + 1]), a.scale_log2, -lse_l2));
+        if (vh != 0xffffffffu) {
+          if (!(vh & (1u << c))) p0 = 0.f;
+          if (!(vh & (2u << c))) p1 = 0.f;
+        }
+        const float d0 = p0 * (__uint_as_float(dp[c]) + nd) * a.scale;
+        const float d1 = p1 * (__uint_as_float(dp[c + 1]) + nd) * a.scale;
+        pw[c >> 1] = pack2(p0, p1);
+        dw[c >> 1] = pack2(d0, d1);
+      }
+      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 3);
+      if (i > 0) {                       // gradient MMAs of pair i-1 done: sP / sdS free, dQ_{i-1} readable
+        mbar_wait(bar_g, (i - 1) & 1);
+        tcgen05_fence_after();
+      }
+      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(smem + B_P + sw128_offset(r, hs * 4 + c)) = pp[c];
+        *reinterpret_cast<uint4*>(smem + B_DS + sw128_offset(r, hs * 4 + c)) = dd[c];
+      }
+      fence_proxy_async_smem();
+      if (i > 0) read_dq();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 5);
+      if (i > 0) stage_dq(q_lo + i - 1);   // overlaps the gradient MMAs of pair i
+      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 6);
     }
-    tmem_ld32(lane_addr + c1, r);
-    tmem_ld_wait();
-    if (key < a.T) store_bf16(dst + 64, r, 16, 1.f);
+    mbar_wait(bar_g, (n - 1) & 1);
+    tcgen05_fence_after();
+    if (tid == 0) { BW_STAMP(2); BW_STAMP(5); }
+    read_dq();
+    stage_dq(nq - 1);
+
+    // ---- flush dV (lanes 0-63) and dK (lanes 64-127) of this key block; each thread 32 (+16) columns
+    {
+      const int key = kb * KB + (r & 63);
+      const bool is_k = r >= 64;
+      __nv_bfloat16* dst = (is_k ? a.dk : a.dv) + (((int64_t)b * a.T + key) * a.H + h) * DH;
+      tmem_ld32(lane_addr + DKV0_COL + (is_k ? 64 : 0) + hs * 32, q0);
+      if (hs == 1) tmem_ld16(lane_addr + DKV1_COL + (is_k ? 16 : 0), q1);
+      tmem_ld_wait();
+      if (key < a.T) {
+        store_bf16(dst + hs * 32, q0, 32, 1.f);
+        if (hs == 1) store_bf16(dst + 64, q1, 16, 1.f);
+      }
+    }
     tcgen05_fence_before();
+    if (tid == 0) bulk_wait_all();
+    if (tid == 0) { BW_STAMP(3); BW_STAMP(6); }
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == BW_MMA) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // attention_mask (B,T) (nonzero = real token) -> one bit per key, 32 keys per word
@@ -544,6 +642,18 @@ static int make_map(CUtensorMap* out, const void* base, int64_t bs, int64_t rs, 
   const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return make_tmap_tiled(out, base, 4, dims, strides, box);
 }
+
+// panel 0: 64 columns SWIZZLE_128B from column 0; panel 1: 16 columns SWIZZLE_32B (coordinate 64)
+static int make_map_p(CUtensorMap* out, const void* base, int64_t bs, int64_t rs, int64_t hs, int B, int T,
+                      int H, int box_rows, int p1) {
+  if (B == 1) bs = rs * (int64_t)T;
+  const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)H, (uint64_t)T, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
+  const uint32_t box[4] = {p1 ? 16u : 64u, 1, (uint32_t)box_rows, 1};
+  return make_tmap_tiled_sw(out, base, 4, dims, strides, box, p1 ? 32 : 128);
+}
+
+static unsigned long long* g_bwd_dbg = nullptr;
 
 static const char* unsupported(const void* q, const void* k, const void* v, int64_t bs, int64_t rs,
                                int64_t hs, int dh, int dtype) {
@@ -622,10 +732,10 @@ extern "C" int unimp_lm_attn_fwd(const void* q, const void* k, const void* v, in
 
 extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, int64_t batch_stride,
                                  int64_t row_stride, int64_t head_stride, const uint32_t* key_bits,
-                                 const void* o, const void* d_o, const float* lse, float* dq32, void* dk,
-                                 void* dv, int B, int T, int H, int dh, float scale, int dtype,
+                                 const void* o, const void* d_o, const float* lse, float* dq32, float* delta,
+                                 void* dk, void* dv, int B, int T, int H, int dh, float scale, int dtype,
                                  void* stream) {
-  UNIMP_CHECK_ARG(q && k && v && o && d_o && lse && dq32 && dk && dv, UNIMP_E_NULL,
+  UNIMP_CHECK_ARG(q && k && v && o && d_o && lse && dq32 && delta && dk && dv, UNIMP_E_NULL,
                   "unimp_lm_attn_bwd: NULL pointer");
   UNIMP_CHECK_ARG(B > 0 && T > 0 && H > 0, UNIMP_E_SHAPE, "unimp_lm_attn_bwd: empty shape");
   const char* why = lm::unsupported(q, k, v, batch_stride, row_stride, head_stride, dh, dtype);
@@ -633,13 +743,15 @@ extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, in
   UNIMP_CHECK_ARG(aligned16(o) && aligned16(d_o) && aligned16(dq32) && aligned16(dk) && aligned16(dv),
                   UNIMP_E_ALIGN, "unimp_lm_attn_bwd: o/d_o/dq32/dk/dv must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tq, tdo, tk, tv;
+  CUtensorMap m[8];
   int rc;
   const int64_t D = (int64_t)H * dh;
-  if ((rc = lm::make_map(&tq, q, batch_stride, row_stride, head_stride, B, T, H, lm::TQ))) return rc;
-  if ((rc = lm::make_map(&tdo, d_o, (int64_t)T * D, D, dh, B, T, H, lm::TQ))) return rc;
-  if ((rc = lm::make_map(&tk, k, batch_stride, row_stride, head_stride, B, T, H, lm::KB))) return rc;
-  if ((rc = lm::make_map(&tv, v, batch_stride, row_stride, head_stride, B, T, H, lm::KB))) return rc;
+  for (int p1 = 0; p1 < 2; ++p1) {
+    if ((rc = lm::make_map_p(&m[4 * p1 + 0], q, batch_stride, row_stride, head_stride, B, T, H, lm::TQ, p1))) return rc;
+    if ((rc = lm::make_map_p(&m[4 * p1 + 1], d_o, (int64_t)T * D, D, dh, B, T, H, lm::TQ, p1))) return rc;
+    if ((rc = lm::make_map_p(&m[4 * p1 + 2], k, batch_stride, row_stride, head_stride, B, T, H, lm::KB, p1))) return rc;
+    if ((rc = lm::make_map_p(&m[4 * p1 + 3], v, batch_stride, row_stride, head_stride, B, T, H, lm::KB, p1))) return rc;
+  }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(lm::lm_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -650,14 +762,22 @@ extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, in
   const int Tp = (T + lm::TQ - 1) / lm::TQ * lm::TQ;
   cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * H * Tp * lm::DQ_PITCH * sizeof(float), st);
   if (e != cudaSuccess) { set_error("lm_attn_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  const int64_t rows = (int64_t)B * H * T;
+  lm::lm_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o,
+                                                                      (const __nv_bfloat16*)d_o, delta, T, H, rows);
+  UNIMP_CHECK_LAUNCH();
   lm::Args a{};
   a.o = (__nv_bfloat16*)const_cast<void*>(o); a.d_o = (const __nv_bfloat16*)d_o;
   a.o_bs = (int64_t)T * D; a.o_rs = D;
-  a.lse = const_cast<float*>(lse); a.kbits = key_bits; a.kwords = 2 * ((T + 63) / 64);
+  a.lse = const_cast<float*>(lse); a.delta = delta; a.kbits = key_bits; a.kwords = 2 * ((T + 63) / 64);
   a.dq32 = dq32; a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
+  a.dbg = lm::g_bwd_dbg;
   a.T = T; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((T + lm::KB - 1) / lm::KB, H, B);
-  lm::lm_attn_bwd_kernel<<<grid, lm::THREADS, lm::B_SMEM, st>>>(tq, tdo, tk, tv, a);
+  lm::lm_attn_bwd_kernel<<<grid, lm::BW_THREADS, lm::B_SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], a);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }
+
+// Test hook (not in the public header): 64 x u64 stamps per CTA of the next unimp_lm_attn_bwd launches.
+extern "C" void unimp__lm_bwd_debug(unsigned long long* buf) { unimp::lm::g_bwd_dbg = buf; }

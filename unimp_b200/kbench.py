@@ -209,25 +209,26 @@ def _run_lm_attn(cfg, wl, dtype, eager, rec):
     byts = es * 4 * B * T * H * dh + 4 * B * H * T          # q, k, v, o + lse
     fl = 4.0 * B * H * dh * T * (T + 1) / 2                 # causal half
     K = _k(byts, cap=16)
-    packs = [torch.randn(B, T, H * 3 * dh, device=dev, dtype=dtype, requires_grad=True) for _ in range(K)]
+    packs = [torch.randn(B, T, H * 3 * dh, device=dev, dtype=dtype) for _ in range(K)]
     gos = [torch.randn(B, T, H * dh, device=dev, dtype=dtype) for _ in range(K)]
 
-    def views(p):
-        return tuple(p.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2) for i in range(3))
+    def views(p):   # leaf q/k/v VIEWS of the packed projection: the backward numbers carry no un-packing glue
+        return tuple(p.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2).requires_grad_() for i in range(3))
 
-    fwd = [lambda p=p: ops.lm_attention(*views(p), None, scale=dh ** -0.5) for p in packs]
+    qkvs = [views(p) for p in packs]
+    fwd = [lambda x=x: ops.lm_attention(*x, None, scale=dh ** -0.5) for x in qkvs]
     rec("lm_attn_fwd", _time_graph(fwd), byts, fl, K)
     os_ = [f() for f in fwd]
-    bwd = [lambda o=o, p=p, g=g: torch.autograd.grad(o, p, g, retain_graph=True) for o, p, g in zip(os_, packs, gos)]
+    bwd = [lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True) for o, x, g in zip(os_, qkvs, gos)]
     rec("lm_attn_bwd", _time_graph(bwd), 2.5 * byts, 2.5 * fl, K)
     if eager:
         F = torch.nn.functional
-        efw = [lambda p=p: F.scaled_dot_product_attention(*views(p), is_causal=True, scale=dh ** -0.5)
-               .transpose(1, 2).reshape(B, T, H * dh) for p in packs]
+        efw = [lambda x=x: F.scaled_dot_product_attention(*x, is_causal=True, scale=dh ** -0.5)
+               .transpose(1, 2).reshape(B, T, H * dh) for x in qkvs]
         rec("eager_lm_attn_fwd", _time_graph(efw), byts, fl, K)
         eos = [f() for f in efw]
-        rec("eager_lm_attn_bwd", _time_graph([lambda o=o, p=p, g=g: torch.autograd.grad(o, p, g, retain_graph=True)
-                                              for o, p, g in zip(eos, packs, gos)]), 2.5 * byts, 2.5 * fl, K)
+        rec("eager_lm_attn_bwd", _time_graph([lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True)
+                                              for o, x, g in zip(eos, qkvs, gos)]), 2.5 * byts, 2.5 * fl, K)
 
 
 def _run_vit_perceiver(cfg, wl, dtype, eager, rec):

@@ -580,12 +580,14 @@ class _LMAttention(torch.autograd.Function):
         B, H, T, dh = q.shape
         d_o = d_o.contiguous()
         dq32 = torch.empty((B, H, (T + 127) // 128 * 128, 84), dtype=torch.float32, device=q.device)
+        delta = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
         dk = torch.empty((B, T, H, dh), dtype=q.dtype, device=q.device)
         dv = torch.empty_like(dk)
         kb = key_bits.data_ptr() if key_bits is not None else None
         check(_lib.load().unimp_lm_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), q.stride(2),
                                             q.stride(1), kb, o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
-                                            dq32.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, H, dh,
+                                            dq32.data_ptr(), delta.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                            B, T, H, dh,
                                             ctx.scale, _dt(q), _stream()), "unimp_lm_attn_bwd")
         return (dq32[:, :, :T, :dh].to(q.dtype), dk.transpose(1, 2), dv.transpose(1, 2), None, None)
 
