@@ -351,6 +351,7 @@ class LaunchCounter:
     # kernels per call: focal CE forward = row pass + fixed-order finish; LN backward = row pass
     # (+ the column/gate fold only when d_gate / d_gamma / d_beta are requested: args 10-12, g_ln = 1)
     PER_CALL = {"unimp_focal_ce_fwd": lambda a: 2, "unimp_focal_ce_rows_fwd": lambda a: 2,
+                "unimp_lm_attn_bwd": lambda a: 2,     # delta = rowsum(dO o O), then the gradient kernel
                 "unimp_gate_residual_ln_bwd": lambda a: 2 if (((a[11] or a[12]) and a[1]) or a[10]) else 1}
 
     def __init__(self):

@@ -175,7 +175,7 @@ def bwd_timeline(B, T, H):
           f"{float(life.sum() / span / 148):.2f} CTAs/SM, CTA lifetime median {life.median():.0f} ns; start->ready "
           f"{(t[:, 1] - t[:, 0]).median():.0f} ns; last gradients -> end {(t[:, 3] - t[:, 2]).median():.0f} ns "
           f"({(t[:, 6] - t[:, 5]).median():.0f} cycles)")
-    for npairs in (1, 2, 4, 8):
+    for npairs in (1, 2, 4, 6):
         sel = t[(t[:, 8 + (npairs - 1) * 8 + 5] > 0) & ((t[:, 8 + npairs * 8 + 5] == 0) if npairs < 6 else True)]
         if len(sel) == 0:
             continue

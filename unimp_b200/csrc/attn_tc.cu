@@ -5,8 +5,7 @@
 //       a 128-query tile walks only the 64-key image blocks its rows reference
 //       (text_time-1); the mask is evaluated in registers, never materialised.
 //   K2  Perceiver latent attention (64 x 320) and K3 ViT-L/14 self-attention (257 x 257):
-//       all of S = Q K^T for the tile lives in TMEM (<= 384 fp32 columns), so softmax is a
-//       plain two-pass row softmax with no online rescaling of O.
+//       forward in flash_fwd.cu (one-sweep online softmax); the Perceiver backward is here.
 //
 // Forward: one CTA = one (128-row query tile, head, batch), 160 threads: warps 0-3 own one query
 // row each (thread t = TMEM lane t: softmax / epilogue); one lane of warp 4, chosen by elect.sync,
@@ -304,210 +303,6 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// K2 / K3 forward, round 2: unmasked attention (Perceiver 64 x 320, ViT 257 x 257, any Lk).
-// Round 1 kept all of S for the tile in TMEM (up to 384 + 64 columns => 512 allocated => ONE CTA
-// per SM) and the 576 CTAs of the ViT call ran as four serial waves.  Here S lives in 64 columns:
-//   sweep 1  S_j = Q K_j^T per key block, row max only;
-//   sweep 2  S_j again (the tensor pipe is idle anyway: +50 % MMA work, no O rescaling),
-//            P_j = exp2(scale*(S_j - max)) -> bf16 -> shared, O += P_j V_j.
-// 128 TMEM columns + 65 KB shared memory => 3 CTAs per SM, K/V streamed through a 2-stage ring
-// (K is read twice, from L2).  Warps whose 32 rows are all beyond Lq (the 257 = 2*128 + 1 tail of
-// the ViT) skip the softmax work; key halves beyond Lk are not exponentiated.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FWD_THREADS, 3)
-attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                    const __grid_constant__ CUtensorMap tv, const FwdArgs a) {
-  constexpr uint32_t S_COL = 0, O_COL = KB, TMEM_COLS = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + XF_STAGES * KV_BYTES;
-  uint8_t* sP = sV + XF_STAGES * KV_BYTES;
-  __shared__ uint64_t bar_q, bar_kv[XF_STAGES], bar_s, bar_p, bar_pv, bar_o;
-  __shared__ uint32_t tmem_slot;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool worker = tid < TQ;
-  const int row0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
-  const int nb = (a.Lk + KB - 1) / KB, nsteps = 2 * nb;
-
-  // step s: key block s % nb; steps [0, nb) = sweep 1 (K only), [nb, 2nb) = sweep 2 (K and V)
-  auto load_step = [&](int s) {
-    const int st = s % XF_STAGES, j = s % nb;
-    if (s < nb) {
-      mbar_arrive_expect_tx(&bar_kv[st], KV_BYTES);
-      tma_load_4d(sK + st * KV_BYTES, &tk, &bar_kv[st], 0, h, j * KB, b);
-    } else {
-      mbar_arrive_expect_tx(&bar_kv[st], 2 * KV_BYTES);
-      tma_load_4d(sK + st * KV_BYTES, &tk, &bar_kv[st], 0, h, j * KB, b);
-      tma_load_4d(sV + st * KV_BYTES, &tv, &bar_kv[st], 0, h, j * KB, b);
-    }
-  };
-
-  if (warp == 4) {
-    if (elect_one_sync()) {
-      mbar_init(&bar_q, 1); mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1);
-      mbar_init(&bar_o, 1);
-#pragma unroll
-      for (int i = 0; i < XF_STAGES; ++i) mbar_init(&bar_kv[i], 1);
-      fence_barrier_init();
-      mbar_arrive_expect_tx(&bar_q, Q_BYTES);
-      tma_load_4d(sQ, &tq, &bar_q, 0, h, row0, b);
-      for (int s = 0; s < nsteps && s < XF_STAGES; ++s) load_step(s);
-    }
-    __syncwarp();
-    tmem_alloc(&tmem_slot, TMEM_COLS);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
-  const uint32_t idesc_o = make_idesc(TQ, DH, 0, 1);
-
-  if (warp == 4 && elect_one_sync()) {
-    // The elected lane runs mostly on the uniform datapath (~12 cycles per dependent instruction):
-    // the step loop is unrolled by the ring depth so that stage offsets and most barrier parities
-    // are compile-time constants.
-    static_assert(XF_STAGES == 2, "the unrolled step loop assumes a 2-stage ring");
-    const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), p_u = smem_u32(sP);
-    mbar_wait(&bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    tcgen05_fence_after();
-#pragma unroll
-    for (int k4 = 0; k4 < DH / 16; ++k4)
-      umma_ss(tmem + S_COL, make_smem_desc(q_u + k4 * 32, 16, 1024), make_smem_desc(k_u + k4 * 32, 16, 1024),
-              idesc_s, k4 > 0);
-    umma_commit(&bar_s);
-    uint32_t ring_ph = 0;                      // parity of stage 0's current fill; stage 1 lags by one step
-    for (int s0 = 0; s0 < nsteps; s0 += 2) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int s = s0 + u;                  // stage = u, bar_p parity = u
-        if (s < nsteps) {
-          const bool sweep2 = s >= nb;
-          mbar_wait(&bar_p, u);                // sweep 1: S_s consumed; sweep 2: P_s in shared memory
-          if (sweep2) {
-            tcgen05_fence_after();
-#pragma unroll
-            for (int k4 = 0; k4 < KB / 16; ++k4)
-              umma_ss(tmem + O_COL, make_smem_desc(p_u + k4 * 32, 16, 1024),
-                      make_smem_desc(v_u + u * KV_BYTES + k4 * 2048, 1024, 1024), idesc_o, (s > nb || k4 > 0));
-            umma_commit(&bar_pv);
-            if (s + 1 == nsteps) umma_commit(&bar_o);
-          }
-          if (s + 1 < nsteps) {
-            // step s+1 lives in stage 1-u; its fill parity: stage 1 (u == 0) shares this round's
-            // parity, stage 0 (u == 1) is one fill ahead
-            mbar_wait(&bar_kv[1 - u], u == 0 ? ring_ph : (ring_ph ^ 1));
-            tcgen05_fence_after();
-#pragma unroll
-            for (int k4 = 0; k4 < DH / 16; ++k4)
-              umma_ss(tmem + S_COL, make_smem_desc(q_u + k4 * 32, 16, 1024),
-                      make_smem_desc(k_u + (1 - u) * KV_BYTES + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-            umma_commit(&bar_s);
-          }
-          if (s + XF_STAGES < nsteps) {
-            if (sweep2) mbar_wait(&bar_pv, (s - nb) & 1);   // PV_s has released stage u
-            load_step(s + XF_STAGES);
-          }
-        }
-      }
-      ring_ph ^= 1;
-    }
-  }
-
-  if (worker) {
-    const int row = row0 + tid;
-    const bool valid = row < a.Lq;
-    const bool active = row0 + (warp << 5) < a.Lq;       // warp-uniform: any valid row in this warp
-    float m = -INFINITY, sum = 0.f, ms = 0.f;
-    uint32_t r[32];
-    for (int s = 0; s < nsteps; ++s) {
-      const int j = s % nb;
-      const int ncols = min(KB, a.Lk - j * KB);          // valid keys in this block (CTA-uniform)
-      mbar_wait(&bar_s, s & 1);
-      tcgen05_fence_after();
-      if (s < nb) {
-        if (active) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half * 32 < ncols) {
-              tmem_ld32(lane_addr + S_COL + half * 32, r);
-              tmem_ld_wait();
-              if (ncols - half * 32 >= 32) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));
-              } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (half * 32 + c < ncols) m = fmaxf(m, __uint_as_float(r[c]));
-              }
-            }
-          }
-        }
-        if (s + 1 == nb) ms = m * a.scale_log2;
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p);
-      } else {
-        if (active) {
-          float psum = 0.f;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float p[32];
-            if (half * 32 < ncols) {
-              tmem_ld32(lane_addr + S_COL + half * 32, r);
-              tmem_ld_wait();
-              if (ncols - half * 32 >= 32) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  p[c] = exp2f(__uint_as_float(r[c]) * a.scale_log2 - ms);
-                  psum += p[c];
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  p[c] = (half * 32 + c < ncols) ? exp2f(__uint_as_float(r[c]) * a.scale_log2 - ms) : 0.f;
-                  psum += p[c];
-                }
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) p[c] = 0.f;
-            }
-            store_p_half(sP, tid, half, p);
-          }
-          sum += psum;
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p);
-      }
-    }
-    mbar_wait(&bar_o, 0);
-    tcgen05_fence_after();
-    if (active) {
-      const float inv = 1.f / sum;
-      __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(lane_addr + O_COL + half * 32, r);
-        tmem_ld_wait();
-        if (valid) store_row_bf16_mul(orow + half * 32, r, inv);
-      }
-      if (valid) a.lse[((int64_t)b * a.H + h) * a.Lq + row] = m * a.scale + logf(sum);
-    }
-    tcgen05_fence_before();
-  }
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
-}
-
 // ---- host ---------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -608,33 +403,6 @@ const char* attn_fwd_tc_unsupported(unimp_view_t q, unimp_view_t k, unimp_view_t
   return nullptr;
 }
 
-static int launch_attn_fwd2(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o, float* lse,
-                            int B, int Lq, int Lk, int H, float scale, cudaStream_t st) {
-  CUtensorMap tq, tk, tv;
-  int rc;
-  if ((rc = make_tmap_bhld(&tq, q.ptr, q.batch_stride, q.row_stride, B, Lq, H, TQ))) return rc;
-  if ((rc = make_tmap_bhld(&tk, k.ptr, k.batch_stride, k.row_stride, B, Lk, H, KB))) return rc;
-  if ((rc = make_tmap_bhld(&tv, v.ptr, v.batch_stride, v.row_stride, B, Lk, H, KB))) return rc;
-  const int smem = 1024 + Q_BYTES + 2 * XF_STAGES * KV_BYTES + P_BYTES;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("attn_fwd2_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaFuncSetAttribute(attn_fwd2_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    attr = true;
-  }
-  FwdArgs a;
-  a.dbg = nullptr;
-  a.o = (__nv_bfloat16*)o.ptr; a.o_bs = o.batch_stride; a.o_rs = o.row_stride;
-  a.lse = lse; a.tt = nullptr; a.Lq = Lq; a.Lk = Lk; a.H = H; a.n = Lk; a.Ti = 1;
-  a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Lq + TQ - 1) / TQ, H, B);
-  attn_fwd2_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tk, tv, a);
-  UNIMP_CHECK_LAUNCH();
-  return 0;
-}
-
 static unsigned long long* g_xf_dbg = nullptr;   // test hook (unimp__xattn_fwd_debug)
 
 static int launch_xattn_fwd(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* tt,
@@ -673,11 +441,9 @@ int launch_attn_fwd_tc(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int
                        float* lse, int B, int Lq, int Lk, int H, int n, int Ti, float scale,
                        cudaStream_t st) {
   if (tt) return launch_xattn_fwd(q, k, v, tt, o, lse, B, Lq, Lk, H, n, Ti, scale, st);
-  // one-sweep kernel (flash_fwd.cu); UNIMP_ATTN_FWD2=1 keeps the two-sweep kernel for A/B runs
-  static const bool two_sweep = getenv("UNIMP_ATTN_FWD2") && atoi(getenv("UNIMP_ATTN_FWD2")) != 0;
-  if (!two_sweep && k.batch_stride == v.batch_stride && k.row_stride == v.row_stride)
-    return launch_flash_fwd_64(q, k, v, o, lse, B, Lq, Lk, H, scale, st);
-  return launch_attn_fwd2(q, k, v, o, lse, B, Lq, Lk, H, scale, st);
+  // K2 / K3: the one-sweep kernel of flash_fwd.cu (it replaced round 2's first two-sweep kernel:
+  // ViT 28.0 -> 22.2 us, Perceiver 13.1 -> 9.1 us at configs[1]; profiles/r2_flash_fwd_vs_two_sweep.log)
+  return launch_flash_fwd_64(q, k, v, o, lse, B, Lq, Lk, H, scale, st);
 }
 
 // ---------------------------------------------------------------------------------------------

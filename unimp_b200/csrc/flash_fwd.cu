@@ -62,17 +62,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
-__device__ __forceinline__ void store_half(uint8_t* tile, int row, int half, const float* p) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 v;
-    v.x = pack2(p[8 * c + 0], p[8 * c + 1]);
-    v.y = pack2(p[8 * c + 2], p[8 * c + 3]);
-    v.z = pack2(p[8 * c + 4], p[8 * c + 5]);
-    v.w = pack2(p[8 * c + 6], p[8 * c + 7]);
-    *reinterpret_cast<uint4*>(tile + sw128_offset(row, half * 4 + c)) = v;
-  }
-}
 __device__ __forceinline__ void store_bf16(__nv_bfloat16* dst, const uint32_t* r, int n, float mul) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -373,8 +362,9 @@ int make_tmap_tiled_sw(CUtensorMap* out, const void* base, int rank, const uint6
 
 // q, k, v: (B, L, H, dh) views given by (batch, row, head) strides in elements.
 template <int DH, bool CAUSAL>
-static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, const void* v,
-                        int64_t k_bs, int64_t k_rs, int64_t k_hs, const uint32_t* kbits, void* o, int64_t o_bs,
+static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs, const void* k, int64_t k_bs,
+                        int64_t k_rs, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_rs, int64_t v_hs,
+                        const uint32_t* kbits, void* o, int64_t o_bs,
                         int64_t o_rs, float* lse, int B, int Lq, int Lk, int H, float scale, cudaStream_t st) {
   using L = ff::Smem<DH>;
   CUtensorMap m[6];
@@ -389,11 +379,11 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
   int rc;
   if ((rc = mk(&m[0], q, q_bs, q_rs, q_hs, Lq, ff::TQ, false))) return rc;
   if ((rc = mk(&m[1], k, k_bs, k_rs, k_hs, Lk, ff::KB, false))) return rc;
-  if ((rc = mk(&m[2], v, k_bs, k_rs, k_hs, Lk, ff::KB, false))) return rc;
+  if ((rc = mk(&m[2], v, v_bs, v_rs, v_hs, Lk, ff::KB, false))) return rc;
   if (L::P1) {
     if ((rc = mk(&m[3], q, q_bs, q_rs, q_hs, Lq, ff::TQ, true))) return rc;
     if ((rc = mk(&m[4], k, k_bs, k_rs, k_hs, Lk, ff::KB, true))) return rc;
-    if ((rc = mk(&m[5], v, k_bs, k_rs, k_hs, Lk, ff::KB, true))) return rc;
+    if ((rc = mk(&m[5], v, v_bs, v_rs, v_hs, Lk, ff::KB, true))) return rc;
   } else {
     m[3] = m[0]; m[4] = m[1]; m[5] = m[2];
   }
@@ -420,17 +410,17 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
 // dh = 64, unmasked (Perceiver / ViT): q (B,Lq,H,64), k/v (B,Lk,H,64) with head stride 64
 int launch_flash_fwd_64(unimp_view_t q, unimp_view_t k, unimp_view_t v, unimp_mview_t o, float* lse, int B,
                         int Lq, int Lk, int H, float scale, cudaStream_t st) {
-  return launch_flash<64, false>(q.ptr, q.batch_stride, q.row_stride, 64, k.ptr, v.ptr, k.batch_stride,
-                                 k.row_stride, 64, nullptr, o.ptr, o.batch_stride, o.row_stride, lse, B, Lq, Lk,
-                                 H, scale, st);
+  return launch_flash<64, false>(q.ptr, q.batch_stride, q.row_stride, 64, k.ptr, k.batch_stride, k.row_stride, 64,
+                                 v.ptr, v.batch_stride, v.row_stride, 64, nullptr, o.ptr, o.batch_stride,
+                                 o.row_stride, lse, B, Lq, Lk, H, scale, st);
 }
 
 // dh = 80, causal + key bits (GPT-NeoX)
 int launch_flash_fwd_80(const void* q, const void* k, const void* v, int64_t bs, int64_t rs, int64_t hs,
                         const uint32_t* kbits, void* o, float* lse, int B, int T, int H, float scale,
                         cudaStream_t st) {
-  return launch_flash<80, true>(q, bs, rs, hs, k, v, bs, rs, hs, kbits, o, (int64_t)T * H * 80, (int64_t)H * 80,
-                                lse, B, T, T, H, scale, st);
+  return launch_flash<80, true>(q, bs, rs, hs, k, bs, rs, hs, v, bs, rs, hs, kbits, o, (int64_t)T * H * 80,
+                                (int64_t)H * 80, lse, B, T, T, H, scale, st);
 }
 
 }  // namespace unimp

@@ -4,22 +4,19 @@
 // upstream `FlamingoLayer.forward` -> `decoder_layer(...)`, call site UniMP/mmrec.py:177-181): after
 // rotary, softmax(scale * q k^T + causal/padding mask) v per head.  SURVEY.md §8 row f3.
 //
-// Head dim 80 on SWIZZLE_128B operands: a head's 80 columns are read as TWO 64-column panels from a
-// tensor map whose innermost extent is 80 — panel 1 (columns 64..127) gets columns 80..127 zero
-// filled by the TMA unit, no padded copy of q/k/v exists in memory.  S = Q K^T takes 4 K-steps from
-// panel 0 and ONE from panel 1 (K = 80 exactly); O and the gradients are produced per panel
-// (N = 64, of which 16 columns are used in panel 1).
+// Head dim 80 = TWO column panels read from tensor maps whose innermost extent is 80: a 64-column
+// SWIZZLE_128B panel and a 16-column SWIZZLE_32B panel (coordinate 64).  S = Q K^T takes 4 K-steps
+// from panel 0 and ONE from panel 1 (K = 80 exactly); O and the gradients are produced per panel
+// (N = 64 and N = 16).  No padded copy of q/k/v exists in memory.
 //
 // Mask: key j is visible to query i iff j <= i and key_bits[b][j] (bit j%32 of word j/32; NULL = all
 // keys valid) — what HF builds from a 2-D attention_mask for a causal LM.  Rows that see no key
 // get o = 0 / lse = -inf.
 //
-// Forward : CTA = (128-query tile, head, sample), two sweeps over the tile's key blocks like
-//           attn_fwd2_tc_kernel (row max, then exp + PV with S recomputed); 2 CTAs per SM.
-// Backward: CTA = (64-key block, head, sample) walks the query tiles at or below the diagonal;
-//           dK/dV accumulate in TMEM across tiles; each pair's dQ tile is staged in shared memory and
-//           added into an fp32 buffer (B,H,Tp,84) with ONE bulk reduce (cp.reduce.async.bulk .add.f32,
-//           43 KB, asynchronous) — per-thread vector atomics were L2-bound (917 us at T=1024).
+// Forward : flash_fwd.cu (one-sweep online softmax, shared with the ViT / Perceiver cores).
+// Backward: this file.  A first version (one CTA-wide step at a time, per-thread fp32 vector atomics
+//           for dQ) measured 917 us at T=1024; the pipelined kernel below 352 us
+//           (profiles/r2_lm_attn_*.log).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -36,7 +33,6 @@ constexpr int TQ = 128, KB = 64, DH = 80;
 constexpr uint32_t QP = TQ * 128;     // one [128 rows][64 cols] bf16 panel, 16 KB
 constexpr uint32_t KP = KB * 128;     // one [64 rows][64 cols] panel, 8 KB
 constexpr uint32_t PB = TQ * 128;     // P / dS: [128 rows][64 keys], 16 KB
-constexpr int THREADS = TQ + 32;
 
 struct Args {
   unsigned long long* dbg;   // test hook (unimp__lm_bwd_debug): 64 x u64 stamps per CTA, NULL = off
@@ -56,18 +52,6 @@ struct Args {
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
-}
-// 32 floats -> half of a 128-byte swizzled row of a [128][64] bf16 tile
-__device__ __forceinline__ void store_half(uint8_t* tile, int row, int half, const float* p) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 v;
-    v.x = pack2(p[8 * c + 0], p[8 * c + 1]);
-    v.y = pack2(p[8 * c + 2], p[8 * c + 3]);
-    v.z = pack2(p[8 * c + 4], p[8 * c + 5]);
-    v.w = pack2(p[8 * c + 6], p[8 * c + 7]);
-    *reinterpret_cast<uint4*>(tile + sw128_offset(row, half * 4 + c)) = v;
-  }
 }
 // n (multiple of 8) fp32 TMEM words -> bf16 row, scaled
 __device__ __forceinline__ void store_bf16(__nv_bfloat16* dst, const uint32_t* r, int n, float mul) {
@@ -93,208 +77,6 @@ __device__ __forceinline__ uint64_t visible(const Args& a, int b, int j, int row
     m &= (uint64_t)w[0] | ((uint64_t)w[1] << 32);
   }
   return m;
-}
-
-// Dynamic shared memory only (no static __shared__): the base of the window is 1024-byte aligned,
-// which SWIZZLE_128B tiles need, without paying 1 KB of slack (two CTAs per SM fit to the byte).
-constexpr uint32_t F_Q0 = 0, F_Q1 = QP, F_RING = 2 * QP, F_STAGE = 4 * KP, F_P = F_RING + 2 * F_STAGE,
-                   F_BAR = F_P + PB, F_SMEM = F_BAR + 128;
-
-__global__ void __launch_bounds__(THREADS, 2)
-lm_attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                   const __grid_constant__ CUtensorMap tv, const Args a) {
-  constexpr uint32_t S_COL = 0, O0_COL = 64, O1_COL = 128, TMEM_COLS = 256;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_BAR);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_s = bars + 3, *bar_p = bars + 4, *bar_pv = bars + 5,
-           *bar_o = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool worker = tid < TQ;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;   // long (late) tiles first
-  const int row0 = qt * TQ, h = blockIdx.y, b = blockIdx.z;
-  const int nb = min((a.T + KB - 1) / KB, (row0 + TQ) / KB), nsteps = 2 * nb;
-
-  // step s: key block s % nb; steps [0, nb) = sweep 1 (K only), [nb, 2nb) = sweep 2 (K and V)
-  auto load_step = [&](int s) {
-    const int st = s & 1, j = s % nb;
-    uint8_t* base = smem + F_RING + st * F_STAGE;
-    if (s < nb) {
-      mbar_arrive_expect_tx(&bar_kv[st], 2 * KP);
-      tma_load_4d(base, &tk, &bar_kv[st], 0, h, j * KB, b);
-      tma_load_4d(base + KP, &tk, &bar_kv[st], 64, h, j * KB, b);
-    } else {
-      mbar_arrive_expect_tx(&bar_kv[st], 4 * KP);
-      tma_load_4d(base, &tk, &bar_kv[st], 0, h, j * KB, b);
-      tma_load_4d(base + KP, &tk, &bar_kv[st], 64, h, j * KB, b);
-      tma_load_4d(base + 2 * KP, &tv, &bar_kv[st], 0, h, j * KB, b);
-      tma_load_4d(base + 3 * KP, &tv, &bar_kv[st], 64, h, j * KB, b);
-    }
-  };
-
-  if (warp == 4) {
-    if (elect_one_sync()) {
-      if (smem_u32(smem) & 1023u) {
-        printf("unimp: lm_attn_fwd: dynamic shared memory is not 1024-byte aligned\n");
-        __trap();
-      }
-      mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_pv, 1);
-      mbar_init(bar_o, 1); mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
-      fence_barrier_init();
-      mbar_arrive_expect_tx(bar_q, 2 * QP);
-      tma_load_4d(smem + F_Q0, &tq, bar_q, 0, h, row0, b);
-      tma_load_4d(smem + F_Q1, &tq, bar_q, 64, h, row0, b);
-      load_step(0);
-      if (nsteps > 1) load_step(1);
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
-  const uint32_t idesc_o = make_idesc(TQ, 64, 0, 1);
-
-  if (warp == 4 && elect_one_sync()) {
-    const uint32_t q0 = smem_u32(smem + F_Q0), q1 = smem_u32(smem + F_Q1), ring = smem_u32(smem + F_RING),
-                   p_u = smem_u32(smem + F_P);
-    auto issue_s = [&](uint32_t stage_u) {        // S = Q K^T over K = 80
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + S_COL, make_smem_desc(q0 + k4 * 32, 16, 1024), make_smem_desc(stage_u + k4 * 32, 16, 1024),
-                idesc_s, k4 > 0);
-      umma_ss(tmem + S_COL, make_smem_desc(q1, 16, 1024), make_smem_desc(stage_u + KP, 16, 1024), idesc_s, 1);
-      umma_commit(bar_s);
-    };
-    mbar_wait(bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    tcgen05_fence_after();
-    issue_s(ring);
-    uint32_t ring_ph = 0;          // parity of stage 0's current fill; stage 1 lags by one step
-    for (int s0 = 0; s0 < nsteps; s0 += 2) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int s = s0 + u;      // stage = u, bar_p parity = u
-        if (s < nsteps) {
-          const bool sweep2 = s >= nb;
-          mbar_wait(bar_p, u);     // sweep 1: S_s consumed; sweep 2: P_s in shared memory
-          if (sweep2) {
-            tcgen05_fence_after();
-            const uint32_t v_u = ring + u * F_STAGE + 2 * KP;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_ss(tmem + O0_COL, make_smem_desc(p_u + k4 * 32, 16, 1024),
-                      make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o, (s > nb || k4 > 0));
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_ss(tmem + O1_COL, make_smem_desc(p_u + k4 * 32, 16, 1024),
-                      make_smem_desc(v_u + KP + k4 * 2048, 1024, 1024), idesc_o, (s > nb || k4 > 0));
-            umma_commit(bar_pv);
-            if (s + 1 == nsteps) umma_commit(bar_o);
-          }
-          if (s + 1 < nsteps) {
-            mbar_wait(&bar_kv[1 - u], u == 0 ? ring_ph : (ring_ph ^ 1));
-            tcgen05_fence_after();
-            issue_s(ring + (1 - u) * F_STAGE);
-          }
-          if (s + 2 < nsteps) {
-            if (sweep2) mbar_wait(bar_pv, (s - nb) & 1);   // PV_s has released stage u
-            load_step(s + 2);
-          }
-        }
-      }
-      ring_ph ^= 1;
-    }
-  }
-
-  if (worker) {
-    const int row = row0 + tid;
-    const bool valid = row < a.T;
-    const bool active = row0 + (warp << 5) < a.T;        // warp-uniform
-    float m = -INFINITY, sum = 0.f, ms = 0.f;
-    uint32_t r[32];
-    for (int s = 0; s < nsteps; ++s) {
-      const int j = s % nb;
-      const uint64_t vis = (active && valid) ? visible(a, b, j, row) : 0ull;
-      const bool any = __any_sync(0xffffffffu, vis != 0ull);      // warp-uniform
-      mbar_wait(bar_s, s & 1);
-      tcgen05_fence_after();
-      if (s < nb) {
-        if (any) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t vh = (uint32_t)(vis >> (32 * half));
-            tmem_ld32(lane_addr + S_COL + half * 32, r);
-            tmem_ld_wait();
-            if (vh == 0xffffffffu) {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if ((vh >> c) & 1u) m = fmaxf(m, __uint_as_float(r[c]));
-            }
-          }
-        }
-        if (s + 1 == nb) ms = (m > -INFINITY) ? m * a.scale_log2 : 0.f;
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      } else {
-        if (active) {
-          float psum = 0.f;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float p[32];
-            const uint32_t vh = (uint32_t)(vis >> (32 * half));
-            if (any) {
-              tmem_ld32(lane_addr + S_COL + half * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                p[c] = ((vh >> c) & 1u) ? exp2f(__uint_as_float(r[c]) * a.scale_log2 - ms) : 0.f;
-                psum += p[c];
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) p[c] = 0.f;
-            }
-            store_half(smem + F_P, tid, half, p);
-          }
-          sum += psum;
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      }
-    }
-    mbar_wait(bar_o, 0);
-    tcgen05_fence_after();
-    if (active) {
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(lane_addr + O0_COL + half * 32, r);
-        tmem_ld_wait();
-        if (valid) store_bf16(orow + half * 32, r, 32, inv);
-      }
-      tmem_ld32(lane_addr + O1_COL, r);
-      tmem_ld_wait();
-      if (valid) {
-        store_bf16(orow + 64, r, 16, inv);
-        a.lse[((int64_t)b * a.H + h) * a.T + row] = sum > 0.f ? m * a.scale + logf(sum) : -INFINITY;
-      }
-    }
-    tcgen05_fence_before();
-  }
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -614,7 +396,8 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       }
     }
     tcgen05_fence_before();
-    if (tid == 0) bulk_wait_all();
+    if (tid == 0) tma_store_wait_read();    // the last reduce has left shared memory (its global side completes
+                                            // before the grid does; waiting for it here cost ~1 us per CTA)
     if (tid == 0) { BW_STAMP(3); BW_STAMP(6); }
   }
   __syncthreads();
@@ -634,15 +417,6 @@ __global__ void key_bits_kernel(const M* __restrict__ mask, uint32_t* __restrict
 }
 
 // ---- host -----------------------------------------------------------------------------------
-static int make_map(CUtensorMap* out, const void* base, int64_t bs, int64_t rs, int64_t hs, int B, int T,
-                    int H, int box_rows) {
-  if (B == 1) bs = rs * (int64_t)T;
-  const uint64_t dims[4] = {(uint64_t)DH, (uint64_t)H, (uint64_t)T, (uint64_t)B};
-  const uint64_t strides[3] = {(uint64_t)hs * 2, (uint64_t)rs * 2, (uint64_t)bs * 2};
-  const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
-  return make_tmap_tiled(out, base, 4, dims, strides, box);
-}
-
 // panel 0: 64 columns SWIZZLE_128B from column 0; panel 1: 16 columns SWIZZLE_32B (coordinate 64)
 static int make_map_p(CUtensorMap* out, const void* base, int64_t bs, int64_t rs, int64_t hs, int B, int T,
                       int H, int box_rows, int p1) {
@@ -701,33 +475,8 @@ extern "C" int unimp_lm_attn_fwd(const void* q, const void* k, const void* v, in
   const char* why = lm::unsupported(q, k, v, batch_stride, row_stride, head_stride, dh, dtype);
   UNIMP_CHECK_ARG(!why, UNIMP_E_SHAPE, "unimp_lm_attn_fwd: %s", why);
   UNIMP_CHECK_ARG(aligned16(o), UNIMP_E_ALIGN, "unimp_lm_attn_fwd: o must be 16-byte aligned");
-  // one-sweep kernel (flash_fwd.cu); UNIMP_LM_FWD1=1 keeps the two-sweep kernel below for A/B runs
-  static const bool two_sweep = getenv("UNIMP_LM_FWD1") && atoi(getenv("UNIMP_LM_FWD1")) != 0;
-  if (!two_sweep)
-    return launch_flash_fwd_80(q, k, v, batch_stride, row_stride, head_stride, key_bits, o, lse, B, T, H, scale,
-                               (cudaStream_t)stream);
-  CUtensorMap tq, tk, tv;
-  int rc;
-  if ((rc = lm::make_map(&tq, q, batch_stride, row_stride, head_stride, B, T, H, lm::TQ))) return rc;
-  if ((rc = lm::make_map(&tk, k, batch_stride, row_stride, head_stride, B, T, H, lm::KB))) return rc;
-  if ((rc = lm::make_map(&tv, v, batch_stride, row_stride, head_stride, B, T, H, lm::KB))) return rc;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lm::lm_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)lm::F_SMEM);
-    if (e != cudaSuccess) { set_error("lm_attn_fwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaFuncSetAttribute(lm::lm_attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-    attr = true;
-  }
-  lm::Args a{};
-  a.o = (__nv_bfloat16*)o; a.o_bs = (int64_t)T * H * dh; a.o_rs = (int64_t)H * dh;
-  a.lse = lse; a.kbits = key_bits; a.kwords = 2 * ((T + 63) / 64);
-  a.T = T; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((T + lm::TQ - 1) / lm::TQ, H, B);
-  lm::lm_attn_fwd_kernel<<<grid, lm::THREADS, lm::F_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  UNIMP_CHECK_LAUNCH();
-  return 0;
+  return launch_flash_fwd_80(q, k, v, batch_stride, row_stride, head_stride, key_bits, o, lse, B, T, H, scale,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, int64_t batch_stride,

@@ -215,20 +215,30 @@ def _run_lm_attn(cfg, wl, dtype, eager, rec):
     def views(p):   # leaf q/k/v VIEWS of the packed projection: the backward numbers carry no un-packing glue
         return tuple(p.view(B, T, H, 3, dh)[:, :, :, i].transpose(1, 2).requires_grad_() for i in range(3))
 
+    # right-padded batch (the workloads' batches are: SURVEY.md §8 synthetic inputs), one full-length sample
+    lens = torch.linspace(T // 2, T, B).long()
+    km = (torch.arange(T)[None, :] < lens[:, None]).to(dev)
+    bits = ops.key_bits(km)
     qkvs = [views(p) for p in packs]
-    fwd = [lambda x=x: ops.lm_attention(*x, None, scale=dh ** -0.5) for x in qkvs]
+    fwd = [lambda x=x: ops.lm_attention(*x, bits, scale=dh ** -0.5) for x in qkvs]
     rec("lm_attn_fwd", _time_graph(fwd), byts, fl, K)
     os_ = [f() for f in fwd]
     bwd = [lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True) for o, x, g in zip(os_, qkvs, gos)]
     rec("lm_attn_bwd", _time_graph(bwd), 2.5 * byts, 2.5 * fl, K)
     if eager:
+        # what the reference runs: HF sdpa attention with the 4-D boolean mask HF builds from a padded
+        # 2-D attention_mask (causal & key padding); and the best case (no padding: is_causal=True)
         F = torch.nn.functional
-        efw = [lambda x=x: F.scaled_dot_product_attention(*x, is_causal=True, scale=dh ** -0.5)
-               .transpose(1, 2).reshape(B, T, H * dh) for x in qkvs]
-        rec("eager_lm_attn_fwd", _time_graph(efw), byts, fl, K)
-        eos = [f() for f in efw]
-        rec("eager_lm_attn_bwd", _time_graph([lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True)
-                                              for o, x, g in zip(eos, qkvs, gos)]), 2.5 * byts, 2.5 * fl, K)
+        mask4 = torch.ones(T, T, dtype=torch.bool, device=dev).tril()[None, None] & km[:, None, None, :]
+        for tag, kw in (("", dict(attn_mask=mask4)), ("_causal_only", dict(is_causal=True))):
+            efw = [lambda x=x: F.scaled_dot_product_attention(*x, scale=dh ** -0.5, **kw)
+                   .transpose(1, 2).reshape(B, T, H * dh) for x in qkvs]
+            rec(f"eager_lm_attn_fwd{tag}", _time_graph(efw), byts, fl, K)
+            eos = [f() for f in efw]
+            rec(f"eager_lm_attn_bwd{tag}",
+                _time_graph([lambda o=o, x=x, g=g: torch.autograd.grad(o, x, g, retain_graph=True)
+                             for o, x, g in zip(eos, qkvs, gos)]), 2.5 * byts, 2.5 * fl, K)
+            del efw, eos
 
 
 def _run_vit_perceiver(cfg, wl, dtype, eager, rec):
