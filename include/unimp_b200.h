@@ -247,6 +247,11 @@ int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, int64_t batch
                       const void* o, const void* d_o, const float* lse, float* dq32, float* delta,
                       void* dk, void* dv, int B, int T, int H, int dh, float scale, int dtype,
                       void* stream);
+/* Same with dq read as fp32 (the dq32 scratch of unimp_lm_attn_bwd, strides in fp32 elements): the
+ * fp32 -> `dtype` conversion of dq happens in this pass instead of in one of its own. */
+int unimp_rotary_qkv_bwd_f32q(const float* dq, const void* dk, const void* dv, const int64_t* strides9,
+                              const void* cos, const void* sin, void* d_qkv, int B, int T, int H,
+                              int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream);
 /* CLIP QuickGELU x*sigmoid(1.702x), in place (ViT MLP; forward only: the tower is frozen). */
 int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream);
 /* Exact (erf) GELU of the FeedForward blocks: open_flamingo helpers.FeedForward's nn.GELU()

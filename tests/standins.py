@@ -76,6 +76,7 @@ def install():
     ops.embedding_acc = lambda ids, w: F.embedding(ids, w)
     ops.key_bits = lambda mask: mask            # the double below takes the 2-D mask itself
     ops.lm_attention_supported = lambda q: False  # K4 stays on SDPA here (fp32 tiny model anyway)
+    ops.lm_attention_supported_shape = lambda x, T, H, dh: False
 
     class _Closure:   # a "graph" that simply re-runs the captured step
         def __init__(self, fn):

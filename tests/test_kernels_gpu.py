@@ -541,12 +541,12 @@ def test_fused_neox_layer_with_own_attention_matches_hf_layer(pad):
     xb = x.clone().requires_grad_(True)
     assert flamingo_lm.LM_ATTN
     calls = []
-    orig = ops().lm_attention
-    ops().lm_attention = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    orig = ops().rotary_lm_attention
+    ops().rotary_lm_attention = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
     try:
         yb = fused_neox_layer(layer, xb, mask4, pe, key_bits=ops().key_bits(km) if pad else True)
     finally:
-        ops().lm_attention = orig
+        ops().rotary_lm_attention = orig
     assert calls, "the layer did not run on unimp_lm_attn_fwd"
     yb.backward(g * km[..., None].to(dt))
     keep = km.bool()

@@ -63,6 +63,8 @@ SIGNATURES = {
     "unimp_lm_attn_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "unimp_lm_attn_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p,
                                _i, _i, _i, _i, _f, _i, _p]),
+    "unimp_rotary_qkv_bwd_f32q": (_i, [_p, _p, _p, C.POINTER(C.c_int64), _p, _p, _p, _i, _i, _i, _i, _i,
+                                       _i64, _i, _p]),
     "unimp_quick_gelu": (_i, [_p, _i64, _i, _p]),
     "unimp_gelu_fwd": (_i, [_p, _p, _i64, _i, _p]),
     "unimp_gelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p]),

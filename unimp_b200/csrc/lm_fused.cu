@@ -85,9 +85,23 @@ __global__ void __launch_bounds__(256) rotary_qkv_fwd_kernel(const T* __restrict
 
 // d_qkv[b,t,h,{q,k,v},:] from dq/dk/dv (B,H,T,dh) strided views: un-rotates dq/dk and packs
 // dq|dk|dv in one pass.
-template <typename T>
+// N consecutive gradient elements -> fp32 (S = the element type of the source: T, or float for the
+// fp32 dq scratch of unimp_lm_attn_bwd)
+template <typename S, int N>
+__device__ __forceinline__ void load_grad(const S* p, float* f) {
+  if constexpr (sizeof(S) == 4 && N == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    Vec16<S> v;
+    v.load_stream(p);
+    v.unpack(f);
+  }
+}
+
+template <typename T, typename QS>
 __global__ void __launch_bounds__(256) rotary_qkv_bwd_kernel(
-    const T* __restrict__ dq, const T* __restrict__ dk, const T* __restrict__ dv, int64_t q_sb, int64_t q_sh,
+    const QS* __restrict__ dq, const T* __restrict__ dk, const T* __restrict__ dv, int64_t q_sb, int64_t q_sh,
     int64_t q_st, int64_t k_sb, int64_t k_sh, int64_t k_st, int64_t v_sb, int64_t v_sh, int64_t v_st,
     const T* __restrict__ cs, const T* __restrict__ sn, T* __restrict__ d_qkv, int Tn, int H, int dh, int rot,
     int64_t cs_bstride, RotaryGeom g) {
@@ -98,27 +112,35 @@ __global__ void __launch_bounds__(256) rotary_qkv_bwd_kernel(
   const int half = rot / 2;
   const T* cp = cs + b * cs_bstride + (int64_t)t * rot;
   const T* sp = sn + b * cs_bstride + (int64_t)t * rot;
-  const T* qb = dq + b * q_sb + (int64_t)t * q_st;
+  const QS* qb = dq + b * q_sb + (int64_t)t * q_st;
   const T* kb = dk + b * k_sb + (int64_t)t * k_st;
   const T* vb = dv + b * v_sb + (int64_t)t * v_st;
   T* drow = d_qkv + row * H * 3 * dh;
   for (int it = threadIdx.x; it < g.items; it += blockDim.x) {
     int h, which, p;
     rotary_item(it, g, h, which, p);
-    const T* src = which == 0 ? qb + h * q_sh : which == 1 ? kb + h * k_sh : vb + h * v_sh;
+    const T* src = which == 1 ? kb + h * k_sh : vb + h * v_sh;
+    const QS* qsrc = qb + h * q_sh;
     T* dst = drow + (h * 3 + which) * dh;
+    float a[N], bb[N];
+    Vec16<T> g1, g2;
     if (p >= g.hv) {
       const int d = rot + (p - g.hv) * N;
-      Vec16<T> x;
-      x.load_stream(src + d);
-      x.store(dst + d);
+      if (which == 0) load_grad<QS, N>(qsrc + d, a); else load_grad<T, N>(src + d, a);
+      g1.pack(a);
+      g1.store(dst + d);
       continue;
     }
     const int d0 = p * N;
-    Vec16<T> g1, g2;
-    g1.load_stream(src + d0);
-    g2.load_stream(src + d0 + half);
+    if (which == 0) {
+      load_grad<QS, N>(qsrc + d0, a);
+      load_grad<QS, N>(qsrc + d0 + half, bb);
+    } else {
+      load_grad<T, N>(src + d0, a);
+      load_grad<T, N>(src + d0 + half, bb);
+    }
     if (which == 2) {
+      g1.pack(a); g2.pack(bb);
       g1.store(dst + d0);
       g2.store(dst + d0 + half);
       continue;
@@ -127,8 +149,8 @@ __global__ void __launch_bounds__(256) rotary_qkv_bwd_kernel(
     Vec16<T> c1, s1, c2, s2;
     c1.load(cp + d0); s1.load(sp + d0);
     c2.load(cp + d0 + half); s2.load(sp + d0 + half);
-    float a[N], bb[N], c1f[N], s1f[N], c2f[N], s2f[N], o1[N], o2[N];
-    g1.unpack(a); g2.unpack(bb); c1.unpack(c1f); s1.unpack(s1f); c2.unpack(c2f); s2.unpack(s2f);
+    float c1f[N], s1f[N], c2f[N], s2f[N], o1[N], o2[N];
+    c1.unpack(c1f); s1.unpack(s1f); c2.unpack(c2f); s2.unpack(s2f);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       o1[i] = a[i] * c1f[i] + bb[i] * s2f[i];
@@ -304,34 +326,55 @@ extern "C" int unimp_rotary_qkv_fwd(const void* qkv, void* out, const void* cos,
   return 0;
 }
 
-extern "C" int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const int64_t* strides9,
-                                    const void* cos, const void* sin, void* d_qkv, int B, int T, int H,
-                                    int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream) {
-  UNIMP_CHECK_ARG(dq && dk && dv && strides9 && cos && sin && d_qkv, UNIMP_E_NULL,
-                  "rotary_qkv_bwd: NULL pointer");
-  int rc = rotary_check("rotary_qkv_bwd", B, T, H, dh, rot, dtype);
+static int rotary_bwd_impl(const char* who, const void* dq, int dq_f32, const void* dk, const void* dv,
+                           const int64_t* strides9, const void* cos, const void* sin, void* d_qkv, int B, int T,
+                           int H, int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(dq && dk && dv && strides9 && cos && sin && d_qkv, UNIMP_E_NULL, "%s: NULL pointer", who);
+  int rc = rotary_check(who, B, T, H, dh, rot, dtype);
   if (rc) return rc;
+  UNIMP_CHECK_ARG(!dq_f32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "%s: an fp32 dq needs dtype bf16", who);
   const int n = dtype == UNIMP_BF16 ? 8 : 4;
   for (int i = 0; i < 9; ++i)
-    UNIMP_CHECK_ARG(strides9[i] % n == 0, UNIMP_E_ALIGN, "rotary_qkv_bwd: stride %d not vector aligned", i);
+    UNIMP_CHECK_ARG(strides9[i] % (i < 3 && dq_f32 ? 4 : n) == 0, UNIMP_E_ALIGN, "%s: stride %d not vector aligned",
+                    who, i);
   UNIMP_CHECK_ARG(aligned16(dq) && aligned16(dk) && aligned16(dv) && aligned16(d_qkv) && aligned16(cos) &&
                       aligned16(sin),
-                  UNIMP_E_ALIGN, "rotary_qkv_bwd: pointers must be 16-byte aligned");
+                  UNIMP_E_ALIGN, "%s: pointers must be 16-byte aligned", who);
   const RotaryGeom g = rotary_geom(H, dh, rot, dtype);
   const unsigned rows = (unsigned)((int64_t)B * T);
   const int threads = rotary_threads(g);
   const int64_t* s = strides9;  // HOST array: {q_sb,q_sh,q_st, k_sb,k_sh,k_st, v_sb,v_sh,v_st} in elements
-  if (dtype == UNIMP_BF16)
-    rotary_qkv_bwd_kernel<__nv_bfloat16><<<rows, threads, 0, (cudaStream_t)stream>>>(
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNIMP_BF16 && dq_f32)
+    rotary_qkv_bwd_kernel<__nv_bfloat16, float><<<rows, threads, 0, st>>>(
+        (const float*)dq, (const __nv_bfloat16*)dk, (const __nv_bfloat16*)dv, s[0], s[1], s[2], s[3], s[4], s[5],
+        s[6], s[7], s[8], (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, (__nv_bfloat16*)d_qkv, T, H, dh,
+        rot, cs_batch_stride, g);
+  else if (dtype == UNIMP_BF16)
+    rotary_qkv_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<rows, threads, 0, st>>>(
         (const __nv_bfloat16*)dq, (const __nv_bfloat16*)dk, (const __nv_bfloat16*)dv, s[0], s[1], s[2], s[3],
         s[4], s[5], s[6], s[7], s[8], (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin,
         (__nv_bfloat16*)d_qkv, T, H, dh, rot, cs_batch_stride, g);
   else
-    rotary_qkv_bwd_kernel<float><<<rows, threads, 0, (cudaStream_t)stream>>>(
+    rotary_qkv_bwd_kernel<float, float><<<rows, threads, 0, st>>>(
         (const float*)dq, (const float*)dk, (const float*)dv, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7],
         s[8], (const float*)cos, (const float*)sin, (float*)d_qkv, T, H, dh, rot, cs_batch_stride, g);
   UNIMP_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int unimp_rotary_qkv_bwd(const void* dq, const void* dk, const void* dv, const int64_t* strides9,
+                                    const void* cos, const void* sin, void* d_qkv, int B, int T, int H,
+                                    int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream) {
+  return rotary_bwd_impl("rotary_qkv_bwd", dq, 0, dk, dv, strides9, cos, sin, d_qkv, B, T, H, dh, rot,
+                         cs_batch_stride, dtype, stream);
+}
+
+extern "C" int unimp_rotary_qkv_bwd_f32q(const float* dq, const void* dk, const void* dv, const int64_t* strides9,
+                                         const void* cos, const void* sin, void* d_qkv, int B, int T, int H,
+                                         int dh, int rot, int64_t cs_batch_stride, int dtype, void* stream) {
+  return rotary_bwd_impl("rotary_qkv_bwd_f32q", dq, 1, dk, dv, strides9, cos, sin, d_qkv, B, T, H, dh, rot,
+                         cs_batch_stride, dtype, stream);
 }
 
 extern "C" int unimp_quick_gelu(void* x, int64_t n, int dtype, void* stream) {

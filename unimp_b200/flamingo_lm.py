@@ -214,11 +214,12 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
         h1 = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
     qkv = F.linear(h1, att.query_key_value.weight, att.query_key_value.bias)
     cos, sin = position_embeddings
-    q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
-                             rotary_dim=rot)
-    if key_bits is not None and kv_step is None and LM_ATTN and ops.lm_attention_supported(q):
-        a = ops.lm_attention(q, k, v, None if key_bits is True else key_bits, scale=att.scaling)
+    if key_bits is not None and kv_step is None and LM_ATTN and ops.lm_attention_supported_shape(x, T, H, dh):
+        a = ops.rotary_lm_attention(qkv, cos.to(x.dtype), sin.to(x.dtype), None if key_bits is True else key_bits,
+                                    heads=H, head_dim=dh, rotary_dim=rot, scale=att.scaling)
     else:
+        q, k, v = ops.rotary_qkv(qkv, cos.to(x.dtype), sin.to(x.dtype), heads=H, head_dim=dh,
+                                 rotary_dim=rot)
         attention_mask = _additive_mask(attention_mask, x.dtype)
         if kv_step is not None:
             k_cache, v_cache, cursor = kv_step

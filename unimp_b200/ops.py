@@ -592,6 +592,73 @@ class _LMAttention(torch.autograd.Function):
         return (dq32[:, :, :T, :dh].to(q.dtype), dk.transpose(1, 2), dv.transpose(1, 2), None, None)
 
 
+class _RotaryLMAttention(torch.autograd.Function):
+    """GPT-NeoX rotary + K4 attention as ONE autograd node: `unimp_rotary_qkv_fwd` -> `unimp_lm_attn_fwd`;
+    backward `unimp_lm_attn_bwd` -> `unimp_rotary_qkv_bwd_f32q`, which reads the fp32 dq scratch
+    directly (no separate fp32 -> bf16 pass, no per-tensor autograd hops)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, key_bits, H, dh, rot, scale):
+        dt = _dt(qkv)
+        B, T, _ = qkv.shape
+        assert qkv.is_contiguous() and qkv.shape[2] == 3 * H * dh
+        cos, sin = cos.contiguous(), sin.contiguous()
+        assert cos.dtype == qkv.dtype and cos.shape[-1] == rot and cos.shape[-2] == T
+        cs_bs = T * rot if (cos.dim() == 3 and cos.shape[0] > 1) else 0
+        lib = _lib.load()
+        rq = torch.empty_like(qkv)
+        check(lib.unimp_rotary_qkv_fwd(qkv.data_ptr(), rq.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, T, H, dh,
+                                       rot, cs_bs, dt, _stream()), "unimp_rotary_qkv_fwd")
+        es = rq.element_size()
+        o = torch.empty((B, T, H * dh), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        kb = key_bits.data_ptr() if key_bits is not None else None
+        base = rq.data_ptr()
+        check(lib.unimp_lm_attn_fwd(base, base + dh * es, base + 2 * dh * es, T * H * 3 * dh, H * 3 * dh, 3 * dh, kb,
+                                    o.data_ptr(), lse.data_ptr(), B, T, H, dh, float(scale), dt, _stream()),
+              "unimp_lm_attn_fwd")
+        ctx.save_for_backward(cos, sin, rq, o, lse, key_bits)
+        ctx.cfg = (B, T, H, dh, rot, cs_bs, dt, float(scale))
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        import ctypes
+        cos, sin, rq, o, lse, key_bits = ctx.saved_tensors
+        B, T, H, dh, rot, cs_bs, dt, scale = ctx.cfg
+        lib = _lib.load()
+        d_o = d_o.contiguous()
+        Tp = (T + 127) // 128 * 128
+        dev = rq.device
+        dq32 = torch.empty((B, H, Tp, 84), dtype=torch.float32, device=dev)
+        delta = torch.empty((B, H, T), dtype=torch.float32, device=dev)
+        dk = torch.empty((B, T, H, dh), dtype=rq.dtype, device=dev)
+        dv = torch.empty_like(dk)
+        kb = key_bits.data_ptr() if key_bits is not None else None
+        es = rq.element_size()
+        base = rq.data_ptr()
+        check(lib.unimp_lm_attn_bwd(base, base + dh * es, base + 2 * dh * es, T * H * 3 * dh, H * 3 * dh, 3 * dh, kb,
+                                    o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dq32.data_ptr(),
+                                    delta.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, H, dh, scale, dt,
+                                    _stream()), "unimp_lm_attn_bwd")
+        # (b, h, t) strides in elements: dq in the fp32 scratch, dk / dv as (B,T,H,dh)
+        strides = (ctypes.c_int64 * 9)(H * Tp * 84, Tp * 84, 84, T * H * dh, dh, H * dh, T * H * dh, dh, H * dh)
+        d_qkv = torch.empty((B, T, 3 * H * dh), dtype=rq.dtype, device=dev)
+        check(lib.unimp_rotary_qkv_bwd_f32q(dq32.data_ptr(), dk.data_ptr(), dv.data_ptr(), strides, cos.data_ptr(),
+                                            sin.data_ptr(), d_qkv.data_ptr(), B, T, H, dh, rot, cs_bs, dt,
+                                            _stream()), "unimp_rotary_qkv_bwd_f32q")
+        return d_qkv, None, None, None, None, None, None, None
+
+
+def rotary_lm_attention(qkv, cos, sin, key_bits=None, *, heads: int, head_dim: int, rotary_dim: int, scale: float):
+    """qkv (B,T,H*3*dh) projection output -> rotary -> causal (+ key padding) attention -> (B,T,H*dh)."""
+    return _RotaryLMAttention.apply(qkv, cos, sin, key_bits, heads, head_dim, rotary_dim, scale)
+
+
+def lm_attention_supported_shape(x, T: int, H: int, dh: int) -> bool:
+    return x.is_cuda and bool(_lib.load().unimp_lm_attn_supported(T, H, dh, _dt(x)))
+
+
 def lm_attention_supported(q) -> bool:
     """bf16, head dim 80 (RedPajama-INCITE 3B: 32 heads x 80)."""
     B, H, T, dh = q.shape
