@@ -11,6 +11,6 @@ cap xblock_c2 xattn_block_fwd_kernel 4 2 C2-rec xattn
 cap xblock_c3 xattn_block_fwd_kernel 4 2 C3-multitask xattn
 cap xcore_c2 xattn_fwd_tc_kernel 4 2 C2-rec xattn
 cap xbwd_c2 attn_bwd_tc_kernel 2 2 C2-rec xattn
-cap vit_c2 attn_fwd2_tc_kernel 4 2 C2-rec vit
+cap vit_c2 flash_fwd_kernel 4 2 C2-rec vit
 cap k5_c2 gate_residual_ln 4 8 C2-rec k5
 ls -la gpurun_out/${P}_ncu_*.ncu-rep

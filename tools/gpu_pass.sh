@@ -21,10 +21,26 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:'xat
 echo "ncu xattn c2 rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'xattn_block_fwd_kernel|xattn_fwd_tc_kernel' -s 8 -c 4 -o gpurun_out/${P}_ncu_xattn_c3 -f python tools/kbench_cli.py --workload C3-multitask --only xattn --no-eager > gpurun_out/${P}_ncu_xattn_c3.log 2>&1
 echo "ncu xattn c3 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'attn_fwd2_tc_kernel' -s 4 -c 3 -o gpurun_out/${P}_ncu_vit -f python tools/kbench_cli.py --workload C2-rec --only vit --no-eager > gpurun_out/${P}_ncu_vit.log 2>&1
-echo "ncu vit rc=$?"; ls -la gpurun_out/${P}_ncu_*.ncu-rep
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel' -s 4 -c 3 -o gpurun_out/${P}_ncu_vit -f python tools/kbench_cli.py --workload C2-rec --only vit --no-eager > gpurun_out/${P}_ncu_vit.log 2>&1
+echo "ncu vit rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel|lm_attn_bwd_kernel' -s 6 -c 4 -o gpurun_out/${P}_ncu_lm_c2 -f python tools/kbench_cli.py --workload C2-rec --only lm --no-eager > gpurun_out/${P}_ncu_lm_c2.log 2>&1
+echo "ncu lm c2 rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel|lm_attn_bwd_kernel' -s 4 -c 4 -o gpurun_out/${P}_ncu_lm_c3 -f python tools/kbench_cli.py --workload C3-multitask --only lm --no-eager > gpurun_out/${P}_ncu_lm_c3.log 2>&1
+echo "ncu lm c3 rc=$?"; ls -la gpurun_out/${P}_ncu_*.ncu-rep
+timeout 300 python tools/kbench_cli.py --workload C2-rec --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB" > gpurun_out/${P}_kbench_attn.log
+timeout 300 python tools/kbench_cli.py --workload C3-multitask --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB" >> gpurun_out/${P}_kbench_attn.log
+UNIMP_LM_ATTN=0 timeout 600 python bench.py --steps 30 --no-cpu-baseline --no-eager-baseline --no-kernel-profile > gpurun_out/${P}_bench_c2_sdpa.json 2> gpurun_out/${P}_bench_c2_sdpa.err
+echo "bench c2 (cuDNN SDPA for K4) rc=$?"
+UNIMP_LM_ATTN=0 timeout 600 python bench.py --workload C3-multitask --steps 12 --no-cpu-baseline --no-eager-baseline --no-kernel-profile > gpurun_out/${P}_bench_c3_sdpa.json 2> gpurun_out/${P}_bench_c3_sdpa.err
+echo "bench c3 (cuDNN SDPA for K4) rc=$?"
 python - <<PY
 import json
+for n in ("c2_sdpa", "c3_sdpa"):
+    try:
+        d = json.load(open("gpurun_out/${P}_bench_%s.json" % n))
+        print(n, "samples/s", round(d["value"], 2), "ms/step", round(d["ms_per_step"], 2), d["clocks"])
+    except Exception as e:
+        print(n, "no json", e)
 for n in ("c2", "c3", "c5"):
     try:
         d = json.load(open("gpurun_out/${P}_bench_%s.json" % n))

@@ -159,7 +159,8 @@ def bwd_timeline(B, T, H):
     qkv = tuple(x.requires_grad_() for x in views(pk, B, T, H))
     o = ops.lm_attention(*qkv, None, scale=dh ** -0.5)
     go = torch.randn_like(o)
-    n_cta = ((T + 63) // 64) * H * B
+    n_items = ((T + 63) // 64) * H * B
+    n_cta = min(n_items, torch.cuda.get_device_properties(0).multi_processor_count)
     buf = torch.zeros(n_cta * 64, dtype=torch.int64, device=dev)
     for _ in range(3):
         torch.autograd.grad(o, qkv, go, retain_graph=True)
@@ -169,25 +170,22 @@ def bwd_timeline(B, T, H):
     torch.cuda.synchronize()
     f(None)
     t = buf.view(n_cta, 64).cpu().double()
-    span = t[:, 3].max() - t[:, 0].min()
-    life = t[:, 3] - t[:, 0]
-    print(f"BW timeline B={B} T={T} H={H}: {n_cta} CTAs, span {span:.0f} ns, concurrency "
-          f"{float(life.sum() / span / 148):.2f} CTAs/SM, CTA lifetime median {life.median():.0f} ns; start->ready "
-          f"{(t[:, 1] - t[:, 0]).median():.0f} ns; last gradients -> end {(t[:, 3] - t[:, 2]).median():.0f} ns "
-          f"({(t[:, 6] - t[:, 5]).median():.0f} cycles)")
-    for npairs in (1, 2, 4, 6):
-        sel = t[(t[:, 8 + (npairs - 1) * 8 + 5] > 0) & ((t[:, 8 + npairs * 8 + 5] == 0) if npairs < 6 else True)]
-        if len(sel) == 0:
-            continue
-        print(f"BW   CTAs with {'>=6' if npairs >= 6 else npairs} pairs: {len(sel)}; lifetime median "
-              f"{(sel[:, 3] - sel[:, 0]).median():.0f} ns; cycles since 'ready':")
-        for i in range(min(npairs, 6)):
-            s_ = 8 + i * 8
-            rel = lambda k: (sel[:, s_ + k] - sel[:, 4]).median()
-            print(f"BW     pair {i}: S/dP ready {rel(2):6.0f} | math done {rel(3):6.0f} | prev grads seen {rel(4):6.0f} | "
-                  f"arrived {rel(5):6.0f} | prev dQ staged {rel(6):6.0f} || MMA got P {rel(0):6.0f} | MMA issued {rel(1):6.0f}",
-                  flush=True)
-        print(f"BW     flush start {(sel[:, 5] - sel[:, 4]).median():6.0f} | end {(sel[:, 6] - sel[:, 4]).median():6.0f}")
+    span = t[:, 7].max() - t[:, 0].min()
+    print(f"BW timeline B={B} T={T} H={H}: {n_items} items on {n_cta} persistent CTAs, span {span:.0f} ns "
+          f"({span / (n_items / n_cta):.0f} ns per item per CTA); start->ready {(t[:, 1] - t[:, 0]).median():.0f} ns; "
+          f"first item: ready -> end {(t[:, 3] - t[:, 1]).median():.0f} ns, last gradients -> end "
+          f"{(t[:, 3] - t[:, 2]).median():.0f} ns ({(t[:, 6] - t[:, 5]).median():.0f} cycles)")
+    sel = t
+    print(f"BW   first item of each CTA (the heaviest key blocks); cycles since 'ready':")
+    for i in range(6):
+        s_ = 8 + i * 8
+        if (sel[:, s_ + 5] > 0).sum() < len(sel) // 2:
+            break
+        rel = lambda k: (sel[:, s_ + k] - sel[:, 4]).median()
+        print(f"BW     pair {i}: S/dP ready {rel(2):6.0f} | math done {rel(3):6.0f} | prev grads seen {rel(4):6.0f} | "
+              f"arrived {rel(5):6.0f} | prev dQ staged {rel(6):6.0f} || MMA got P {rel(0):6.0f} | MMA issued {rel(1):6.0f}",
+              flush=True)
+    print(f"BW     flush start {(sel[:, 5] - sel[:, 4]).median():6.0f} | item end {(sel[:, 6] - sel[:, 4]).median():6.0f}")
 
 
 if "bwd_timeline" in sys.argv[1:]:

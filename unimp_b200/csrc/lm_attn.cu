@@ -45,7 +45,8 @@ struct Args {
   int kwords;
   float* dq32;               // bwd: (B,H,Tp,84) fp32 (Tp = T rounded up to 128), zeroed by the launcher
   __nv_bfloat16 *dk, *dv;    // bwd: (B,T,H,80) bf16 contiguous
-  int T, H;
+  int T, H, B;
+  int flags;                 // experiments (UNIMP_LM_BWD_FLAGS): 1 = skip the dQ bulk reduce, 2 = skip dQ staging too
   float scale, scale_log2;
 };
 
@@ -94,17 +95,18 @@ __device__ __forceinline__ uint64_t visible(const Args& a, int b, int j, int row
 // gradient MMAs of pair i run while they stage dQ of pair i-1.
 // TMEM (512 columns): S 2x64 | dP 2x64 | dKV p0 128 | dQ p0 64 | dKV p1 32 | dQ p1 16.
 // ---------------------------------------------------------------------------------------------
-// stamps: 0 start (ns), 1 ready (ns), 2 last pair's gradients seen (ns), 3 end (ns), 4 ready (cycles),
-// 5 flush start (cycles), 6 end (cycles); pair i < 6 -> 8 + i*8 + k (cycles): 0 MMA lane got P_i,
+// stamps of a CTA's FIRST item: 0 start (ns), 1 ready (ns), 2 last pair's gradients seen (ns), 3 item end
+// (ns), 4 ready (cycles), 5 flush start (cycles), 6 item end (cycles), 7 CTA end (ns); pair i < 6 ->
+// 8 + i*8 + k (cycles): 0 MMA lane got P_i,
 // 1 MMA lane done with pair i, 2 worker S/dP ready, 3 math done, 4 previous gradients seen,
 // 5 arrived, 6 dQ of the previous pair staged
 #define BW_STAMP(slot)                                                                                   \
   do {                                                                                                   \
     if (a.dbg) {                                                                                         \
       unsigned long long t__;                                                                            \
-      if ((slot) < 4) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
+      if ((slot) < 4 || (slot) == 7) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));              \
       else t__ = (unsigned long long)clock64();                                                          \
-      a.dbg[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = t__;        \
+      a.dbg[blockIdx.x * 64 + (slot)] = t__;                                                             \
     }                                                                                                    \
   } while (0)
 
@@ -155,21 +157,30 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                    const __grid_constant__ CUtensorMap tq1, const __grid_constant__ CUtensorMap tdo1,
                    const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1,
                    const Args a) {
+  // PERSISTENT: one CTA per SM walks work items (key block, head, sample), heavy key blocks first.
+  // TMEM, the barriers and the three roles live across items; the producer fetches the next item's
+  // K/V and first Q/dO tiles while the threads flush the current item's dK/dV (a 1-2 pair item at
+  // T=256 spent 2/3 of its life in prologue, flush and CTA turnover: profiles/r2_lm_attn_bwd_timeline.log).
   constexpr uint32_t S_COL = 0, DP_COL = 128, DKV0_COL = 256, DQ0_COL = 384, DKV1_COL = 448, DQ1_COL = 480,
                      TMEM_COLS = 512;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BAR);
-  uint64_t *bar_kv = bars, *qdo_full = bars + 1, *qdo_free = qdo_full + NQS, *bar_s = qdo_free + NQS,
-           *bar_p = bar_s + 2, *bar_g = bar_s + 3;
+  uint64_t *kv_full = bars, *kv_free = bars + 1, *qdo_full = bars + 2, *qdo_free = qdo_full + NQS,
+           *bar_s = qdo_free + NQS, *bar_p = bar_s + 2, *bar_g = bar_s + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = tid < 2 * TQ;
   if (tid == 0) BW_STAMP(0);
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nq = (a.T + TQ - 1) / TQ;
-  const int q_lo = (kb * KB) / TQ;            // first query tile with a row at or after key kb*64
-  const int n = nq - q_lo;                    // pairs of this CTA (>= 1)
+  const int nq = (a.T + TQ - 1) / TQ, nkb = (a.T + KB - 1) / KB;
+  const int HB = a.H * a.B, n_items = nkb * HB;
+  // item w -> key block w / (H*B) (small key blocks = many query tiles first), head, sample
+  auto decode = [&](int w, int& kb, int& h, int& b) {
+    kb = w / HB;
+    const int rem = w - kb * HB;
+    b = rem / a.H;
+    h = rem - b * a.H;
+  };
 
   if (warp == BW_MMA) {
     if (elect_one_sync()) {
@@ -177,8 +188,8 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         printf("unimp: lm_attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
         __trap();
       }
-      mbar_init(bar_kv, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 8);
-      mbar_init(bar_g, 1);
+      mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
+      mbar_init(bar_p, 8); mbar_init(bar_g, 1);
 #pragma unroll
       for (int i = 0; i < NQS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_free[i], 1); }
       fence_barrier_init();
@@ -194,29 +205,32 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const uint32_t su = smem_u32(smem);
   if (tid == 0) { BW_STAMP(1); BW_STAMP(4); }
 
-  // The single-lane loops are unrolled by 6 = lcm(3 ring stages, 2 S/dP buffers): stage offsets,
-  // TMEM buffers and most barrier parities are compile-time constants (uniform-datapath code).
+  // g = running pair count of this CTA (all roles count alike): Q/dO ring stage g % 3 (fill g / 3),
+  // S/dP buffer g & 1 (use g / 2), bar_p / bar_g phase g; it = running item count (kv_full / kv_free).
   if (warp == BW_TMA && elect_one_sync()) {
-    mbar_arrive_expect_tx(bar_kv, 2 * KP + 2 * KP1);
-    tma_load_4d(smem + B_K0, &tk, bar_kv, 0, h, kb * KB, b);
-    tma_load_4d(smem + B_K1, &tk1, bar_kv, 64, h, kb * KB, b);
-    tma_load_4d(smem + B_V0, &tv, bar_kv, 0, h, kb * KB, b);
-    tma_load_4d(smem + B_V1, &tv1, bar_kv, 64, h, kb * KB, b);
-    for (int i0 = 0; i0 < n; i0 += 6) {
-#pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int i = i0 + u;
-        if (i < n) {
-          const int st = u % NQS;
-          uint8_t* d = smem + B_RING + st * ST_BYTES;
-          const int r0 = (q_lo + i) * TQ;
-          if (i >= NQS) mbar_wait(&qdo_free[st], ((u / NQS) + 1) & 1);
-          mbar_arrive_expect_tx(&qdo_full[st], ST_BYTES);
-          tma_load_4d(d + ST_Q0, &tq, &qdo_full[st], 0, h, r0, b);
-          tma_load_4d(d + ST_Q1, &tq1, &qdo_full[st], 64, h, r0, b);
-          tma_load_4d(d + ST_DO0, &tdo, &qdo_full[st], 0, h, r0, b);
-          tma_load_4d(d + ST_DO1, &tdo1, &qdo_full[st], 64, h, r0, b);
-        }
+    int it = 0, st = 0;
+    uint32_t g = 0, free_par = 1;                          // parity of the stage's previous release
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int kb, h, b;
+      decode(w, kb, h, b);
+      const int q_lo = (kb * KB) / TQ, n = nq - q_lo;
+      if (it > 0) mbar_wait(kv_free, (it - 1) & 1);        // the previous item's last MMAs have read K / V
+      mbar_arrive_expect_tx(kv_full, 2 * KP + 2 * KP1);
+      tma_load_4d(smem + B_K0, &tk, kv_full, 0, h, kb * KB, b);
+      tma_load_4d(smem + B_K1, &tk1, kv_full, 64, h, kb * KB, b);
+      tma_load_4d(smem + B_V0, &tv, kv_full, 0, h, kb * KB, b);
+      tma_load_4d(smem + B_V1, &tv1, kv_full, 64, h, kb * KB, b);
+#pragma unroll 1
+      for (int i = 0; i < n; ++i, ++g) {
+        uint8_t* d = smem + B_RING + st * ST_BYTES;
+        const int r0 = (q_lo + i) * TQ;
+        if (g >= NQS) mbar_wait(&qdo_free[st], free_par);
+        mbar_arrive_expect_tx(&qdo_full[st], ST_BYTES);
+        tma_load_4d(d + ST_Q0, &tq, &qdo_full[st], 0, h, r0, b);
+        tma_load_4d(d + ST_Q1, &tq1, &qdo_full[st], 64, h, r0, b);
+        tma_load_4d(d + ST_DO0, &tdo, &qdo_full[st], 0, h, r0, b);
+        tma_load_4d(d + ST_DO1, &tdo1, &qdo_full[st], 64, h, r0, b);
+        if (st == NQS - 1) { st = 0; free_par ^= 1; } else { ++st; }
       }
     }
   } else if (warp == BW_MMA && elect_one_sync()) {
@@ -225,58 +239,83 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     constexpr uint32_t idesc_dq1 = make_idesc(TQ, 16, 0, 1);
     constexpr uint32_t idesc_dkv0 = make_idesc(128, 128, 1, 1);    // [P|dS]^T [dO|Q] panel 0
     constexpr uint32_t idesc_dkv1 = make_idesc(128, 32, 1, 1);     // panel 1: N = 16 + 16
-    auto issue_sdp = [&](int st, int buf, uint32_t par) {
-      const uint32_t t_u = su + B_RING + st * ST_BYTES;
+    // Descriptors of the fixed tiles, built once and kept as (lo, hi) halves: K-steps and ring stages
+    // are 32-bit adds of (byte offset >> 4) to the start-address field in `lo` (every tile stays below
+    // the 256 KB the field covers); ring stage and parities are carried incrementally, no div / mod.
+    auto lo = [](uint64_t d) { return (uint32_t)d; };
+    auto hi = [](uint64_t d) { return (uint32_t)(d >> 32); };
+    const uint64_t D_k0 = make_smem_desc(su + B_K0, 16, 1024), D_k1 = make_smem_desc32(su + B_K1, 16, 256);
+    const uint64_t D_v0 = make_smem_desc(su + B_V0, 16, 1024), D_v1 = make_smem_desc32(su + B_V1, 16, 256);
+    const uint64_t D_k0mn = make_smem_desc(su + B_K0, 1024, 1024), D_k1mn = make_smem_desc32(su + B_K1, 256, 256);
+    const uint64_t D_p = make_smem_desc(su + B_P, PB, 1024), D_ds = make_smem_desc(su + B_DS, 16, 1024);
+    const uint64_t D_q0 = make_smem_desc(su + B_RING + ST_Q0, 16, 1024),
+                   D_q1 = make_smem_desc32(su + B_RING + ST_Q1, 16, 256);
+    const uint64_t D_do0 = make_smem_desc(su + B_RING + ST_DO0, 16, 1024),
+                   D_do1 = make_smem_desc32(su + B_RING + ST_DO1, 16, 256);
+    const uint64_t D_do0mn = make_smem_desc(su + B_RING + ST_DO0, QP, 1024),
+                   D_do1mn = make_smem_desc32(su + B_RING + ST_DO1, QP1, 256);
+    const uint32_t h128 = hi(D_k0), h32 = hi(D_k1);       // hi halves: SBO 1024 / SWIZZLE_128B, SBO 256 / SWIZZLE_32B
+    constexpr uint32_t ST16 = ST_BYTES >> 4;
+    // S / dP of a pair into S/dP buffer `buf`, from ring stage `st` (so = st * ST16), fill parity `par`
+    auto issue_sdp = [&](int st, uint32_t so, int buf, uint32_t par) {
       mbar_wait(&qdo_full[st], par);
       tcgen05_fence_after();
+      const uint32_t q0l = lo(D_q0) + so, do0l = lo(D_do0) + so;
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + S_COL + buf * 64, make_smem_desc(t_u + ST_Q0 + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_K0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-      umma_ss(tmem + S_COL + buf * 64, make_smem_desc32(t_u + ST_Q1, 16, 256), make_smem_desc32(su + B_K1, 16, 256),
-              idesc_s, 1);
+        umma_ss_lohi(tmem + S_COL + buf * 64, q0l + k4 * 2, h128, lo(D_k0) + k4 * 2, h128, idesc_s, k4 > 0);
+      umma_ss_lohi(tmem + S_COL + buf * 64, lo(D_q1) + so, h32, lo(D_k1), h32, idesc_s, 1);
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + DP_COL + buf * 64, make_smem_desc(t_u + ST_DO0 + k4 * 32, 16, 1024),
-                make_smem_desc(su + B_V0 + k4 * 32, 16, 1024), idesc_s, k4 > 0);
-      umma_ss(tmem + DP_COL + buf * 64, make_smem_desc32(t_u + ST_DO1, 16, 256),
-              make_smem_desc32(su + B_V1, 16, 256), idesc_s, 1);
+        umma_ss_lohi(tmem + DP_COL + buf * 64, do0l + k4 * 2, h128, lo(D_v0) + k4 * 2, h128, idesc_s, k4 > 0);
+      umma_ss_lohi(tmem + DP_COL + buf * 64, lo(D_do1) + so, h32, lo(D_v1), h32, idesc_s, 1);
       umma_commit(&bar_s[buf]);
     };
-    mbar_wait(bar_kv, 0);
-    issue_sdp(0, 0, 0);
-    if (n > 1) issue_sdp(1, 1, 0);
-    for (int i0 = 0; i0 < n; i0 += 6) {
+    // running state of pair g: ring stage / its fill parity, and the same for pairs g+1, g+2 (look-ahead)
+    int it = 0;
+    uint32_t g = 0;
+    int st0 = 0, st1 = 1, st2 = 2;                 // stages of pairs g, g+1, g+2
+    uint32_t par0 = 0, par1 = 0, par2 = 0;         // fill parities of those stages for those pairs
+    auto advance = [&]() {                         // g -> g + 1
+      ++g;
+      st0 = st1; par0 = par1;
+      st1 = st2; par1 = par2;
+      if (st2 == NQS - 1) { st2 = 0; par2 ^= 1; } else { ++st2; }
+    };
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int kb, h, b;
+      decode(w, kb, h, b);
+      const int n = nq - (kb * KB) / TQ;
+      mbar_wait(kv_full, it & 1);
+      issue_sdp(st0, st0 * ST16, g & 1, par0);
+      if (n > 1) issue_sdp(st1, st1 * ST16, (g + 1) & 1, par1);
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        const uint32_t so = st0 * ST16;
+        mbar_wait(bar_p, g & 1);            // P / dS in shared memory, S/dP buffer and dQ columns released
+        if (it == 0 && i < 6) BW_STAMP(8 + i * 8 + 0);
+        tcgen05_fence_after();
+        const uint32_t do0mn = lo(D_do0mn) + so, do1mn = lo(D_do1mn) + so;
+        const uint32_t hp = hi(D_p), hdo0 = hi(D_do0mn), hdo1 = hi(D_do1mn), hds = hi(D_ds), hk0 = hi(D_k0mn),
+                       hk1 = hi(D_k1mn);
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int i = i0 + u;
-        if (i < n) {
-          const int st = u % NQS;
-          const uint32_t t_u = su + B_RING + st * ST_BYTES;
-          mbar_wait(bar_p, u & 1);          // P_i / dS_i in shared memory, S/dP buffer and dQ columns released
-          if (i < 6) BW_STAMP(8 + i * 8 + 0);
-          tcgen05_fence_after();
+        for (int k8 = 0; k8 < TQ / 16; ++k8)
+          umma_ss_lohi(tmem + DKV0_COL, lo(D_p) + k8 * 128, hp, do0mn + k8 * 128, hdo0, idesc_dkv0, (i > 0 || k8 > 0));
 #pragma unroll
-          for (int k8 = 0; k8 < TQ / 16; ++k8)
-            umma_ss(tmem + DKV0_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
-                    make_smem_desc(t_u + ST_DO0 + k8 * 2048, QP, 1024), idesc_dkv0, (i > 0 || k8 > 0));
+        for (int k8 = 0; k8 < TQ / 16; ++k8)
+          umma_ss_lohi(tmem + DKV1_COL, lo(D_p) + k8 * 128, hp, do1mn + k8 * 32, hdo1, idesc_dkv1, (i > 0 || k8 > 0));
 #pragma unroll
-          for (int k8 = 0; k8 < TQ / 16; ++k8)
-            umma_ss(tmem + DKV1_COL, make_smem_desc(su + B_P + k8 * 2048, PB, 1024),
-                    make_smem_desc32(t_u + ST_DO1 + k8 * 512, QP1, 256), idesc_dkv1, (i > 0 || k8 > 0));
+        for (int k4 = 0; k4 < KB / 16; ++k4)
+          umma_ss_lohi(tmem + DQ0_COL, lo(D_ds) + k4 * 2, hds, lo(D_k0mn) + k4 * 128, hk0, idesc_dq0, k4 > 0);
 #pragma unroll
-          for (int k4 = 0; k4 < KB / 16; ++k4)
-            umma_ss(tmem + DQ0_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
-                    make_smem_desc(su + B_K0 + k4 * 2048, 1024, 1024), idesc_dq0, k4 > 0);
-#pragma unroll
-          for (int k4 = 0; k4 < KB / 16; ++k4)
-            umma_ss(tmem + DQ1_COL, make_smem_desc(su + B_DS + k4 * 32, 16, 1024),
-                    make_smem_desc32(su + B_K1 + k4 * 512, 256, 256), idesc_dq1, k4 > 0);
-          umma_commit(bar_g);
-          umma_commit(&qdo_free[st]);
-          if (i + 2 < n) issue_sdp((u + 2) % NQS, u & 1, ((u + 2) / NQS) & 1);
-          if (i < 6) BW_STAMP(8 + i * 8 + 1);
-        }
+        for (int k4 = 0; k4 < KB / 16; ++k4)
+          umma_ss_lohi(tmem + DQ1_COL, lo(D_ds) + k4 * 2, hds, lo(D_k1mn) + k4 * 32, hk1, idesc_dq1, k4 > 0);
+        umma_commit(bar_g);
+        umma_commit(&qdo_free[st0]);
+        if (i + 1 == n) umma_commit(kv_free);
+        if (i + 2 < n) issue_sdp(st2, st2 * ST16, g & 1, par2);
+        if (it == 0 && i < 6) BW_STAMP(8 + i * 8 + 1);
+        advance();
       }
     }
   }
@@ -286,119 +325,129 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const float l2e = 1.4426950408889634f;
     float* stg = reinterpret_cast<float*>(smem + B_STG);
     const int Tp = nq * TQ;
-    float* dq_head = a.dq32 + ((int64_t)b * a.H + h) * Tp * DQ_PITCH;
-    const float* lse_h = a.lse + ((int64_t)b * a.H + h) * a.T;
-    const float* del_h = a.delta + ((int64_t)b * a.H + h) * a.T;
     if (hs == 1) *reinterpret_cast<float4*>(stg + r * DQ_PITCH + DH) = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t q0[32], q1[16];                              // dQ of the previous pair, on its way to staging
+    int g = 0, it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int kb, h, b;
+      decode(w, kb, h, b);
+      const int q_lo = (kb * KB) / TQ, n = nq - q_lo;
+      float* dq_head = a.dq32 + ((int64_t)b * a.H + h) * Tp * DQ_PITCH;
+      const float* lse_h = a.lse + ((int64_t)b * a.H + h) * a.T;
+      const float* del_h = a.delta + ((int64_t)b * a.H + h) * a.T;
 
-    // dQ tile `qt` (already in q0 / q1) -> staging -> one bulk reduce into dq32
-    auto stage_dq = [&](int qt) {
-      if (tid == 0) tma_store_wait_read();                // the previous reduce has left the staging buffer
-      workers_sync();
-      float* dst = stg + r * DQ_PITCH + hs * 32;
+      // dQ tile `qt` (already in q0 / q1) -> staging -> one bulk reduce into dq32
+      auto stage_dq = [&](int qt) {
+        if (a.flags & 2) return;
+        if (tid == 0) tma_store_wait_read();              // the previous reduce has left the staging buffer
+        workers_sync();
+        float* dst = stg + r * DQ_PITCH + hs * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<float4*>(dst + c * 4) = make_float4(__uint_as_float(q0[4 * c]), __uint_as_float(q0[4 * c + 1]),
-                                                              __uint_as_float(q0[4 * c + 2]), __uint_as_float(q0[4 * c + 3]));
-      if (hs == 1) {
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(dst + c * 4) =
+              make_float4(__uint_as_float(q0[4 * c]), __uint_as_float(q0[4 * c + 1]), __uint_as_float(q0[4 * c + 2]),
+                          __uint_as_float(q0[4 * c + 3]));
+        if (hs == 1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(stg + r * DQ_PITCH + 64 + c * 4) =
-              make_float4(__uint_as_float(q1[4 * c]), __uint_as_float(q1[4 * c + 1]), __uint_as_float(q1[4 * c + 2]),
-                          __uint_as_float(q1[4 * c + 3]));
-      }
-      fence_proxy_async_smem();
-      workers_sync();
-      if (tid == 0) {
-        bulk_reduce_add_f32(dq_head + (int64_t)qt * TQ * DQ_PITCH, stg, STG_BYTES);
-        tma_store_commit();
-      }
-    };
-    auto read_dq = [&]() {
-      tmem_ld32(lane_addr + DQ0_COL + hs * 32, q0);
-      if (hs == 1) tmem_ld16(lane_addr + DQ1_COL, q1);
-      tmem_ld_wait();
-    };
-
-    for (int i = 0; i < n; ++i) {
-      const int row = (q_lo + i) * TQ + r;
-      const bool valid = row < a.T;
-      float lse_l2 = 0.f, delta = 0.f;
-      uint32_t vh = 0u;
-      if (valid) {
-        const float lse = lse_h[row];
-        delta = del_h[row];
-        lse_l2 = lse * l2e;
-        if (lse > -INFINITY) vh = (uint32_t)(visible(a, b, kb, row) >> (32 * hs));
-      }
-      mbar_wait(&bar_s[i & 1], (i >> 1) & 1);
-      tcgen05_fence_after();
-      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 2);
-      uint32_t sv[32], dp[32];
-      tmem_ld32(lane_addr + S_COL + (i & 1) * 64 + hs * 32, sv);
-      tmem_ld32(lane_addr + DP_COL + (i & 1) * 64 + hs * 32, dp);
-      tmem_ld_wait();
-      uint4 pp[4], dd[4];
-      uint32_t* pw = reinterpret_cast<uint32_t*>(pp);
-      uint32_t* dw = reinterpret_cast<uint32_t*>(dd);
-      const float nd = -delta;
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float p0 = exp2f(fmaf(__uint_as_float(sv[c]), a.scale_log2, -lse_l2));
-        float p1 = exp2f(fmaf(__uint_as_float(sv[c + 1]), a.scale_log2, -lse_l2));
-        if (vh != 0xffffffffu) {
-          if (!(vh & (1u << c))) p0 = 0.f;
-          if (!(vh & (2u << c))) p1 = 0.f;
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(stg + r * DQ_PITCH + 64 + c * 4) =
+                make_float4(__uint_as_float(q1[4 * c]), __uint_as_float(q1[4 * c + 1]), __uint_as_float(q1[4 * c + 2]),
+                            __uint_as_float(q1[4 * c + 3]));
         }
-        const float d0 = p0 * (__uint_as_float(dp[c]) + nd) * a.scale;
-        const float d1 = p1 * (__uint_as_float(dp[c + 1]) + nd) * a.scale;
-        pw[c >> 1] = pack2(p0, p1);
-        dw[c >> 1] = pack2(d0, d1);
-      }
-      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 3);
-      if (i > 0) {                       // gradient MMAs of pair i-1 done: sP / sdS free, dQ_{i-1} readable
-        mbar_wait(bar_g, (i - 1) & 1);
-        tcgen05_fence_after();
-      }
-      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 4);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<uint4*>(smem + B_P + sw128_offset(r, hs * 4 + c)) = pp[c];
-        *reinterpret_cast<uint4*>(smem + B_DS + sw128_offset(r, hs * 4 + c)) = dd[c];
-      }
-      fence_proxy_async_smem();
-      if (i > 0) read_dq();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 5);
-      if (i > 0) stage_dq(q_lo + i - 1);   // overlaps the gradient MMAs of pair i
-      if (tid == 0 && i < 6) BW_STAMP(8 + i * 8 + 6);
-    }
-    mbar_wait(bar_g, (n - 1) & 1);
-    tcgen05_fence_after();
-    if (tid == 0) { BW_STAMP(2); BW_STAMP(5); }
-    read_dq();
-    stage_dq(nq - 1);
+        fence_proxy_async_smem();
+        workers_sync();
+        if (tid == 0 && !(a.flags & 1)) {
+          bulk_reduce_add_f32(dq_head + (int64_t)qt * TQ * DQ_PITCH, stg, STG_BYTES);
+          tma_store_commit();
+        }
+      };
+      auto read_dq = [&]() {
+        tmem_ld32(lane_addr + DQ0_COL + hs * 32, q0);
+        if (hs == 1) tmem_ld16(lane_addr + DQ1_COL, q1);
+        tmem_ld_wait();
+      };
 
-    // ---- flush dV (lanes 0-63) and dK (lanes 64-127) of this key block; each thread 32 (+16) columns
-    {
-      const int key = kb * KB + (r & 63);
-      const bool is_k = r >= 64;
-      __nv_bfloat16* dst = (is_k ? a.dk : a.dv) + (((int64_t)b * a.T + key) * a.H + h) * DH;
-      tmem_ld32(lane_addr + DKV0_COL + (is_k ? 64 : 0) + hs * 32, q0);
-      if (hs == 1) tmem_ld16(lane_addr + DKV1_COL + (is_k ? 16 : 0), q1);
-      tmem_ld_wait();
-      if (key < a.T) {
-        store_bf16(dst + hs * 32, q0, 32, 1.f);
-        if (hs == 1) store_bf16(dst + 64, q1, 16, 1.f);
+#pragma unroll 1
+      for (int i = 0; i < n; ++i, ++g) {
+        const int row = (q_lo + i) * TQ + r;
+        const bool valid = row < a.T;
+        float lse_l2 = 0.f, delta = 0.f;
+        uint32_t vh = 0u;
+        if (valid) {
+          const float lse = lse_h[row];
+          delta = del_h[row];
+          lse_l2 = lse * l2e;
+          if (lse > -INFINITY) vh = (uint32_t)(visible(a, b, kb, row) >> (32 * hs));
+        }
+        mbar_wait(&bar_s[g & 1], (g >> 1) & 1);
+        tcgen05_fence_after();
+        if (tid == 0 && it == 0 && i < 6) BW_STAMP(8 + i * 8 + 2);
+        uint32_t sv[32], dp[32];
+        tmem_ld32(lane_addr + S_COL + (g & 1) * 64 + hs * 32, sv);
+        tmem_ld32(lane_addr + DP_COL + (g & 1) * 64 + hs * 32, dp);
+        tmem_ld_wait();
+        uint4 pp[4], dd[4];
+        uint32_t* pw = reinterpret_cast<uint32_t*>(pp);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dd);
+        const float nd = -delta;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(sv[c]), a.scale_log2, -lse_l2));
+          float p1 = exp2f(fmaf(__uint_as_float(sv[c + 1]), a.scale_log2, -lse_l2));
+          if (vh != 0xffffffffu) {
+            if (!(vh & (1u << c))) p0 = 0.f;
+            if (!(vh & (2u << c))) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dp[c]) + nd) * a.scale;
+          const float d1 = p1 * (__uint_as_float(dp[c + 1]) + nd) * a.scale;
+          pw[c >> 1] = pack2(p0, p1);
+          dw[c >> 1] = pack2(d0, d1);
+        }
+        if (tid == 0 && it == 0 && i < 6) BW_STAMP(8 + i * 8 + 3);
+        if (i > 0) {                     // gradient MMAs of pair i-1 done: sP / sdS free, dQ_{i-1} readable
+          mbar_wait(bar_g, (g - 1) & 1);
+          tcgen05_fence_after();
+        }
+        if (tid == 0 && it == 0 && i < 6) BW_STAMP(8 + i * 8 + 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(smem + B_P + sw128_offset(r, hs * 4 + c)) = pp[c];
+          *reinterpret_cast<uint4*>(smem + B_DS + sw128_offset(r, hs * 4 + c)) = dd[c];
+        }
+        fence_proxy_async_smem();
+        if (i > 0) read_dq();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+        if (tid == 0 && it == 0 && i < 6) BW_STAMP(8 + i * 8 + 5);
+        if (i > 0) stage_dq(q_lo + i - 1);   // overlaps the gradient MMAs of pair i
+        if (tid == 0 && it == 0 && i < 6) BW_STAMP(8 + i * 8 + 6);
       }
+      mbar_wait(bar_g, (g - 1) & 1);
+      tcgen05_fence_after();
+      if (tid == 0 && it == 0) { BW_STAMP(2); BW_STAMP(5); }
+      read_dq();
+      stage_dq(nq - 1);
+
+      // ---- flush dV (lanes 0-63) and dK (lanes 64-127) of this key block; each thread 32 (+16) columns
+      {
+        const int key = kb * KB + (r & 63);
+        const bool is_k = r >= 64;
+        __nv_bfloat16* dst = (is_k ? a.dk : a.dv) + (((int64_t)b * a.T + key) * a.H + h) * DH;
+        tmem_ld32(lane_addr + DKV0_COL + (is_k ? 64 : 0) + hs * 32, q0);
+        if (hs == 1) tmem_ld16(lane_addr + DKV1_COL + (is_k ? 16 : 0), q1);
+        tmem_ld_wait();
+        if (key < a.T) {
+          store_bf16(dst + hs * 32, q0, 32, 1.f);
+          if (hs == 1) store_bf16(dst + 64, q1, 16, 1.f);
+        }
+      }
+      tcgen05_fence_before();     // orders the TMEM reads above before this warp's next bar_p arrival
+      if (tid == 0 && it == 0) { BW_STAMP(3); BW_STAMP(6); }
     }
-    tcgen05_fence_before();
     if (tid == 0) tma_store_wait_read();    // the last reduce has left shared memory (its global side completes
-                                            // before the grid does; waiting for it here cost ~1 us per CTA)
-    if (tid == 0) { BW_STAMP(3); BW_STAMP(6); }
+                                            // before the grid does)
+    if (tid == 0) BW_STAMP(7);
   }
   __syncthreads();
   if (warp == BW_MMA) tmem_dealloc(tmem, TMEM_COLS);
@@ -521,8 +570,18 @@ extern "C" int unimp_lm_attn_bwd(const void* q, const void* k, const void* v, in
   a.lse = const_cast<float*>(lse); a.delta = delta; a.kbits = key_bits; a.kwords = 2 * ((T + 63) / 64);
   a.dq32 = dq32; a.dk = (__nv_bfloat16*)dk; a.dv = (__nv_bfloat16*)dv;
   a.dbg = lm::g_bwd_dbg;
-  a.T = T; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((T + lm::KB - 1) / lm::KB, H, B);
+  static const int flags = getenv("UNIMP_LM_BWD_FLAGS") ? atoi(getenv("UNIMP_LM_BWD_FLAGS")) : 0;
+  a.flags = flags;
+  a.T = T; a.H = H; a.B = B; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  const int64_t n_items = (int64_t)((T + lm::KB - 1) / lm::KB) * H * B;
+  static int n_sms = 0;
+  if (!n_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0)
+      n_sms = UNIMP_NUM_SMS;
+  }
+  const unsigned grid = (unsigned)(n_items < n_sms ? n_items : n_sms);   // persistent: one CTA per SM
   lm::lm_attn_bwd_kernel<<<grid, lm::BW_THREADS, lm::B_SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], a);
   UNIMP_CHECK_LAUNCH();
   return 0;
