@@ -24,7 +24,8 @@ for r in rows:
     agg[name][1] += us
 tot = sum(v[1] for v in agg.values())
 n = sum(v[0] for v in agg.values())
-ours = {k: v for k, v in agg.items() if "unimp::" in k}
+# ncu prints nested namespaces without the outer one: unimp::lm::x -> lm::x, unimp::ff::x -> ff::x
+ours = {k: v for k, v in agg.items() if "unimp::" in k or re.search(r"\b(lm|ff)::", k)}
 print(f"launches: {n}; sum of durations {tot / 1e3:.2f} ms; our kernels: {sum(v[0] for v in ours.values())} launches, "
       f"{sum(v[1] for v in ours.values()) / 1e3:.2f} ms ({100 * sum(v[1] for v in ours.values()) / tot:.1f} % of the sum)"
       + (f"; bench.py's live number for the same step: {sys.argv[2]} ms" if len(sys.argv) > 2 else ""))

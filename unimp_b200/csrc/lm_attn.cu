@@ -339,7 +339,9 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       // dQ tile `qt` (already in q0 / q1) -> staging -> one bulk reduce into dq32
       auto stage_dq = [&](int qt) {
         if (a.flags & 2) return;
-        if (tid == 0) tma_store_wait_read();              // the previous reduce has left the staging buffer
+        // (bulk-copy instructions take uniform operands: one ELECTED lane of warp 0 issues, commits and
+        // waits — under `tid == 0` ptxas wraps the reduce in a waterfall loop)
+        if (warp == 0 && elect_one_sync()) tma_store_wait_read();   // the previous reduce has left the staging buffer
         workers_sync();
         float* dst = stg + r * DQ_PITCH + hs * 32;
 #pragma unroll
@@ -356,7 +358,7 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         }
         fence_proxy_async_smem();
         workers_sync();
-        if (tid == 0 && !(a.flags & 1)) {
+        if (warp == 0 && elect_one_sync() && !(a.flags & 1)) {
           bulk_reduce_add_f32(dq_head + (int64_t)qt * TQ * DQ_PITCH, stg, STG_BYTES);
           tma_store_commit();
         }
@@ -445,8 +447,8 @@ lm_attn_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       tcgen05_fence_before();     // orders the TMEM reads above before this warp's next bar_p arrival
       if (tid == 0 && it == 0) { BW_STAMP(3); BW_STAMP(6); }
     }
-    if (tid == 0) tma_store_wait_read();    // the last reduce has left shared memory (its global side completes
-                                            // before the grid does)
+    if (warp == 0 && elect_one_sync()) tma_store_wait_read();   // the last reduce has left shared memory (its
+                                                                // global side completes before the grid does)
     if (tid == 0) BW_STAMP(7);
   }
   __syncthreads();
