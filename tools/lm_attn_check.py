@@ -192,6 +192,54 @@ if "bwd_timeline" in sys.argv[1:]:
     bwd_timeline(6, 256, 32)
     bwd_timeline(6, 1024, 32)
 
+def timeline3(kind):
+    """Per-tile step stamps of one flash_fwd3 launch (three query tiles per CTA)."""
+    import ctypes
+    from unimp_b200 import _lib
+    lib = _lib.load()
+    f = lib.unimp__flash_fwd_debug
+    f.argtypes = [ctypes.c_void_p]
+    f.restype = None
+    if kind == "lm":
+        B, T, H = 6, 1024, 32
+        pk = torch.randn(B, T, H * 3 * dh, device=dev, dtype=bf)
+        run = lambda: ops.lm_attention(*views(pk, B, T, H), None, scale=dh ** -0.5)
+        n_items = ((T // 128 + 2) // 3) * H * B
+    else:
+        Bt, L, Hh = 48, 257, 16
+        q = torch.randn(Bt, L, Hh * 64, device=dev, dtype=bf)
+        kv = torch.randn(Bt, L, 2 * Hh * 64, device=dev, dtype=bf)
+        run = lambda: ops.attention(q, kv, heads=Hh, scale=0.125)
+        n_items = Hh * Bt
+    n_cta = min(n_items, torch.cuda.get_device_properties(0).multi_processor_count)
+    buf = torch.zeros(n_cta * 64, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        f(buf.data_ptr())
+        run()
+        torch.cuda.synchronize()
+        f(None)
+    t = buf.view(n_cta, 64).cpu().double()
+    span = t[:, 5].max() - t[:, 0].min()
+    print(f"F3 timeline {kind}: {n_items} items on {n_cta} persistent CTAs, span {span:.0f} ns "
+          f"({span / (n_items / n_cta):.0f} ns per item per CTA); first item: ready -> end "
+          f"{(t[:, 3] - t[:, 1]).median():.0f} ns")
+    full = t[(t[:, 8 + 2 * 16 + 3 * 4 + 2] > 0)] if kind == "lm" else t[(t[:, 8 + 1 * 16 + 3 * 4 + 2] > 0)]
+    print(f"F3   {len(full)} CTAs whose FIRST item has >= 4 steps in every tile; medians, SM cycles since 'ready':")
+    for j in range(4):
+        for tl in range(3):
+            s_ = 8 + tl * 16 + j * 4
+            rel = lambda k: (full[:, s_ + k] - full[:, 4]).median()
+            print(f"F3   step {j} tile {tl}: S ready {rel(0):7.0f} | math done {rel(1):7.0f} | arrived {rel(2):7.0f} | "
+                  f"MMA lane served {rel(3):7.0f}", flush=True)
+
+
+if "timeline3" in sys.argv[1:]:
+    timeline3("lm")
+    timeline3("vit")
+
 if "timeline" in sys.argv[1:]:
     timeline("lm")
     timeline("vit")

@@ -18,6 +18,8 @@
 // CTA = (128-query tile, head, sample); warps 0-3: one query row per thread (TMEM lane = row);
 // warp 4: one elected lane issues every tcgen05.mma; warp 5: one elected lane issues every TMA.
 // All mbarrier waits are bounded.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -41,7 +43,7 @@ struct Args {
   float* lse;                // (B,H,Lq)
   const uint32_t* kbits;     // (B, kwords) key-valid bits or NULL
   int kwords;
-  int Lq, Lk, H;
+  int Lq, Lk, H, Bt;
   float scale, scale_log2;
 };
 
@@ -231,9 +233,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
 
   if (worker) {
     // One thread per query row (TMEM lane = row).  A second thread per row on the other 32 columns
-    // was tried: it needs the row maximum over all 64 scores, i.e. a second TMEM read of S, and the
-    // TMEM read port (64 B/cycle: 512 cycles per 128 x 64 fp32 block) is what bounds the step —
-    // 104 -> 109 us at T=1024 (profiles/r2_flash_fwd_timeline_two_threads_per_row.log).
+    // was tried: it needs the row maximum over all 64 scores (a second TMEM read and max pass per
+    // row) and the exponentials are MUFU-bound however many warps share them (535 cycles per
+    // 128 x 64 block, tools/probes/softmax_probe.cu): 104 -> 109 us at T=1024
+    // (profiles/r2_flash_fwd_timeline_two_threads_per_row.log).
     const int row = row0 + tid;
     const bool valid = row < a.Lq;
     const bool active = row0 + (warp << 5) < a.Lq;   // warp-uniform: any valid row in this warp
@@ -352,6 +355,319 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
   if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Three query tiles per CTA (384 rows, 12 softmax warps), ONE CTA per SM, one K/V stream.
+// The serial part of a softmax step (wait for S, TMEM read, wait for PV, store P, proxy fence, arrive,
+// wait for the next S: ~1200 of the ~2350 cycles of a step, profiles/r2_flash_fwd_timeline.log) can only
+// be hidden by OTHER warps; TMEM (2 x 256 columns) caps the two-CTA form at 8 softmax warps per SM.  Here
+// S is single-buffered (64 columns per tile) so that three tiles fit (3 x (64 + 80) = 432 columns): while
+// one tile's threads are in their serial part the other two keep the TMEM port and the MUFU busy, and
+// every K/V block is fetched once for 384 query rows instead of once per 128.
+// Causal: the tiles of a group have 6c+2, 6c+4, 6c+6 key blocks; a tile drops out when it is done.
+// ---------------------------------------------------------------------------------------------
+constexpr int NT = 3, THREADS3 = NT * TQ + 64, W3_MMA = NT * 4, W3_TMA = NT * 4 + 1;
+
+template <int DH>
+struct Smem3 {
+  static constexpr bool P1 = DH > 64;
+  static constexpr uint32_t QT = QP0 + (P1 ? QP1 : 0);        // one Q tile: panel 0 (+ panel 1)
+  static constexpr uint32_t KST = KP0 + (P1 ? KP1 : 0);
+  static constexpr uint32_t Q = 0, KR = NT * QT, VR = KR + NST * KST, P = VR + NST * KST, BAR = P + NT * PB,
+                            TOTAL = BAR + 256;
+};
+
+template <int DH, bool CAUSAL>
+__global__ void __launch_bounds__(THREADS3, 1)
+flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                  const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tq1,
+                  const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1, const Args a) {
+  // PERSISTENT: gridDim.x CTAs (one per SM) walk work items (tile group, head, sample), long groups
+  // first.  TMEM, barriers and roles live across items; the K/V rings run on into the next item and its Q
+  // tiles are fetched as soon as this item's last S has been issued, so prologue and epilogue of
+  // neighbouring items overlap (they were ~30 % of a ViT CTA's life: profiles/r2_flash_fwd3_timeline_per_cta.log).
+  using L = Smem3<DH>;
+  constexpr bool P1 = L::P1;
+  constexpr uint32_t S_COL = 0, O0_COL = 64 * NT, O1_COL = 128 * NT, TMEM_COLS = 512;   // per tile: +64t, +64t, +16t
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t *bar_q = bars, *q_free = bars + 1, *bar_k = bars + 2, *bar_v = bar_k + NST, *k_free = bar_v + NST,
+           *v_free = k_free + NST, *bar_s = v_free + NST, *bar_p = bar_s + NT, *bar_pv = bar_p + NT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_pv + NT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) FF_STAMP(0);
+  const int n_tiles = (a.Lq + TQ - 1) / TQ, n_grp = (n_tiles + NT - 1) / NT;
+  const int HB = a.H * a.Bt, n_items = n_grp * HB;
+  const int nb_all = (a.Lk + KB - 1) / KB;
+  // item w -> group (causal: the long groups first), head, sample
+  auto decode = [&](int w, int& grp, int& h, int& b) {
+    const int gi = w / HB, rem = w - gi * HB;
+    grp = CAUSAL ? n_grp - 1 - gi : gi;
+    b = rem / a.H;
+    h = rem - b * a.H;
+  };
+  auto nb_of = [&](int grp, int t) { return CAUSAL ? min(nb_all, ((grp * NT + t) * TQ + TQ) / KB) : nb_all; };
+
+  if (warp == W3_MMA) {
+    if (elect_one_sync()) {
+      if (smem_u32(smem) & 1023u) {
+        printf("unimp: flash_fwd3: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+      }
+      mbar_init(bar_q, 1); mbar_init(q_free, 1);
+#pragma unroll
+      for (int i = 0; i < NST; ++i) {
+        mbar_init(&bar_k[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_free[i], 1);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) { mbar_init(&bar_s[t], 1); mbar_init(&bar_p[t], 4); mbar_init(&bar_pv[t], 1); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) { FF_STAMP(1); FF_STAMP(4); }
+
+  // Running counters, kept alike by every role: it = items done by this CTA (bar_q / q_free phase),
+  // kc = K/V blocks streamed so far (ring stage kc % 3, fill kc / 3), c_t = softmax steps of tile t so far
+  // (phase of bar_s[t], bar_p[t], bar_pv[t]).
+  if (warp == W3_TMA && elect_one_sync()) {
+    // ---- TMA producer ------------------------------------------------------------------------
+    int it = 0, st = 0;
+    uint32_t kc = 0, free_par = 1;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int grp, h, b;
+      decode(w, grp, h, b);
+      const int nt_act = min(NT, n_tiles - grp * NT), nb_max = nb_of(grp, nt_act - 1);
+      if (it > 0) mbar_wait(q_free, (it - 1) & 1);        // the previous item's last S has read the Q tiles
+      mbar_arrive_expect_tx(bar_q, nt_act * L::QT);
+      for (int t = 0; t < nt_act; ++t) {
+        tma_load_4d(smem + L::Q + t * L::QT, &tq, bar_q, 0, h, (grp * NT + t) * TQ, b);
+        if (P1) tma_load_4d(smem + L::Q + t * L::QT + QP0, &tq1, bar_q, 64, h, (grp * NT + t) * TQ, b);
+      }
+#pragma unroll 1
+      for (int j = 0; j < nb_max; ++j, ++kc) {
+        uint8_t* kd = smem + L::KR + st * L::KST;
+        uint8_t* vd = smem + L::VR + st * L::KST;
+        if (kc >= NST) mbar_wait(&k_free[st], free_par);
+        mbar_arrive_expect_tx(&bar_k[st], L::KST);
+        tma_load_4d(kd, &tk, &bar_k[st], 0, h, j * KB, b);
+        if (P1) tma_load_4d(kd + KP0, &tk1, &bar_k[st], 64, h, j * KB, b);
+        if (kc >= NST) mbar_wait(&v_free[st], free_par);
+        mbar_arrive_expect_tx(&bar_v[st], L::KST);
+        tma_load_4d(vd, &tv, &bar_v[st], 0, h, j * KB, b);
+        if (P1) tma_load_4d(vd + KP0, &tv1, &bar_v[st], 64, h, j * KB, b);
+        if (st == NST - 1) { st = 0; free_par ^= 1; } else { ++st; }
+      }
+    }
+  } else if (warp == W3_MMA && elect_one_sync()) {
+    // ---- MMA issuer: per key block j, round robin over the tiles: S_t(j), then PV_t(j-1) ------------
+    constexpr uint32_t idesc_s = make_idesc(TQ, KB, 0, 0);
+    constexpr uint32_t idesc_o0 = make_idesc(TQ, 64, 0, 1);
+    constexpr uint32_t idesc_o1 = make_idesc(TQ, 16, 0, 1);
+    const uint32_t su = smem_u32(smem);
+    auto issue_s = [&](int t, int kst) {            // S_t = Q_t K^T from K stage kst
+      const uint32_t k_u = su + L::KR + kst * L::KST, q_u = su + L::Q + t * L::QT;
+      const uint32_t d = tmem + S_COL + t * 64;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(d, make_smem_desc(q_u + k4 * 32, 16, 1024), make_smem_desc(k_u + k4 * 32, 16, 1024), idesc_s, k4 > 0);
+      if (P1) umma_ss(d, make_smem_desc32(q_u + QP0, 16, 256), make_smem_desc32(k_u + KP0, 16, 256), idesc_s, 1);
+      umma_commit(&bar_s[t]);
+    };
+    auto issue_pv = [&](int t, int vst, bool acc) {  // O_t (+)= P_t V from V stage vst
+      const uint32_t v_u = su + L::VR + vst * L::KST, p_u = su + L::P + t * PB;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ss(tmem + O0_COL + t * 64, make_smem_desc(p_u + k4 * 32, 16, 1024),
+                make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (acc || k4 > 0));
+      if (P1) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_ss(tmem + O1_COL + t * 16, make_smem_desc(p_u + k4 * 32, 16, 1024),
+                  make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (acc || k4 > 0));
+      }
+      umma_commit(&bar_pv[t]);
+    };
+    int it = 0, st = 0, vst = NST - 1;             // K stage of block j; V stage of block j - 1
+    uint32_t kpar = 0, vpar = 1;                   // fill parities of those
+    uint32_t c[NT] = {0u, 0u, 0u};                 // steps started per tile (phase of bar_p[t] for the previous step = c - 1)
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int grp, h, b;
+      decode(w, grp, h, b);
+      const int nt_act = min(NT, n_tiles - grp * NT);
+      const int nb0 = nb_of(grp, 0), nb1 = nb_of(grp, 1), nb2 = nb_of(grp, 2);
+      auto nbt = [&](int t) { return t == 0 ? nb0 : (t == 1 ? nb1 : nb2); };
+      const int nb_max = nbt(nt_act - 1);
+      mbar_wait(bar_q, it & 1);
+#pragma unroll 1
+      for (int j = 0; j < nb_max; ++j) {
+        mbar_wait(&bar_k[st], kpar);
+        if (j > 0) mbar_wait(&bar_v[vst], vpar);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (t < nt_act && j - 1 < nbt(t)) {                 // tile t still has work at this block
+            if (j > 0) {                                      // P_t(j-1) stored, S_t consumed
+              mbar_wait(&bar_p[t], (c[t] - 1) & 1);
+              tcgen05_fence_after();
+            }
+            if (j < nbt(t)) { issue_s(t, st); ++c[t]; }
+            if (j > 0) issue_pv(t, vst, j > 1);
+            if (it == 0 && j < 4) FF_STAMP(8 + t * 16 + j * 4 + 3);
+          }
+        }
+        umma_commit(&k_free[st]);
+        if (j > 0) umma_commit(&v_free[vst]);
+        if (j + 1 == nb_max) umma_commit(q_free);             // every S of this item has been issued
+        vst = st; vpar = kpar;
+        if (st == NST - 1) { st = 0; kpar ^= 1; } else { ++st; }
+      }
+      // the last PV of the tiles that run to nb_max (shorter tiles issued theirs inside the loop)
+      mbar_wait(&bar_v[vst], vpar);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (t < nt_act && nbt(t) == nb_max) {
+          mbar_wait(&bar_p[t], (c[t] - 1) & 1);
+          tcgen05_fence_after();
+          issue_pv(t, vst, nb_max > 1);
+        }
+      }
+      umma_commit(&v_free[vst]);
+    }
+  } else if (warp < NT * 4) {
+    // ---- softmax threads of tile t: one query row per thread -----------------------------------
+    const int t = warp >> 2, r = tid - t * TQ;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* sP = smem + L::P + t * PB;
+    const float tau = 8.f / a.scale_log2, sl2 = a.scale_log2;
+    float f0[32], f1[32];
+    uint32_t* s0 = reinterpret_cast<uint32_t*>(f0);
+    uint32_t* s1 = reinterpret_cast<uint32_t*>(f1);
+    uint32_t c = 0;                                   // steps of this tile so far (all items)
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int grp, h, b;
+      decode(w, grp, h, b);
+      if (t >= min(NT, n_tiles - grp * NT)) continue;   // this tile does not exist in the group
+      const int row0 = (grp * NT + t) * TQ, row = row0 + r;
+      const int nb = nb_of(grp, t);
+      const bool valid = row < a.Lq;
+      const bool active = row0 + ((warp & 3) << 5) < a.Lq;
+      float m_ref = -INFINITY, sum = 0.f;
+      for (int j = 0; j < nb; ++j, ++c) {
+        const uint64_t vis = (active && valid) ? visible<CAUSAL>(a, b, j, row) : 0ull;
+        const bool any = __any_sync(0xffffffffu, vis != 0ull);
+        mbar_wait(&bar_s[t], c & 1);
+        tcgen05_fence_after();
+        if (r == 0 && it == 0 && j < 4) FF_STAMP(8 + t * 16 + j * 4 + 0);
+        float alpha = 1.f;
+        bool grow = false;
+        uint4 pk[8];
+        if (any) {
+          const uint32_t sc = lane_addr + S_COL + t * 64;
+          tmem_ld32(sc, s0);
+          tmem_ld32(sc + 32, s1);
+          tmem_ld_wait();
+          if (vis != ~0ull) {
+            const uint32_t v0 = (uint32_t)vis, v1 = (uint32_t)(vis >> 32);
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+              if (!(v0 & (1u << cc))) f0[cc] = -INFINITY;
+              if (!(v1 & (1u << cc))) f1[cc] = -INFINITY;
+            }
+          }
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) mx[cc & 3] = fmaxf(mx[cc & 3], fmaxf(f0[cc], f1[cc]));
+          const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          if (bm > m_ref + tau || (m_ref == -INFINITY && bm > -INFINITY)) {
+            grow = m_ref > -INFINITY;
+            alpha = grow ? exp2f((m_ref - bm) * sl2) : 1.f;
+            m_ref = bm;
+          }
+          const float nms = m_ref > -INFINITY ? -m_ref * sl2 : 0.f;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+          for (int cc = 0; cc < 32; cc += 2) {
+            const float e0 = exp2f(fmaf(f0[cc], sl2, nms)), e1 = exp2f(fmaf(f0[cc + 1], sl2, nms));
+            const float g0 = exp2f(fmaf(f1[cc], sl2, nms)), g1 = exp2f(fmaf(f1[cc + 1], sl2, nms));
+            ps[(cc >> 1) & 3] += (e0 + e1) + (g0 + g1);
+            pw[cc >> 1] = pack2(e0, e1);
+            pw[16 + (cc >> 1)] = pack2(g0, g1);
+          }
+          sum = sum * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) pk[cc] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (r == 0 && it == 0 && j < 4) FF_STAMP(8 + t * 16 + j * 4 + 1);
+        if (j > 0) {                                   // sP_t and O_t are free once PV_t(j-1) has finished
+          mbar_wait(&bar_pv[t], (c - 1) & 1);
+          tcgen05_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {
+            uint32_t tt[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              tmem_ld32(lane_addr + O0_COL + t * 64 + half * 32, tt);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 32; ++cc) tt[cc] = __float_as_uint(__uint_as_float(tt[cc]) * alpha);
+              tmem_st32(lane_addr + O0_COL + t * 64 + half * 32, tt);
+            }
+            if (P1) {
+              tmem_ld16(lane_addr + O1_COL + t * 16, tt);
+              tmem_ld_wait();
+#pragma unroll
+              for (int cc = 0; cc < 16; ++cc) tt[cc] = __float_as_uint(__uint_as_float(tt[cc]) * alpha);
+              tmem_st16(lane_addr + O1_COL + t * 16, tt);
+            }
+            tmem_st_wait();
+          }
+        }
+        if (active) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(sP + sw128_offset(r, cc)) = pk[cc];
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[t]);
+        if (r == 0 && it == 0 && j < 4) FF_STAMP(8 + t * 16 + j * 4 + 2);
+      }
+      mbar_wait(&bar_pv[t], (c - 1) & 1);
+      tcgen05_fence_after();
+      if (tid == 0 && it == 0) FF_STAMP(2);
+      if (active) {
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        __nv_bfloat16* orow = a.o + (int64_t)b * a.o_bs + (int64_t)row * a.o_rs + h * DH;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(lane_addr + O0_COL + t * 64 + half * 32, s0);
+          tmem_ld_wait();
+          if (valid) store_bf16(orow + half * 32, s0, 32, inv);
+        }
+        if (P1) {
+          tmem_ld16(lane_addr + O1_COL + t * 16, s0);
+          tmem_ld_wait();
+          if (valid) store_bf16(orow + 64, s0, 16, inv);
+        }
+        if (valid) a.lse[((int64_t)b * a.H + h) * a.Lq + row] = sum > 0.f ? m_ref * a.scale + logf(sum) : -INFINITY;
+      }
+      tcgen05_fence_before();     // orders the O reads above before this warp's next bar_p arrival
+      if (tid == 0 && it == 0) FF_STAMP(3);
+    }
+    if (tid == 0) FF_STAMP(5);
+  }
+  __syncthreads();
+  if (warp == W3_MMA) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 static unsigned long long* g_dbg = nullptr;
 
 }  // namespace ff
@@ -396,12 +712,41 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
                          cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
+  // Which of the two kernels?  The persistent three-tile kernel wins once there are at least two items
+  // per SM and more than one query tile (configs[2]: ViT 81 -> 68 us, K4 105 -> 90 us); below that its
+  // one-CTA-per-SM quantisation loses to the two-CTA kernel (configs[1]: ViT 22 vs 26 us, K4 20 vs 21 us).
+  // UNIMP_FLASH3 = 0 / 1 forces one or the other (A/B runs).
+  static const int force3 = getenv("UNIMP_FLASH3") ? atoi(getenv("UNIMP_FLASH3")) : -1;
+  static int n_sms = 0;
+  if (!n_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0)
+      n_sms = UNIMP_NUM_SMS;
+  }
+  const int n_tiles = (Lq + ff::TQ - 1) / ff::TQ;
+  const int64_t n_items = (int64_t)((n_tiles + ff::NT - 1) / ff::NT) * H * B;
+  const bool three = force3 >= 0 ? force3 != 0 : (n_tiles >= 2 && n_items >= 2 * (int64_t)n_sms);
+  using L3 = ff::Smem3<DH>;
+  static bool attr3 = false;
+  if (three && !attr3) {
+    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd3_kernel<DH, CAUSAL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3::TOTAL);
+    if (e != cudaSuccess) { set_error("flash_fwd3: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    attr3 = true;
+  }
   ff::Args a{};
   a.dbg = ff::g_dbg;
   a.o = (__nv_bfloat16*)o; a.o_bs = o_bs; a.o_rs = o_rs; a.lse = lse;
   a.kbits = kbits; a.kwords = 2 * ((Lk + 63) / 64);
-  a.Lq = Lq; a.Lk = Lk; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Lq + ff::TQ - 1) / ff::TQ, H, B);
+  a.Lq = Lq; a.Lk = Lk; a.H = H; a.Bt = B; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+  if (three) {
+    const unsigned grid3 = (unsigned)(n_items < n_sms ? n_items : n_sms);    // persistent: one CTA per SM
+    ff::flash_fwd3_kernel<DH, CAUSAL><<<grid3, ff::THREADS3, L3::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+    UNIMP_CHECK_LAUNCH();
+    return 0;
+  }
+  dim3 grid(n_tiles, H, B);
   ff::flash_fwd_kernel<DH, CAUSAL><<<grid, ff::THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
   UNIMP_CHECK_LAUNCH();
   return 0;
