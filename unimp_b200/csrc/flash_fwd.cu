@@ -102,14 +102,17 @@ struct Smem {
                             P = VR + NST * KST, BAR = P + PB, TOTAL = BAR + 256;
 };
 
-template <int DH, bool CAUSAL>
+template <int DH, bool CAUSAL, bool PT>
 __global__ void __launch_bounds__(THREADS, 2)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                  const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tq1,
                  const __grid_constant__ CUtensorMap tk1, const __grid_constant__ CUtensorMap tv1, const Args a) {
   using L = Smem<DH>;
   constexpr bool P1 = L::P1;
-  constexpr uint32_t S_COL = 0, O0_COL = 128, O1_COL = 192, TMEM_COLS = 256;
+  // PT: P goes to the MMA through TENSOR memory (tcgen05.st by the row's thread, A operand of PV read
+  // from TMEM) instead of shared memory: no 16 KB store + generic->async proxy fence per step, and the PV
+  // MMAs read only V from shared memory.
+  constexpr uint32_t S_COL = 0, O0_COL = 128, O1_COL = 192, P_COL = 208, TMEM_COLS = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
   // full barriers (TMA -> MMA), empty barriers (tcgen05.commit -> TMA producer), S / P / PV handshakes
@@ -211,15 +214,28 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
           mbar_wait(&bar_v[st], (u / NST) & 1);
           tcgen05_fence_after();
           const uint32_t v_u = su + L::VR + st * L::KST;
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_ss(tmem + O0_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
-                    make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (j > 0 || k4 > 0));
-          if (P1) {
+          if (PT) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
-              umma_ss(tmem + O1_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
-                      make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (j > 0 || k4 > 0));
+              umma_ts(tmem + O0_COL, tmem + P_COL + k4 * 8, make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0,
+                      (j > 0 || k4 > 0));
+            if (P1) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ts(tmem + O1_COL, tmem + P_COL + k4 * 8, make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256),
+                        idesc_o1, (j > 0 || k4 > 0));
+            }
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_ss(tmem + O0_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                      make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (j > 0 || k4 > 0));
+            if (P1) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ss(tmem + O1_COL, make_smem_desc(su + L::P + k4 * 32, 16, 1024),
+                        make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (j > 0 || k4 > 0));
+            }
           }
           umma_commit(bar_pv);
           umma_commit(&v_free[st]);
@@ -319,11 +335,16 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
           tmem_st_wait();
         }
       }
-      if (active) {
+      if (PT) {
+        if (active) tmem_st32(lane_addr + P_COL, reinterpret_cast<const uint32_t*>(pk));
+        tmem_st_wait();
+      } else {
+        if (active) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(smem + L::P + sw128_offset(tid, c)) = pk[c];
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(smem + L::P + sw128_offset(tid, c)) = pk[c];
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
@@ -376,7 +397,7 @@ struct Smem3 {
                             TOTAL = BAR + 256;
 };
 
-template <int DH, bool CAUSAL>
+template <int DH, bool CAUSAL, bool PT>
 __global__ void __launch_bounds__(THREADS3, 1)
 flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tq1,
@@ -388,6 +409,12 @@ flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
   using L = Smem3<DH>;
   constexpr bool P1 = L::P1;
   constexpr uint32_t S_COL = 0, O0_COL = 64 * NT, O1_COL = 128 * NT, TMEM_COLS = 512;   // per tile: +64t, +64t, +16t
+  // PT: P_t goes to the PV MMA through tensor memory.  Head dim 64 has room for it (columns 384 + 32t);
+  // head dim 80 does not (3 x (64 + 80 + 32) > 512): there P_t overwrites the first 32 columns of S_t once
+  // the row's thread has read them, and the MMA lane issues PV_t(j) BEFORE S_t(j+1) (the tensor pipe runs
+  // in issue order, so S_t(j+1) cannot overtake the PV that still reads P_t).
+  constexpr bool P_ALIAS = PT && P1;
+  constexpr uint32_t P_COL = P_ALIAS ? S_COL : 128 * NT, P_STRIDE = P_ALIAS ? 64 : 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
   uint64_t *bar_q = bars, *q_free = bars + 1, *bar_k = bars + 2, *bar_v = bar_k + NST, *k_free = bar_v + NST,
@@ -481,15 +508,26 @@ flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
     };
     auto issue_pv = [&](int t, int vst, bool acc) {  // O_t (+)= P_t V from V stage vst
       const uint32_t v_u = su + L::VR + vst * L::KST, p_u = su + L::P + t * PB;
+      const uint32_t p_t = tmem + P_COL + t * P_STRIDE;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4)
-        umma_ss(tmem + O0_COL + t * 64, make_smem_desc(p_u + k4 * 32, 16, 1024),
-                make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (acc || k4 > 0));
+      for (int k4 = 0; k4 < 4; ++k4) {
+        if (PT)
+          umma_ts(tmem + O0_COL + t * 64, p_t + k4 * 8, make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0,
+                  (acc || k4 > 0));
+        else
+          umma_ss(tmem + O0_COL + t * 64, make_smem_desc(p_u + k4 * 32, 16, 1024),
+                  make_smem_desc(v_u + k4 * 2048, 1024, 1024), idesc_o0, (acc || k4 > 0));
+      }
       if (P1) {
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          umma_ss(tmem + O1_COL + t * 16, make_smem_desc(p_u + k4 * 32, 16, 1024),
-                  make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (acc || k4 > 0));
+        for (int k4 = 0; k4 < 4; ++k4) {
+          if (PT)
+            umma_ts(tmem + O1_COL + t * 16, p_t + k4 * 8, make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256),
+                    idesc_o1, (acc || k4 > 0));
+          else
+            umma_ss(tmem + O1_COL + t * 16, make_smem_desc(p_u + k4 * 32, 16, 1024),
+                    make_smem_desc32(v_u + KP0 + k4 * 512, 256, 256), idesc_o1, (acc || k4 > 0));
+        }
       }
       umma_commit(&bar_pv[t]);
     };
@@ -516,8 +554,13 @@ flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
               mbar_wait(&bar_p[t], (c[t] - 1) & 1);
               tcgen05_fence_after();
             }
-            if (j < nbt(t)) { issue_s(t, st); ++c[t]; }
-            if (j > 0) issue_pv(t, vst, j > 1);
+            if (P_ALIAS) {                                    // P_t lives in S_t's columns: PV first
+              if (j > 0) issue_pv(t, vst, j > 1);
+              if (j < nbt(t)) { issue_s(t, st); ++c[t]; }
+            } else {
+              if (j < nbt(t)) { issue_s(t, st); ++c[t]; }
+              if (j > 0) issue_pv(t, vst, j > 1);
+            }
             if (it == 0 && j < 4) FF_STAMP(8 + t * 16 + j * 4 + 3);
           }
         }
@@ -630,11 +673,16 @@ flash_fwd3_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
             tmem_st_wait();
           }
         }
-        if (active) {
+        if (PT) {
+          if (active) tmem_st32(lane_addr + P_COL + t * P_STRIDE, reinterpret_cast<const uint32_t*>(pk));
+          tmem_st_wait();
+        } else {
+          if (active) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(sP + sw128_offset(r, cc)) = pk[cc];
+            for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(sP + sw128_offset(r, cc)) = pk[cc];
+          }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[t]);
@@ -705,10 +753,15 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
   }
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL>,
+    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)L::TOTAL);
     if (e != cudaSuccess) { set_error("flash_fwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ff::flash_fwd_kernel<DH, CAUSAL, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
@@ -717,6 +770,8 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
   // one-CTA-per-SM quantisation loses to the two-CTA kernel (configs[1]: ViT 22 vs 26 us, K4 20 vs 21 us).
   // UNIMP_FLASH3 = 0 / 1 forces one or the other (A/B runs).
   static const int force3 = getenv("UNIMP_FLASH3") ? atoi(getenv("UNIMP_FLASH3")) : -1;
+  // P through tensor memory (default) or through shared memory (UNIMP_FLASH_PT=0, A/B runs)
+  static const bool pt = !(getenv("UNIMP_FLASH_PT") && atoi(getenv("UNIMP_FLASH_PT")) == 0);
   static int n_sms = 0;
   if (!n_sms) {
     int dev = 0;
@@ -730,8 +785,11 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
   using L3 = ff::Smem3<DH>;
   static bool attr3 = false;
   if (three && !attr3) {
-    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd3_kernel<DH, CAUSAL>,
+    cudaError_t e = cudaFuncSetAttribute(ff::flash_fwd3_kernel<DH, CAUSAL, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3::TOTAL);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(ff::flash_fwd3_kernel<DH, CAUSAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)L3::TOTAL);
     if (e != cudaSuccess) { set_error("flash_fwd3: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr3 = true;
   }
@@ -742,12 +800,18 @@ static int launch_flash(const void* q, int64_t q_bs, int64_t q_rs, int64_t q_hs,
   a.Lq = Lq; a.Lk = Lk; a.H = H; a.Bt = B; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
   if (three) {
     const unsigned grid3 = (unsigned)(n_items < n_sms ? n_items : n_sms);    // persistent: one CTA per SM
-    ff::flash_fwd3_kernel<DH, CAUSAL><<<grid3, ff::THREADS3, L3::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+    if (pt)
+      ff::flash_fwd3_kernel<DH, CAUSAL, true><<<grid3, ff::THREADS3, L3::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+    else
+      ff::flash_fwd3_kernel<DH, CAUSAL, false><<<grid3, ff::THREADS3, L3::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
     UNIMP_CHECK_LAUNCH();
     return 0;
   }
   dim3 grid(n_tiles, H, B);
-  ff::flash_fwd_kernel<DH, CAUSAL><<<grid, ff::THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+  if (pt)
+    ff::flash_fwd_kernel<DH, CAUSAL, true><<<grid, ff::THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
+  else
+    ff::flash_fwd_kernel<DH, CAUSAL, false><<<grid, ff::THREADS, L::TOTAL, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
   UNIMP_CHECK_LAUNCH();
   return 0;
 }
@@ -778,18 +842,18 @@ extern "C" void unimp__flash_fwd_debug(unsigned long long* buf) { unimp::ff::g_d
 extern "C" int unimp__flash_fwd_occupancy(int dh) {
   int n = -1;
   if (dh == 80) {
-    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)unimp::ff::Smem<80>::TOTAL);
-    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<80, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<80, true>, unimp::ff::THREADS,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<80, true, false>, unimp::ff::THREADS,
                                                   unimp::ff::Smem<80>::TOTAL);
   } else {
-    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)unimp::ff::Smem<64>::TOTAL);
-    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(unimp::ff::flash_fwd_kernel<64, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<64, false>, unimp::ff::THREADS,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, unimp::ff::flash_fwd_kernel<64, false, false>, unimp::ff::THREADS,
                                                   unimp::ff::Smem<64>::TOTAL);
   }
   return n;

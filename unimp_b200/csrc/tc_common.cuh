@@ -306,6 +306,20 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (K-major only) is read from tensor memory — 128 lanes x
+// 8 columns per K = 16 step, each 32-bit cell holding two consecutive bf16 K-elements (what a thread
+// owning one row writes with tcgen05.st of packed pairs).
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Same, with each 64-bit shared-memory descriptor passed as (lo, hi) 32-bit halves: the start-address
 // and LBO fields live in `lo`, so stepping through K-steps / ring stages is ONE 32-bit add per operand
 // on the issuing lane (64-bit descriptor arithmetic on the uniform datapath costs several dependent ops).
