@@ -1,13 +1,12 @@
 #!/usr/bin/env bash
-# Round-2 measurement pass (dev tool, under gpurun): full GPU suite, bench lines for configs[1..4],
-# ncu launch list of one timed step, ncu --set full captures of the attention kernels.
+# Final artifacts with the final code (dev tool): GPU suite, smoke, bench lines, launch lists, ncu of the flash kernels.
 mkdir -p gpurun_out
-P=${1:-r2q}
+P=${1:-r2f}
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${P}_tests.log 2>&1
 echo "pytest rc=$?"; tail -n 3 gpurun_out/${P}_tests.log; grep -E "^(FAILED|ERROR)|^E  " gpurun_out/${P}_tests.log | head -30
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/${P}_smoke.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 4 gpurun_out/${P}_smoke.log
 timeout 700 python bench.py > gpurun_out/${P}_bench_c2.json 2> gpurun_out/${P}_bench_c2.err
-echo "bench c2 rc=$?"; tail -c 300 gpurun_out/${P}_bench_c2.err
+echo "bench c2 rc=$?"
 timeout 700 python bench.py --workload C3-multitask --steps 20 --no-cpu-baseline > gpurun_out/${P}_bench_c3.json 2> gpurun_out/${P}_bench_c3.err
 echo "bench c3 rc=$?"
 timeout 700 python bench.py --workload C5-imggen --steps 20 --no-cpu-baseline > gpurun_out/${P}_bench_c5.json 2> gpurun_out/${P}_bench_c5.err
@@ -17,30 +16,16 @@ echo "decode rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${P}_launches.csv \
   python bench.py --steps 1 --warmup 1 --soak-s 0 --no-cpu-baseline --no-eager-baseline --no-kernel-profile --ncu-range > gpurun_out/${P}_ncu_bench.log 2>&1
 echo "ncu launches rc=$?"; wc -l gpurun_out/${P}_launches.csv
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'xattn_block_fwd_kernel|xattn_fwd_tc_kernel|attn_bwd_tc_kernel' -s 12 -c 6 -o gpurun_out/${P}_ncu_xattn_c2 -f python tools/kbench_cli.py --workload C2-rec --only xattn --no-eager > gpurun_out/${P}_ncu_xattn_c2.log 2>&1
-echo "ncu xattn c2 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'xattn_block_fwd_kernel|xattn_fwd_tc_kernel' -s 8 -c 4 -o gpurun_out/${P}_ncu_xattn_c3 -f python tools/kbench_cli.py --workload C3-multitask --only xattn --no-eager > gpurun_out/${P}_ncu_xattn_c3.log 2>&1
-echo "ncu xattn c3 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel' -s 4 -c 3 -o gpurun_out/${P}_ncu_vit -f python tools/kbench_cli.py --workload C2-rec --only vit --no-eager > gpurun_out/${P}_ncu_vit.log 2>&1
-echo "ncu vit rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel|lm_attn_bwd_kernel' -s 6 -c 4 -o gpurun_out/${P}_ncu_lm_c2 -f python tools/kbench_cli.py --workload C2-rec --only lm --no-eager > gpurun_out/${P}_ncu_lm_c2.log 2>&1
-echo "ncu lm c2 rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd_kernel|lm_attn_bwd_kernel' -s 4 -c 4 -o gpurun_out/${P}_ncu_lm_c3 -f python tools/kbench_cli.py --workload C3-multitask --only lm --no-eager > gpurun_out/${P}_ncu_lm_c3.log 2>&1
-echo "ncu lm c3 rc=$?"; ls -la gpurun_out/${P}_ncu_*.ncu-rep
-timeout 300 python tools/kbench_cli.py --workload C2-rec --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB" > gpurun_out/${P}_kbench_attn.log
-timeout 300 python tools/kbench_cli.py --workload C3-multitask --only lm vit --tag $P 2>&1 >/dev/null | grep "^KB" >> gpurun_out/${P}_kbench_attn.log
-UNIMP_LM_ATTN=0 timeout 600 python bench.py --steps 30 --no-cpu-baseline --no-eager-baseline --no-kernel-profile > gpurun_out/${P}_bench_c2_sdpa.json 2> gpurun_out/${P}_bench_c2_sdpa.err
-echo "bench c2 (cuDNN SDPA for K4) rc=$?"
-UNIMP_LM_ATTN=0 timeout 600 python bench.py --workload C3-multitask --steps 12 --no-cpu-baseline --no-eager-baseline --no-kernel-profile > gpurun_out/${P}_bench_c3_sdpa.json 2> gpurun_out/${P}_bench_c3_sdpa.err
-echo "bench c3 (cuDNN SDPA for K4) rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${P}_launches_c3.csv \
+  python bench.py --workload C3-multitask --steps 1 --warmup 1 --soak-s 0 --no-cpu-baseline --no-eager-baseline --no-kernel-profile --ncu-range > gpurun_out/${P}_ncu_bench_c3.log 2>&1
+echo "ncu launches c3 rc=$?"; wc -l gpurun_out/${P}_launches_c3.csv
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd' -s 4 -c 3 -o gpurun_out/${P}_ncu_vit_c2 -f python tools/kbench_cli.py --workload C2-rec --only vit --no-eager > gpurun_out/${P}_ncu_vit_c2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd' -s 4 -c 3 -o gpurun_out/${P}_ncu_vit_c3 -f python tools/kbench_cli.py --workload C3-multitask --only vit --no-eager > gpurun_out/${P}_ncu_vit_c3.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd' -s 2 -c 2 -o gpurun_out/${P}_ncu_lmf_c2 -f python tools/kbench_cli.py --workload C2-rec --only lm --no-eager > gpurun_out/${P}_ncu_lmf_c2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'flash_fwd' -s 2 -c 2 -o gpurun_out/${P}_ncu_lmf_c3 -f python tools/kbench_cli.py --workload C3-multitask --only lm --no-eager > gpurun_out/${P}_ncu_lmf_c3.log 2>&1
+echo "ncu captures done"; ls gpurun_out/${P}_ncu_*.ncu-rep
 python - <<PY
 import json
-for n in ("c2_sdpa", "c3_sdpa"):
-    try:
-        d = json.load(open("gpurun_out/${P}_bench_%s.json" % n))
-        print(n, "samples/s", round(d["value"], 2), "ms/step", round(d["ms_per_step"], 2), d["clocks"])
-    except Exception as e:
-        print(n, "no json", e)
 for n in ("c2", "c3", "c5"):
     try:
         d = json.load(open("gpurun_out/${P}_bench_%s.json" % n))
