@@ -188,6 +188,15 @@ def bwd_timeline(B, T, H):
     print(f"BW     flush start {(sel[:, 5] - sel[:, 4]).median():6.0f} | item end {(sel[:, 6] - sel[:, 4]).median():6.0f}")
 
 
+if "small" in sys.argv[1:]:      # for compute-sanitizer runs: every kernel variant once, small shapes
+    for B, T, H, pad in [(1, 200, 2, True), (2, 513, 1, True)]:
+        check(B, T, H, pad)
+    q = torch.randn(2, 257, 2 * 64, device=dev, dtype=bf)
+    kv = torch.randn(2, 257, 2 * 2 * 64, device=dev, dtype=bf)
+    o = ops.attention(q, kv, heads=2, scale=0.125)
+    torch.cuda.synchronize()
+    print("SMALL attention (dh 64) ok", float(o.float().abs().mean()))
+
 if "bwd_timeline" in sys.argv[1:]:
     bwd_timeline(6, 256, 32)
     bwd_timeline(6, 1024, 32)
