@@ -3,20 +3,23 @@
 //   K2  Perceiver latent attention 64 x 320, K3 ViT-L/14 self-attention 257 x 257  (DH = 64)
 //   K4  GPT-NeoX causal self-attention with key padding                            (DH = 80)
 //
-// vs attn_fwd2_tc_kernel (two sweeps, S recomputed) and the first lm_attn_fwd_kernel:
+// Common to both kernels below (vs round 2's first, two-sweep kernels: S recomputed, 3 CTAs per SM):
 //   * ONE sweep over the key blocks with an online softmax; O is rescaled in TMEM only when a row's
 //     running maximum grows by more than 2^8 (rare after the first blocks), so the common step is
-//     S -> registers -> exp2 -> P (bf16, shared) with no TMEM round trip of O;
-//   * S is double-buffered in TMEM (2 x 64 columns): S_{j+1} = Q K_{j+1}^T runs on the tensor pipe
-//     while the 128 softmax threads work on S_j, and PV_j runs while they work on S_{j+1};
+//     S -> registers -> exp2 -> P (bf16) with no TMEM round trip of O;
+//   * P reaches the PV MMA through TENSOR memory: the row's thread writes its 64 probabilities with
+//     tcgen05.st (32 columns of packed bf16 pairs) and the MMA reads its A operand from TMEM — no
+//     shared-memory store, no generic->async proxy fence, PV reads only V from shared memory;
 //   * K and V travel through two 3-stage TMA rings fed by a dedicated producer lane (full / empty
-//     mbarriers: tcgen05.commit releases a stage): K_{j+3} is requested as soon as S_j has run,
-//     V_{j+3} as soon as PV_j has;
+//     mbarriers: tcgen05.commit releases a stage);
 //   * head dim 80 = a 64-column SWIZZLE_128B panel + a 16-column SWIZZLE_32B panel (2 KB per 64-row
-//     tile instead of the 8 KB a zero-padded 128-byte panel costs): 106 KB of shared memory, two
-//     CTAs per SM.
-// CTA = (128-query tile, head, sample); warps 0-3: one query row per thread (TMEM lane = row);
-// warp 4: one elected lane issues every tcgen05.mma; warp 5: one elected lane issues every TMA.
+//     tile instead of the 8 KB a zero-padded 128-byte panel costs) read through two tensor maps over
+//     the same memory.
+// flash_fwd_kernel : CTA = (128-query tile, head, sample), two CTAs per SM; S double-buffered in TMEM
+//     (S_{j+1} = Q K_{j+1}^T runs while the 128 softmax threads work on S_j); warps 0-3: one query row
+//     per thread (TMEM lane = row), warp 4: MMA lane, warp 5: TMA lane.
+// flash_fwd3_kernel: three query tiles per CTA, one persistent CTA per SM (see its header); chosen by
+//     launch_flash for large workloads.
 // All mbarrier waits are bounded.
 #include <stdlib.h>
 
