@@ -120,9 +120,14 @@ class MaskedCrossAttention(nn.Module):
         self.to_out = nn.Linear(inner, dim, bias=False)
         self.only_attend_immediate_media = True
         self._kv_cache = None  # decode-time cache of to_kv(media) (new)
-        # K1-fused (one cluster kernel for to_q -> attention -> to_out) where the shape allows
-        # (bf16, 8 x 64 heads, 64 latents, D <= 2560); UNIMP_XATTN_FUSED=0 keeps the three-launch form
-        self.fused = os.environ.get("UNIMP_XATTN_FUSED", "1") != "0"
+        # K1-fused (one cluster kernel for to_q -> attention -> to_out) where the shape allows (bf16,
+        # 8 x 64 heads, 64 latents, D <= 2560) AND its 8-CTA clusters run as one wave: 12 clusters are
+        # co-resident on a B200, i.e. B * ceil(T / 128) <= 12 row tiles (configs[1]: 12).  Beyond that
+        # the clusters queue in waves and cuBLAS + core + cuBLAS is faster (configs[2], 48 tiles: 103 vs
+        # 46 us in isolation, -0.7 % samples/s in the step).  UNIMP_XATTN_FUSED=0 never fuses, =2 always.
+        self.fused = int(os.environ.get("UNIMP_XATTN_FUSED", "1"))
+
+    FUSED_MAX_TILES = 12   # co-resident 8-CTA clusters per B200
 
     def project_media(self, media):
         """to_kv over (B, Ti*n, Dv) -> packed (B, Ti*n, 2*inner)."""
@@ -156,7 +161,8 @@ class MaskedCrossAttention(nn.Module):
         if x_ln is None:
             x_ln = ops.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         cached = use_cached_media and not torch.is_grad_enabled()
-        if self.fused and not (cached and T == 1):
+        fuse = self.fused == 2 or (self.fused == 1 and B * ((T + 127) // 128) <= self.FUSED_MAX_TILES)
+        if fuse and not (cached and T == 1):
             kv = self.cached_media_kv(media) if cached else self.project_media(media)
             if not cached:
                 self._kv_cache = None
