@@ -161,3 +161,26 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         _lib.load()
     with pytest.raises(_lib.UnimpError):
         ops.gelu(torch.zeros(8))
+
+
+def test_lm_attn_rejects_unsupported_geometry_before_launching():
+    """K4 covers bf16 with head dim 80 only; anything else must be refused with a message naming the
+    constraint, before any CUDA call (the host keeps SDPA for those cases: flamingo_lm.fused_neox_layer)."""
+    lib = _lib.load()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)          # 16-byte aligned dummy pointer, never dereferenced
+    p = ctypes.c_void_p((p.value + 15) & ~15)
+    assert lib.unimp_lm_attn_supported(256, 32, 80, _lib.BF16) == 1
+    assert lib.unimp_lm_attn_supported(256, 32, 64, _lib.BF16) == 0
+    assert lib.unimp_lm_attn_supported(256, 32, 80, _lib.F32) == 0
+    for dh, dtype, stride, what in ((64, _lib.BF16, 240, "head dim"), (80, _lib.F32, 240, "bf16"),
+                                    (80, _lib.BF16, 241, "strides")):
+        rc = lib.unimp_lm_attn_fwd(p, p, p, 256 * 32 * 240, 32 * 240, stride, None, p, p, 1, 256, 32, dh, 0.1,
+                                   dtype, None)
+        assert rc < 0, (dh, dtype, stride, rc)
+        assert what in lib.unimp_last_error_string().decode(), lib.unimp_last_error_string().decode()
+        rc = lib.unimp_lm_attn_bwd(p, p, p, 256 * 32 * 240, 32 * 240, stride, None, p, p, p, p, p, p, p, 1, 256,
+                                   32, dh, 0.1, dtype, None)
+        assert rc < 0
+    rc = lib.unimp_key_bits(p, 4, p, 1, 64, None)   # element size must be 1 or 8
+    assert rc < 0 and "mask" in lib.unimp_last_error_string().decode()
