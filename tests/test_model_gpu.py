@@ -342,7 +342,8 @@ def _build_4b_pair(dtype_product):
 def test_4b_bf16_product_matches_fp32_oracle_logits_and_loss():
     """end-to-end parity at the 4B shapes on configs[1]'s micro-batch (B=3, T=256,
     Ti=2) — north-star bars: bf16 rel 2e-2 on logits, 1e-3 on loss — for the dense path and for the
-    head+loss fusion (the bf16 path includes the K1-fused cluster kernel)."""
+    head+loss fusion (the bf16 path includes the K1-fused cluster kernel and the K4 causal-attention
+    kernels of all 32 decoder layers)."""
     from unimp_b200.config import Workload
     from unimp_b200.train import unimp_loss
 
@@ -361,7 +362,15 @@ def test_4b_bf16_product_matches_fp32_oracle_logits_and_loss():
             ac = oracle(vision_x=gb["patch_images"].unsqueeze(2), lang_x=gb["input_ids"],
                         attention_mask=gb["attention_masks"], labels=labels)
         ac_loss = focal_loss(ac.logits.float(), labels, gb["weights"], gamma=2.0)
-        loss, hf_loss, logits = unimp_loss(model, gb, cfg.tokens)
+        from unimp_b200 import ops as _ops
+        k4_calls, k4_orig = [], _ops.rotary_lm_attention
+        _ops.rotary_lm_attention = lambda *a, **k: (k4_calls.append(k.get("head_dim")), k4_orig(*a, **k))[1]
+        try:
+            loss, hf_loss, logits = unimp_loss(model, gb, cfg.tokens)
+        finally:
+            _ops.rotary_lm_attention = k4_orig
+        # K4: all 32 decoder layers ran on unimp_lm_attn_fwd (head dim 80, padded batch -> key bits)
+        assert len(k4_calls) == cfg.lm_layers and set(k4_calls) == {80}, k4_calls
         loss_r, hf_r, logits_r = unimp_loss(model, gb, cfg.tokens, label_rows=True)
     valid = gb["attention_masks"].bool()
     e_logits = rel_err(logits[valid], ref.logits[valid])
