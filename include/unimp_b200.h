@@ -133,6 +133,31 @@ int unimp_xattn_decode(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int
                        unimp_mview_t o, int B, int Ti, int n, int H, int dh, float scale,
                        int dtype, void* stream);
 
+/* ---- a12 / f4: the language model's side of a decode step (configs[3]) ------------------
+ * Replaces, per GPT-NeoX layer and generated token, what HF runs inside `GenerationMixin.generate`
+ * (reference call `UniMP/pipeline/eval/eval_exp.py:101-114`): apply_rotary_pos_emb on the new
+ * token's q/k, `DynamicCache.update`, the attention over the cache, and — for beam search — the
+ * `reorder_cache` copy of every layer's K/V.
+ *   qkv (B, H, 3, dh): the packed query_key_value projection of the new token (HF layout);
+ *   cos, sin (B, rot) of the token's position; k_cache, v_cache (B, H, Tmax, dh), written in place
+ *   at slot *cursor (int64 on the device: capturable in a CUDA graph);
+ *   indir (B, Tmax) int32: cache ROW that holds position t of beam b's history.  The kernel sets
+ *   indir[b][*cursor] = b; a beam re-ordering step permutes the ROWS OF indir (B*Tmax ints), never
+ *   the caches;  add_mask (B, Tmax) in `dtype`: 0 = visible, -inf = padding;
+ *   out (B, H*dh) = softmax(q k^T * scale + add_mask) v over positions 0..*cursor.
+ * dh in {32, 64, 80, 96, 128}; rot even, <= dh; Tmax <= 5120; fp32 or bf16. */
+int unimp_lm_decode_attn(const void* qkv, const void* cos, const void* sin, void* k_cache,
+                         void* v_cache, int32_t* indir, const void* add_mask, const int64_t* cursor,
+                         void* out, int B, int H, int Tmax, int dh, int rot, float scale, int dtype,
+                         void* stream);
+
+/* y (M, N) = act(x (M, K) . w (N, K)^T + bias (N) or NULL), M <= 8 rows (the beams of one decode
+ * step): `nn.Linear` of GPT-NeoX / GatedCrossAttentionBlock at one token per sequence, as a
+ * weight-streaming kernel (each weight is read once, 16-byte loads).  act: 0 none, 1 exact (erf)
+ * GELU.  bf16 only; K % 32 == 0; x, w 16-byte aligned, rows contiguous. */
+int unimp_linear_small_m(const void* x, const void* w, const void* bias, void* y, int M, int N, int K,
+                         int act, int dtype, void* stream);
+
 /* ---- a6 / K5: tanh-gate + residual + LayerNorm epilogue -------------------------------
  * Replaces `x = f(x) * tanh(gate) + x` of `GatedCrossAttentionBlock.forward` fused with
  * the LayerNorm that consumes it (the FF's LN, or MaskedCrossAttention.norm) — SURVEY §9.

@@ -60,6 +60,32 @@ def install():
         q, k = apply_rotary_pos_emb(q, k, cos, sin)
         return q, k, v
 
+    def lm_decode_attention(qkv, cos, sin, k_cache, v_cache, indir, add_mask, cursor, *, heads, head_dim,
+                            rotary_dim, scale):
+        """The contract of `unimp_lm_decode_attn`, densely: rotary, cache write at the cursor, attention
+        over positions 0..cursor with position t of beam b read from cache row indir[b, t]."""
+        from transformers.models.gpt_neox.modeling_gpt_neox import apply_rotary_pos_emb
+
+        B, Tmax = qkv.shape[0], k_cache.shape[2]
+        v5 = qkv.view(B, 1, heads, 3, head_dim)
+        q, k, v = (v5[:, :, :, i].transpose(1, 2) for i in range(3))          # (B,H,1,dh)
+        q, k = apply_rotary_pos_emb(q, k, cos.view(B, 1, rotary_dim), sin.view(B, 1, rotary_dim))
+        cur = int(cursor)
+        k_cache[:, :, cur], v_cache[:, :, cur] = k[:, :, 0], v[:, :, 0]
+        indir[:, cur] = torch.arange(B, dtype=torch.int32)
+        rows, t = indir.long(), torch.arange(Tmax)
+        kg, vg = k_cache[rows, :, t[None, :]], v_cache[rows, :, t[None, :]]   # (B,Tmax,H,dh)
+        s = torch.einsum("bhd,bthd->bht", q[:, :, 0], kg) * scale + add_mask.view(B, 1, Tmax)
+        s[:, :, cur + 1:] = float("-inf")
+        return torch.einsum("bht,bthd->bhd", s.softmax(-1), vg).reshape(B, 1, heads * head_dim)
+
+    def linear_rows(x, w, b=None, act_gelu=False):
+        y = F.linear(x, w, b)
+        return F.gelu(y) if act_gelu else y
+
+    ops.lm_decode_attention = lm_decode_attention
+    ops.linear_rows = linear_rows
+    ops.small_m_eligible = lambda x, w: False
     ops.text_time = text_time
     ops.masked_cross_attention = lambda q, kv, tt, *, heads, n_latents, scale, force_simt=False: \
         _dense_attention(q, kv, tt.long(), heads, n_latents, scale)

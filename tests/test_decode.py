@@ -128,6 +128,23 @@ def test_graphed_decoder_equals_flamingo_generate(nb, nrs, early, new):
 
 
 @pytest.mark.gpu
+def test_graphed_decoder_beam_indirection_equals_reordered_caches():
+    """The default decoder never copies K/V caches between beams (an indirection table read by
+    `unimp_lm_decode_attn`); the legacy path (HF `reorder_cache` semantics: gather every layer's K/V,
+    SDPA over them) must return the same token matrix."""
+    from unimp_b200.decode import GraphedDecoder
+
+    cfg, model, ids, vis = _tiny_flamingo(torch.float32)
+    kw = dict(num_beams=5, max_new_tokens=14, eos_token_id=cfg.tokens.endofchunk, pad_token_id=cfg.tokens.pad,
+              num_return_sequences=5, early_stopping=False)
+    new = GraphedDecoder(model)
+    assert new.use_indirection
+    old = GraphedDecoder(model)
+    old.use_indirection = False
+    assert torch.equal(new.generate(vis, ids, None, **kw), old.generate(vis, ids, None, **kw))
+
+
+@pytest.mark.gpu
 def test_graphed_decoder_ragged_prompts_and_bf16():
     from unimp_b200.decode import GraphedDecoder
 

@@ -167,6 +167,85 @@ def test_xattn_decode_matches_full(dtype, tol):
     assert out[2].abs().max() == 0
 
 
+# ------------------------------------------------------------------ decode: LM self-attention step, skinny linear
+
+def _rotate_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("B,H,dh,rot,Tmax,cur", [(5, 32, 80, 80, 784, 600), (4, 4, 32, 8, 48, 0), (3, 8, 64, 32, 300, 299),
+                                                 (2, 2, 128, 128, 1040, 1031), (6, 3, 96, 48, 64, 17),
+                                                 (5, 32, 80, 80, 768, 767)])
+def test_lm_decode_attn_matches_dense(dtype, tol, B, H, dh, rot, Tmax, cur):
+    """`unimp_lm_decode_attn` (rotary + cache write at a device-side cursor + attention through the
+    beam indirection) against the dense statement of what HF runs per generated token:
+    apply_rotary_pos_emb, DynamicCache.update, reorder_cache, softmax(q k^T * scale + mask) v."""
+    torch.manual_seed(B * 1000 + cur)
+    qkv = torch.randn(B, 1, H * 3 * dh).to(dtype)
+    ang = torch.rand(B, rot) * 6.28
+    cos, sin = ang.cos().to(dtype), ang.sin().to(dtype)
+    kc, vc = torch.randn(B, H, Tmax, dh).to(dtype), torch.randn(B, H, Tmax, dh).to(dtype)
+    indir = torch.randint(0, B, (B, Tmax), dtype=torch.int32)
+    mask = torch.zeros(B, Tmax)
+    mask[torch.rand(B, Tmax) < 0.2] = float("-inf")
+    mask[:, cur] = 0.0
+    mask = mask.to(dtype)
+    cursor = torch.tensor([cur], dtype=torch.int64)
+    # ---- fp64 reference on the dtype-rounded inputs
+    v5 = qkv.double().view(B, H, 3, dh)
+    q, k, v = v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
+    c, sn = cos.double()[:, None, :], sin.double()[:, None, :]
+    q = torch.cat((q[..., :rot] * c + _rotate_half(q[..., :rot]) * sn, q[..., rot:]), -1)
+    k = torch.cat((k[..., :rot] * c + _rotate_half(k[..., :rot]) * sn, k[..., rot:]), -1)
+    kr, vr, ir = kc.double().clone(), vc.double().clone(), indir.clone()
+    kr[:, :, cur], vr[:, :, cur] = k, v
+    ir[:, cur] = torch.arange(B, dtype=torch.int32)
+    t = torch.arange(Tmax)
+    kg, vg = kr[ir.long(), :, t[None, :]], vr[ir.long(), :, t[None, :]]            # (B,Tmax,H,dh)
+    sc = torch.einsum("bhd,bthd->bht", q, kg) * (dh ** -0.5) + mask.double()[:, None, :]
+    sc[:, :, cur + 1:] = float("-inf")
+    want = torch.einsum("bht,bthd->bhd", sc.softmax(-1), vg).reshape(B, 1, H * dh)
+    # ---- the kernel
+    kd, vd, idd = kc.to(DEV), vc.to(DEV), indir.to(DEV)
+    got = ops().lm_decode_attention(qkv.to(DEV), cos.to(DEV), sin.to(DEV), kd, vd, idd, mask.to(DEV), cursor.to(DEV),
+                                    heads=H, head_dim=dh, rotary_dim=rot, scale=dh ** -0.5)
+    assert_close(got, want, tol, "decode attention")
+    assert_close(kd[:, :, cur], k, tol / 4, "new key at the cursor")
+    assert torch.equal(vd[:, :, cur].cpu(), v5[:, :, 2].to(dtype))
+    assert torch.equal(idd.cpu(), ir)
+    keep = torch.ones(Tmax, dtype=torch.bool)
+    keep[cur] = False
+    assert torch.equal(kd[:, :, keep].cpu(), kc[:, :, keep]) and torch.equal(vd[:, :, keep].cpu(), vc[:, :, keep])
+
+
+@pytest.mark.parametrize("M,N,K", [(5, 7680, 2560), (1, 16, 32), (8, 2560, 10240), (3, 1005, 512), (7, 512, 2560),
+                                   (5, 2560, 512), (2, 40, 64)])
+@pytest.mark.parametrize("bias,gelu", [(True, False), (False, False), (True, True), (False, True)])
+def test_linear_small_m_matches_f_linear(M, N, K, bias, gelu):
+    """`unimp_linear_small_m` (weight-streaming skinny linear of the decode step, mma.sync fragments
+    loaded straight from global memory) against fp64 `F.linear` (+ exact GELU); N not a multiple of
+    the 16-row tile, every M in 1..8 across the cases."""
+    torch.manual_seed(N + K)
+    x = torch.randn(M, K).to(torch.bfloat16)
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N).to(torch.bfloat16) if bias else None
+    want = torch.nn.functional.linear(x.double(), w.double(), None if b is None else b.double())
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    with torch.no_grad():
+        assert ops().small_m_eligible(x.to(DEV), w.to(DEV))
+        got = ops().linear_rows(x.to(DEV).view(M, 1, K), w.to(DEV), None if b is None else b.to(DEV), act_gelu=gelu)
+    assert got.shape == (M, 1, N) and got.dtype == torch.bfloat16
+    assert_close(got.view(M, N), want, 5e-3, "skinny linear")
+    # with autograd on, or more than 8 rows, the call is an ordinary F.linear (cuBLAS)
+    assert not ops().small_m_eligible(x.to(DEV), w.to(DEV))
+    with torch.no_grad():
+        assert not ops().small_m_eligible(torch.zeros(9, K, device=DEV, dtype=torch.bfloat16), w.to(DEV))
+        assert not ops().small_m_eligible(x.to(DEV).float(), w.to(DEV).float())
+
+
 # ------------------------------------------------------------------ gate + residual + LN
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])

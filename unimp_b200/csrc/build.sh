@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fa
 mkdir -p ../../build
 objs=()
 pids=()
-for f in capi focal_ce gate_ln misc attn_simt attn_tc xattn_block lm_attn flash_fwd lm_fused; do
+for f in capi focal_ce gate_ln misc attn_simt attn_tc xattn_block lm_attn flash_fwd lm_fused decode; do
   o=../../build/$f.o
   if [ ! -f "$o" ] || [ "$f.cu" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/unimp_b200.h -nt "$o" ] || { [ -f tc_common.cuh ] && [ tc_common.cuh -nt "$o" ]; }; then
     $NVCC $FLAGS -c $f.cu -o $o &

@@ -1,0 +1,291 @@
+// Decode-side kernels of the language model (SURVEY.md §8 a12 / f4, configs[3]: explanation generation,
+// reference call `UniMP/pipeline/eval/eval_exp.py:101-114` -> upstream `Flamingo.generate` -> HF beam
+// search).  One new token per beam and step: everything here is HBM-bound streaming work.
+//
+//   lm_decode_attn_kernel   the GPT-NeoX self-attention of ONE new token against static K/V caches:
+//                           rotary on the packed qkv projection, the new key/value written at the
+//                           device-side cursor, scores / softmax / PV over the cached positions.  Beam
+//                           re-ordering is an INDIRECTION table (cache row per (beam, position)) read by
+//                           the kernel, not a copy of the caches: HF's `reorder_cache` (and round 2's first
+//                           decoder) moved 2 x 32 x 20 MB per token, 1.4 ms of a 6.3 ms step.
+//   linear_small_m_kernel   y = act(x W^T + b) for <= 8 rows of x (the beams): the weight matrix is
+//                           streamed once with 16-byte loads straight into `mma.sync` fragments (the
+//                           legacy warp-level tensor path: the FLOPs are irrelevant, the point is that
+//                           the SIMT pipes do not have to unpack and multiply 5 x 3.6 G weights per
+//                           token), split-K over the 8 warps of a CTA, fixed-order shared-memory fold.
+#include "common.cuh"
+
+namespace unimp {
+
+// ------------------------------------------------------------------------------------------------
+// K4-decode
+// ------------------------------------------------------------------------------------------------
+constexpr int LD_THREADS = 256;
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(LD_THREADS)
+lm_decode_attn_kernel(const T* __restrict__ qkv,        // (B, H, {q,k,v}, DH): HF's packed projection
+                      const T* __restrict__ cs, const T* __restrict__ sn,   // (B, rot)
+                      T* __restrict__ kc, T* __restrict__ vc,               // (B, H, Tmax, DH)
+                      int32_t* __restrict__ indir,                          // (B, Tmax): cache row of position t
+                      const T* __restrict__ add_mask,                       // (B, Tmax): 0 or -inf
+                      const int64_t* __restrict__ cursor,                   // slot of the new token
+                      T* __restrict__ out,                                  // (B, H*DH)
+                      int H, int Tmax, int rot, float scale) {
+  constexpr int N = Vec16<T>::N, VEC = DH / N, G = LD_THREADS / VEC, CH = 10;
+  extern __shared__ float dsm[];            // probabilities [Tmax] | cache rows [Tmax]
+  float* ssc = dsm;
+  int* srow = reinterpret_cast<int*>(dsm + Tmax);
+  __shared__ float sq[DH], sk[DH], sv[DH], sred[32];
+  __shared__ float sacc[G * DH];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int cur = (int)*cursor;
+  if (cur < 0 || cur >= Tmax) return;       // the host sizes the caches for prompt + max_new_tokens
+  const int half = rot >> 1;
+  const T* src = qkv + ((int64_t)b * H + h) * 3 * DH;
+  if (tid < DH) {
+    const int d = tid;
+    float q = Elem<T>::to_f(src[d]), k = Elem<T>::to_f(src[DH + d]);
+    const T v = src[2 * DH + d];
+    if (d < rot) {
+      // q*cos + rotate_half(q)*sin: first half x1 c1 - x2 s1, second half x2 c2 + x1 s2
+      const int dp = d < half ? d + half : d - half;
+      const float c = Elem<T>::to_f(cs[(int64_t)b * rot + d]), s = Elem<T>::to_f(sn[(int64_t)b * rot + d]);
+      const float qp = Elem<T>::to_f(src[dp]), kp = Elem<T>::to_f(src[DH + dp]);
+      q = d < half ? q * c - qp * s : q * c + qp * s;
+      k = d < half ? k * c - kp * s : k * c + kp * s;
+    }
+    const T qr = Elem<T>::from_f(q), kr = Elem<T>::from_f(k);   // rounded to the storage type, as prefill does
+    sq[d] = Elem<T>::to_f(qr);
+    sk[d] = Elem<T>::to_f(kr);
+    sv[d] = Elem<T>::to_f(v);
+    const int64_t slot = (((int64_t)b * H + h) * Tmax + cur) * DH + d;
+    kc[slot] = kr;
+    vc[slot] = v;
+    if (h == 0 && d == 0) indir[(int64_t)b * Tmax + cur] = b;
+  }
+  __syncthreads();
+  // ---- scores: one cached key per thread (its whole row: VEC independent 16-byte loads) -------------
+  float m = -INFINITY;
+  for (int j = tid; j < cur; j += LD_THREADS) {
+    const int row = indir[(int64_t)b * Tmax + j];
+    const T* kp = kc + (((int64_t)row * H + h) * Tmax + j) * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < VEC; c0 += CH) {
+      Vec16<T> kv[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (c0 + c < VEC) kv[c].load(kp + (c0 + c) * N);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (c0 + c < VEC) {
+          float f[N];
+          kv[c].unpack(f);
+#pragma unroll
+          for (int i = 0; i < N; ++i) s = fmaf(f[i], sq[(c0 + c) * N + i], s);
+        }
+    }
+    s = s * scale + Elem<T>::to_f(add_mask[(int64_t)b * Tmax + j]);
+    ssc[j] = s;
+    srow[j] = row;
+    m = fmaxf(m, s);
+  }
+  if (tid == 0) {                           // the new token's own key never leaves the SM
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(sq[d], sk[d], s);
+    s = s * scale + Elem<T>::to_f(add_mask[(int64_t)b * Tmax + cur]);
+    ssc[cur] = s;
+    m = fmaxf(m, s);
+  }
+  m = block_max(m, sred);
+  float l = 0.f;
+  for (int j = tid; j <= cur; j += LD_THREADS) {
+    const float p = __expf(ssc[j] - m);
+    ssc[j] = p;
+    l += p;
+  }
+  l = block_sum(l, sred);                   // (its barriers also publish ssc)
+  // ---- PV: VEC threads per cached row (coalesced 16-byte loads), G rows in flight per pass ----------
+  const int g = tid / VEC, c = tid - g * VEC;
+  if (g < G) {
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int j = g; j < cur; j += G) {
+      Vec16<T> vv;
+      vv.load(vc + (((int64_t)srow[j] * H + h) * Tmax + j) * DH + c * N);
+      float f[N];
+      vv.unpack(f);
+      const float p = ssc[j];
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = fmaf(p, f[i], acc[i]);
+    }
+    if (g == 0) {
+      const float p = ssc[cur];
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = fmaf(p, sv[c * N + i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) sacc[g * DH + c * N + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < DH) {
+    float s = 0.f;
+    for (int gg = 0; gg < G; ++gg) s += sacc[gg * DH + tid];   // fixed order
+    out[((int64_t)b * H + h) * DH + tid] = Elem<T>::from_f(s / l);
+  }
+}
+
+template <typename T, int DH>
+static int launch_lm_decode_attn(const void* qkv, const void* cs, const void* sn, void* kc, void* vc,
+                                 int32_t* indir, const void* add_mask, const int64_t* cursor, void* out,
+                                 int B, int H, int Tmax, int rot, float scale, cudaStream_t st) {
+  const size_t smem = (size_t)Tmax * 8;
+  lm_decode_attn_kernel<T, DH><<<dim3(H, B), LD_THREADS, smem, st>>>(
+      (const T*)qkv, (const T*)cs, (const T*)sn, (T*)kc, (T*)vc, indir, (const T*)add_mask, cursor, (T*)out, H,
+      Tmax, rot, scale);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinny linear
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_WARPS = 8, SM_ROWS = 16, SM_U = 4;
+
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// CTA = 16 weight rows x all of K; warp w takes the 32-wide K steps w, w+8, ...  Lane (g = lane/4,
+// t = lane%4) loads 16 bytes (8 consecutive k) of weight rows g and g+8 and of x row g: the eight
+// values fill the k slots {2t,2t+1,2t+8,2t+9} of TWO m16n8k16 MMAs.  A dot product does not care in
+// which order its terms are added, so the A (weights) and B (x) fragments only have to agree on the
+// slot -> k assignment, and both come from the same 16-byte chunk index.
+template <int ACT>
+__global__ void __launch_bounds__(SM_WARPS * 32)
+linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+                      const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int M, int N,
+                      int K) {
+  __shared__ float red[SM_WARPS][SM_ROWS][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * SM_ROWS;
+  // rows past N / beams past M read a valid row instead and are dropped at the store
+  const int r0 = min(n0 + g, N - 1), r1 = min(n0 + g + 8, N - 1), xr = min(g, M - 1);
+  const uint4* wa = reinterpret_cast<const uint4*>(W + (int64_t)r0 * K) + t;
+  const uint4* wb = reinterpret_cast<const uint4*>(W + (int64_t)r1 * K) + t;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)xr * K) + t;
+  const int steps = K >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s0 = warp; s0 < steps; s0 += SM_WARPS * SM_U) {
+    uint4 a[SM_U], bq[SM_U], xv[SM_U];
+#pragma unroll
+    for (int u = 0; u < SM_U; ++u) {
+      const int s = s0 + u * SM_WARPS;
+      if (s < steps) {
+        a[u] = ldg_stream16(wa + s * 4);
+        bq[u] = ldg_stream16(wb + s * 4);
+        xv[u] = __ldg(xp + s * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SM_U; ++u) {
+      const int s = s0 + u * SM_WARPS;
+      if (s < steps) {                      // warp-uniform
+        mma_16816(acc, a[u].x, bq[u].x, a[u].y, bq[u].y, xv[u].x, xv[u].y);
+        mma_16816(acc, a[u].z, bq[u].z, a[u].w, bq[u].w, xv[u].z, xv[u].w);
+      }
+    }
+  }
+  // D fragment: c0 = (row g, beam 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+  red[warp][g][2 * t] = acc[0];
+  red[warp][g][2 * t + 1] = acc[1];
+  red[warp][g + 8][2 * t] = acc[2];
+  red[warp][g + 8][2 * t + 1] = acc[3];
+  __syncthreads();
+  if (tid < SM_ROWS * 8) {
+    const int r = tid & (SM_ROWS - 1), mrow = tid >> 4;
+    const int n = n0 + r;
+    if (mrow < M && n < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < SM_WARPS; ++w) s += red[w][r][mrow];   // fixed order
+      if (bias) s += __bfloat162float(bias[n]);
+      if (ACT == 1) s = 0.5f * s * (1.f + erff(s * 0.70710678118654752f));   // exact GELU
+      y[(int64_t)mrow * N + n] = __float2bfloat16_rn(s);
+    }
+  }
+}
+
+}  // namespace unimp
+
+using namespace unimp;
+
+extern "C" int unimp_lm_decode_attn(const void* qkv, const void* cos, const void* sin, void* k_cache,
+                                    void* v_cache, int32_t* indir, const void* add_mask,
+                                    const int64_t* cursor, void* out, int B, int H, int Tmax, int dh, int rot,
+                                    float scale, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(qkv && cos && sin && k_cache && v_cache && indir && add_mask && cursor && out, UNIMP_E_NULL,
+                  "lm_decode_attn: NULL pointer");
+  UNIMP_CHECK_ARG(dtype == UNIMP_F32 || dtype == UNIMP_BF16, UNIMP_E_DTYPE, "lm_decode_attn: dtype");
+  UNIMP_CHECK_ARG(B > 0 && H > 0 && Tmax > 0 && Tmax <= 5120, UNIMP_E_SHAPE,
+                  "lm_decode_attn: bad B/H/Tmax (Tmax=%d must be in 1..5120)", Tmax);
+  UNIMP_CHECK_ARG(rot >= 0 && rot <= dh && rot % 2 == 0, UNIMP_E_SHAPE,
+                  "lm_decode_attn: rotary_dim=%d must be even and <= head_dim=%d", rot, dh);
+  UNIMP_CHECK_ARG(aligned16(k_cache) && aligned16(v_cache), UNIMP_E_ALIGN,
+                  "lm_decode_attn: the caches must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+#define UNIMP_LD_CASE(DHV)                                                                                   \
+  case DHV:                                                                                                  \
+    return dtype == UNIMP_BF16                                                                               \
+               ? launch_lm_decode_attn<__nv_bfloat16, DHV>(qkv, cos, sin, k_cache, v_cache, indir, add_mask, \
+                                                           cursor, out, B, H, Tmax, rot, scale, st)          \
+               : launch_lm_decode_attn<float, DHV>(qkv, cos, sin, k_cache, v_cache, indir, add_mask, cursor, \
+                                                   out, B, H, Tmax, rot, scale, st)
+  switch (dh) {
+    UNIMP_LD_CASE(32);
+    UNIMP_LD_CASE(64);
+    UNIMP_LD_CASE(80);
+    UNIMP_LD_CASE(96);
+    UNIMP_LD_CASE(128);
+    default:
+      set_error("lm_decode_attn: head_dim=%d not built (32, 64, 80, 96, 128)", dh);
+      return UNIMP_E_SHAPE;
+  }
+#undef UNIMP_LD_CASE
+}
+
+extern "C" int unimp_linear_small_m(const void* x, const void* w, const void* bias, void* y, int M, int N,
+                                    int K, int act, int dtype, void* stream) {
+  UNIMP_CHECK_ARG(x && w && y, UNIMP_E_NULL, "linear_small_m: NULL pointer");
+  UNIMP_CHECK_ARG(dtype == UNIMP_BF16, UNIMP_E_DTYPE, "linear_small_m: bf16 only");
+  UNIMP_CHECK_ARG(M >= 1 && M <= 8, UNIMP_E_SHAPE, "linear_small_m: M=%d rows (1..8: the beams of one decode step)", M);
+  UNIMP_CHECK_ARG(N >= 1 && K >= 32 && K % 32 == 0, UNIMP_E_SHAPE,
+                  "linear_small_m: K=%d must be a positive multiple of 32", K);
+  UNIMP_CHECK_ARG(act == 0 || act == 1, UNIMP_E_SHAPE, "linear_small_m: act must be 0 (none) or 1 (exact GELU)");
+  UNIMP_CHECK_ARG(aligned16(x) && aligned16(w), UNIMP_E_ALIGN, "linear_small_m: x / w must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((N + SM_ROWS - 1) / SM_ROWS);
+  if (act == 1)
+    linear_small_m_kernel<1><<<grid, SM_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                             (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, M, N, K);
+  else
+    linear_small_m_kernel<0><<<grid, SM_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                             (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, M, N, K);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}

@@ -12,8 +12,10 @@ by the GPU.  `GraphedDecoder` is the same computation arranged f
 * every later token is ONE replay of a captured CUDA graph: static K/V caches
   (B*beams, H, T_max, dh) written in place at a device-side cursor, `to_kv(media)` projected once
   per block and cached, single-token masked cross-attention by `unimp_xattn_decode`, GPT-NeoX
-  layers through `fused_neox_layer`, and the beam-search bookkeeping (log-softmax, top-k, beam
-  re-ordering of the caches) as static-shape tensor ops inside the same graph.  The host only
+  layers through `fused_neox_layer` — rotary + cache write + attention in `unimp_lm_decode_attn`,
+  every projection streamed once by `unimp_linear_small_m` — and the beam-search bookkeeping
+  (log-softmax, top-k) as static-shape tensor ops inside the same graph.  Beam re-ordering moves the
+  rows of an INDIRECTION table (cache row per beam and position), never the caches.  The host only
   launches the graph and reads one "unfinished" flag every `sync_every` tokens.
 
 `BeamSearch` / `GreedySearch` restate the decoding rules of HF `GenerationMixin._beam_search` /
@@ -23,6 +25,8 @@ cursors instead of Python integers so that a step is capturable.  They are pure 
 tested on CPU against `transformers`' own `generate` (tests/test_decode.py).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn.functional as F
@@ -214,6 +218,9 @@ class GraphedDecoder:
         if not all(isinstance(l.decoder_layer, GPTNeoXLayer) for l in self.layers):
             raise TypeError("GraphedDecoder drives GPT-NeoX decoder layers")
         self.sync_every = max(1, int(sync_every))
+        # K/V caches addressed through a beam indirection table by unimp_lm_decode_attn (default), or
+        # SDPA over caches that are re-ordered (copied) after every beam step (UNIMP_DECODE_INDIR=0)
+        self.use_indirection = os.environ.get("UNIMP_DECODE_INDIR", "1") != "0"
         self.last_n_steps, self.last_logits_finite = 0, True   # of the last generate() (diagnostics)
 
     # -------------------------------------------------------------------------------- one token
@@ -231,8 +238,9 @@ class GraphedDecoder:
             if blk is not None:
                 x = blk(x, layer.vis_x, media_locations=layer.media_locations, use_cached_media=True,
                         text_time=S.n_media)
-            x = fused_neox_layer(layer.decoder_layer, x, S.add_mask, pos_emb,
-                                 kv_step=(S.k[i], S.v[i], S.cur))
+            kv_step = ((S.k[i], S.v[i], S.cur, S.indir, S.mask2d) if S.indir is not None
+                       else (S.k[i], S.v[i], S.cur))
+            x = fused_neox_layer(layer.decoder_layer, x, S.add_mask, pos_emb, kv_step=kv_step)
         h = lm.gpt_neox.final_layer_norm(x)
         S.logits.copy_(lm.embed_out(h)[:, -1, :])
         S.cur += 1
@@ -252,6 +260,13 @@ class GraphedDecoder:
         return graph
 
     def _reorder(self, S, source):
+        """New beam i continues old beam source[i].  With the indirection table only ITS rows move
+        (B*beams x T_max ints); the caches stay where they are and `unimp_lm_decode_attn` reads
+        position t of beam i from cache row indir[i][t].  (UNIMP_DECODE_INDIR=0: HF's `reorder_cache`
+        semantics, every layer's K and V gathered — 2 x 32 x 20 MB per token at configs[3].)"""
+        if S.indir is not None:
+            S.indir.copy_(S.indir.index_select(0, source))
+            return
         for i in range(len(self.layers)):
             S.k[i].copy_(S.k[i].index_select(0, source))
             S.v[i].copy_(S.v[i].index_select(0, source))
@@ -313,6 +328,11 @@ class GraphedDecoder:
         S.logits = torch.zeros((Bf, out.logits.shape[-1]), dtype=torch.float32, device=dev)
         S.add_mask = torch.full((Bf, 1, 1, Tmax), self.MASK_FILL, dtype=dtype, device=dev)
         S.add_mask[:, 0, 0, :T0] = torch.zeros((), dtype=dtype, device=dev).expand(Bf, T0).masked_fill(mask == 0, self.MASK_FILL)
+        # beam indirection: cache row that holds position t of beam i's history (identity at first)
+        S.indir = S.mask2d = None
+        if self.use_indirection:
+            S.indir = torch.arange(Bf, dtype=torch.int32, device=dev)[:, None].repeat(1, Tmax).contiguous()
+            S.mask2d = S.add_mask.view(Bf, Tmax)
         S.k, S.v = [], []
         for i in range(len(self.layers)):
             k, v = cache.layers[i].keys, cache.layers[i].values          # (Bf,H,T0,dh)

@@ -204,7 +204,9 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     input_layernorm); if given, returns (y, next_ln(y)) from the same launch as the last residual.
     `kv_step` = (k_cache, v_cache, cursor): single-token decode against static (B,H,T_max,dh)
     caches — the new key/value are written at the device-side `cursor` (capturable in a CUDA
-    graph) and attention runs over the whole cache under the additive `attention_mask`."""
+    graph) and attention runs over the whole cache under the additive `attention_mask` (SDPA).
+    `kv_step` = (k_cache, v_cache, cursor, indir, mask2d): the same step on `unimp_lm_decode_attn`
+    (beam indirection `indir` (B,T_max) int32 instead of re-ordered caches, `mask2d` (B,T_max) 0/-inf)."""
     F = torch.nn.functional
     att = layer.attention
     B, T, D = x.shape
@@ -212,9 +214,18 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
     ln1, ln2 = layer.input_layernorm, layer.post_attention_layernorm
     if h1 is None:
         h1 = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
-    qkv = F.linear(h1, att.query_key_value.weight, att.query_key_value.bias)
+    # decode steps (<= 8 rows, no autograd) stream each weight once through unimp_linear_small_m
+    lin = ops.linear_rows if kv_step is not None else (lambda a, w, b, act_gelu=False: F.linear(a, w, b))
+    qkv = lin(h1, att.query_key_value.weight, att.query_key_value.bias)
     cos, sin = position_embeddings
-    if key_bits is not None and kv_step is None and LM_ATTN and ops.lm_attention_supported_shape(x, T, H, dh):
+    if kv_step is not None and len(kv_step) == 5:
+        # one new token against static caches with beam indirection (unimp_lm_decode_attn): rotary,
+        # the cache write at the cursor and the attention in ONE launch; beams are never copied
+        k_cache, v_cache, cursor, indir, mask2d = kv_step
+        assert T == 1
+        a = ops.lm_decode_attention(qkv, cos.to(x.dtype), sin.to(x.dtype), k_cache, v_cache, indir, mask2d,
+                                    cursor, heads=H, head_dim=dh, rotary_dim=rot, scale=att.scaling)
+    elif key_bits is not None and kv_step is None and LM_ATTN and ops.lm_attention_supported_shape(x, T, H, dh):
         a = ops.rotary_lm_attention(qkv, cos.to(x.dtype), sin.to(x.dtype), None if key_bits is True else key_bits,
                                     heads=H, head_dim=dh, rotary_dim=rot, scale=att.scaling)
     else:
@@ -230,18 +241,25 @@ def fused_neox_layer(layer, x, attention_mask, position_embeddings, h1=None, nex
                                            is_causal=attention_mask is None and T > 1 and kv_step is None,
                                            scale=att.scaling)
         a = a.transpose(1, 2).reshape(B, T, D)
-    o = F.linear(a, att.dense.weight, att.dense.bias)
+    o = lin(a, att.dense.weight, att.dense.bias)
     mlp = layer.mlp
-    act = ops.gelu if _is_exact_gelu(mlp.act) else mlp.act
+    exact = _is_exact_gelu(mlp.act)
+    act = ops.gelu if exact else mlp.act
+
+    def mlp_fwd(h2):
+        if kv_step is not None and exact:      # GELU in the epilogue of the first projection
+            u = lin(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias, act_gelu=True)
+        else:
+            u = act(lin(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias))
+        return lin(u, mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+
     if layer.use_parallel_residual:
         h2 = ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps)
-        m = F.linear(act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
-                     mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+        m = mlp_fwd(h2)
         x1 = ops.gate_residual(o, x, None)
     else:
         x1, h2 = ops.gate_residual_ln(o, x, None, ln2.weight, ln2.bias, ln2.eps)
-        m = F.linear(act(F.linear(h2, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
-                     mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+        m = mlp_fwd(h2)
     if next_ln is not None:
         return ops.gate_residual_ln(m, x1, None, next_ln.weight, next_ln.bias, next_ln.eps)
     return ops.gate_residual(m, x1, None)

@@ -34,6 +34,8 @@ def FeedForward(dim: int, mult: int = 4) -> nn.Sequential:
 
 def _ff_tail(ff: nn.Sequential, ln_out: torch.Tensor) -> torch.Tensor:
     """Linear -> GELU -> Linear of a FeedForward whose LayerNorm was already applied (fused)."""
+    if ops.small_m_eligible(ln_out, ff[1].weight):     # a decode step: weight-streaming kernels
+        return ops.linear_rows(ops.linear_rows(ln_out, ff[1].weight, None, act_gelu=True), ff[3].weight)
     h = ops.linear_acc(ln_out, ff[1].weight)
     h = ops.gelu(h)
     return ops.linear_acc(h, ff[3].weight)
@@ -174,16 +176,18 @@ class MaskedCrossAttention(nn.Module):
             out = ops.masked_cross_attention(q, kv, text_time, heads=self.heads, n_latents=n,
                                              scale=self.scale)
             return ops.linear_acc(out, self.to_out.weight)
-        q = ops.linear_acc(x_ln, self.to_q.weight)
-        if use_cached_media and not torch.is_grad_enabled():
+        if cached and T == 1:
             # keyed on the media tensor (identity + version) and on the projection weights'
             # version: new images of the same batch size, or an optimizer step between two
             # cached forwards, rebuild the cache (upstream recomputes to_kv(media) every call)
             kv = self.cached_media_kv(media)
-            if T == 1:
-                out = ops.xattn_decode(q, kv, text_time[:, 0].contiguous(), heads=self.heads,
-                                       n_latents=n, scale=self.scale)
-                return ops.linear_acc(out, self.to_out.weight)
+            q = ops.linear_rows(x_ln, self.to_q.weight)
+            out = ops.xattn_decode(q, kv, text_time[:, 0].contiguous(), heads=self.heads,
+                                   n_latents=n, scale=self.scale)
+            return ops.linear_rows(out, self.to_out.weight)
+        q = ops.linear_acc(x_ln, self.to_q.weight)
+        if cached:
+            kv = self.cached_media_kv(media)
         else:
             self._kv_cache = None
             kv = self.project_media(media)

@@ -5,6 +5,8 @@ hand-written sm_100a kernels through ctypes.  No CPU path, no fallback: non-CUDA
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -259,6 +261,59 @@ def xattn_decode(q, kv, n_media_i32, *, heads: int, n_latents: int, scale: float
                                          inner // heads, float(scale), dt, _stream()),
           "unimp_xattn_decode")
     return o
+
+
+def lm_decode_attention(qkv, cos, sin, k_cache, v_cache, indir, add_mask, cursor, *, heads: int,
+                        head_dim: int, rotary_dim: int, scale: float):
+    """a12 / f4: one GPT-NeoX self-attention decode step (`unimp_lm_decode_attn`): rotary on the new
+    token's packed qkv (B,1,H*3*dh), K/V written in place at the device-side `cursor`, attention
+    over cache positions 0..cursor through the beam indirection `indir` (B,Tmax) int32.
+    `add_mask` (B,Tmax): 0 / -inf.  Returns (B,1,H*dh)."""
+    dt = _dt(qkv)
+    B = qkv.shape[0]
+    Tmax = k_cache.shape[2]
+    assert qkv.is_contiguous() and k_cache.is_contiguous() and v_cache.is_contiguous()
+    assert k_cache.shape == (B, heads, Tmax, head_dim) and k_cache.dtype == qkv.dtype
+    assert indir.dtype == torch.int32 and indir.shape == (B, Tmax) and indir.is_contiguous()
+    assert add_mask.dtype == qkv.dtype and add_mask.numel() == B * Tmax and add_mask.is_contiguous()
+    assert cursor.dtype == torch.int64 and cursor.is_cuda
+    cos = cos.reshape(B, rotary_dim).contiguous()
+    sin = sin.reshape(B, rotary_dim).contiguous()
+    out = torch.empty((B, 1, heads * head_dim), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.load().unimp_lm_decode_attn(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), k_cache.data_ptr(),
+                                           v_cache.data_ptr(), indir.data_ptr(), add_mask.data_ptr(),
+                                           cursor.data_ptr(), out.data_ptr(), B, heads, Tmax, head_dim,
+                                           rotary_dim, float(scale), dt, _stream()), "unimp_lm_decode_attn")
+    return out
+
+
+SMALL_M_LINEAR = os.environ.get("UNIMP_DECODE_GEMV", "1") != "0"   # A/B switch: 0 = cuBLAS for decode steps
+
+
+def small_m_eligible(x, w) -> bool:
+    """True if y = x w^T of this call runs on `unimp_linear_small_m`: inference, bf16, <= 8 rows."""
+    K = x.shape[-1]
+    return (SMALL_M_LINEAR and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.bfloat16
+            and w.dtype == torch.bfloat16 and x.numel() // K <= 8 and K % 32 == 0 and w.is_contiguous()
+            and w.data_ptr() % 16 == 0)
+
+
+def linear_rows(x, w, b=None, act_gelu: bool = False):
+    """Inference-time `F.linear(x, w, b)` (optionally followed by the exact GELU).  With <= 8 rows —
+    the beams of one decode step — the weight is streamed once by `unimp_linear_small_m`
+    (bias / GELU in its epilogue); otherwise cuBLAS + `gelu`."""
+    if not small_m_eligible(x, w):
+        y = torch.nn.functional.linear(x, w, b)
+        return gelu(y) if act_gelu else y
+    K = x.shape[-1]
+    N = w.shape[0]
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous() or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    y = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    check(_lib.load().unimp_linear_small_m(x2.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), x2.shape[0], N, K,
+                                           1 if act_gelu else 0, _DT[x.dtype], _stream()), "unimp_linear_small_m")
+    return y
 
 
 # --------------------------------------------------------------------------- gate + residual + LN
