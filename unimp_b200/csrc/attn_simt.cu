@@ -285,31 +285,36 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, unimp_mview_t d
   for (int e = 0; e < 4; ++e) dst[e] = Elem<T>::from_f(src[e]);
 }
 
-// Decode: one 64-thread CTA per (b, h); the single query attends the n keys of image n_media[b]-1
-// (all Ti*n keys, uniformly, if n_media[b] > Ti).  Thread j owns key j — its whole 64-wide dot
-// product, independent loads — the softmax is a two-warp reduction, and thread d then owns output
-// column d (coalesced V rows).  (Round 2's first version walked the keys serially in one warp: 64
-// dependent load -> shuffle -> exp rounds, 38 us per launch, 0.6 ms of a 6.3 ms decode step.)
+// Decode: one CTA per (b, h); the single query attends the n keys of image n_media[b]-1 (all Ti*n
+// keys, uniformly, if n_media[b] > Ti).  A thread owns one key — its whole 64-wide dot product,
+// independent 16-byte loads — the softmax is a block reduction, and for P.V the 256 threads are 4 key
+// groups x 64 output columns (coalesced V rows, 16 independent loads each), folded in shared memory.
+// (Round 2's first version walked the keys serially in one warp: 64 dependent load -> shuffle -> exp
+// rounds, 38 us per launch, 0.6 ms of a 6.3 ms decode step.)
+constexpr int XD_THREADS = 256;
 template <typename T>
-__global__ void __launch_bounds__(SD) xattn_decode_kernel(unimp_view_t q, unimp_view_t k, unimp_view_t v,
-                                                          const int32_t* __restrict__ n_media, unimp_mview_t o,
-                                                          int Ti, int n, int H, float scale) {
+__global__ void __launch_bounds__(XD_THREADS) xattn_decode_kernel(unimp_view_t q, unimp_view_t k, unimp_view_t v,
+                                                                  const int32_t* __restrict__ n_media,
+                                                                  unimp_mview_t o, int Ti, int n, int H,
+                                                                  float scale) {
   extern __shared__ float xd_p[];           // one probability per attended key
-  __shared__ float sq[SD], sred[32];
+  __shared__ float sq[SD], sred[32], sacc[XD_THREADS];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y, h = blockIdx.x, tid = threadIdx.x;
   const int tt = n_media[b];
   T* op = (T*)o.ptr + b * o.batch_stride + h * SD;
   if (tt <= 0) {
-    op[tid] = Elem<T>::from_f(0.f);
+    if (tid < SD) op[tid] = Elem<T>::from_f(0.f);
     return;
   }
   const bool uni = tt > Ti;
   const int lo = uni ? 0 : (tt - 1) * n, nk = uni ? Ti * n : n;
   const T* qp = (const T*)q.ptr + b * q.batch_stride + h * SD;
-  sq[tid] = Elem<T>::to_f(qp[tid]) * scale;
+  if (tid < SD) sq[tid] = Elem<T>::to_f(qp[tid]) * scale;
   __syncthreads();
   float m = -INFINITY;
-  for (int j = tid; j < nk; j += SD) {
+  for (int j = tid; j < nk; j += XD_THREADS) {
     float s = 0.f;
     if (!uni) {
       const T* kp = (const T*)k.ptr + b * k.batch_stride + (int64_t)(lo + j) * k.row_stride + h * SD;
@@ -338,17 +343,20 @@ __global__ void __launch_bounds__(SD) xattn_decode_kernel(unimp_view_t q, unimp_
   }
   m = block_max(m, sred);
   float l = 0.f;
-  for (int j = tid; j < nk; j += SD) {
+  for (int j = tid; j < nk; j += XD_THREADS) {
     const float p = __expf(xd_p[j] - m);
     xd_p[j] = p;
     l += p;
   }
   l = block_sum(l, sred);                   // (its barriers also publish xd_p)
-  const T* vp = (const T*)v.ptr + b * v.batch_stride + (int64_t)lo * v.row_stride + h * SD + tid;
+  const int g = tid >> 6, d = tid & (SD - 1);
+  const T* vp = (const T*)v.ptr + b * v.batch_stride + (int64_t)lo * v.row_stride + h * SD + d;
   float acc = 0.f;
 #pragma unroll 8
-  for (int j = 0; j < nk; ++j) acc = fmaf(xd_p[j], Elem<T>::to_f(vp[(int64_t)j * v.row_stride]), acc);
-  op[tid] = Elem<T>::from_f(acc / l);
+  for (int j = g; j < nk; j += XD_THREADS / SD) acc = fmaf(xd_p[j], Elem<T>::to_f(vp[(int64_t)j * v.row_stride]), acc);
+  sacc[tid] = acc;
+  __syncthreads();
+  if (tid < SD) op[tid] = Elem<T>::from_f((sacc[tid] + sacc[tid + 64] + sacc[tid + 128] + sacc[tid + 192]) / l);
 }
 
 // ---- host launchers (used by capi.cu) -----------------------------------------------------
@@ -395,8 +403,9 @@ int launch_attn_bwd_simt(unimp_view_t q, unimp_view_t k, unimp_view_t v, const i
 template <typename T>
 int launch_xattn_decode(unimp_view_t q, unimp_view_t k, unimp_view_t v, const int32_t* n_media,
                         unimp_mview_t o, int B, int Ti, int n, int H, float scale, cudaStream_t st) {
-  xattn_decode_kernel<T><<<dim3(H, B), SD, (size_t)Ti * n * sizeof(float), st>>>(q, k, v, n_media, o, Ti, n, H, scale);
-  UNIMP_CHECK_LAUNCH();
+  cudaError_t e = launch_pdl(xattn_decode_kernel<T>, dim3(H, B), dim3(XD_THREADS), (size_t)Ti * n * sizeof(float), st,
+                             q, k, v, n_media, o, Ti, n, H, scale);
+  if (e != cudaSuccess) { set_error("xattn_decode launch: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 

@@ -2,11 +2,22 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace unimp {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("UNIMP_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -94,6 +94,33 @@ __device__ __forceinline__ void Vec16<__nv_bfloat16>::pack(const float* f) {
   raw.x = w[0]; raw.y = w[1]; raw.z = w[2]; raw.w = w[3];
 }
 
+// Programmatic dependent launch (decode path: ~500 small dependent kernels per token).  A kernel
+// launched through launch_pdl() may START while its predecessor in the stream is still running; it must
+// call pdl_wait() before it reads anything an earlier kernel wrote and before its first global write
+// (until then it may only touch data that no kernel of the step writes: weights).  Every kernel calls
+// pdl_launch_dependents() at its top so that ITS successor may be scheduled early as well.  Both are
+// no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // capi.cu: UNIMP_PDL != 0 (default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

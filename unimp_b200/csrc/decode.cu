@@ -13,6 +13,8 @@
 //                           legacy warp-level tensor path: the FLOPs are irrelevant, the point is that
 //                           the SIMT pipes do not have to unpack and multiply 5 x 3.6 G weights per
 //                           token), split-K over the 8 warps of a CTA, fixed-order shared-memory fold.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace unimp {
@@ -39,6 +41,8 @@ lm_decode_attn_kernel(const T* __restrict__ qkv,        // (B, H, {q,k,v}, DH): 
   __shared__ float sq[DH], sk[DH], sv[DH], sred[32];
   __shared__ float sacc[G * DH];
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();                               // qkv, the cursor, indir and the caches all come from earlier kernels
   const int cur = (int)*cursor;
   if (cur < 0 || cur >= Tmax) return;       // the host sizes the caches for prompt + max_new_tokens
   const int half = rot >> 1;
@@ -144,17 +148,17 @@ static int launch_lm_decode_attn(const void* qkv, const void* cs, const void* sn
                                  int32_t* indir, const void* add_mask, const int64_t* cursor, void* out,
                                  int B, int H, int Tmax, int rot, float scale, cudaStream_t st) {
   const size_t smem = (size_t)Tmax * 8;
-  lm_decode_attn_kernel<T, DH><<<dim3(H, B), LD_THREADS, smem, st>>>(
-      (const T*)qkv, (const T*)cs, (const T*)sn, (T*)kc, (T*)vc, indir, (const T*)add_mask, cursor, (T*)out, H,
-      Tmax, rot, scale);
-  UNIMP_CHECK_LAUNCH();
+  cudaError_t e = launch_pdl(lm_decode_attn_kernel<T, DH>, dim3(H, B), dim3(LD_THREADS), smem, st, (const T*)qkv,
+                             (const T*)cs, (const T*)sn, (T*)kc, (T*)vc, indir, (const T*)add_mask, cursor,
+                             (T*)out, H, Tmax, rot, scale);
+  if (e != cudaSuccess) { set_error("lm_decode_attn launch: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // skinny linear
 // ------------------------------------------------------------------------------------------------
-constexpr int SM_WARPS = 8, SM_ROWS = 16, SM_U = 4;
+constexpr int SM_ROWS = 16;
 
 __device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
@@ -171,64 +175,126 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
   return r;
 }
 
-// CTA = 16 weight rows x all of K; warp w takes the 32-wide K steps w, w+8, ...  Lane (g = lane/4,
-// t = lane%4) loads 16 bytes (8 consecutive k) of weight rows g and g+8 and of x row g: the eight
-// values fill the k slots {2t,2t+1,2t+8,2t+9} of TWO m16n8k16 MMAs.  A dot product does not care in
-// which order its terms are added, so the A (weights) and B (x) fragments only have to agree on the
-// slot -> k assignment, and both come from the same 16-byte chunk index.
-template <int ACT>
-__global__ void __launch_bounds__(SM_WARPS * 32)
+// CTA = RT tiles of 16 weight rows x all of K; warp w takes the 32-wide K steps w, w+WARPS, ...  Lane
+// (g = lane/4, t = lane%4) loads 16 bytes (8 consecutive k) of weight rows g and g+8 of each tile and
+// of x row g: the eight values fill the k slots {2t,2t+1,2t+8,2t+9} of TWO m16n8k16 MMAs.  A dot
+// product does not care in which order its terms are added, so the A (weights) and B (x) fragments
+// only have to agree on the slot -> k assignment, and both come from the same 16-byte chunk index.
+// The weights do not depend on the previous kernel: the first batch of weight loads is issued BEFORE
+// the programmatic-dependency wait (it streams while the producer of x drains).
+// U = K steps per batch (loads in flight per lane: U x RT x 32 bytes).
+template <int ACT, int WARPS, int U, int RT>
+__global__ void __launch_bounds__(WARPS * 32)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int M, int N,
                       int K) {
-  __shared__ float red[SM_WARPS][SM_ROWS][8];
+  __shared__ float red[WARPS][RT * SM_ROWS][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int n0 = blockIdx.x * SM_ROWS;
+  const int n0 = blockIdx.x * (RT * SM_ROWS);
   // rows past N / beams past M read a valid row instead and are dropped at the store
-  const int r0 = min(n0 + g, N - 1), r1 = min(n0 + g + 8, N - 1), xr = min(g, M - 1);
-  const uint4* wa = reinterpret_cast<const uint4*>(W + (int64_t)r0 * K) + t;
-  const uint4* wb = reinterpret_cast<const uint4*>(W + (int64_t)r1 * K) + t;
-  const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)xr * K) + t;
-  const int steps = K >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s0 = warp; s0 < steps; s0 += SM_WARPS * SM_U) {
-    uint4 a[SM_U], bq[SM_U], xv[SM_U];
+  const uint4 *wa[RT], *wb[RT];
 #pragma unroll
-    for (int u = 0; u < SM_U; ++u) {
-      const int s = s0 + u * SM_WARPS;
+  for (int r = 0; r < RT; ++r) {
+    wa[r] = reinterpret_cast<const uint4*>(W + (int64_t)min(n0 + r * SM_ROWS + g, N - 1) * K) + t;
+    wb[r] = reinterpret_cast<const uint4*>(W + (int64_t)min(n0 + r * SM_ROWS + g + 8, N - 1) * K) + t;
+  }
+  const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)min(g, M - 1) * K) + t;
+  const int steps = K >> 5;
+  constexpr int STRIDE = WARPS * U;
+  float acc[RT][4];
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
+  pdl_launch_dependents();
+  {                                         // first batch: weights before the dependency wait, x after it
+    uint4 a[RT][U], bq[RT][U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = warp + u * WARPS;
       if (s < steps) {
-        a[u] = ldg_stream16(wa + s * 4);
-        bq[u] = ldg_stream16(wb + s * 4);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          a[r][u] = ldg_stream16(wa[r] + s * 4);
+          bq[r][u] = ldg_stream16(wb[r] + s * 4);
+        }
+      }
+    }
+    pdl_wait();                             // x (and the buffer y may reuse) belong to earlier kernels
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = warp + u * WARPS;
+      if (s < steps) xv[u] = __ldg(xp + s * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = warp + u * WARPS;
+      if (s < steps) {                      // warp-uniform
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          mma_16816(acc[r], a[r][u].x, bq[r][u].x, a[r][u].y, bq[r][u].y, xv[u].x, xv[u].y);
+          mma_16816(acc[r], a[r][u].z, bq[r][u].z, a[r][u].w, bq[r][u].w, xv[u].z, xv[u].w);
+        }
+      }
+    }
+  }
+  for (int s0 = warp + STRIDE; s0 < steps; s0 += STRIDE) {
+    uint4 a[RT][U], bq[RT][U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u * WARPS;
+      if (s < steps) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          a[r][u] = ldg_stream16(wa[r] + s * 4);
+          bq[r][u] = ldg_stream16(wb[r] + s * 4);
+        }
         xv[u] = __ldg(xp + s * 4);
       }
     }
 #pragma unroll
-    for (int u = 0; u < SM_U; ++u) {
-      const int s = s0 + u * SM_WARPS;
-      if (s < steps) {                      // warp-uniform
-        mma_16816(acc, a[u].x, bq[u].x, a[u].y, bq[u].y, xv[u].x, xv[u].y);
-        mma_16816(acc, a[u].z, bq[u].z, a[u].w, bq[u].w, xv[u].z, xv[u].w);
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u * WARPS;
+      if (s < steps) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          mma_16816(acc[r], a[r][u].x, bq[r][u].x, a[r][u].y, bq[r][u].y, xv[u].x, xv[u].y);
+          mma_16816(acc[r], a[r][u].z, bq[r][u].z, a[r][u].w, bq[r][u].w, xv[u].z, xv[u].w);
+        }
       }
     }
   }
   // D fragment: c0 = (row g, beam 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
-  red[warp][g][2 * t] = acc[0];
-  red[warp][g][2 * t + 1] = acc[1];
-  red[warp][g + 8][2 * t] = acc[2];
-  red[warp][g + 8][2 * t + 1] = acc[3];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    red[warp][r * SM_ROWS + g][2 * t] = acc[r][0];
+    red[warp][r * SM_ROWS + g][2 * t + 1] = acc[r][1];
+    red[warp][r * SM_ROWS + g + 8][2 * t] = acc[r][2];
+    red[warp][r * SM_ROWS + g + 8][2 * t + 1] = acc[r][3];
+  }
   __syncthreads();
-  if (tid < SM_ROWS * 8) {
-    const int r = tid & (SM_ROWS - 1), mrow = tid >> 4;
+  for (int o = tid; o < RT * SM_ROWS * 8; o += WARPS * 32) {
+    const int r = o % (RT * SM_ROWS), mrow = o / (RT * SM_ROWS);
     const int n = n0 + r;
     if (mrow < M && n < N) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < SM_WARPS; ++w) s += red[w][r][mrow];   // fixed order
+      for (int w = 0; w < WARPS; ++w) s += red[w][r][mrow];   // fixed order
       if (bias) s += __bfloat162float(bias[n]);
       if (ACT == 1) s = 0.5f * s * (1.f + erff(s * 0.70710678118654752f));   // exact GELU
       y[(int64_t)mrow * N + n] = __float2bfloat16_rn(s);
     }
   }
+}
+
+template <int WARPS, int U, int RT>
+static cudaError_t launch_linear_small_m(int act, cudaStream_t st, const __nv_bfloat16* x, const __nv_bfloat16* w,
+                                         const __nv_bfloat16* bias, __nv_bfloat16* y, int M, int N, int K) {
+  const unsigned grid = (unsigned)((N + RT * SM_ROWS - 1) / (RT * SM_ROWS));
+  return act == 1 ? launch_pdl(linear_small_m_kernel<1, WARPS, U, RT>, dim3(grid), dim3(WARPS * 32), 0, st, x, w,
+                               bias, y, M, N, K)
+                  : launch_pdl(linear_small_m_kernel<0, WARPS, U, RT>, dim3(grid), dim3(WARPS * 32), 0, st, x, w,
+                               bias, y, M, N, K);
 }
 
 }  // namespace unimp
@@ -279,13 +345,29 @@ extern "C" int unimp_linear_small_m(const void* x, const void* w, const void* bi
   UNIMP_CHECK_ARG(act == 0 || act == 1, UNIMP_E_SHAPE, "linear_small_m: act must be 0 (none) or 1 (exact GELU)");
   UNIMP_CHECK_ARG(aligned16(x) && aligned16(w), UNIMP_E_ALIGN, "linear_small_m: x / w must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)((N + SM_ROWS - 1) / SM_ROWS);
-  if (act == 1)
-    linear_small_m_kernel<1><<<grid, SM_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                             (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, M, N, K);
-  else
-    linear_small_m_kernel<0><<<grid, SM_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                             (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, M, N, K);
-  UNIMP_CHECK_LAUNCH();
+  const __nv_bfloat16 *xb = (const __nv_bfloat16*)x, *wb = (const __nv_bfloat16*)w, *bb = (const __nv_bfloat16*)bias;
+  __nv_bfloat16* yb = (__nv_bfloat16*)y;
+  static int cfg = -1;                             // UNIMP_GEMV_CFG=<warps><u><rt> (e.g. 841): experiments
+  if (cfg < 0) { const char* ev = getenv("UNIMP_GEMV_CFG"); cfg = ev ? atoi(ev) : 0; }
+  int c = cfg;
+  // measured per shape on a B200 (tools/gemv_bench.py, cold weights): with >= 2 row tiles per SM small
+  // batches at high occupancy win (48 registers, 8 CTAs / SM); few tiles over a long K want deep batches;
+  // a handful of tiles (to_q: N = 512) wants 16 warps splitting K
+  if (!c) c = (N + SM_ROWS - 1) / SM_ROWS >= 2 * UNIMP_NUM_SMS ? 821 : (N <= 1024 ? 1641 : 881);
+  cudaError_t e;
+  switch (c) {
+#define UNIMP_SM_CASE(code, WARPS, U, RT) \
+    case code: e = launch_linear_small_m<WARPS, U, RT>(act, st, xb, wb, bb, yb, M, N, K); break
+    UNIMP_SM_CASE(821, 8, 2, 1);
+    UNIMP_SM_CASE(881, 8, 8, 1);
+    UNIMP_SM_CASE(1641, 16, 4, 1);
+    UNIMP_SM_CASE(841, 8, 4, 1);
+    UNIMP_SM_CASE(842, 8, 4, 2);
+#undef UNIMP_SM_CASE
+    default:
+      set_error("linear_small_m: unknown UNIMP_GEMV_CFG=%d", c);
+      return UNIMP_E_SHAPE;
+  }
+  if (e != cudaSuccess) { set_error("linear_small_m launch: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }

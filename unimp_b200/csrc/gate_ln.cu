@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(SMALL ? 128 : 1024, SMALL ? 9 : 1) gate_residu
   constexpr int N = Vec16<T>::N;
   const int64_t row = blockIdx.x;
   const int nvec = D / N;
+  pdl_launch_dependents();                  // decode steps launch this kernel with a programmatic
+  pdl_wait();                               // dependency (common.cuh); no-ops otherwise
   const T* xr = x + row * D;
   const T* br = branch ? branch + row * D : nullptr;
   const float tg = br ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
@@ -439,10 +441,21 @@ extern "C" int unimp_gate_residual_ln_fwd(const void* branch, const void* x, con
   if (rows == 0) return 0;
   const int threads = ln_threads(D, npv);
   cudaStream_t st = (cudaStream_t)stream;
-#define UNIMP_LN_FWD_LAUNCH(TT, SM)                                                                   \
-  gate_residual_ln_fwd_kernel<TT, SM><<<(unsigned)rows, threads, 0, st>>>(                             \
-      (const TT*)branch, (const TT*)x, (const TT*)gate, (const TT*)gamma, (const TT*)beta, (TT*)x_out, \
-      (TT*)ln_out, mean, rstd, D, eps)
+  // a decode step (a handful of rows, ~150 of these launches per token) is launched with a programmatic
+  // dependency so that it is scheduled while its predecessor drains
+#define UNIMP_LN_FWD_LAUNCH(TT, SM)                                                                       \
+  do {                                                                                                    \
+    if (rows <= 64) {                                                                                     \
+      cudaError_t e_ = launch_pdl(gate_residual_ln_fwd_kernel<TT, SM>, dim3((unsigned)rows), dim3(threads), 0, \
+                                  st, (const TT*)branch, (const TT*)x, (const TT*)gate, (const TT*)gamma,  \
+                                  (const TT*)beta, (TT*)x_out, (TT*)ln_out, mean, rstd, D, eps);           \
+      if (e_ != cudaSuccess) { set_error("gate_residual_ln_fwd launch: %s", cudaGetErrorString(e_)); return (int)e_; } \
+    } else {                                                                                              \
+      gate_residual_ln_fwd_kernel<TT, SM><<<(unsigned)rows, threads, 0, st>>>(                             \
+          (const TT*)branch, (const TT*)x, (const TT*)gate, (const TT*)gamma, (const TT*)beta, (TT*)x_out, \
+          (TT*)ln_out, mean, rstd, D, eps);                                                               \
+    }                                                                                                     \
+  } while (0)
   if (dtype == UNIMP_BF16) {
     if (threads <= 128) UNIMP_LN_FWD_LAUNCH(__nv_bfloat16, true);
     else UNIMP_LN_FWD_LAUNCH(__nv_bfloat16, false);

@@ -233,16 +233,21 @@ class GraphedDecoder:
         pos_emb = lm.gpt_neox.rotary_emb(x, position_ids=S.pos[:, None])
         # the new key position becomes visible; everything beyond stays masked
         S.add_mask.index_fill_(3, S.cur, 0.0)
+        # every LayerNorm rides on the residual add that produces its input (one K5 launch): the block /
+        # layer that ends at x also returns first_ln_of_the_next(x), as FlamingoLayer.forward does
+        x_ln = None
+        n_layers = len(self.layers)
         for i, layer in enumerate(self.layers):
-            blk = layer.gated_cross_attn_layer
+            blk, dl = layer.gated_cross_attn_layer, layer.decoder_layer
+            next_ln = self.layers[i + 1].first_ln() if i + 1 < n_layers else lm.gpt_neox.final_layer_norm
+            h1 = x_ln
             if blk is not None:
-                x = blk(x, layer.vis_x, media_locations=layer.media_locations, use_cached_media=True,
-                        text_time=S.n_media)
+                x, h1 = blk(x, layer.vis_x, media_locations=layer.media_locations, use_cached_media=True,
+                            text_time=S.n_media, next_ln=dl.input_layernorm, x_ln=x_ln)
             kv_step = ((S.k[i], S.v[i], S.cur, S.indir, S.mask2d) if S.indir is not None
                        else (S.k[i], S.v[i], S.cur))
-            x = fused_neox_layer(layer.decoder_layer, x, S.add_mask, pos_emb, kv_step=kv_step)
-        h = lm.gpt_neox.final_layer_norm(x)
-        S.logits.copy_(lm.embed_out(h)[:, -1, :])
+            x, x_ln = fused_neox_layer(dl, x, S.add_mask, pos_emb, h1=h1, next_ln=next_ln, kv_step=kv_step)
+        S.logits.copy_(lm.embed_out(x_ln)[:, -1, :])       # x_ln == final_layer_norm(x)
         S.cur += 1
         S.pos += 1
 
