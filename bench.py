@@ -326,15 +326,41 @@ def decode_bench(args, cfg):
               "what": "Flamingo.generate -> transformers beam search (the reference's call chain) on our kernels"}
     except Exception as ex:  # noqa: BLE001
         hf = {"error": repr(ex)[:200]}
+    # HBM floor of one token: every projection weight of the step once (GPT-NeoX layers, the x-attn
+    # blocks' to_q / to_out / FF, the output head) + the K/V rows the beams attend (LM caches up to the
+    # mean cursor, the last image's cached cross-attention K/V); peak = MEASURED_PEAKS.json copy bandwidth
+    lm = model.lang_encoder
+    w_bytes = 0
+    for layer in lm._get_decoder_layers():
+        blk, dl = layer.gated_cross_attn_layer, layer.decoder_layer
+        ws = [dl.attention.query_key_value.weight, dl.attention.dense.weight, dl.mlp.dense_h_to_4h.weight,
+              dl.mlp.dense_4h_to_h.weight]
+        if blk is not None:
+            ws += [blk.attn.to_q.weight, blk.attn.to_out.weight, blk.ff[1].weight, blk.ff[3].weight]
+        w_bytes += sum(w.numel() * w.element_size() for w in ws)
+    w_bytes += lm.embed_out.weight.numel() * lm.embed_out.weight.element_size()
+    n_lm = len(list(lm._get_decoder_layers()))
+    kv_bytes = int(2 * n_lm * beams * cfg.lm_hidden * (L + new / 2) * 2)
+    _pk = load_peaks()
+    peak_gbs, peak_src = _pk["hbm_gbs"], _pk["source"]
+    floor_ms = (w_bytes + kv_bytes) / (peak_gbs * 1e9) * 1e3
     line = {"metric": "decode tokens/s (C4: explanation generation, beams 5)", "unit": "tokens/s",
             "value": 1e3 / per_tok, "higher_is_better": True, "n_gpus": 1, "dtype": "bf16",
             "data": "synthetic", "steps": reps, "warmup": 2,
             "config": {"workload": f"C4-decode: {cfg.name}, batch 1, beams {beams}, prompt {L} tokens "
                                    f"(T=512 padded), Ti=5 images, {new} new tokens, cached vision latents + "
-                                   "cached cross-attention K/V, one CUDA-graph replay per token",
+                                   "cached cross-attention K/V, one CUDA-graph replay per token; beams re-ordered through an "
+                                   "indirection table (unimp_lm_decode_attn), projections on unimp_linear_small_m, "
+                                   "programmatic dependent launch between the step's kernels",
                        "value_is": "steady-state tokens/s of the graph replays (CUDA events around the replay "
                                    "loop, median of runs); prefill and graph capture reported separately"},
             "median_ms": med, "ms_per_token": per_tok,
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src,
+                         "weight_bytes_per_token": w_bytes, "kv_bytes_per_token": kv_bytes,
+                         "achieved": (w_bytes + kv_bytes) / (per_tok * 1e-3) / 1e9,
+                         "frac": floor_ms / per_tok, "hbm_floor_ms_per_token": floor_ms,
+                         "what": "whole decode step (one CUDA-graph replay: ~460 kernels) against streaming "
+                                 "its weights and K/V rows once"},
             "end_to_end_tokens_per_s": {"incl_prefill_and_capture": new / (med["wall_ms"] * 1e-3),
                                         "excl_capture": new / ((med["prefill_ms"] + med["replay_ms"]) * 1e-3)},
             "runs": runs, "hf_generate_path": hf}

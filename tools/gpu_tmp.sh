@@ -1,6 +1,11 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 300 python tools/gemv_bench.py 2>&1 | tail -6 > gpurun_out/d6_gemv.log; cat gpurun_out/d6_gemv.log
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "linear_small or decode" 2>&1 | tail -2
-timeout 600 python tools/decode_profile.py 34 > gpurun_out/d6_prof.log 2>&1; echo "prof rc=$?"; sed -n 4,4p gpurun_out/d6_prof.log | cut -c1-150
-UNIMP_PDL=0 timeout 600 python tools/decode_profile.py 34 > gpurun_out/d6_prof_nopdl.log 2>&1; echo "prof rc=$?"; sed -n 4,40p gpurun_out/d6_prof_nopdl.log | cut -c1-160
+timeout 900 python -m pytest tests/test_decode.py tests/test_kernels_gpu.py -x -q -m gpu -k "decode or linear_small or graphed" 2>&1 | tail -2
+timeout 900 python bench.py --mode decode > gpurun_out/d9_decode.json 2> gpurun_out/d9_decode.err; echo "bench rc=$?"; python - <<'P'
+import json
+for l in open('gpurun_out/d9_decode.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_token'], d['roofline'], d['median_ms'], d['hf_generate_path'])
+P
+tail -3 gpurun_out/d9_decode.err
+UNIMP_PDL=0 timeout 600 python tools/decode_profile.py 34 > gpurun_out/d9_prof_nopdl.log 2>&1; sed -n 1,1p gpurun_out/d9_prof_nopdl.log;  sed -n 4,12p gpurun_out/d9_prof_nopdl.log | cut -c1-130

@@ -69,31 +69,48 @@ lm_decode_attn_kernel(const T* __restrict__ qkv,        // (B, H, {q,k,v}, DH): 
     if (h == 0 && d == 0) indir[(int64_t)b * Tmax + cur] = b;
   }
   __syncthreads();
-  // ---- scores: one cached key per thread (its whole row: VEC independent 16-byte loads) -------------
+  // ---- scores: one cached key per thread (its whole row: VEC independent 16-byte loads), two keys'
+  // worth of loads in flight per thread and pass
   float m = -INFINITY;
-  for (int j = tid; j < cur; j += LD_THREADS) {
-    const int row = indir[(int64_t)b * Tmax + j];
-    const T* kp = kc + (((int64_t)row * H + h) * Tmax + j) * DH;
-    float s = 0.f;
+  for (int j0 = tid; j0 < cur; j0 += 2 * LD_THREADS) {
+    const int j1 = j0 + LD_THREADS;
+    const bool two = j1 < cur;
+    const int row0 = indir[(int64_t)b * Tmax + j0], row1 = two ? indir[(int64_t)b * Tmax + j1] : row0;
+    const T* kp0 = kc + (((int64_t)row0 * H + h) * Tmax + j0) * DH;
+    const T* kp1 = kc + (((int64_t)row1 * H + h) * Tmax + (two ? j1 : j0)) * DH;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int c0 = 0; c0 < VEC; c0 += CH) {
-      Vec16<T> kv[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (c0 + c < VEC) kv[c].load(kp + (c0 + c) * N);
+      Vec16<T> ka[CH], kb[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c)
         if (c0 + c < VEC) {
-          float f[N];
-          kv[c].unpack(f);
+          ka[c].load(kp0 + (c0 + c) * N);
+          kb[c].load(kp1 + (c0 + c) * N);
+        }
 #pragma unroll
-          for (int i = 0; i < N; ++i) s = fmaf(f[i], sq[(c0 + c) * N + i], s);
+      for (int c = 0; c < CH; ++c)
+        if (c0 + c < VEC) {
+          float f[N], e[N];
+          ka[c].unpack(f);
+          kb[c].unpack(e);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            s0 = fmaf(f[i], sq[(c0 + c) * N + i], s0);
+            s1 = fmaf(e[i], sq[(c0 + c) * N + i], s1);
+          }
         }
     }
-    s = s * scale + Elem<T>::to_f(add_mask[(int64_t)b * Tmax + j]);
-    ssc[j] = s;
-    srow[j] = row;
-    m = fmaxf(m, s);
+    s0 = s0 * scale + Elem<T>::to_f(add_mask[(int64_t)b * Tmax + j0]);
+    ssc[j0] = s0;
+    srow[j0] = row0;
+    m = fmaxf(m, s0);
+    if (two) {
+      s1 = s1 * scale + Elem<T>::to_f(add_mask[(int64_t)b * Tmax + j1]);
+      ssc[j1] = s1;
+      srow[j1] = row1;
+      m = fmaxf(m, s1);
+    }
   }
   if (tid == 0) {                           // the new token's own key never leaves the SM
     float s = 0.f;
@@ -117,15 +134,25 @@ lm_decode_attn_kernel(const T* __restrict__ qkv,        // (B, H, {q,k,v}, DH): 
     float acc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (int j = g; j < cur; j += G) {
-      Vec16<T> vv;
-      vv.load(vc + (((int64_t)srow[j] * H + h) * Tmax + j) * DH + c * N);
-      float f[N];
-      vv.unpack(f);
-      const float p = ssc[j];
+    constexpr int PB = 8;                   // cached rows in flight per thread and pass
+    for (int j0 = g; j0 < cur; j0 += PB * G) {
+      Vec16<T> vv[PB];
 #pragma unroll
-      for (int i = 0; i < N; ++i) acc[i] = fmaf(p, f[i], acc[i]);
+      for (int u = 0; u < PB; ++u) {
+        const int j = j0 + u * G;
+        if (j < cur) vv[u].load(vc + (((int64_t)srow[j] * H + h) * Tmax + j) * DH + c * N);
+      }
+#pragma unroll
+      for (int u = 0; u < PB; ++u) {
+        const int j = j0 + u * G;
+        if (j < cur) {
+          float f[N];
+          vv[u].unpack(f);
+          const float p = ssc[j];
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i] = fmaf(p, f[i], acc[i]);
+        }
+      }
     }
     if (g == 0) {
       const float p = ssc[cur];
@@ -183,7 +210,11 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
 // The weights do not depend on the previous kernel: the first batch of weight loads is issued BEFORE
 // the programmatic-dependency wait (it streams while the producer of x drains).
 // U = K steps per batch (loads in flight per lane: U x RT x 32 bytes).
-template <int ACT, int WARPS, int U, int RT>
+// KS > 1: split-K over a thread-block cluster of KS CTAs (grid.y): each CTA streams 1/KS of K for the
+// same row tile, the partial sums meet in CTA 0's shared memory (distributed shared memory stores, one
+// cluster barrier) and CTA 0 runs the epilogue — for the projections with few rows and a long K
+// (4h -> h: 160 row tiles x 20 KB rows), which otherwise leave most SMs with one CTA's loads in flight.
+template <int ACT, int WARPS, int U, int RT, int KS>
 __global__ void __launch_bounds__(WARPS * 32)
 linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int M, int N,
@@ -199,7 +230,16 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
     wb[r] = reinterpret_cast<const uint4*>(W + (int64_t)min(n0 + r * SM_ROWS + g + 8, N - 1) * K) + t;
   }
   const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)min(g, M - 1) * K) + t;
-  const int steps = K >> 5;
+  int steps = K >> 5;
+  unsigned ks = 0;
+  if (KS > 1) {                             // this CTA's share of the K steps
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(ks));
+    const int lo = (int)(((int64_t)steps * ks) / KS), hi = (int)(((int64_t)steps * (ks + 1)) / KS);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { wa[r] += lo * 4; wb[r] += lo * 4; }
+    xp += lo * 4;
+    steps = hi - lo;
+  }
   constexpr int STRIDE = WARPS * U;
   float acc[RT][4];
 #pragma unroll
@@ -273,13 +313,33 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
     red[warp][r * SM_ROWS + g + 8][2 * t + 1] = acc[r][3];
   }
   __syncthreads();
+  __shared__ float xchg[KS > 1 ? KS : 1][RT * SM_ROWS * 8];
+  if (KS > 1) {
+    for (int o = tid; o < RT * SM_ROWS * 8; o += WARPS * 32) {
+      const int r = o % (RT * SM_ROWS), mrow = o / (RT * SM_ROWS);
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s += red[w][r][mrow];   // fixed order
+      uint32_t local = (uint32_t)__cvta_generic_to_shared(&xchg[ks][o]), remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(s) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (ks != 0) return;
+  }
   for (int o = tid; o < RT * SM_ROWS * 8; o += WARPS * 32) {
     const int r = o % (RT * SM_ROWS), mrow = o / (RT * SM_ROWS);
     const int n = n0 + r;
     if (mrow < M && n < N) {
       float s = 0.f;
+      if (KS > 1) {
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) s += red[w][r][mrow];   // fixed order
+        for (int c = 0; c < KS; ++c) s += xchg[c][o];         // fixed order
+      } else {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += red[w][r][mrow];   // fixed order
+      }
       if (bias) s += __bfloat162float(bias[n]);
       if (ACT == 1) s = 0.5f * s * (1.f + erff(s * 0.70710678118654752f));   // exact GELU
       y[(int64_t)mrow * N + n] = __float2bfloat16_rn(s);
@@ -287,14 +347,31 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   }
 }
 
-template <int WARPS, int U, int RT>
+template <int WARPS, int U, int RT, int KS>
 static cudaError_t launch_linear_small_m(int act, cudaStream_t st, const __nv_bfloat16* x, const __nv_bfloat16* w,
                                          const __nv_bfloat16* bias, __nv_bfloat16* y, int M, int N, int K) {
-  const unsigned grid = (unsigned)((N + RT * SM_ROWS - 1) / (RT * SM_ROWS));
-  return act == 1 ? launch_pdl(linear_small_m_kernel<1, WARPS, U, RT>, dim3(grid), dim3(WARPS * 32), 0, st, x, w,
-                               bias, y, M, N, K)
-                  : launch_pdl(linear_small_m_kernel<0, WARPS, U, RT>, dim3(grid), dim3(WARPS * 32), 0, st, x, w,
-                               bias, y, M, N, K);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((N + RT * SM_ROWS - 1) / (RT * SM_ROWS)), KS);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (KS > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = KS;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return act == 1 ? cudaLaunchKernelEx(&cfg, linear_small_m_kernel<1, WARPS, U, RT, KS>, x, w, bias, y, M, N, K)
+                  : cudaLaunchKernelEx(&cfg, linear_small_m_kernel<0, WARPS, U, RT, KS>, x, w, bias, y, M, N, K);
 }
 
 }  // namespace unimp
@@ -347,22 +424,27 @@ extern "C" int unimp_linear_small_m(const void* x, const void* w, const void* bi
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *xb = (const __nv_bfloat16*)x, *wb = (const __nv_bfloat16*)w, *bb = (const __nv_bfloat16*)bias;
   __nv_bfloat16* yb = (__nv_bfloat16*)y;
-  static int cfg = -1;                             // UNIMP_GEMV_CFG=<warps><u><rt> (e.g. 841): experiments
+  static int cfg = -1;                             // UNIMP_GEMV_CFG=[<ks>]<warps><u><rt> (e.g. 841, 4441): experiments
   if (cfg < 0) { const char* ev = getenv("UNIMP_GEMV_CFG"); cfg = ev ? atoi(ev) : 0; }
   int c = cfg;
-  // measured per shape on a B200 (tools/gemv_bench.py, cold weights): with >= 2 row tiles per SM small
-  // batches at high occupancy win (48 registers, 8 CTAs / SM); few tiles over a long K want deep batches;
-  // a handful of tiles (to_q: N = 512) wants 16 warps splitting K
-  if (!c) c = (N + SM_ROWS - 1) / SM_ROWS >= 2 * UNIMP_NUM_SMS ? 821 : (N <= 1024 ? 1641 : 881);
+  // measured per shape on a B200 (tools/gemv_bench.py, cold weights; profiles/r2_decode_gemv_sweep.log):
+  // with >= 2 row tiles per SM small batches at high occupancy win (48 registers, 8 CTAs / SM); few
+  // tiles over a long K (4h -> h) want the K range split over a 4-CTA cluster; a handful of tiles
+  // (to_q: N = 512) likewise; the rest (N = 2560, K <= 2560) deep batches in one CTA per tile
+  if (!c) {
+    const int tiles = (N + SM_ROWS - 1) / SM_ROWS;
+    c = tiles >= 2 * UNIMP_NUM_SMS ? 821 : (N <= 1024 ? 4841 : (K >= 4096 ? 4441 : 881));
+  }
   cudaError_t e;
   switch (c) {
-#define UNIMP_SM_CASE(code, WARPS, U, RT) \
-    case code: e = launch_linear_small_m<WARPS, U, RT>(act, st, xb, wb, bb, yb, M, N, K); break
-    UNIMP_SM_CASE(821, 8, 2, 1);
-    UNIMP_SM_CASE(881, 8, 8, 1);
-    UNIMP_SM_CASE(1641, 16, 4, 1);
-    UNIMP_SM_CASE(841, 8, 4, 1);
-    UNIMP_SM_CASE(842, 8, 4, 2);
+#define UNIMP_SM_CASE(code, WARPS, U, RT, KS) \
+    case code: e = launch_linear_small_m<WARPS, U, RT, KS>(act, st, xb, wb, bb, yb, M, N, K); break
+    UNIMP_SM_CASE(821, 8, 2, 1, 1);
+    UNIMP_SM_CASE(881, 8, 8, 1, 1);
+    UNIMP_SM_CASE(841, 8, 4, 1, 1);
+    UNIMP_SM_CASE(1641, 16, 4, 1, 1);
+    UNIMP_SM_CASE(4841, 8, 4, 1, 4);      // 4-CTA cluster split-K
+    UNIMP_SM_CASE(4441, 4, 4, 1, 4);
 #undef UNIMP_SM_CASE
     default:
       set_error("linear_small_m: unknown UNIMP_GEMV_CFG=%d", c);
