@@ -1,11 +1,6 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_decode.py tests/test_kernels_gpu.py -x -q -m gpu -k "decode or linear_small or graphed" 2>&1 | tail -2
-timeout 900 python bench.py --mode decode > gpurun_out/d9_decode.json 2> gpurun_out/d9_decode.err; echo "bench rc=$?"; python - <<'P'
-import json
-for l in open('gpurun_out/d9_decode.json'):
-    if l.startswith('{'):
-        d=json.loads(l); print(d['value'], d['ms_per_token'], d['roofline'], d['median_ms'], d['hf_generate_path'])
-P
-tail -3 gpurun_out/d9_decode.err
-UNIMP_PDL=0 timeout 600 python tools/decode_profile.py 34 > gpurun_out/d9_prof_nopdl.log 2>&1; sed -n 1,1p gpurun_out/d9_prof_nopdl.log;  sed -n 4,12p gpurun_out/d9_prof_nopdl.log | cut -c1-130
+timeout 300 python tools/xblock_check.py check > gpurun_out/x1_check.log 2>&1; echo "check rc=$?"; grep "XB check" gpurun_out/x1_check.log; tail -3 gpurun_out/x1_check.log | grep -v "XB check"
+timeout 300 python tools/xblock_check.py timeline > gpurun_out/x1_timeline.log 2>&1; grep "XB" gpurun_out/x1_timeline.log | head -14
+timeout 300 python tools/xblock_check.py bench > gpurun_out/x1_bench.log 2>&1; grep "XB bench" gpurun_out/x1_bench.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "xattn_block or fused" 2>&1 | tail -2

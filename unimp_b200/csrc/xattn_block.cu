@@ -17,8 +17,9 @@
 //            softmax on the 128 TMEM-lane-owning threads, O = P V); Q goes TMEM -> bf16 ->
 //            swizzled shared memory (A operand) and to global (saved for backward).
 //   phase 3  O_h (bf16) goes to global (saved for backward); after a cluster barrier every CTA
-//            multicasts ITS head's O tile back from L2 into all 8 CTAs, so each holds the full
-//            128 x 512 O tile as an A operand, and computes 1/8 of the output columns:
+//            multicasts ITS head's O tile back from L2 into all 8 CTAs (one mbarrier per tile: the MMAs
+//            of K chunk kk start when tile kk is in), so each holds the full 128 x 512 O tile as an A
+//            operand, and computes 1/8 of the output columns:
 //            y[:, c*D/8 : (c+1)*D/8] = O_all . Wout[c*D/8 : ...]^T  (Wout streamed by TMA, 2 stages).
 // Warp roles (192 threads): warps 0-3 own one query row / TMEM lane each (conversion, softmax,
 // epilogues); warp 4 = TMA producer, warp 5 = MMA issuer (warp 5 owns TMEM): one lane of each,
@@ -135,7 +136,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   uint8_t* sW = smem + OFF_W;
   uint8_t* sO = smem + OFF_O;
   __shared__ uint64_t full1[S1], empty1[S1], bar_qacc, bar_qs, bar_kv[2], bar_s, bar_p, bar_pv, bar_o,
-      full_o, full_w[2], empty_w[2], bar_y;
+      full_o[xb::H], full_w[2], empty_w[2], bar_y;
   __shared__ uint32_t tmem_slot;
   __shared__ int s_j[2];
 
@@ -152,12 +153,30 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
       mbar_init(&bar_qacc, 1); mbar_init(&bar_qs, 4);
       mbar_init(&bar_kv[0], 1); mbar_init(&bar_kv[1], 1);
       mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_pv, 1); mbar_init(&bar_o, 1);
-      mbar_init(&full_o, 1);
+#pragma unroll
+      for (int i = 0; i < H; ++i) mbar_init(&full_o[i], 1);
       mbar_init(&full_w[0], 1); mbar_init(&full_w[1], 1);
       mbar_init(&empty_w[0], 1); mbar_init(&empty_w[1], 1);
       mbar_init(&bar_y, 1);
       fence_barrier_init();
       tma_prefetch_desc(&tx); tma_prefetch_desc(&twq); tma_prefetch_desc(&twout);
+      // per-CTA x_ln loads touch only THIS CTA's barriers: the first three ring stages go out now, under
+      // the text_time reads, the TMEM allocation and the CTA-wide sync (phase 1 is paced by data arrival)
+      if (a.flags & 1) {
+#pragma unroll
+        for (int s = 0; s < S1; ++s) {
+          if (s < a.NK / 2) {
+            mbar_arrive_expect_tx(&full1[s], 2 * STAGE1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int k = 2 * s + c;
+              uint8_t* st = smem + stage1_off(2 * s + c);
+              tma_load_3d(st, &tx, &full1[s], k * 64, t0, b);
+              tma_load_2d(st + A_BYTES, &twq, &full1[s], k * 64, h * DH);
+            }
+          }
+        }
+      }
     }
     // image blocks referenced by the tile's rows (same for the 8 CTAs of the cluster)
     int lo = 1 << 30, hi = -1;
@@ -198,9 +217,11 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   const int blk = (ttr >= 1 && !uniform) ? ttr - 1 : -1;
 
   if (tid == 0) XB_STAMP(0);
-  // cluster barrier #1: every CTA's barriers are initialised before any multicast / remote arrive
+  // barrier #1: every CTA's barriers are initialised before any multicast / remote arrive.  Without
+  // multicast nothing crosses CTAs before cluster barrier #2: a CTA-wide barrier is enough.
   tcgen05_fence_before();
-  cluster_sync_all();
+  if (a.flags & 1) __syncthreads();
+  else cluster_sync_all();
   tcgen05_fence_after();
   if (tid == 0) XB_STAMP(1);
   const uint32_t tmem = tmem_slot;
@@ -224,7 +245,7 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
 #pragma unroll
         for (int s = 0; s < S1; ++s) {
           const int p = p0 + s;
-          if (p < NP) {
+          if (p < NP && !(p0 == 0 && (a.flags & 1))) {      // (p0 == 0 went out in the prologue)
             if (p0 > 0) mbar_wait_tag(&empty1[s], ph, T_EMPTY1 + s);
             mbar_arrive_expect_tx(&full1[s], 2 * STAGE1);
 #pragma unroll
@@ -391,7 +412,8 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
       tcgen05_fence_after();
     }
     if (tid == 0) XB_STAMP(3);     // attention MMAs done
-    __nv_bfloat16* orow = a.o + ((int64_t)b * a.T + row) * INNER + h * DH;
+    // normalised O -> bf16 -> the (dead) P tile in the TMA box layout -> ONE bulk store (rows beyond T are
+    // clipped by the tensor map) instead of 128 bytes of strided STG per thread
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       if (nblk > 0) {
@@ -401,11 +423,19 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 32; ++c) r[c] = 0u;
       }
-      if (valid) xb_store_global32(orow + half * 32, r, inv, 32);
+      xb_store_half(sP, tid, half, r, inv);
     }
     if (valid) a.lse[((int64_t)b * H + h) * a.T + row] = lse_val;
-    fence_proxy_async_all();      // the O rows just written are read back by TMA (async proxy)
-    if (warp == 0 && elect_one_sync()) tma_store_wait_read();   // q store done with sQ (peers overwrite it next)
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 0 && elect_one_sync()) {
+      tma_store_4d(&to, sP, 0, h, t0, b);
+      tma_store_commit();
+      // complete (not only read): the peers' multicast loads after the cluster barrier fetch this tile
+      // from L2, and they overwrite sQ / sP next — the q store is in the same wait
+      tma_store_wait_all();
+      fence_proxy_async_all();
+    }
     tcgen05_fence_before();
   }
 
@@ -420,8 +450,11 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
   if (warp == 4) {
     if (elect_one_sync()) {
       fence_proxy_async_all();
-      mbar_arrive_expect_tx(&full_o, H * Q_BYTES);
-      tma_load_4d_mc(sO + h * Q_BYTES, &to, &full_o, 0, h, t0, b, ALL);
+      // one barrier per head's tile: the to_out MMAs of K chunk kk start when tile kk is in, under the
+      // remaining tiles' arrival
+#pragma unroll
+      for (int i = 0; i < H; ++i) mbar_arrive_expect_tx(&full_o[i], Q_BYTES);
+      tma_load_4d_mc(sO + h * Q_BYTES, &to, &full_o[h], 0, h, t0, b, ALL);
       for (int kk = 2; kk < H; ++kk) {
         const int s = kk & 1;
         mbar_wait_tag(&empty_w[s], ((kk >> 1) - 1) & 1, T_EMPTYW + s);
@@ -433,13 +466,13 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one_sync()) {
-      mbar_wait_tag(&full_o, 0, T_FULLO);
-      XB_STAMP(6);                 // all 8 O tiles arrived
       const uint32_t so_base = smem_u32(sO), sw_base = smem_u32(sW);
       const uint32_t half_off = (uint32_t)NSH * 128u;
 #pragma unroll
       for (int kk = 0; kk < H; ++kk) {              // fully unrolled: constant offsets, constant parities
         const int s = kk & 1;
+        mbar_wait_tag(&full_o[kk], 0, T_FULLO + kk);
+        if (kk == 0) XB_STAMP(6);  // the first O tile arrived
         mbar_wait_tag(&full_w[s], (kk >> 1) & 1, T_FULLW + s);
         tcgen05_fence_after();
         const uint32_t sa = so_base + kk * Q_BYTES, sb = sw_base + s * W_STAGE;
@@ -491,8 +524,11 @@ xattn_block_fwd_kernel(const __grid_constant__ CUtensorMap tx, const __grid_cons
     tcgen05_fence_before();
   }
   if (tid == 0) XB_STAMP(8);       // y stored
-  // nobody leaves while a peer may still multicast into its shared memory
-  cluster_sync_all();
+  // nobody leaves while a peer may still write into its shared memory.  Without x_ln multicast the only
+  // remote writes are the O tiles, and every CTA has waited for all eight of them (full_o): a CTA-wide
+  // barrier (all tcgen05.ld done before TMEM is freed) is enough.
+  if (a.flags & 1) __syncthreads();
+  else cluster_sync_all();
   if (tid == 0) XB_STAMP(9);
   if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
 }
