@@ -344,6 +344,12 @@ def decode_bench(args, cfg):
     _pk = load_peaks()
     peak_gbs, peak_src = _pk["hbm_gbs"], _pk["source"]
     floor_ms = (w_bytes + kv_bytes) / (peak_gbs * 1e9) * 1e3
+    kernels = None
+    if not args.no_kernel_profile:
+        from unimp_b200 import kbench
+        del dec
+        torch.cuda.empty_cache()
+        kernels = kbench.run(cfg, wl, _pk, only={"decode"}, eager=not args.no_eager_baseline)
     line = {"metric": "decode tokens/s (C4: explanation generation, beams 5)", "unit": "tokens/s",
             "value": 1e3 / per_tok, "higher_is_better": True, "n_gpus": 1, "dtype": "bf16",
             "data": "synthetic", "steps": reps, "warmup": 2,
@@ -363,7 +369,7 @@ def decode_bench(args, cfg):
                                  "its weights and K/V rows once"},
             "end_to_end_tokens_per_s": {"incl_prefill_and_capture": new / (med["wall_ms"] * 1e-3),
                                         "excl_capture": new / ((med["prefill_ms"] + med["replay_ms"]) * 1e-3)},
-            "runs": runs, "hf_generate_path": hf}
+            "runs": runs, "hf_generate_path": hf, "kernels": kernels}
     print(json.dumps(line))
 
 

@@ -177,7 +177,8 @@ def _rotate_half(x):
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,H,dh,rot,Tmax,cur", [(5, 32, 80, 80, 784, 600), (4, 4, 32, 8, 48, 0), (3, 8, 64, 32, 300, 299),
                                                  (2, 2, 128, 128, 1040, 1031), (6, 3, 96, 48, 64, 17),
-                                                 (5, 32, 80, 80, 768, 767)])
+                                                 (5, 32, 80, 80, 768, 767), (2, 4, 80, 80, 256, 1),
+                                                 (3, 4, 80, 40, 512, 0), (2, 4, 64, 64, 256, 6)])
 def test_lm_decode_attn_matches_dense(dtype, tol, B, H, dh, rot, Tmax, cur):
     """`unimp_lm_decode_attn` (rotary + cache write at a device-side cursor + attention through the
     beam indirection) against the dense statement of what HF runs per generated token:

@@ -1,6 +1,11 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 300 python tools/xblock_check.py check > gpurun_out/x1_check.log 2>&1; echo "check rc=$?"; grep "XB check" gpurun_out/x1_check.log; tail -3 gpurun_out/x1_check.log | grep -v "XB check"
-timeout 300 python tools/xblock_check.py timeline > gpurun_out/x1_timeline.log 2>&1; grep "XB" gpurun_out/x1_timeline.log | head -14
-timeout 300 python tools/xblock_check.py bench > gpurun_out/x1_bench.log 2>&1; grep "XB bench" gpurun_out/x1_bench.log
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "xattn_block or fused" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_decode.py tests/test_kernels_gpu.py -x -q -m gpu -k "decode or graphed" 2>&1 | tail -3
+timeout 300 python tools/kbench_cli.py --only decode --no-eager 2>&1 | grep "^KB" | grep "attn"
+UNIMP_DECODE_ATTN_SPLIT=1 timeout 300 python tools/kbench_cli.py --only decode --no-eager 2>&1 | grep "^KB" | grep "lm_decode"
+timeout 900 python bench.py --mode decode --no-kernel-profile > gpurun_out/e2_decode.json 2> gpurun_out/e2_decode.err; echo "bench rc=$?"; python - <<'P'
+import json
+for l in open('gpurun_out/e2_decode.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_token'], d['roofline']['frac'], d['median_ms'])
+P

@@ -124,6 +124,8 @@ def run(cfg, wl, peaks, *, dtype=torch.bfloat16, n_valid_rows=None, eager=True, 
         _run_focal(cfg, wl, dtype, eager, rec, out, n_valid_rows)
     if want("misc"):
         _run_misc(cfg, wl, dtype, rec)
+    if only is not None and "decode" in only:
+        _run_decode(cfg, dtype, eager, rec)
     if eager:
         for name in list(out):
             e = out.get("eager_" + name)
@@ -414,3 +416,70 @@ def _run_misc(cfg, wl, dtype, rec):
         npar * (2 * es + 6 * 4), 0.0, 3)
     rec("grad_sumsq", _time_graph([lambda: ops.sumsq_(pg, gn)] * 3), npar * es, 0.0, 3)
     del pw, pg, ma, m1, m2
+
+
+def _run_decode(cfg, dtype, eager, rec, beams=5, cursor=640, t_max=768, ti=5):
+    """The decode step's own kernels at configs[3] shapes (batch 1 x 5 beams, prompt 512 + 128 generated
+    tokens in the caches), each beside what the library path launches for the same work."""
+    F = torch.nn.functional
+    dev = "cuda"
+    D, Hl = cfg.lm_hidden, cfg.lm_heads
+    dl = D // Hl
+    rot = int(dl * cfg.rotary_pct)
+    M = beams
+    with torch.no_grad():
+        # ---- projections of one token: M rows against a cold weight matrix ------------------------
+        inner = cfg.xattn_heads * cfg.xattn_dim_head
+        for name, N, K in (("qkv", 3 * D, D), ("dense", D, D), ("h_to_4h", cfg.lm_ffn, D), ("4h_to_h", D, cfg.lm_ffn),
+                           ("to_q", inner, D), ("to_out", D, inner)):
+            nb = _k(N * K * 2, cap=64)
+            ws = [torch.randn(N, K, device=dev, dtype=dtype) * K ** -0.5 for _ in range(nb)]
+            b = torch.randn(N, device=dev, dtype=dtype)
+            x = torch.randn(M, 1, K, device=dev, dtype=dtype)
+            assert ops.small_m_eligible(x, ws[0])
+            rec("decode_linear_" + name, _time_graph([lambda w=w: ops.linear_rows(x, w, b) for w in ws]), N * K * 2, 0.0, nb)
+            if eager:
+                rec("eager_decode_linear_" + name, _time_graph([lambda w=w: F.linear(x, w, b) for w in ws]), N * K * 2, 0.0, nb)
+            del ws
+        # ---- the LM self-attention of one token: rotary + cache write + attention over `cursor` keys --
+        kvb = 2 * M * Hl * cursor * dl * 2
+        nb = _k(kvb, cap=12)
+        kc = [torch.randn(M, Hl, t_max, dl, device=dev, dtype=dtype) for _ in range(nb)]
+        vc = [torch.randn(M, Hl, t_max, dl, device=dev, dtype=dtype) for _ in range(nb)]
+        qkv = torch.randn(M, 1, 3 * D, device=dev, dtype=dtype)
+        cos, sin = torch.randn(M, 1, rot, device=dev, dtype=dtype), torch.randn(M, 1, rot, device=dev, dtype=dtype)
+        indir = torch.randint(0, M, (M, t_max), device=dev, dtype=torch.int32)
+        cur = torch.tensor([cursor], device=dev, dtype=torch.int64)
+        mask = torch.zeros(M, t_max, device=dev, dtype=dtype)
+        mask[:, cursor + 1:] = float("-inf")
+        rec("lm_decode_attn", _time_graph([lambda k=k, v=v: ops.lm_decode_attention(
+            qkv, cos, sin, k, v, indir, mask, cur, heads=Hl, head_dim=dl, rotary_dim=rot, scale=dl ** -0.5)
+            for k, v in zip(kc, vc)]), kvb, 0.0, nb)
+        if eager:
+            src = torch.randint(0, M, (M,), device=dev)
+            m4 = mask.view(M, 1, 1, t_max)
+
+            def lib_step(k, v):      # what HF's generate does per layer and token on this GPU
+                q, kn, vn = ops.rotary_qkv(qkv, cos, sin, heads=Hl, head_dim=dl, rotary_dim=rot)
+                k.index_copy_(2, cur, kn)
+                v.index_copy_(2, cur, vn)
+                a = F.scaled_dot_product_attention(q, k, v, attn_mask=m4, scale=dl ** -0.5)
+                k.copy_(k.index_select(0, src))      # reorder_cache after the beam step
+                v.copy_(v.index_select(0, src))
+                return a
+
+            rec("eager_lm_decode_attn", _time_graph([lambda k=k, v=v: lib_step(k, v) for k, v in zip(kc, vc)]),
+                kvb, 0.0, nb)
+        del kc, vc
+        # ---- single-token masked cross-attention against the cached to_kv(media) ------------------
+        n, Hx, dx = cfg.n_latents, cfg.xattn_heads, cfg.xattn_dim_head
+        q1 = torch.randn(M, 1, Hx * dx, device=dev, dtype=dtype)
+        kvs = [torch.randn(M, ti * n, 2 * Hx * dx, device=dev, dtype=dtype) for _ in range(16)]
+        nm = torch.full((M,), ti, device=dev, dtype=torch.int32)
+        xb = 2 * M * n * Hx * dx * 2
+        rec("xattn_decode", _time_graph([lambda kv=kv: ops.xattn_decode(q1, kv, nm, heads=Hx, n_latents=n, scale=dx ** -0.5)
+                                         for kv in kvs]), xb, 0.0, len(kvs))
+        if eager:
+            tt = nm[:, None]
+            rec("eager_xattn_decode", _time_graph([lambda kv=kv: _eager_xattn(q1, kv, tt, Hx, n, dx ** -0.5) for kv in kvs]),
+                xb, 0.0, len(kvs))
