@@ -30,7 +30,20 @@ __global__ void __launch_bounds__(SMALL ? 128 : 1024, SMALL ? 9 : 1) gate_residu
   const int64_t row = blockIdx.x;
   const int nvec = D / N;
   pdl_launch_dependents();                  // decode steps launch this kernel with a programmatic
-  pdl_wait();                               // dependency (common.cuh); no-ops otherwise
+                                            // dependency (common.cuh); no-ops otherwise
+  // gamma / beta are weights (no kernel of a step writes them): pull this thread's vectors towards L1
+  // now — no registers held — so that the loads after the two reductions do not pay an L2 round trip
+  if (gamma) {
+#pragma unroll
+    for (int k = 0; k < LN_VPT; ++k) {
+      const int j = threadIdx.x + k * blockDim.x;
+      if (j < nvec) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(gamma + j * N));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(beta + j * N));
+      }
+    }
+  }
+  pdl_wait();
   const T* xr = x + row * D;
   const T* br = branch ? branch + row * D : nullptr;
   const float tg = br ? (gate ? tanhf(Elem<T>::to_f(*gate)) : 1.f) : 0.f;
