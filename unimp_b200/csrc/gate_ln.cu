@@ -31,9 +31,11 @@ __global__ void __launch_bounds__(SMALL ? 128 : 1024, SMALL ? 9 : 1) gate_residu
   const int nvec = D / N;
   pdl_launch_dependents();                  // decode steps launch this kernel with a programmatic
                                             // dependency (common.cuh); no-ops otherwise
-  // gamma / beta are weights (no kernel of a step writes them): pull this thread's vectors towards L1
-  // now — no registers held — so that the loads after the two reductions do not pay an L2 round trip
-  if (gamma) {
+  // gamma / beta are weights (no kernel of a step writes them).  A decode step (a handful of rows: the
+  // launch is one latency chain) pulls this thread's vectors towards L1 now — no registers held — so that
+  // the loads after the two reductions do not pay an L2 round trip; with a full grid the extra requests
+  // cost more than they save (1536 rows: 6.9 -> 10.9 us, measured).
+  if (gamma && gridDim.x <= 64) {
 #pragma unroll
     for (int k = 0; k < LN_VPT; ++k) {
       const int j = threadIdx.x + k * blockDim.x;
