@@ -151,6 +151,17 @@ int unimp_lm_decode_attn(const void* qkv, const void* cos, const void* sin, void
                          void* out, int B, int H, int Tmax, int dh, int rot, float scale, int dtype,
                          void* stream);
 
+/* Beam-search candidate selection of one decode step — what HF `GenerationMixin._beam_search` computes
+ * with `log_softmax(logits)`, `+ running_beam_scores[:, :, None]` and `topk(2 * num_beams)` over the
+ * flattened (beams * V) axis (reference call chain: `UniMP/pipeline/eval/eval_exp.py:101-114`).
+ *   logits (B*nb, V) fp32, row stride ld; running (B*nb) fp32;
+ *   top_lp (B, K) fp32 sorted descending, top_idx (B, K) int64 = beam_in_item * V + token.
+ * K <= 16, K <= V, nb <= 64, nb * V < 2^31; ties break towards the smaller index.  workspace: device
+ * buffer of unimp_beam_topk_workspace(B*nb, V) bytes. */
+int64_t unimp_beam_topk_workspace(int rows, int V);
+int unimp_beam_topk(const float* logits, int64_t ld, const float* running, int B, int nb, int V, int K,
+                    void* workspace, float* top_lp, int64_t* top_idx, void* stream);
+
 /* y (M, N) = act(x (M, K) . w (N, K)^T + bias (N) or NULL), M <= 8 rows (the beams of one decode
  * step): `nn.Linear` of GPT-NeoX / GatedCrossAttentionBlock at one token per sequence, as a
  * weight-streaming kernel (each weight is read once, 16-byte loads).  act: 0 none, 1 exact (erf)

@@ -86,6 +86,7 @@ def install():
     ops.lm_decode_attention = lm_decode_attention
     ops.linear_rows = linear_rows
     ops.small_m_eligible = lambda x, w: False
+    ops.BEAM_TOPK = False                    # candidate selection stays on torch's log_softmax + topk here
     ops.text_time = text_time
     ops.masked_cross_attention = lambda q, kv, tt, *, heads, n_latents, scale, force_simt=False: \
         _dense_attention(q, kv, tt.long(), heads, n_latents, scale)

@@ -247,6 +247,31 @@ def test_linear_small_m_matches_f_linear(M, N, K, bias, gelu):
         assert not ops().small_m_eligible(x.to(DEV).float(), w.to(DEV).float())
 
 
+@pytest.mark.parametrize("B,nb,V,K", [(1, 5, 74053, 10), (2, 3, 512, 6), (3, 1, 5000, 2), (1, 8, 4096, 16), (2, 5, 4097, 10),
+                                     (1, 2, 100, 4)])
+def test_beam_topk_matches_log_softmax_topk(B, nb, V, K):
+    """`unimp_beam_topk` against what HF's `_beam_search` runs: log_softmax, + running scores, topk over
+    the flattened (beams * V) axis — same candidates in the same order, scores to fp32 round-off; first
+    step (only beam 0 live, the others at -1e9) included."""
+    torch.manual_seed(V + K)
+    for first_step in (False, True):
+        logits = (torch.randn(B * nb, V) * 3).to(DEV)
+        running = (torch.randn(B, nb) * 2).to(DEV)
+        if first_step:
+            running[:, 1:] = -1.0e9
+            running[:, 0] = 0.0
+        lp = torch.log_softmax(logits, dim=-1).view(B, nb, V) + running[:, :, None]
+        want_lp, want_idx = torch.topk(lp.view(B, nb * V), k=K)
+        got_lp, got_idx = ops().beam_topk(logits, running, nb, K)
+        torch.testing.assert_close(got_lp, want_lp, rtol=1e-5, atol=1e-5)
+        # candidates whose scores differ by more than round-off must agree exactly
+        gap_ok = (want_lp[:, :-1] - want_lp[:, 1:]).abs().min() > 1e-4
+        if gap_ok and not (first_step and K > V):
+            assert torch.equal(got_idx, want_idx)
+        # in any case every returned index carries the score it is listed with
+        assert torch.allclose(lp.view(B, nb * V).gather(1, got_idx), got_lp, rtol=1e-5, atol=1e-5)
+
+
 # ------------------------------------------------------------------ gate + residual + LN
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])

@@ -42,6 +42,8 @@ SIGNATURES = {
                                    _f, _i, _p]),
     "unimp_xattn_decode": (_i, [View, View, View, _p, View, _i, _i, _i, _i, _i, _f, _i, _p]),
     "unimp_lm_decode_attn": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "unimp_beam_topk_workspace": (_i64, [_i, _i]),
+    "unimp_beam_topk": (_i, [_p, _i64, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "unimp_linear_small_m": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "unimp_gate_residual_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "unimp_gate_residual_ln_bwd_workspace": (_i64, [_i64, _i]),

@@ -374,9 +374,154 @@ static cudaError_t launch_linear_small_m(int act, cudaStream_t st, const __nv_bf
                   : cudaLaunchKernelEx(&cfg, linear_small_m_kernel<0, WARPS, U, RT, KS>, x, w, bias, y, M, N, K);
 }
 
+// ------------------------------------------------------------------------------------------------
+// beam search: log-softmax + running score + top-K over (beams x vocabulary) per batch item
+// ------------------------------------------------------------------------------------------------
+// HF `_beam_search` per step: `log_softmax(logits)`, `+ running_beam_scores[:, :, None]`, `topk(2 * num_beams)`
+// over the flattened (beams * V) axis — in torch a softmax kernel, an add and an 8-kernel radix top-k over
+// 370 k floats (~130 us of a 2.6 ms token).  Here: one pass over the logits (each CTA: a 4096-wide chunk of
+// one row -> chunk max, chunk sum of exponentials, chunk top-K by K rounds of block arg-max in shared
+// memory), then one small merge per batch item.  Ties break towards the smaller flat index.
+constexpr int BT_THREADS = 256, BT_CHUNK = 4096, BT_KMAX = 16;
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax argmax_pick(ArgMax a, ArgMax b) {
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax a, ArgMax* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = argmax_pick(a, b);
+  }
+  __syncthreads();
+  if (lane == 0) sh[w] = a;
+  __syncthreads();
+  ArgMax r = sh[0];
+#pragma unroll
+  for (int k = 1; k < BT_THREADS / 32; ++k) r = argmax_pick(r, sh[k]);
+  return r;
+}
+
+// grid (splits, rows); partial layout per (row, split): [max, sum, K values, K token ids (as float bits)]
+__global__ void __launch_bounds__(BT_THREADS)
+beam_partial_kernel(const float* __restrict__ logits, int64_t ld, int V, int K, float* __restrict__ part) {
+  __shared__ float sx[BT_CHUNK];
+  __shared__ float sred[32];
+  __shared__ ArgMax sam[BT_THREADS / 32];
+  const int row = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
+  const int c0 = split * BT_CHUNK, n = min(BT_CHUNK, V - c0);
+  const float* x = logits + (int64_t)row * ld + c0;
+  float m = -INFINITY;
+  for (int i = tid; i < n; i += BT_THREADS) {
+    const float v = x[i];
+    sx[i] = v;
+    m = fmaxf(m, v);
+  }
+  m = block_max(m, sred);
+  float s = 0.f;
+  if (m > -INFINITY)
+    for (int i = tid; i < n; i += BT_THREADS) s += __expf(sx[i] - m);
+  s = block_sum(s, sred);
+  float* out = part + ((int64_t)row * gridDim.x + split) * (2 + 2 * BT_KMAX);
+  if (tid == 0) { out[0] = m; out[1] = s; }
+  for (int k = 0; k < K; ++k) {
+    ArgMax a = {-INFINITY, 0x7fffffff};
+    for (int i = tid; i < n; i += BT_THREADS) {
+      ArgMax b = {sx[i], i};
+      a = argmax_pick(a, b);
+    }
+    a = block_argmax(a, sam);
+    if (tid == 0) {
+      out[2 + k] = a.v;
+      out[2 + BT_KMAX + k] = __int_as_float(a.i < n ? c0 + a.i : -1);
+      if (a.i < n) sx[a.i] = -INFINITY;        // taken
+    }
+    __syncthreads();
+  }
+}
+
+// grid (B); one batch item: nb rows x splits partials -> top-K of log_softmax + running score
+__global__ void __launch_bounds__(BT_THREADS)
+beam_merge_kernel(const float* __restrict__ part, const float* __restrict__ running, int nb, int splits, int V,
+                  int K, float* __restrict__ top_lp, int64_t* __restrict__ top_idx) {
+  extern __shared__ float dsm2[];            // candidate scores [nb*splits*K] | flat ids (int) [nb*splits*K]
+  __shared__ float lse[64];
+  __shared__ ArgMax sam[BT_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ncand = nb * splits * K;
+  float* cv = dsm2;
+  int* ci = reinterpret_cast<int*>(dsm2 + ncand);
+  const int stride = 2 + 2 * BT_KMAX;
+  if (tid < nb) {                            // log-sum-exp of the row from its chunk partials (fixed order)
+    const float* p = part + (int64_t)(b * nb + tid) * splits * stride;
+    float M = -INFINITY;
+    for (int s = 0; s < splits; ++s) M = fmaxf(M, p[s * stride]);
+    float S = 0.f;
+    for (int s = 0; s < splits; ++s) S += p[s * stride + 1] * __expf(p[s * stride] - M);
+    lse[tid] = M + logf(S);
+  }
+  __syncthreads();
+  for (int c = tid; c < ncand; c += BT_THREADS) {
+    const int r = c / (splits * K), rem = c - r * splits * K, s = rem / K, k = rem - s * K;
+    const float* p = part + ((int64_t)(b * nb + r) * splits + s) * stride;
+    const int tok = __float_as_int(p[2 + BT_KMAX + k]);
+    cv[c] = tok >= 0 ? (p[2 + k] - lse[r]) + running[b * nb + r] : -INFINITY;
+    ci[c] = tok >= 0 ? r * V + tok : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    ArgMax a = {-INFINITY, 0x7fffffff};
+    int pos = -1;
+    for (int c = tid; c < ncand; c += BT_THREADS) {
+      ArgMax bb = {cv[c], ci[c]};
+      const ArgMax n2 = argmax_pick(a, bb);
+      if (n2.i != a.i || n2.v != a.v) pos = c;
+      a = n2;
+    }
+    const ArgMax w = block_argmax(a, sam);
+    if (pos >= 0 && a.i == w.i && a.v == w.v) cv[pos] = -INFINITY;     // the winner's owner retires it (ids are unique)
+    if (tid == 0) {
+      top_lp[b * K + k] = w.v;
+      top_idx[b * K + k] = w.i;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace unimp
 
 using namespace unimp;
+
+extern "C" int64_t unimp_beam_topk_workspace(int rows, int V) {
+  const int splits = (V + BT_CHUNK - 1) / BT_CHUNK;
+  return (int64_t)rows * splits * (2 + 2 * BT_KMAX) * sizeof(float);
+}
+
+extern "C" int unimp_beam_topk(const float* logits, int64_t ld, const float* running, int B, int nb, int V, int K,
+                               void* workspace, float* top_lp, int64_t* top_idx, void* stream) {
+  UNIMP_CHECK_ARG(logits && running && workspace && top_lp && top_idx, UNIMP_E_NULL, "beam_topk: NULL pointer");
+  UNIMP_CHECK_ARG(B > 0 && nb > 0 && nb <= 64 && V > 0 && K > 0 && K <= BT_KMAX && (int64_t)nb * V < 0x7fffffff &&
+                      K <= V,
+                  UNIMP_E_SHAPE, "beam_topk: need 1 <= K <= %d, K <= V, beams <= 64, beams * V < 2^31", BT_KMAX);
+  const int splits = (V + BT_CHUNK - 1) / BT_CHUNK;
+  const size_t smem = (size_t)nb * splits * K * 8;
+  UNIMP_CHECK_ARG(smem <= 48 * 1024, UNIMP_E_SHAPE, "beam_topk: beams * ceil(V / 4096) * K = %d candidates exceed 6144",
+                  nb * splits * K);
+  cudaStream_t st = (cudaStream_t)stream;
+  beam_partial_kernel<<<dim3(splits, B * nb), BT_THREADS, 0, st>>>(logits, ld, V, K, (float*)workspace);
+  UNIMP_CHECK_LAUNCH();
+  beam_merge_kernel<<<B, BT_THREADS, smem, st>>>((const float*)workspace, running, nb, splits, V, K, top_lp, top_idx);
+  UNIMP_CHECK_LAUNCH();
+  return 0;
+}
+
 
 extern "C" int unimp_lm_decode_attn(const void* qkv, const void* cos, const void* sin, void* k_cache,
                                     void* v_cache, int32_t* indir, const void* add_mask,

@@ -31,6 +31,8 @@ import os
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 NEG = -1.0e9
 
 
@@ -113,8 +115,12 @@ class BeamSearch:
         B, nb, K = self.B, self.nb, self.K
         V = logits.shape[-1]
         cur = self.cur
-        lp = F.log_softmax(logits.float(), dim=-1).view(B, nb, V) + self.running_scores[:, :, None]
-        top_lp, top_idx = torch.topk(lp.view(B, nb * V), k=K)
+        if logits.is_cuda and ops.BEAM_TOPK and K <= 16 and K <= V and nb <= 64:
+            # log_softmax + running score + top-2*nb in two launches (torch: softmax, add, radix top-k)
+            top_lp, top_idx = ops.beam_topk(logits.float(), self.running_scores, nb, K)
+        else:
+            lp = F.log_softmax(logits.float(), dim=-1).view(B, nb, V) + self.running_scores[:, :, None]
+            top_lp, top_idx = torch.topk(lp.view(B, nb * V), k=K)
         src_beam = torch.div(top_idx, V, rounding_mode="floor")
         tok = top_idx - src_beam * V
         cand_seq = _gather(self.running_seq, src_beam)

@@ -287,6 +287,26 @@ def lm_decode_attention(qkv, cos, sin, k_cache, v_cache, indir, add_mask, cursor
     return out
 
 
+BEAM_TOPK = os.environ.get("UNIMP_BEAM_TOPK", "1") != "0"   # A/B switch: 0 = torch log_softmax + topk
+
+
+def beam_topk(logits, running_scores, num_beams: int, k: int):
+    """One beam-search step's candidate selection (`unimp_beam_topk`): logits (B*nb, V) fp32,
+    running_scores (B, nb) fp32 -> (top_lp (B, k) sorted descending, top_idx (B, k) int64 over the
+    flattened (nb * V) axis) — HF's log_softmax + running score + topk(2 * num_beams)."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.stride(1) == 1
+    R, V = logits.shape
+    B = R // num_beams
+    running_scores = running_scores.reshape(-1).to(torch.float32).contiguous()
+    lib = _lib.load()
+    ws = torch.empty(lib.unimp_beam_topk_workspace(R, V), dtype=torch.uint8, device=logits.device)
+    top_lp = torch.empty((B, k), dtype=torch.float32, device=logits.device)
+    top_idx = torch.empty((B, k), dtype=torch.int64, device=logits.device)
+    check(lib.unimp_beam_topk(logits.data_ptr(), logits.stride(0), running_scores.data_ptr(), B, num_beams, V, k,
+                              ws.data_ptr(), top_lp.data_ptr(), top_idx.data_ptr(), _stream()), "unimp_beam_topk")
+    return top_lp, top_idx
+
+
 SMALL_M_LINEAR = os.environ.get("UNIMP_DECODE_GEMV", "1") != "0"   # A/B switch: 0 = cuBLAS for decode steps
 
 
