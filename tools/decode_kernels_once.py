@@ -29,4 +29,10 @@ with torch.no_grad():
     torch.cuda.synchronize()
     ops.xattn_decode(q1, kv, torch.full((M,), 5, device=dev, dtype=torch.int32), heads=8, n_latents=64, scale=0.125)
     torch.cuda.synchronize()
+    lp, idx = ops.beam_topk(torch.randn(M, 74053, device=dev), torch.zeros(1, M, device=dev), M, 10)
+    torch.cuda.synchronize()
+    # ragged shapes: N not a multiple of the row tile, K = 32, one beam
+    ops.linear_rows(torch.randn(1, 1, 32, device=dev, dtype=bf), torch.randn(1005, 32, device=dev, dtype=bf))
+    ops.linear_rows(torch.randn(3, 1, 10240, device=dev, dtype=bf), torch.randn(40, 10240, device=dev, dtype=bf))
+    torch.cuda.synchronize()
 print("ok")

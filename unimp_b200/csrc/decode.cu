@@ -233,6 +233,9 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   int steps = K >> 5;
   unsigned ks = 0;
   if (KS > 1) {                             // this CTA's share of the K steps
+    // a CTA may only write into a peer's shared memory once that peer has started: everybody arrives at
+    // the cluster barrier here (non-blocking) and waits for it right before the remote stores
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(ks));
     const int lo = (int)(((int64_t)steps * ks) / KS), hi = (int)(((int64_t)steps * (ks + 1)) / KS);
 #pragma unroll
@@ -315,6 +318,7 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   __syncthreads();
   __shared__ float xchg[KS > 1 ? KS : 1][RT * SM_ROWS * 8];
   if (KS > 1) {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");    // every CTA of the cluster is running
     for (int o = tid; o < RT * SM_ROWS * 8; o += WARPS * 32) {
       const int r = o % (RT * SM_ROWS), mrow = o / (RT * SM_ROWS);
       float s = 0.f;
