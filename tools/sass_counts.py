@@ -35,10 +35,12 @@ print("# SASS instruction counts of the shipped library (round 2)\n")
 print("`cuobjdump -sass unimp_b200/libunimp_b200.so`, per kernel (`tools/sass_counts.py`); the mnemonics of "
       "B200_PROFILING.md: `UTCHMMA` = tcgen05.mma, `LDTM` / `STTM` = tcgen05.ld / st, `UTMALDG` / `UTMASTG` / `UBLKRED` = "
       "TMA load / store / bulk reduce, `UTCBAR` = tcgen05.commit (`.MULTICAST`: to all CTAs of the cluster), `UCGABAR_ARV` "
-      "= cluster barrier.  `BRA.U.ANY` (the waterfall loops of round 1, DESIGN.md §4.2) must be 0 everywhere; no legacy "
-      "`HMMA`.\n")
+      "= cluster barrier.  `BRA.U.ANY` (the waterfall loops of round 1, DESIGN.md §4.2) must be 0 everywhere.  Warp-level "
+      "`HMMA` (`mma.sync`) appears in exactly one place, `linear_small_m_kernel` — the decode step's weight-streaming "
+      "projection for <= 8 rows, an HBM-bound kernel whose fragments are filled straight from global memory "
+      "(DESIGN.md §8); every contraction of the training path is `UTCHMMA`.\n")
 print("| kernel | " + " | ".join(pats) + " |")
 print("|---|" + "---:|" * len(pats))
 for k, c in counts.items():
-    if c["UTCHMMA"] or c["UTMALDG"] or c["LDTM"]:
+    if c["UTCHMMA"] or c["UTMALDG"] or c["LDTM"] or c["HMMA"]:
         print(f"| `{k}` | " + " | ".join(str(c[p]) for p in pats) + " |")
