@@ -341,7 +341,10 @@ class GraphedDecoder:
         S.add_mask[:, 0, 0, :T0] = torch.zeros((), dtype=dtype, device=dev).expand(Bf, T0).masked_fill(mask == 0, self.MASK_FILL)
         # beam indirection: cache row that holds position t of beam i's history (identity at first)
         S.indir = S.mask2d = None
-        if self.use_indirection:
+        head_dim = self.layers[0].decoder_layer.attention.head_size
+        # unimp_lm_decode_attn covers head dims 32..128 and caches up to 5120 positions; beyond that the
+        # step runs on re-ordered caches + SDPA (same tokens, tests/test_decode.py)
+        if self.use_indirection and Tmax <= 5120 and head_dim in (32, 64, 80, 96, 128):
             S.indir = torch.arange(Bf, dtype=torch.int32, device=dev)[:, None].repeat(1, Tmax).contiguous()
             S.mask2d = S.add_mask.view(Bf, Tmax)
         S.k, S.v = [], []
